@@ -1,0 +1,167 @@
+"""CPU: the oracle (oracle/yond_oracle.py) replays the golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  This is what pins the oracle; the GPU tests then compare CUDA to the oracle."""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import yond_oracle as O
+
+ARCHS = {
+    "unet": {"name": "UNetSeeInDark", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
+    "gru": {"name": "GuidedResUnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1,
+            "res": True, "norm": True},
+    "snr": {"name": "SNRnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1,
+            "res": True, "norm": True},
+}
+PIPE = {"k": 29, "full_dn": False, "vst_type": "exact", "bias_corr": "pre", "iter": "iter", "max_iter": 1}
+
+
+def crc(a):
+    return np.uint32(zlib.crc32(np.ascontiguousarray(a).tobytes()))
+
+
+def test_pack_bit_exact(golden):
+    g = golden("pack")
+    assert np.array_equal(O.bayer2rggb(g["bayer"]), g["rggb"])
+    assert np.array_equal(O.rggb2bayer(g["rggb"]), g["back"])
+    assert np.array_equal(g["back"], g["bayer"])
+
+
+def test_vst_and_inverse(golden):
+    g = golden("vst")
+    K, s = np.float64(g["K"]), np.float64(g["sigma"])
+    z = O.VST(g["x"], s, gain=K)
+    assert z.dtype == np.float64  # NumPy-2 promotion: the reference runs this stage in float64
+    np.testing.assert_array_equal(z, g["z"])
+    np.testing.assert_array_equal(O.inverse_VST(z, s, gain=K, exact=False), g["inv_alg"])
+    np.testing.assert_allclose(O.inverse_VST(np.concatenate([z, [0.0, -1.0]]), s, gain=K, exact=True), g["inv_exact"],
+                               rtol=1e-15, atol=0)
+    assert O.VST(0, s, gain=K) == g["lower"] and O.VST(959.0, s, gain=K) == g["upper"]
+
+
+def test_biaslut(golden, lut_table):
+    g = golden("biaslut")
+    assert crc(lut_table) == g["lut_crc"], "stand-in LUT differs from the one the goldens were made with"
+    lut = O.BiasLUT(lut_table)
+    np.testing.assert_array_equal(lut.x_lut, g["x_lut"])
+    np.testing.assert_array_equal(lut.sg_lut, g["sg_lut"])
+    for i, (K, s) in enumerate(g["cases"]):
+        out = lut.get_lut(g["x"], K=np.float64(K), sigGs=np.float64(s))
+        np.testing.assert_array_equal(out, g[f"bias{i}"])
+        row = lut.sigma_row(np.float64(K), np.float64(s))
+        assert row.shape == (1921,)
+
+
+def test_fallback_bias_table(golden):
+    g = golden("getbias")
+    f = O.get_bias(np.float32(700.0), np.float64(6.0), np.float64(4.0))
+    np.testing.assert_array_equal(f.x, g["nodes"])
+    np.testing.assert_allclose(f(g["x"]), g["bias"], rtol=0, atol=1e-12)
+    f2 = O.get_bias(np.float32(40.0), np.float64(0.9), np.float64(0.4))
+    np.testing.assert_array_equal(f2.x, g["nodes2"])
+    np.testing.assert_allclose(f2(g["x2"]), g["bias2"], rtol=0, atol=1e-12)
+
+
+def test_stdfilt_and_blur(golden):
+    g = golden("stdfilt")
+    np.testing.assert_array_equal(O.stdfilt(g["img"], 29), g["std29"])
+    np.testing.assert_array_equal(O.stdfilt(g["img"], 5), g["std5"])
+    np.testing.assert_array_equal(O.blur(g["img"], 19), g["blur19"])
+    # the NumPy restatement of cv2.blur (used when cv2 is missing, and as the spec for the CUDA kernel)
+    np.testing.assert_allclose(O.box_blur_np(g["img"], 19), g["blur19"], rtol=0, atol=6e-8)
+    np.testing.assert_allclose(O.box_blur_np(g["img"], 29), O.blur(g["img"], 29), rtol=0, atol=6e-8)
+
+
+def test_estimators(golden):
+    g = golden("nlf")
+    r2 = np.random.default_rng(int(g["seed"]))
+    clean = O.synth_clean(r2, 256, 384)
+    noisy = O.synth_noisy(r2, clean, 6.0, 9.0)
+    rggb = O.bayer2rggb(noisy)
+    var, mean, lap = O.self_maps(rggb, 29)
+    assert crc(lap) == g["lap_crc"]
+    np.testing.assert_array_equal(mean[::16, ::16], g["mean_sub"])
+    np.testing.assert_array_equal(var[::16, ::16], g["var_sub"])
+    th, pct, _ = O.get_threshold_score3(lap, mean, step=5)
+    assert th == g["th"] and pct == g["pct"]
+    np.testing.assert_allclose(O.SimpleNLF(noisy, k=29, setting={"mode": "self"}), g["reg_self"], rtol=1e-12)
+    blocks_c = np.stack([O.synth_clean(r2, 64, 64) for _ in range(32)])
+    blocks_n = np.stack([O.synth_noisy(r2, b, 6.0, 9.0) for b in blocks_c])
+    blocks_d = np.stack([np.clip(b + 0.004 * r2.standard_normal(b.shape), 0, 1).astype(np.float32) for b in blocks_c])
+    mos_n, mos_d = np.concatenate(list(blocks_n), -1), np.concatenate(list(blocks_d), -1)
+    np.testing.assert_allclose(O.SimpleNLF(mos_n, mos_d, 29, {"mode": "collab", "SIDD_256": True}), g["reg_collab"],
+                               rtol=1e-12)
+    np.testing.assert_allclose(O.SimpleNLF(mos_n, mos_d, 29, {"mode": "collab"}), g["reg_collab_plain"], rtol=1e-12)
+
+
+def test_get_p2d(golden):
+    g = golden("p2d")
+    for s, p in zip(g["shapes"], g["p2d"]):
+        assert O.get_p2d(tuple(int(v) for v in s), base=32) == tuple(int(v) for v in p)
+
+
+@pytest.mark.parametrize("key", ["unet", "gru", "snr"])
+def test_networks(golden, key):
+    g = golden(f"net_{key}")
+    arch = ARCHS[key]
+    sd = O.init_state_dict(arch, seed=5)
+    assert [str(k) for k in g["keys"]] == list(sd.keys())
+    assert [str(s) for s in g["shapes"]] == [str(tuple(v.shape)) for v in sd.values()]
+    assert np.array_equal(np.array([crc(v.numpy()) for v in sd.values()], np.uint32), g["sd_crc"])
+    assert int(g["nparams"]) == {"unet": 7760484, "gru": 11173668, "snr": 11176612}[key]
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        y = O.net_forward(arch, sd, x, torch.tensor(0.043) if "guided" in arch else None)
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-6)
+    # bf16 emulation of the CUDA path's stores must stay well inside the 2e-3 budget on random-init weights
+    with torch.no_grad():
+        yb = O.net_forward(arch, sd, x, torch.tensor(0.043) if "guided" in arch else None, bf16=True)
+    assert float((yb - y).abs().max()) < 5e-4
+
+
+def test_vst_denoiser(golden, lut_table):
+    g = golden("vst_denoiser")
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "scale": 959.0, "gain": np.float64(g["gain"]), "sigma": np.float64(g["sigma"])}
+    lut = O.BiasLUT(lut_table)
+    for key, out, kw in (("gru", "out_gru", dict(biaslut=lut)), ("snr", "out_snr", dict(biaslut=lut)),
+                         ("unet", "out_unet", dict(biaslut=None)),
+                         ("unet", "out_unet_nobias", dict(biaslut=None, bias_corr=None))):
+        sd = O.init_state_dict(ARCHS[key], seed=5)
+        bc = kw.pop("bias_corr", "pre")
+        res = O.VST_Denoiser(ARCHS[key], sd, g["noisy"], p, bias_corr=bc, **kw)
+        np.testing.assert_allclose(res, g[out], rtol=0, atol=3e-6, err_msg=out)
+    sd = O.init_state_dict(ARCHS["unet"], seed=5)
+    np.testing.assert_allclose(O.Simple_Denoiser(ARCHS["unet"], sd, g["noisy"]), g["out_simple"], rtol=0, atol=3e-6)
+
+
+def _blocks(seed, K, S):
+    r4 = np.random.default_rng(seed)
+    return np.stack([O.synth_noisy(r4, O.synth_clean(r4, 256, 256), K, S) for _ in range(32)])
+
+
+@pytest.mark.parametrize("key", ["gru", "unet"])
+def test_iterdenoise_random_init(golden, lut_table, key):
+    g = golden(f"iter_{key}")
+    blocks = _blocks(int(g["seed"]), float(g["K"]), float(g["sigma"]))
+    assert crc(blocks) == g["blocks_crc"], "synthetic input generator drifted"
+    sd = O.init_state_dict(ARCHS[key], seed=5)
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+    res = O.IterDenoise(ARCHS[key], sd, blocks, p, PIPE, biaslut=O.BiasLUT(lut_table) if key == "gru" else None)
+    assert len(res["raw_dns"]) == int(g["nrounds"]) == 1  # random weights: round 2 aborts on beta1 < 0 (:445-447)
+    np.testing.assert_allclose(np.array(res["regs"][0]), g["regs"][0], rtol=1e-10)
+    np.testing.assert_allclose(res["raw_dns"][0][::8, ::8], g["dn0_sub"], rtol=0, atol=3e-6)
+
+
+@pytest.mark.parametrize("key", ["gru", "unet"])
+def test_iterdenoise_two_rounds(golden, lut_table, key):
+    g = golden(f"iter2_{key}")
+    blocks = _blocks(int(g["seed"]), float(g["K"]), float(g["sigma"]))
+    sd = O.smoother_state_dict(ARCHS[key])
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+    res = O.IterDenoise(ARCHS[key], sd, blocks, p, PIPE, biaslut=O.BiasLUT(lut_table))
+    assert len(res["raw_dns"]) == 2
+    np.testing.assert_allclose(np.array([np.asarray(r) for r in res["regs"]]), g["regs"], rtol=1e-9)
+    np.testing.assert_allclose(res["raw_dns"][0][::8, ::8], g["dn0_sub"], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(res["raw_dns"][1][::8, ::8], g["dn1_sub"], rtol=0, atol=3e-6)

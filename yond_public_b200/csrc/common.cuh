@@ -1,0 +1,68 @@
+// Shared helpers for libyond_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/yond_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+int yond_set_error(int code, const char* fmt, ...);
+void yond_count_launch(int n = 1);
+
+#define YOND_CUDA_CHECK(expr)                                                                        \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return yond_set_error(YOND_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                            __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define YOND_LAUNCH_CHECK()                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = cudaGetLastError();                                                             \
+    if (_e != cudaSuccess)                                                                           \
+      return yond_set_error(YOND_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                                     \
+    yond_count_launch();                                                                             \
+  } while (0)
+
+#define YOND_REQUIRE(cond, ...)                                                                      \
+  do {                                                                                               \
+    if (!(cond)) return yond_set_error(YOND_ERR_INVALID, __VA_ARGS__);                               \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// Number of SMs of the current device (148 on B200); cached.
+int yond_num_sms();
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+// cv2.blur's border rule (BORDER_REFLECT_101) and torch's F.pad(mode='reflect') are the same map.
+__host__ __device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+  }
+  return i;
+}
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_stream_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}

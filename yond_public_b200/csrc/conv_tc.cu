@@ -1,0 +1,624 @@
+// Implicit-GEMM convolution for the YOND denoisers on Blackwell tensor cores (sm_100a).
+//
+// Replaces the torch.nn.Conv2d / ConvTranspose2d calls of archs/Unet.py:17-52, :393-421 and
+// archs/modules.py:117-125,163-233 (library kernels in the reference) with one persistent,
+// warp-specialised kernel:
+//
+//   warp 0   TMA producer  — activations: halo-extended NHWC tiles (cp.async.bulk.tensor.4d, OOB zero-fill
+//                            gives the conv's zero padding for free); weights: per-tap K-major tiles (2d)
+//   warp 1   MMA issuer    — one elected thread issues tcgen05.mma (M=128 pixels, N<=256 channels, K=16),
+//                            accumulating over taps x channel blocks into TMEM; tcgen05.commit frees stages
+//   warps 2-5 epilogue     — tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's MMAs
+//                            overlap), bias / FiLM / activation / residual, bf16 NHWC stores
+//
+// GEMM view: M = output pixels (a tile is TH rows x NB images x TW columns = 128), N = Cout, K = taps*Cin.
+// A 3x3 stride-1 conv loads, per channel block, three W-shifted slabs of (TH+2) rows; the three vertical
+// taps of each slab are reached by advancing the UMMA descriptor start address by one image row
+// (NB*TW pixels = a whole number of 8-row swizzle atoms), so A traffic is 3 slabs instead of 9 tiles.
+#include "conv_tc.cuh"
+
+#include <mutex>
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStagesA = 8;
+constexpr int kMaxStagesB = 8;
+
+struct TcParams {
+  int B, H, W;  // tile-space dims (output dims; input dims for CONVT_2X2)
+  int TH, TW, NB;
+  int tiles_h, tiles_w, tiles_b, tiles_n;
+  int NT;     // N tile (UMMA N)
+  int N;      // GEMM N total
+  int Cout;   // real output channels
+  int CB;     // channel block (32 | 64)
+  int ncb0, ncb1;
+  int mode;
+  int wres;   // weights resident in smem
+  int SA, SB; // pipeline depths
+  uint32_t a_stage_bytes, b_stage_bytes;
+  uint32_t smem_b_off, smem_bar_off;
+  int tmem_cols;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int act;
+  float slope;
+  const bf16* res;
+  bf16* out0;
+  bf16* out1;
+};
+
+struct TcMaps {
+  CUtensorMap a[8];
+  CUtensorMap w;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (an error on the host), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 0x3ff) == 0x3ff) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 6000000000LL) __trap();  // ~3 s at 1.9 GHz
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, 64B / 128B swizzle (rows of CB bf16, 8-row atoms).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t row_bytes) {
+  const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;  // SWIZZLE_128B : SWIZZLE_64B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address, bits [0,14)
+  d |= 1ull << 16;                                 // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;    // stride byte offset: next 8-row group
+  d |= 1ull << 46;                                 // descriptor version (Blackwell)
+  d |= layout << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(h);
+}
+
+// One activation ("A") pipeline stage of the K loop, decoded identically by producer and MMA issuer.
+struct AStage {
+  int map;       // index into TcMaps::a
+  int c;         // channel coordinate
+  int dw, dh;    // tile-origin offsets of the load
+  int ntaps;     // weight tiles consumed from this stage (3 for the slab mode, else 1)
+  int widx0;     // first weight-tile index; tap r uses widx0 + r*wstep
+  int wstep;
+};
+__device__ __forceinline__ AStage decode_astage(const TcParams& p, int ai) {
+  AStage s;
+  if (p.mode == CONV_3X3_S1) {
+    int cbg = ai / 3, sx = ai - cbg * 3;
+    int src = cbg >= p.ncb0;
+    s.map = src;
+    s.c = (src ? cbg - p.ncb0 : cbg) * p.CB;
+    s.dw = sx - 1;
+    s.dh = -1;
+    s.ntaps = 3;
+    s.widx0 = cbg * 9 + sx;  // tap = r*3 + sx
+    s.wstep = 3;
+  } else if (p.mode == CONV_3X3_S2) {
+    int cbg = ai / 9, tap = ai - cbg * 9;
+    int r = tap / 3, sx = tap - r * 3;
+    int src = cbg >= p.ncb0;
+    s.map = src * 4 + (r != 1) * 2 + (sx != 1);
+    s.c = (src ? cbg - p.ncb0 : cbg) * p.CB;
+    s.dh = (r == 0) ? -1 : 0;
+    s.dw = (sx == 0) ? -1 : 0;
+    s.ntaps = 1;
+    s.widx0 = cbg * 9 + tap;
+    s.wstep = 0;
+  } else {
+    int src = ai >= p.ncb0;
+    s.map = src;
+    s.c = (src ? ai - p.ncb0 : ai) * p.CB;
+    s.dw = 0;
+    s.dh = 0;
+    s.ntaps = 1;
+    s.widx0 = ai;
+    s.wstep = 0;
+  }
+  return s;
+}
+__device__ __forceinline__ int num_astages(const TcParams& p) {
+  int ncb = p.ncb0 + p.ncb1;
+  return p.mode == CONV_3X3_S1 ? ncb * 3 : (p.mode == CONV_3X3_S2 ? ncb * 9 : ncb);
+}
+__device__ __forceinline__ int num_wtiles(const TcParams& p) {
+  int ncb = p.ncb0 + p.ncb1;
+  return (p.mode == CONV_3X3_S1 || p.mode == CONV_3X3_S2) ? ncb * 9 : ncb;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: swizzle atoms (8 rows x 128 B) must start on their own boundary.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + p.smem_b_off;
+  const uint32_t bars = smem_base + p.smem_bar_off;
+  // barrier layout (8 bytes each)
+  const uint32_t a_full = bars, a_empty = a_full + 8 * kMaxStagesA;
+  const uint32_t b_full = a_empty + 8 * kMaxStagesA, b_empty = b_full + 8 * kMaxStagesB;
+  const uint32_t acc_full = b_empty + 8 * kMaxStagesB, acc_empty = acc_full + 16;
+  const uint32_t w_full = acc_empty + 16;
+  const uint32_t tmem_slot = w_full + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t row_bytes = p.CB * 2;
+  const int total_tiles = p.tiles_b * p.tiles_h * p.tiles_w * p.tiles_n;
+  const int n_ast = num_astages(p);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.w);
+      tma_prefetch_desc(&maps.a[0]);
+      if (p.wres) {  // all weight tiles of this layer stay in smem for the kernel's lifetime
+        const int nwt = num_wtiles(p);
+        mbar_expect_tx(w_full, nwt * p.b_stage_bytes);
+        for (int i = 0; i < nwt; ++i) tma_load_2d(smem_b + i * p.b_stage_bytes, &maps.w, w_full, 0, i * p.N);
+      }
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % p.tiles_n;
+        int m = tile / p.tiles_n;
+        const int tw_i = m % p.tiles_w; m /= p.tiles_w;
+        const int th_i = m % p.tiles_h;
+        const int tb_i = m / p.tiles_h;
+        const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tb_i * p.NB, n0 = n_idx * p.NT;
+        for (int ai = 0; ai < n_ast; ++ai) {
+          const AStage s = decode_astage(p, ai);
+          mbar_wait(a_empty + 8 * sa, pa ^ 1);
+          mbar_expect_tx(a_full + 8 * sa, p.a_stage_bytes);
+          tma_load_4d(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full + 8 * sa, s.c, w0 + s.dw, b0, h0 + s.dh);
+          if (++sa == p.SA) { sa = 0; pa ^= 1; }
+          if (!p.wres) {
+            for (int r = 0; r < s.ntaps; ++r) {
+              mbar_wait(b_empty + 8 * sb, pb ^ 1);
+              mbar_expect_tx(b_full + 8 * sb, p.b_stage_bytes);
+              tma_load_2d(smem_b + sb * p.b_stage_bytes, &maps.w, b_full + 8 * sb, 0,
+                          (s.widx0 + r * s.wstep) * p.N + n0);
+              if (++sb == p.SB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t row_shift_bytes = (uint32_t)(p.NB * p.TW) * row_bytes;  // one image row of the slab
+      const int ksteps = p.CB / 16;
+      if (p.wres) mbar_wait(w_full, 0);
+      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(acc_empty + 8 * as, pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.NT);
+        uint32_t accum = 0;
+        for (int ai = 0; ai < n_ast; ++ai) {
+          const AStage s = decode_astage(p, ai);
+          mbar_wait(a_full + 8 * sa, pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_a + sa * p.a_stage_bytes;
+          for (int r = 0; r < s.ntaps; ++r) {
+            uint32_t b_base;
+            if (p.wres) {
+              b_base = smem_b + (uint32_t)(s.widx0 + r * s.wstep) * p.b_stage_bytes;
+            } else {
+              mbar_wait(b_full + 8 * sb, pb);
+              tc_fence_after();
+              b_base = smem_b + sb * p.b_stage_bytes;
+            }
+            const uint32_t a_tap = a_base + (p.mode == CONV_3X3_S1 ? r * row_shift_bytes : 0u);
+            for (int k = 0; k < ksteps; ++k) {
+              umma_bf16(d_tmem, umma_desc(a_tap + k * 32, row_bytes), umma_desc(b_base + k * 32, row_bytes), idesc, accum);
+              accum = 1;
+            }
+            if (!p.wres) {
+              umma_commit(b_empty + 8 * sb);
+              if (++sb == p.SB) { sb = 0; pb ^= 1; }
+            }
+          }
+          umma_commit(a_empty + 8 * sa);
+          if (++sa == p.SA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(acc_full + 8 * as);
+        if (++as == 2) { as = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int w_i = row % p.TW;
+    const int b_i = (row / p.TW) % p.NB;
+    const int h_i = row / (p.TW * p.NB);
+    int as = 0, pacc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_idx = tile % p.tiles_n;
+      int m = tile / p.tiles_n;
+      const int tw_i = m % p.tiles_w; m /= p.tiles_w;
+      const int th_i = m % p.tiles_h;
+      const int tb_i = m / p.tiles_h;
+      const int w = tw_i * p.TW + w_i, h = th_i * p.TH + h_i, b = tb_i * p.NB + b_i;
+      const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
+      mbar_wait(acc_full + 8 * as, pacc);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.NT);
+      for (int c = 0; c < p.NT; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_base + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int n = n_idx * p.NT + c;  // first GEMM column of this chunk
+          int co = n;
+          size_t pix;
+          if (p.mode == CONVT_2X2) {
+            const int quad = n / p.Cout;
+            co = n - quad * p.Cout;
+            pix = ((size_t)b * (2 * p.H) + (2 * h + (quad >> 1))) * (size_t)(2 * p.W) + (2 * w + (quad & 1));
+          } else {
+            pix = ((size_t)b * p.H + h) * (size_t)p.W + w;
+          }
+          const size_t off = pix * p.Cout + co;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + co + j);
+          if (p.scale) {
+            const float* sc = p.scale + (size_t)b * p.Cout + co;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= __ldg(sc + j);
+          }
+          if (p.shift) {
+            const float* sh = p.shift + (size_t)b * p.Cout + co;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(sh + j);
+          }
+          if (p.act == ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+          } else if (p.act == ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+          }
+          if (p.res) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u = __ldg(r4 + g);
+              float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
+              f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
+            }
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(p.out0 + off);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+            u.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+            u.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+            u.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+            o4[g] = u;
+          }
+          if (p.out1) {
+            uint4* s4 = reinterpret_cast<uint4*>(p.out1 + off);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_bf16x2(silu_f(f[g * 8 + 0]), silu_f(f[g * 8 + 1]));
+              u.y = pack_bf16x2(silu_f(f[g * 8 + 2]), silu_f(f[g * 8 + 3]));
+              u.z = pack_bf16x2(silu_f(f[g * 8 + 4]), silu_f(f[g * 8 + 5]));
+              u.w = pack_bf16x2(silu_f(f[g * 8 + 6]), silu_f(f[g * 8 + 7]));
+              s4[g] = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+      if (++as == 2) { as = 0; pacc ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// Activation map over an NHWC bf16 tensor viewed as dims (C, W, B, H) so that a box lands in smem as
+// [h][b][w][c]: one image row of the tile (NB*TW pixels) is contiguous, whatever NB is.
+int make_act_map(CUtensorMap* m, const bf16* base, int C, int W, int B, int H, uint64_t strideW, uint64_t strideB,
+                 uint64_t strideH, int CB, int TW, int NB, int rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return yond_set_error(YOND_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)B, (cuuint64_t)H};
+  cuuint64_t strides[3] = {strideW, strideB, strideH};
+  cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)TW, (cuuint32_t)NB, (cuuint32_t)rows};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return yond_set_error(YOND_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d B=%d H=%d box=%d,%d,%d,%d)",
+                          (int)r, C, W, B, H, CB, TW, NB, rows);
+  return YOND_OK;
+}
+
+int make_weight_map(CUtensorMap* m, const bf16* base, int CB, size_t rows, int NT) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return yond_set_error(YOND_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)CB, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)CB * 2};
+  cuuint32_t box[2] = {(cuuint32_t)CB, (cuuint32_t)NT};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return yond_set_error(YOND_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return YOND_OK;
+}
+
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+int conv_tc_channel_block(int Cin0, int Cin1) {
+  return (Cin0 % 64 == 0 && Cin1 % 64 == 0) ? 64 : 32;
+}
+
+size_t conv_tc_packed_elems(int mode, int Cin_total, int Cout) {
+  int taps = (mode == CONV_3X3_S1 || mode == CONV_3X3_S2) ? 9 : 1;
+  int N = (mode == CONVT_2X2) ? 4 * Cout : Cout;
+  return (size_t)taps * Cin_total * N;
+}
+
+int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
+  YOND_REQUIRE(L.Cin0 % 32 == 0 && L.Cin1 % 32 == 0 && L.Cin0 > 0, "conv_tc: Cin must be a multiple of 32 (got %d,%d)",
+               L.Cin0, L.Cin1);
+  YOND_REQUIRE(L.Cout % 32 == 0, "conv_tc: Cout must be a multiple of 32 (got %d)", L.Cout);
+  TcParams p{};
+  p.mode = L.mode;
+  p.B = L.B;
+  if (L.mode == CONV_3X3_S2) {
+    YOND_REQUIRE(L.Hin % 2 == 0 && L.Win % 2 == 0, "conv_tc: stride-2 conv needs even input dims");
+    p.H = L.Hin / 2;
+    p.W = L.Win / 2;
+  } else {
+    p.H = L.Hin;
+    p.W = L.Win;
+  }
+  p.Cout = L.Cout;
+  p.N = (L.mode == CONVT_2X2) ? 4 * L.Cout : L.Cout;
+  p.CB = conv_tc_channel_block(L.Cin0, L.Cin1);
+  p.ncb0 = L.Cin0 / p.CB;
+  p.ncb1 = L.Cin1 / p.CB;
+  p.NT = p.N < 256 ? p.N : 256;
+  YOND_REQUIRE(p.N % p.NT == 0 && (p.NT & (p.NT - 1)) == 0, "conv_tc: unsupported N=%d", p.N);
+  p.tiles_n = p.N / p.NT;
+  // tile shape: TH rows x NB images x TW columns = 128 GEMM rows
+  p.TW = p.W > 8 ? 16 : 8;
+  const int rows = 128 / p.TW;
+  p.TH = pow2_ceil(p.H) < rows ? pow2_ceil(p.H) : rows;
+  p.NB = rows / p.TH;
+  p.tiles_w = ceil_div(p.W, p.TW);
+  p.tiles_h = ceil_div(p.H, p.TH);
+  p.tiles_b = ceil_div(p.B, p.NB);
+  const int slab_rows = (L.mode == CONV_3X3_S1) ? p.TH + 2 : p.TH;
+  const uint32_t row_bytes = p.CB * 2;
+  p.a_stage_bytes = (uint32_t)slab_rows * p.NB * p.TW * row_bytes;
+  p.b_stage_bytes = (uint32_t)p.NT * row_bytes;
+  YOND_REQUIRE(p.a_stage_bytes % 1024 == 0 && p.b_stage_bytes % 1024 == 0, "conv_tc: stage sizes not 1024-aligned");
+
+  const int ncb = p.ncb0 + p.ncb1;
+  const int nwt = ((L.mode == CONV_3X3_S1 || L.mode == CONV_3X3_S2) ? 9 : 1) * ncb;
+  const size_t smem_budget = 227 * 1024 - 2048;  // dynamic smem minus alignment slack and barriers
+  const size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
+  p.wres = (p.tiles_n == 1 && wres_bytes <= 96 * 1024) ? 1 : 0;
+  size_t b_region;
+  if (p.wres) {
+    p.SB = 1;
+    b_region = wres_bytes;
+  } else {
+    p.SB = 4;
+    while (p.SB > 2 && (size_t)p.SB * p.b_stage_bytes > 128 * 1024) --p.SB;
+    b_region = (size_t)p.SB * p.b_stage_bytes;
+  }
+  p.SA = (int)((smem_budget - b_region) / p.a_stage_bytes);
+  if (p.SA > kMaxStagesA) p.SA = kMaxStagesA;
+  YOND_REQUIRE(p.SA >= 2, "conv_tc: not enough shared memory for the activation pipeline");
+  p.smem_b_off = (uint32_t)p.SA * p.a_stage_bytes;
+  p.smem_bar_off = (uint32_t)align_up(p.smem_b_off + b_region, 1024);
+  const size_t smem_bytes = p.smem_bar_off + 512 + 1024;  // barriers + alignment slack
+  p.tmem_cols = 2 * p.NT < 32 ? 32 : 2 * p.NT;
+
+  p.bias = L.bias;
+  p.scale = L.scale;
+  p.shift = L.shift;
+  p.act = L.act;
+  p.slope = L.slope;
+  p.res = L.res;
+  p.out0 = L.out0;
+  p.out1 = L.out1;
+
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const bf16* srcs[2] = {L.src0, L.src1};
+  const int cins[2] = {L.Cin0, L.Cin1};
+  for (int s = 0; s < 2; ++s) {
+    if (cins[s] == 0) continue;
+    const int C = cins[s];
+    if (L.mode == CONV_3X3_S2) {
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const bf16* base = srcs[s] + ((size_t)ph * L.Win + pw) * C;
+          int rc = make_act_map(&maps.a[s * 4 + ph * 2 + pw], base, C, L.Win / 2, L.B, L.Hin / 2, (uint64_t)2 * C * 2,
+                                (uint64_t)L.Hin * L.Win * C * 2, (uint64_t)2 * L.Win * C * 2, p.CB, p.TW, p.NB, slab_rows);
+          if (rc) return rc;
+        }
+    } else {
+      int rc = make_act_map(&maps.a[s], srcs[s], C, L.Win, L.B, L.Hin, (uint64_t)C * 2, (uint64_t)L.Hin * L.Win * C * 2,
+                            (uint64_t)L.Win * C * 2, p.CB, p.TW, p.NB, slab_rows);
+      if (rc) return rc;
+    }
+  }
+  {
+    int rc = make_weight_map(&maps.w, L.wpacked, p.CB, (size_t)nwt * p.N, p.NT);
+    if (rc) return rc;
+  }
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess)
+    return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_kernel) failed: %s", cudaGetErrorString(attr_err));
+
+  const int total_tiles = p.tiles_b * p.tiles_h * p.tiles_w * p.tiles_n;
+  int grid = yond_num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(maps, p);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}

@@ -1,0 +1,37 @@
+// Implicit-GEMM convolution on tcgen05 / TMEM / TMA (sm_100a) — host-side interface.
+#pragma once
+#include "common.cuh"
+
+enum ConvMode {
+  CONV_3X3_S1 = 0,  // 3x3, stride 1, pad 1 (halo slab in smem shared by the 3 vertical taps)
+  CONV_1X1 = 1,     // 1x1 (plain GEMM over pixels)
+  CONV_3X3_S2 = 2,  // 3x3, stride 2, pad 1 (GuidedResUnet / SNRnet "pool"; parity-split tensor maps)
+  CONVT_2X2 = 3,    // ConvTranspose2d 2x2 stride 2 (GEMM with N = 4*Cout, scatter epilogue)
+};
+enum ConvAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_SILU = 2 };
+
+struct ConvLayer {
+  int mode;
+  int B, Hin, Win;          // input spatial size per image
+  int Cin0, Cin1;           // channels of the (up to two, concatenated) NHWC bf16 sources
+  const bf16* src0;
+  const bf16* src1;
+  int Cout;                 // real output channels
+  const bf16* wpacked;      // [cbg][tap][N][CB] bf16, N = Cout (x4 for CONVT_2X2: n = (a*2+b)*Cout + co)
+  const float* bias;        // [Cout]
+  const float* scale;       // [B][Cout] or null: v = v*scale + shift   (FiLM / SNR gates)
+  const float* shift;       // [B][Cout] or null
+  int act;                  // applied after scale/shift
+  float slope;
+  const bf16* res;          // [B,Hout,Wout,Cout] or null, added after the activation
+  bf16* out0;               // [B,Hout,Wout,Cout]
+  bf16* out1;               // optional second output = SiLU(out0 value)
+};
+
+// Channel block (K slice per pipeline stage) used for a layer: 64 when every source allows it, else 32.
+int conv_tc_channel_block(int Cin0, int Cin1);
+// Packed weight size in elements for a layer.
+size_t conv_tc_packed_elems(int mode, int Cin_total, int Cout);
+int conv_tc_launch(const ConvLayer& L, cudaStream_t stream);
+// CUDA-core direct convolution with identical semantics (debug cross-check; reads the same packed weights).
+int conv_ref_launch(const ConvLayer& L, cudaStream_t stream);

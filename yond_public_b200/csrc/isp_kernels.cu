@@ -1,0 +1,372 @@
+// Elementwise / LUT kernels of the YOND path: Bayer pack/unpack, generalized-Anscombe VST with LUT bias
+// correction, normalisation, reflect padding, inverse VST.  All HBM-bound: one pass, 64/128-bit accesses.
+//   reference: utils/isp_ops.py:57-63, utils/isp_algos.py:5-33,162-231, YOND_SIDD.py:238-299.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// ------------------------------------------------------------------ A1 / A2
+// One thread packs two adjacent quads: two 128-bit loads (rows 2i, 2i+1), two 128-bit stores.
+__global__ void pack_kernel(const float* __restrict__ bayer, float* __restrict__ rggb, int B, int H, int W) {
+  const int h = H >> 1, w2 = W >> 2;  // w2 = pairs of quads per row
+  const size_t total = (size_t)B * h * w2;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int jp = (int)(idx % w2);
+    const int i = (int)((idx / w2) % h);
+    const int b = (int)(idx / ((size_t)w2 * h));
+    const float* r0 = bayer + ((size_t)b * H + 2 * i) * W + 4 * jp;
+    const float4 a = ldg_stream_f4(reinterpret_cast<const float4*>(r0));
+    const float4 c = ldg_stream_f4(reinterpret_cast<const float4*>(r0 + W));
+    float4* o = reinterpret_cast<float4*>(rggb + (((size_t)b * h + i) * (W >> 1) + 2 * jp) * 4);
+    o[0] = make_float4(a.x, a.y, c.x, c.y);
+    o[1] = make_float4(a.z, a.w, c.z, c.w);
+  }
+}
+__global__ void pack_kernel_scalar(const float* __restrict__ bayer, float* __restrict__ rggb, int B, int H, int W) {
+  const int h = H >> 1, w = W >> 1;
+  const size_t total = (size_t)B * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % w);
+    const int i = (int)((idx / w) % h);
+    const int b = (int)(idx / ((size_t)w * h));
+    const float* r0 = bayer + ((size_t)b * H + 2 * i) * W + 2 * j;
+    float* o = rggb + idx * 4;
+    o[0] = r0[0]; o[1] = r0[1]; o[2] = r0[W]; o[3] = r0[W + 1];
+  }
+}
+__global__ void unpack_kernel(const float* __restrict__ rggb, float* __restrict__ bayer, int B, int h, int w) {
+  const int W = 2 * w, H = 2 * h;
+  const size_t total = (size_t)B * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % w);
+    const int i = (int)((idx / w) % h);
+    const int b = (int)(idx / ((size_t)w * h));
+    const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(rggb) + idx);
+    float* r0 = bayer + ((size_t)b * H + 2 * i) * W + 2 * j;
+    *reinterpret_cast<float2*>(r0) = make_float2(v.x, v.y);
+    *reinterpret_cast<float2*>(r0 + W) = make_float2(v.z, v.w);
+  }
+}
+
+// ------------------------------------------------------------------ A3 / A4 / A5 device functions
+struct VstConst {
+  float K, c0, two_over_K, lower, inv_range, range, scale, inv_scale, sig2e, sigma;
+  int lut_row, table_n, exact;
+};
+__device__ __forceinline__ VstConst load_const(const yond_vst_params& q) {
+  VstConst c;
+  c.K = q.gain;
+  c.sigma = q.sigma;
+  c.c0 = 0.375f * q.gain * q.gain + q.sigma * q.sigma;
+  c.two_over_K = 2.0f / q.gain;
+  c.lower = q.lower;
+  c.range = q.upper - q.lower;
+  c.inv_range = 1.0f / c.range;
+  c.scale = q.scale;
+  c.inv_scale = 1.0f / q.scale;
+  const float se = q.sigma / q.gain;
+  c.sig2e = se * se;
+  c.lut_row = q.lut_row;
+  c.table_n = q.table_n;
+  c.exact = q.exact_inverse;
+  return c;
+}
+__device__ __forceinline__ float vst_f(float x, const VstConst& c) {
+  return c.two_over_K * sqrtf(fmaxf(fmaf(c.K, x, c.c0), 0.f));
+}
+// Foi's closed-form bias (utils/isp_algos.py:84-96), used beyond the table like the reference does (:228-230).
+__device__ __forceinline__ float close_form_bias_f(float x, const VstConst& c) {
+  const float y = x / c.K, s2 = c.sig2e;
+  const float yh = y + 0.375f + s2;
+  const float m1 = (y + s2) / (yh * yh);
+  const float m2 = y / (yh * yh * yh);
+  const float m3 = (y + 3.f * (y + s2) * (y + s2)) / (yh * yh * yh * yh);
+  return 2.f * sqrtf(yh) * (-0.125f * m1 + 0.0625f * m2 - 0.0390625f * m3);
+}
+// Piecewise-linear table lookup with the reference's node inversion (pos_interp + data_merge).
+//   `nodes` ascending, n entries; LUT mode (analytic first guess on the lin+log grid) or generic (binary search).
+__device__ __forceinline__ float table_eval(float xq, const float* __restrict__ row, const float* __restrict__ nodes, int n,
+                                            bool lut_grid) {
+  if (xq <= __ldg(nodes)) return __ldg(row);
+  int l;
+  if (lut_grid) {
+    int g = xq < 0.0625f ? (int)(xq * 2048.f) : 128 + (int)floorf(128.f * (log2f(xq) + 4.f));
+    g = max(0, min(g, n - 2));
+    while (g + 1 < n - 1 && __ldg(nodes + g + 1) < xq) ++g;
+    while (g > 0 && __ldg(nodes + g) >= xq) --g;
+    l = g;
+  } else {
+    int lo = 0, hi = n - 1;  // invariant: nodes[lo] < xq, find last such lo with lo <= n-2
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(nodes + mid) < xq) lo = mid; else hi = mid;
+    }
+    l = lo;
+  }
+  const float xl = __ldg(nodes + l), xr = __ldg(nodes + l + 1);
+  float wr = (xq - xl) / (xr - xl);
+  wr = fminf(wr, 1.0f);  // beyond the last node the reference clips the position (data_merge)
+  const float yl = __ldg(row + l), yr = __ldg(row + l + 1);
+  return yl * (1.f - wr) + yr * wr;
+}
+__device__ __forceinline__ float bias_eval(float x_dn, const VstConst& c, const float* __restrict__ rows,
+                                           const float* __restrict__ xnodes, int row_stride) {
+  if (c.lut_row < 0) return 0.f;
+  const float xb = fmaxf(x_dn, 0.f);
+  const float* row = rows + (size_t)c.lut_row * row_stride;
+  if (c.table_n > 0) {  // fallback get_bias table: nodes in DN, one node array per row
+    const float* nodes = xnodes + (size_t)c.lut_row * row_stride;
+    const float xc = fminf(xb, __ldg(nodes + c.table_n - 1));
+    return table_eval(xc, row, nodes, c.table_n, false);
+  }
+  const float xe = xb / c.K;  // electrons
+  const int nx = 1921;
+  const float last = __ldg(xnodes + nx - 1), prev = __ldg(xnodes + nx - 2);
+  if (xe >= last + (last - prev)) return close_form_bias_f(xb, c);  // x_pos >= len(x_lut): isp_algos.py:228-230
+  return table_eval(xe, row, xnodes, nx, true);
+}
+__device__ __forceinline__ float inverse_vst_f(float z, const VstConst& c) {
+  float f;
+  if (c.exact) {
+    if (z > 0.f) {
+      const float iz = 1.f / z;
+      f = 0.25f * z * z + 0.30618621784789724f * iz - 1.375f * iz * iz + 0.7654655446197431f * iz * iz * iz - 0.125f - c.sig2e;
+    } else {
+      f = 0.f;
+    }
+  } else {
+    f = 0.25f * z * z - 0.375f - c.sig2e;
+  }
+  return fmaxf(f, 0.f) * c.K;
+}
+
+__device__ __forceinline__ void block_max_to(float v, float* dst) {
+  // v >= 0: integer order == float order
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __shared__ float wmax[kBlock / 32];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m = threadIdx.x < kBlock / 32 ? wmax[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(m));
+  }
+}
+
+// ------------------------------------------------------------------ A18 front: fused pack+bias+VST+normalise+clamp+pad
+// grid = (blocks per frame, B); every block stays inside one frame so the per-frame constants are uniform.
+template <bool kVst>
+__global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict__ bayer, float* __restrict__ z,
+                                                         float* __restrict__ ub, int H, int W, int pl, int pt, int hp, int wp,
+                                                         const yond_vst_params* __restrict__ params,
+                                                         const float* __restrict__ rows, const float* __restrict__ xnodes,
+                                                         int row_stride) {
+  const int b = blockIdx.y;
+  const int h = H >> 1, w = W >> 1;
+  VstConst c{};
+  if (kVst) c = load_const(params[b]);
+  const float* frame = bayer + (size_t)b * H * W;
+  float4* zo = reinterpret_cast<float4*>(z) + (size_t)b * hp * wp;
+  const int npix = hp * wp;
+  float vmax = 0.f;
+  for (int idx = blockIdx.x * kBlock + threadIdx.x; idx < npix; idx += gridDim.x * kBlock) {
+    const int j = idx % wp, i = idx / wp;
+    const int si = reflect101(i - pt, h), sj = reflect101(j - pl, w);
+    const float* r0 = frame + (size_t)(2 * si) * W + 2 * sj;
+    const float2 a = ldg_stream_f2(reinterpret_cast<const float2*>(r0));
+    const float2 d = ldg_stream_f2(reinterpret_cast<const float2*>(r0 + W));
+    float v[4] = {a.x, a.y, d.x, d.y};
+    if (kVst) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x = v[k] * c.scale;
+        const float zz = vst_f(x, c) - bias_eval(x, c, rows, xnodes, row_stride);
+        v[k] = (zz - c.lower) * c.inv_range;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = fminf(fmaxf(v[k], 0.f), 1.f);
+      vmax = fmaxf(vmax, v[k]);
+    }
+    zo[idx] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  block_max_to(vmax, ub + b);
+}
+
+// ------------------------------------------------------------------ A18 back: clamp+crop+denorm+inverse+unpack(+clip)
+template <bool kVst>
+__global__ void __launch_bounds__(kBlock) vst_inv_kernel(const float* __restrict__ y, float* __restrict__ bayer, int H, int W,
+                                                         int pl, int pt, int hp, int wp,
+                                                         const yond_vst_params* __restrict__ params, int clip01) {
+  const int b = blockIdx.y;
+  const int h = H >> 1, w = W >> 1;
+  VstConst c{};
+  if (kVst) c = load_const(params[b]);
+  const float4* yi = reinterpret_cast<const float4*>(y) + (size_t)b * hp * wp;
+  float* frame = bayer + (size_t)b * H * W;
+  const int npix = h * w;
+  for (int idx = blockIdx.x * kBlock + threadIdx.x; idx < npix; idx += gridDim.x * kBlock) {
+    const int j = idx % w, i = idx / w;
+    const float4 q = ldg_stream_f4(yi + (size_t)(i + pt) * wp + (j + pl));
+    float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float t = fminf(fmaxf(v[k], 0.f), 1.f);
+      if (kVst) {
+        t = inverse_vst_f(fmaf(t, c.range, c.lower), c) * c.inv_scale;
+        if (clip01) t = fminf(fmaxf(t, 0.f), 1.f);
+      }
+      v[k] = t;
+    }
+    float* r0 = frame + (size_t)(2 * i) * W + 2 * j;
+    *reinterpret_cast<float2*>(r0) = make_float2(v[0], v[1]);
+    *reinterpret_cast<float2*>(r0 + W) = make_float2(v[2], v[3]);
+  }
+}
+
+// ------------------------------------------------------------------ function-level surface
+__global__ void vst_elem_kernel(const float* __restrict__ x, float* __restrict__ z, size_t n, float K, float c0) {
+  const float tk = 2.f / K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    z[i] = tk * sqrtf(fmaxf(fmaf(K, x[i], c0), 0.f));
+}
+__global__ void ivst_elem_kernel(const float* __restrict__ z, float* __restrict__ x, size_t n, VstConst c) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = inverse_vst_f(z[i], c);
+}
+__global__ void lut_row_kernel(const float* __restrict__ lut, int nx, int nsg, int l, int r, float wr, float* __restrict__ row) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nx) row[i] = lut[(size_t)i * nsg + l] * (1.f - wr) + lut[(size_t)i * nsg + r] * wr;
+}
+__global__ void lut_apply_kernel(const float* __restrict__ x, float* __restrict__ bias, size_t n, const float* __restrict__ row,
+                                 const float* __restrict__ xnodes, int nx, VstConst c) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    bias[i] = bias_eval(x[i], c, row, xnodes, nx);
+}
+
+inline int grid_for(size_t n, int per_thread = 1) {
+  size_t g = (n + (size_t)kBlock * per_thread - 1) / ((size_t)kBlock * per_thread);
+  const size_t cap = (size_t)yond_num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int yond_pack(const float* bayer, float* rggb, int B, int H, int W, void* stream) {
+  YOND_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "yond_pack: H,W must be even (got %d,%d)", H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = (W % 4 == 0) && ((uintptr_t)bayer % 16 == 0) && ((uintptr_t)rggb % 16 == 0);
+  if (vec) pack_kernel<<<grid_for((size_t)B * (H / 2) * (W / 4)), kBlock, 0, s>>>(bayer, rggb, B, H, W);
+  else pack_kernel_scalar<<<grid_for((size_t)B * (H / 2) * (W / 2)), kBlock, 0, s>>>(bayer, rggb, B, H, W);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_unpack(const float* rggb, float* bayer, int B, int h, int w, void* stream) {
+  YOND_REQUIRE(B > 0 && h > 0 && w > 0, "yond_unpack: bad shape");
+  unpack_kernel<<<grid_for((size_t)B * h * w), kBlock, 0, (cudaStream_t)stream>>>(rggb, bayer, B, h, w);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_vst(const float* x, float* z, size_t n, double sigma, double gain, void* stream) {
+  YOND_REQUIRE(gain > 0, "yond_vst: gain must be positive");
+  vst_elem_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, z, n, (float)gain,
+                                                                    (float)(0.375 * gain * gain + sigma * sigma));
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_inverse_vst(const float* z, float* x, size_t n, double sigma, double gain, int exact, void* stream) {
+  YOND_REQUIRE(gain > 0, "yond_inverse_vst: gain must be positive");
+  VstConst c{};
+  c.K = (float)gain;
+  c.sig2e = (float)((sigma / gain) * (sigma / gain));
+  c.exact = exact;
+  ivst_elem_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(z, x, n, c);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_lut_row(const float* lut2d, int nx, int nsg, double sg_pos, float* row, void* stream) {
+  YOND_REQUIRE(nx > 1 && nsg > 1, "yond_lut_row: bad table shape");
+  if (sg_pos < 0) sg_pos = 0;
+  if (sg_pos > nsg - 1) sg_pos = nsg - 1;  // the reference clips with len(x_lut)-1 (isp_algos.py:189): guarded here
+  const int l = (int)floor(sg_pos), r = (int)ceil(sg_pos);
+  lut_row_kernel<<<ceil_div(nx, kBlock), kBlock, 0, (cudaStream_t)stream>>>(lut2d, nx, nsg, l, r, (float)(sg_pos - l), row);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_lut_apply(const float* x, float* bias, size_t n, const float* row, const float* xnodes, int nx, double gain,
+                   double sigma, void* stream) {
+  YOND_REQUIRE(nx == 1921, "yond_lut_apply: expects the 1921-node BiasLUT grid");
+  VstConst c{};
+  c.K = (float)gain;
+  c.lut_row = 0;
+  c.table_n = 0;
+  c.sig2e = (float)((sigma / gain) * (sigma / gain));
+  lut_apply_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, bias, n, row, xnodes, nx, c);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+static int launch_fwd(bool vst, const float* bayer, float* z, float* ub, int B, int H, int W, int pl, int pr, int pt, int pb,
+                      const yond_vst_params* params, const float* rows, const float* xnodes, int row_stride, void* stream) {
+  YOND_REQUIRE(B > 0 && H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0, "vst_fwd: H,W must be even");
+  const int h = H / 2, w = W / 2;
+  YOND_REQUIRE(pl >= 0 && pr >= 0 && pt >= 0 && pb >= 0 && pl < w && pr < w && pt < h && pb < h,
+               "vst_fwd: reflect padding must be smaller than the frame");
+  const int hp = h + pt + pb, wp = w + pl + pr;
+  cudaStream_t s = (cudaStream_t)stream;
+  YOND_CUDA_CHECK(cudaMemsetAsync(ub, 0, sizeof(float) * B, s));
+  int gx = ceil_div(hp * wp, kBlock * 4);
+  if (gx < 1) gx = 1;
+  if (gx > 65535) gx = 65535;
+  dim3 grid(gx, B);
+  if (vst) vst_fwd_kernel<true><<<grid, kBlock, 0, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, params, rows, xnodes, row_stride);
+  else vst_fwd_kernel<false><<<grid, kBlock, 0, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, nullptr, nullptr, nullptr, 0);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_vst_fwd(const float* bayer, float* z, float* ub, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
+                 const yond_vst_params* params_dev, const float* rows, const float* xnodes, int row_stride, void* stream) {
+  YOND_REQUIRE(params_dev != nullptr, "yond_vst_fwd: params required");
+  return launch_fwd(true, bayer, z, ub, B, H, W, pad_l, pad_r, pad_t, pad_b, params_dev, rows, xnodes, row_stride, stream);
+}
+int yond_pack_pad(const float* bayer, float* z, float* ub, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
+                  void* stream) {
+  return launch_fwd(false, bayer, z, ub, B, H, W, pad_l, pad_r, pad_t, pad_b, nullptr, nullptr, nullptr, 0, stream);
+}
+
+static int launch_inv(bool vst, const float* y, float* bayer, int B, int H, int W, int pl, int pr, int pt, int pb,
+                      const yond_vst_params* params, int clip01, void* stream) {
+  YOND_REQUIRE(B > 0 && H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0, "vst_inv: H,W must be even");
+  const int h = H / 2, w = W / 2, hp = h + pt + pb, wp = w + pl + pr;
+  int gx = ceil_div(h * w, kBlock * 4);
+  if (gx < 1) gx = 1;
+  if (gx > 65535) gx = 65535;
+  dim3 grid(gx, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vst) vst_inv_kernel<true><<<grid, kBlock, 0, s>>>(y, bayer, H, W, pl, pt, hp, wp, params, clip01);
+  else vst_inv_kernel<false><<<grid, kBlock, 0, s>>>(y, bayer, H, W, pl, pt, hp, wp, nullptr, 0);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+int yond_vst_inv(const float* y, float* bayer, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
+                 const yond_vst_params* params_dev, int clip01, void* stream) {
+  YOND_REQUIRE(params_dev != nullptr, "yond_vst_inv: params required");
+  return launch_inv(true, y, bayer, B, H, W, pad_l, pad_r, pad_t, pad_b, params_dev, clip01, stream);
+}
+int yond_crop_unpack(const float* y, float* bayer, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
+                     void* stream) {
+  return launch_inv(false, y, bayer, B, H, W, pad_l, pad_r, pad_t, pad_b, nullptr, 0, stream);
+}
+
+}  // extern "C"
