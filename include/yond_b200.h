@@ -121,6 +121,10 @@ void yond_net_destroy(yond_net_t* net);
 /* `host_data`: f32 tensor in the reference's (PyTorch) layout — Conv2d (Cout,Cin,kh,kw), ConvTranspose2d
  * (Cin,Cout,2,2), bias (C).  Repacked once to the kernels' layouts (per-tap K-major bf16).  utils/utils.py:160-209. */
 int yond_net_set_tensor(yond_net_t* net, const char* key, const float* host_data, const int64_t* shape, int ndim);
+/* The state_dict this network expects, in the reference's registration order (keys, shapes). */
+int yond_net_num_keys(yond_net_t* net);
+const char* yond_net_key(yond_net_t* net, int i);
+int yond_net_key_shape(yond_net_t* net, int i, int64_t* shape4); /* returns ndim */
 /* Returns the number of state-dict tensors still unset (0 = ready); `missing` receives a ';'-joined key list. */
 int yond_net_missing(yond_net_t* net, char* missing, size_t cap);
 size_t yond_net_workspace_bytes(yond_net_t* net, int B, int H, int W);
@@ -140,6 +144,16 @@ int yond_net_set_conv_impl(yond_net_t* net, int impl);
  * `stream` when profiling is enabled (bench.py's live roofline). */
 int yond_net_profile(yond_net_t* net, int enable);
 int yond_net_profile_read(yond_net_t* net, double* conv_ms, double* conv_flops, int* launches, int reset);
+
+/* ---- single conv layer on NHWC bf16 activations (the building block of the networks above; torch.nn.Conv2d /
+ * ConvTranspose2d in archs/Unet.py).  mode: 0 = 3x3 s1 p1, 1 = 1x1, 2 = 3x3 s2 p1, 3 = ConvTranspose 2x2 s2.
+ * The input is the channel concatenation of src0 (Cin0) and src1 (Cin1, may be 0/NULL).  `weight_host`: f32 in the
+ * PyTorch layout; bias/scale/shift/res/out are device pointers.  Epilogue: v = acc + bias; v = v*scale[b] + shift[b];
+ * act (0 none, 1 LeakyReLU(slope), 2 SiLU); v += res; out0 = bf16(v); out1 = bf16(SiLU(v)) if given.
+ * impl: 0 = tcgen05 kernel, 1 = CUDA-core cross-check.  Synchronous (packs and uploads the weights per call). */
+int yond_conv2d(int mode, int impl, int B, int Hin, int Win, int Cin0, int Cin1, const void* src0, const void* src1,
+                int Cout, const float* weight_host, const float* bias, const float* scale, const float* shift, int act,
+                float slope, const void* res, void* out0, void* out1, void* stream);
 
 /* ---- tiling helpers (new design; reference semantics utils/utils.py:254-268 + whole-frame forward) ----
  * Copies a halo-extended tile out of / back into a padded NHWC4 frame; out-of-frame halo pixels are zero

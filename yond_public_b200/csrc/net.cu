@@ -1,0 +1,591 @@
+// Denoiser networks of the YOND path on B200: UNetSeeInDark, GuidedResUnet, SNRnet.
+//   reference: archs/Unet.py:4-104, :288-378, :380-470; archs/modules.py:117-125, :163-233; archs/__init__.py:10-17.
+// The handle owns device copies of the weights, repacked once from the reference's state_dict layout
+// (utils/utils.py:160-209) into the tensor-core kernels' layout; activations live in a caller-provided workspace.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "net_kernels.cuh"
+
+namespace {
+
+struct LayerW {
+  int mode = 0, Cin0 = 0, Cin1 = 0, Cout = 0;
+  std::string wkey, bkey;
+  bf16* w = nullptr;
+  float* bias = nullptr;
+};
+
+struct Bump {  // workspace carve-up; with base == nullptr it only measures
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 1024);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+struct yond_net {
+  int arch = 0, in_nc = 4, out_nc = 4, nf = 32, res = 1, norm = 0, conv_impl = 0;
+  std::vector<std::string> keys;
+  std::map<std::string, std::vector<int64_t>> shapes;
+  std::map<std::string, std::vector<float>> host;
+  std::map<std::string, float*> f32;   // device copies of small fp32 tensors, torch layout
+  std::map<std::string, LayerW> conv;  // tensor-core layers by module name
+  float* head_w = nullptr;             // [9][4][nf]
+  float* tail_w = nullptr;             // [nf][4]
+  bool finalized = false;
+  // live profiling of the tensor-core conv launches
+  int profile = 0;
+  std::vector<cudaEvent_t> events;
+  size_t ev_used = 0;
+  double acc_ms = 0, acc_flops = 0, pending_flops = 0;
+  int acc_launches = 0;
+  int ch(int lvl) const { return nf << lvl; }
+};
+
+namespace {
+
+void add_key(yond_net* n, const std::string& k, std::vector<int64_t> shape) {
+  n->keys.push_back(k);
+  n->shapes[k] = std::move(shape);
+}
+void add_conv_keys(yond_net* n, const std::string& name, int cout, int cin, int k) {
+  add_key(n, name + ".weight", {cout, cin, k, k});
+  add_key(n, name + ".bias", {cout});
+}
+void add_convT_keys(yond_net* n, const std::string& name, int cin, int cout) {
+  add_key(n, name + ".weight", {cin, cout, 2, 2});
+  add_key(n, name + ".bias", {cout});
+}
+void add_layer(yond_net* n, const std::string& name, int mode, int cin0, int cin1, int cout) {
+  LayerW L;
+  L.mode = mode;
+  L.Cin0 = cin0;
+  L.Cin1 = cin1;
+  L.Cout = cout;
+  L.wkey = name + ".weight";
+  L.bkey = name + ".bias";
+  n->conv[name] = L;
+}
+
+// state_dict keys in the reference's registration order + the tensor-core layer table
+void describe(yond_net* n) {
+  const int nf = n->nf, cin = n->in_nc, cout = n->out_nc;
+  if (n->arch == YOND_ARCH_UNET) {  // archs/Unet.py:17-52
+    int prev = cin;
+    for (int l = 1; l <= 5; ++l) {
+      const int c = n->ch(l - 1);
+      const std::string a = "conv" + std::to_string(l) + "_1", b = "conv" + std::to_string(l) + "_2";
+      add_conv_keys(n, a, c, prev, 3);
+      add_conv_keys(n, b, c, c, 3);
+      if (l > 1) add_layer(n, a, CONV_3X3_S1, prev, 0, c);
+      add_layer(n, b, CONV_3X3_S1, c, 0, c);
+      prev = c;
+    }
+    for (int i = 0; i < 4; ++i) {
+      const int c = n->ch(3 - i);
+      const std::string l = std::to_string(6 + i);
+      add_convT_keys(n, "upv" + l, 2 * c, c);
+      add_conv_keys(n, "conv" + l + "_1", c, 2 * c, 3);
+      add_conv_keys(n, "conv" + l + "_2", c, c, 3);
+      add_layer(n, "upv" + l, CONVT_2X2, 2 * c, 0, c);
+      add_layer(n, "conv" + l + "_1", CONV_3X3_S1, c, c, c);
+      add_layer(n, "conv" + l + "_2", CONV_3X3_S1, c, 0, c);
+    }
+    add_conv_keys(n, "conv10_1", cout, nf, 1);
+  } else {  // GuidedResUnet archs/Unet.py:393-421 / SNRnet :301-329; blocks archs/modules.py:163-218
+    const bool guided = n->arch == YOND_ARCH_GUIDED;
+    auto block = [&](const std::string& p, int ci, int co) {
+      add_conv_keys(n, p + ".conv1", co, co, 3);
+      add_conv_keys(n, p + ".conv2", co, co, 3);
+      if (guided) {
+        add_conv_keys(n, p + ".gamma.0", co, 1, 1);
+        add_conv_keys(n, p + ".gamma.2", co, co, 1);
+        add_conv_keys(n, p + ".beta.1", co, co, 1);
+      } else {
+        add_conv_keys(n, p + ".sfm1.0", co, 1, 1);
+        add_conv_keys(n, p + ".sfm1.2", co, co, 1);
+        add_conv_keys(n, p + ".sfm2.0", co, 1, 1);
+        add_conv_keys(n, p + ".sfm2.2", co, co, 1);
+      }
+      if (ci != co) {
+        add_conv_keys(n, p + ".short_cut.0", co, ci, 1);
+        add_layer(n, p + ".short_cut.0", CONV_1X1, co, co, co);  // input = cat[up, skip], co channels each
+      }
+      add_layer(n, p + ".conv1", CONV_3X3_S1, co, 0, co);
+      add_layer(n, p + ".conv2", CONV_3X3_S1, co, 0, co);
+    };
+    add_conv_keys(n, "conv_in", nf, cin, 3);
+    for (int l = 1; l <= 4; ++l) {
+      const int c = n->ch(l - 1);
+      block("conv" + std::to_string(l), c, c);
+      add_conv_keys(n, "pool" + std::to_string(l) + ".conv", 2 * c, c, 3);
+      add_layer(n, "pool" + std::to_string(l) + ".conv", CONV_3X3_S2, c, 0, 2 * c);
+    }
+    block("conv5", n->ch(4), n->ch(4));
+    for (int i = 0; i < 4; ++i) {
+      const int c = n->ch(3 - i);
+      const std::string l = std::to_string(6 + i);
+      add_convT_keys(n, "upv" + l, 2 * c, c);
+      add_layer(n, "upv" + l, CONVT_2X2, 2 * c, 0, c);
+      block("conv" + l, 2 * c, c);
+    }
+    add_conv_keys(n, "conv10", cout, nf, 1);
+  }
+}
+
+void free_device(yond_net* n) {
+  for (auto& kv : n->f32) cudaFree(kv.second);
+  n->f32.clear();
+  for (auto& kv : n->conv) {
+    if (kv.second.w) cudaFree(kv.second.w);
+    kv.second.w = nullptr;
+    kv.second.bias = nullptr;
+  }
+  if (n->head_w) cudaFree(n->head_w);
+  if (n->tail_w) cudaFree(n->tail_w);
+  n->head_w = n->tail_w = nullptr;
+  n->finalized = false;
+}
+
+// torch layout -> [cbg][tap][N][CB] bf16 (K-major tiles the weight TMA map walks)
+std::vector<bf16> pack_weights(const LayerW& L, const std::vector<float>& w) {
+  const int Cin = L.Cin0 + L.Cin1, CB = conv_tc_channel_block(L.Cin0, L.Cin1);
+  const int taps = (L.mode == CONV_3X3_S1 || L.mode == CONV_3X3_S2) ? 9 : 1;
+  const int N = L.mode == CONVT_2X2 ? 4 * L.Cout : L.Cout;
+  std::vector<bf16> out((size_t)taps * Cin * N);
+  for (int cbg = 0; cbg < Cin / CB; ++cbg)
+    for (int tap = 0; tap < taps; ++tap)
+      for (int nn = 0; nn < N; ++nn)
+        for (int j = 0; j < CB; ++j) {
+          const int ci = cbg * CB + j;
+          float v;
+          if (L.mode == CONVT_2X2) {  // (Cin, Cout, 2, 2); n = (a*2+b)*Cout + co
+            const int q = nn / L.Cout, co = nn % L.Cout;
+            v = w[(((size_t)ci * L.Cout + co) * 2 + (q >> 1)) * 2 + (q & 1)];
+          } else {  // (Cout, Cin, k, k); tap = r*k + s
+            v = w[((size_t)nn * Cin + ci) * taps + tap];
+          }
+          out[(((size_t)cbg * taps + tap) * N + nn) * CB + j] = __float2bfloat16_rn(v);
+        }
+  return out;
+}
+
+int upload_f32(yond_net* n, const std::string& key) {
+  const std::vector<float>& h = n->host[key];
+  float* d = nullptr;
+  YOND_CUDA_CHECK(cudaMalloc(&d, h.size() * sizeof(float)));
+  YOND_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  n->f32[key] = d;
+  return YOND_OK;
+}
+
+int finalize(yond_net* n) {
+  if (n->finalized) return YOND_OK;
+  for (const auto& k : n->keys)
+    if (!n->host.count(k)) return yond_set_error(YOND_ERR_INVALID, "network tensor '%s' has not been set", k.c_str());
+  free_device(n);
+  for (const auto& k : n->keys) {
+    const bool is_tc_weight = k.size() > 7 && k.compare(k.size() - 7, 7, ".weight") == 0 && n->conv.count(k.substr(0, k.size() - 7));
+    if (!is_tc_weight) {
+      int rc = upload_f32(n, k);
+      if (rc) return rc;
+    }
+  }
+  for (auto& kv : n->conv) {
+    LayerW& L = kv.second;
+    std::vector<bf16> packed = pack_weights(L, n->host[L.wkey]);
+    YOND_CUDA_CHECK(cudaMalloc(&L.w, packed.size() * sizeof(bf16)));
+    YOND_CUDA_CHECK(cudaMemcpy(L.w, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    L.bias = n->f32[L.bkey];
+  }
+  {  // head: (nf,4,3,3) -> [tap][ci][co];  tail: (4,nf,1,1) -> [ci][4]
+    const std::string hk = n->arch == YOND_ARCH_UNET ? "conv1_1.weight" : "conv_in.weight";
+    const std::string tk = n->arch == YOND_ARCH_UNET ? "conv10_1.weight" : "conv10.weight";
+    const std::vector<float>& hw = n->host[hk];
+    std::vector<float> h((size_t)36 * n->nf);
+    for (int co = 0; co < n->nf; ++co)
+      for (int ci = 0; ci < 4; ++ci)
+        for (int t = 0; t < 9; ++t) h[((size_t)t * 4 + ci) * n->nf + co] = hw[((size_t)co * 4 + ci) * 9 + t];
+    YOND_CUDA_CHECK(cudaMalloc(&n->head_w, h.size() * sizeof(float)));
+    YOND_CUDA_CHECK(cudaMemcpy(n->head_w, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const std::vector<float>& tw = n->host[tk];
+    std::vector<float> t((size_t)n->nf * 4);
+    for (int co = 0; co < 4; ++co)
+      for (int ci = 0; ci < n->nf; ++ci) t[(size_t)ci * 4 + co] = tw[(size_t)co * n->nf + ci];
+    YOND_CUDA_CHECK(cudaMalloc(&n->tail_w, t.size() * sizeof(float)));
+    YOND_CUDA_CHECK(cudaMemcpy(n->tail_w, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  n->finalized = true;
+  return YOND_OK;
+}
+
+double layer_flops(const LayerW& L, int B, int Hin, int Win) {
+  const double cin = L.Cin0 + L.Cin1;
+  switch (L.mode) {
+    case CONV_3X3_S1: return 2.0 * B * Hin * Win * 9.0 * cin * L.Cout;
+    case CONV_3X3_S2: return 2.0 * B * (Hin / 2) * (Win / 2) * 9.0 * cin * L.Cout;
+    case CONV_1X1: return 2.0 * B * Hin * Win * cin * L.Cout;
+    default: return 2.0 * B * Hin * Win * cin * 4.0 * L.Cout;  // CONVT_2X2
+  }
+}
+
+struct Runner {
+  yond_net* n;
+  cudaStream_t s;
+  int B;
+  int rc = YOND_OK;
+  double flops = 0;
+  bool dry;  // only count FLOPs / workspace
+  int conv(const std::string& name, int Hin, int Win, const bf16* src0, const bf16* src1, const float* scale,
+           const float* shift, int act, float slope, const bf16* res, bf16* out0, bf16* out1) {
+    const LayerW& L = n->conv.at(name);
+    const double f = layer_flops(L, B, Hin, Win);
+    flops += f;
+    if (dry || rc) return rc;
+    ConvLayer c{};
+    c.mode = L.mode;
+    c.B = B;
+    c.Hin = Hin;
+    c.Win = Win;
+    c.Cin0 = L.Cin0;
+    c.Cin1 = L.Cin1;
+    c.src0 = src0;
+    c.src1 = src1;
+    c.Cout = L.Cout;
+    c.wpacked = L.w;
+    c.bias = L.bias;
+    c.scale = scale;
+    c.shift = shift;
+    c.act = act;
+    c.slope = slope;
+    c.res = res;
+    c.out0 = out0;
+    c.out1 = out1;
+    const bool prof = n->profile && n->ev_used + 2 <= n->events.size();
+    if (prof) cudaEventRecord(n->events[n->ev_used], s);
+    rc = n->conv_impl ? conv_ref_launch(c, s) : conv_tc_launch(c, s);
+    if (prof) {
+      cudaEventRecord(n->events[n->ev_used + 1], s);
+      n->ev_used += 2;
+      n->pending_flops += f;
+    }
+    return rc;
+  }
+};
+
+// One forward pass; with ws == nullptr only measures workspace bytes and FLOPs.
+int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, float* y, int B, int H, int W, void* ws,
+                 size_t* ws_bytes, double* flops, cudaStream_t s) {
+  const bool dry = ws == nullptr;
+  Bump bump(ws);
+  Runner R{n, s, B};
+  R.dry = dry;
+  const int nf = n->nf;
+  const float* ubn = n->norm ? ub : nullptr;
+  auto act_buf = [&](int lvl, int C) { return bump.take<bf16>((size_t)B * (H >> lvl) * (W >> lvl) * C); };
+  const double head_tail_flops = 2.0 * B * H * W * (36.0 * nf + 4.0 * nf);
+  int rc = YOND_OK;
+#define RUN(expr)                 \
+  do {                            \
+    if (!dry && rc == YOND_OK) rc = (expr); \
+  } while (0)
+
+  if (n->arch == YOND_ARCH_UNET) {
+    bf16* a = act_buf(0, nf);
+    RUN(head_conv_launch(z, ubn, n->head_w, n->f32["conv1_1.bias"], B, H, W, nf, 0.2f, a, nullptr, s));
+    bf16* skip[5];
+    bf16* cur = a;
+    for (int l = 1; l <= 5; ++l) {
+      const int lv = l - 1, C = n->ch(lv), h = H >> lv, w = W >> lv;
+      const std::string p = "conv" + std::to_string(l);
+      if (l > 1) {
+        bf16* t1 = act_buf(lv, C);
+        rc = rc ? rc : R.conv(p + "_1", h, w, cur, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t1, nullptr);
+        cur = t1;
+      }
+      bf16* c2 = act_buf(lv, C);
+      rc = rc ? rc : R.conv(p + "_2", h, w, cur, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c2, nullptr);
+      skip[lv] = c2;
+      cur = c2;
+      if (l < 5) {
+        bf16* pl = act_buf(lv + 1, C);
+        RUN(maxpool2_launch(c2, pl, B, h, w, C, s));
+        cur = pl;
+      }
+    }
+    for (int i = 0; i < 4; ++i) {
+      const int lv = 3 - i, C = n->ch(lv), h = H >> lv, w = W >> lv;
+      const std::string l = std::to_string(6 + i);
+      bf16* up = act_buf(lv, C);
+      rc = rc ? rc : R.conv("upv" + l, h / 2, w / 2, cur, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, up, nullptr);
+      bf16* t1 = act_buf(lv, C);
+      rc = rc ? rc : R.conv("conv" + l + "_1", h, w, up, skip[lv], nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t1, nullptr);
+      bf16* c2 = act_buf(lv, C);
+      rc = rc ? rc : R.conv("conv" + l + "_2", h, w, t1, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c2, nullptr);
+      cur = c2;
+    }
+    RUN(tail_conv_launch(cur, n->tail_w, n->f32["conv10_1.bias"], z, ubn, n->res, B, H, W, nf, y, s));
+  } else {
+    const bool guided = n->arch == YOND_ARCH_GUIDED;
+    if (!dry && t == nullptr) return yond_set_error(YOND_ERR_INVALID, "guided network needs the per-sample t vector");
+    // conditioning vectors of the 9 blocks
+    float* va[10];
+    float* vb[10];
+    for (int l = 1; l <= 9; ++l) {
+      const int lv = l <= 5 ? l - 1 : 9 - l, C = n->ch(lv);
+      va[l] = bump.take<float>((size_t)B * C);
+      vb[l] = bump.take<float>((size_t)B * C);
+      if (!dry && rc == YOND_OK) {
+        const std::string p = "conv" + std::to_string(l);
+        FilmWeights fw{};
+        if (guided) {
+          fw.w0 = n->f32[p + ".gamma.0.weight"]; fw.b0 = n->f32[p + ".gamma.0.bias"];
+          fw.w2 = n->f32[p + ".gamma.2.weight"]; fw.b2 = n->f32[p + ".gamma.2.bias"];
+          fw.w3 = n->f32[p + ".beta.1.weight"];  fw.b3 = n->f32[p + ".beta.1.bias"];
+        } else {
+          fw.w0 = n->f32[p + ".sfm1.0.weight"]; fw.b0 = n->f32[p + ".sfm1.0.bias"];
+          fw.w2 = n->f32[p + ".sfm1.2.weight"]; fw.b2 = n->f32[p + ".sfm1.2.bias"];
+          fw.w3 = n->f32[p + ".sfm2.0.weight"]; fw.b3 = n->f32[p + ".sfm2.0.bias"];
+          fw.w4 = n->f32[p + ".sfm2.2.weight"]; fw.b4 = n->f32[p + ".sfm2.2.bias"];
+        }
+        rc = film_launch(fw, t, ubn, B, C, guided ? 1 : 0, va[l], vb[l], s);
+      }
+    }
+    // One residual block: x (raw) and xs = SiLU(x) come from the producer's dual store.
+    auto block = [&](int l, int lv, const bf16* x, const bf16* xs, bf16* out) {
+      const int C = n->ch(lv), h = H >> lv, w = W >> lv;
+      const std::string p = "conv" + std::to_string(l);
+      bf16* zb = act_buf(lv, C);
+      if (guided) {  // z = SiLU(conv1(SiLU(x)) * tk + tb); out = conv2(z) + x
+        rc = rc ? rc : R.conv(p + ".conv1", h, w, xs, nullptr, va[l], vb[l], ACT_SILU, 0.f, nullptr, zb, nullptr);
+        rc = rc ? rc : R.conv(p + ".conv2", h, w, zb, nullptr, nullptr, nullptr, ACT_NONE, 0.f, x, out, nullptr);
+      } else {  // z = SiLU(conv1(SiLU(x)) * a1); out = conv2(z) * a2 + x
+        rc = rc ? rc : R.conv(p + ".conv1", h, w, xs, nullptr, va[l], nullptr, ACT_SILU, 0.f, nullptr, zb, nullptr);
+        rc = rc ? rc : R.conv(p + ".conv2", h, w, zb, nullptr, vb[l], nullptr, ACT_NONE, 0.f, x, out, nullptr);
+      }
+    };
+    bf16* x = act_buf(0, nf);
+    bf16* xs = act_buf(0, nf);
+    RUN(head_conv_launch(z, ubn, n->head_w, n->f32["conv_in.bias"], B, H, W, nf, 0.01f, x, xs, s));
+    bf16* skip[5];
+    for (int l = 1; l <= 5; ++l) {
+      const int lv = l - 1, C = n->ch(lv), h = H >> lv, w = W >> lv;
+      bf16* c = act_buf(lv, C);
+      block(l, lv, x, xs, c);
+      skip[lv] = c;
+      if (l < 5) {  // stride-2 conv, no activation (modules.py:117-125); dual store feeds the next block
+        x = act_buf(lv + 1, 2 * C);
+        xs = act_buf(lv + 1, 2 * C);
+        rc = rc ? rc : R.conv("pool" + std::to_string(l) + ".conv", h, w, c, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x, xs);
+      }
+    }
+    bf16* cur = skip[4];
+    for (int i = 0; i < 4; ++i) {
+      const int lv = 3 - i, C = n->ch(lv), h = H >> lv, w = W >> lv, l = 6 + i;
+      bf16* up = act_buf(lv, C);
+      rc = rc ? rc : R.conv("upv" + std::to_string(l), h / 2, w / 2, cur, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, up, nullptr);
+      x = act_buf(lv, C);
+      xs = act_buf(lv, C);
+      rc = rc ? rc : R.conv("conv" + std::to_string(l) + ".short_cut.0", h, w, up, skip[lv], nullptr, nullptr, ACT_NONE, 0.f, nullptr, x, xs);
+      bf16* c = act_buf(lv, C);
+      block(l, lv, x, xs, c);
+      cur = c;
+    }
+    RUN(tail_conv_launch(cur, n->tail_w, n->f32["conv10.bias"], z, ubn, n->res, B, H, W, nf, y, s));
+  }
+#undef RUN
+  if (R.rc) rc = R.rc;
+  if (ws_bytes) *ws_bytes = align_up(bump.off, 1024);
+  if (flops) *flops = R.flops + head_tail_flops;
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yond_net_create(int arch, int in_nc, int out_nc, int nf, int res, int norm, yond_net_t** out) {
+  YOND_REQUIRE(out != nullptr, "yond_net_create: null output");
+  YOND_REQUIRE(arch >= YOND_ARCH_UNET && arch <= YOND_ARCH_SNR, "yond_net_create: unknown arch %d", arch);
+  YOND_REQUIRE(in_nc == 4 && out_nc == 4, "yond_net_create: only packed-Bayer nets (in_nc = out_nc = 4, nframes = 1) are built");
+  YOND_REQUIRE(nf >= 32 && nf % 32 == 0, "yond_net_create: nf must be a multiple of 32 (got %d)", nf);
+  yond_net* n = new yond_net();
+  n->arch = arch;
+  n->in_nc = in_nc;
+  n->out_nc = out_nc;
+  n->nf = nf;
+  n->res = res;
+  n->norm = norm;
+  describe(n);
+  *out = n;
+  return YOND_OK;
+}
+
+void yond_net_destroy(yond_net_t* n) {
+  if (!n) return;
+  free_device(n);
+  for (auto e : n->events) cudaEventDestroy(e);
+  delete n;
+}
+
+int yond_net_set_tensor(yond_net_t* n, const char* key, const float* host_data, const int64_t* shape, int ndim) {
+  YOND_REQUIRE(n && key && host_data, "yond_net_set_tensor: null argument");
+  auto it = n->shapes.find(key);
+  if (it == n->shapes.end()) return yond_set_error(YOND_ERR_INVALID, "unexpected state-dict key '%s'", key);
+  const std::vector<int64_t>& exp = it->second;
+  bool ok = (int)exp.size() == ndim;
+  size_t numel = 1;
+  for (int i = 0; ok && i < ndim; ++i) ok = exp[i] == shape[i];
+  for (auto d : exp) numel *= (size_t)d;
+  if (!ok) return yond_set_error(YOND_ERR_INVALID, "shape mismatch for '%s'", key);
+  n->host[key].assign(host_data, host_data + numel);
+  n->finalized = false;
+  return YOND_OK;
+}
+
+int yond_net_missing(yond_net_t* n, char* missing, size_t cap) {
+  int cnt = 0;
+  std::string s;
+  for (const auto& k : n->keys)
+    if (!n->host.count(k)) {
+      ++cnt;
+      s += k + ";";
+    }
+  if (missing && cap) {
+    snprintf(missing, cap, "%s", s.c_str());
+  }
+  return cnt;
+}
+
+int yond_net_num_keys(yond_net_t* n) { return (int)n->keys.size(); }
+const char* yond_net_key(yond_net_t* n, int i) { return (i >= 0 && i < (int)n->keys.size()) ? n->keys[i].c_str() : nullptr; }
+int yond_net_key_shape(yond_net_t* n, int i, int64_t* shape4) {
+  if (i < 0 || i >= (int)n->keys.size()) return -1;
+  const std::vector<int64_t>& s = n->shapes[n->keys[i]];
+  for (size_t d = 0; d < s.size(); ++d) shape4[d] = s[d];
+  return (int)s.size();
+}
+
+size_t yond_net_workspace_bytes(yond_net_t* n, int B, int H, int W) {
+  size_t bytes = 0;
+  forward_impl(n, nullptr, nullptr, nullptr, nullptr, B, H, W, nullptr, &bytes, nullptr, nullptr);
+  // extras of the NCHW surface: z, y (B,H,W,4) f32 and ub (B)
+  return bytes + 2 * align_up((size_t)B * H * W * 4 * sizeof(float), 1024) + align_up((size_t)B * sizeof(float), 1024) + 4096;
+}
+
+double yond_net_flops(yond_net_t* n, int B, int H, int W) {
+  double f = 0;
+  forward_impl(n, nullptr, nullptr, nullptr, nullptr, B, H, W, nullptr, nullptr, &f, nullptr);
+  return f;
+}
+
+int yond_net_set_conv_impl(yond_net_t* n, int impl) {
+  n->conv_impl = impl ? 1 : 0;
+  return YOND_OK;
+}
+
+int yond_net_forward(yond_net_t* n, const float* z, const float* ub, const float* t, float* y, int B, int H, int W,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  YOND_REQUIRE(n && z && y && workspace, "yond_net_forward: null argument");
+  YOND_REQUIRE(B > 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, "yond_net_forward: H,W must be multiples of 16 (got %d,%d)", H, W);
+  YOND_REQUIRE(!n->norm || ub, "yond_net_forward: norm=1 needs ub");
+  YOND_REQUIRE((uintptr_t)workspace % 1024 == 0, "yond_net_forward: workspace must be 1024-byte aligned");
+  int rc = finalize(n);
+  if (rc) return rc;
+  size_t need = 0;
+  forward_impl(n, nullptr, nullptr, nullptr, nullptr, B, H, W, nullptr, &need, nullptr, nullptr);
+  YOND_REQUIRE(workspace_bytes >= need, "yond_net_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
+  return forward_impl(n, z, ub, t, y, B, H, W, workspace, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int yond_net_forward_nchw(yond_net_t* n, const float* x, const float* t, float* y, int B, int H, int W, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  YOND_REQUIRE(n && x && y && workspace, "yond_net_forward_nchw: null argument");
+  YOND_REQUIRE((uintptr_t)workspace % 1024 == 0, "yond_net_forward_nchw: workspace must be 1024-byte aligned");
+  YOND_REQUIRE(workspace_bytes >= yond_net_workspace_bytes(n, B, H, W), "yond_net_forward_nchw: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  const size_t img = align_up((size_t)B * H * W * 4 * sizeof(float), 1024);
+  float* z = reinterpret_cast<float*>(base);
+  float* yy = reinterpret_cast<float*>(base + img);
+  float* ub = reinterpret_cast<float*>(base + 2 * img);
+  uint8_t* rest = base + 2 * img + align_up((size_t)B * sizeof(float), 1024);
+  int rc = nchw_to_nhwc4_launch(x, z, ub, B, H, W, s);
+  if (rc) return rc;
+  rc = yond_net_forward(n, z, ub, t, yy, B, H, W, rest, workspace_bytes - (rest - base), stream);
+  if (rc) return rc;
+  return nhwc4_to_nchw_launch(yy, y, B, H, W, s);
+}
+
+int yond_conv2d(int mode, int impl, int B, int Hin, int Win, int Cin0, int Cin1, const void* src0, const void* src1, int Cout,
+                const float* weight_host, const float* bias, const float* scale, const float* shift, int act, float slope,
+                const void* res, void* out0, void* out1, void* stream) {
+  YOND_REQUIRE(mode >= 0 && mode <= 3 && weight_host && src0 && out0 && bias, "yond_conv2d: bad arguments");
+  LayerW L;
+  L.mode = mode;
+  L.Cin0 = Cin0;
+  L.Cin1 = Cin1;
+  L.Cout = Cout;
+  const int taps = (mode == CONV_3X3_S1 || mode == CONV_3X3_S2) ? 9 : 1;
+  const size_t nw = (size_t)taps * (Cin0 + Cin1) * Cout * (mode == CONVT_2X2 ? 4 : 1);
+  std::vector<float> w(weight_host, weight_host + nw);
+  std::vector<bf16> packed = pack_weights(L, w);
+  bf16* dw = nullptr;
+  YOND_CUDA_CHECK(cudaMalloc(&dw, packed.size() * sizeof(bf16)));
+  YOND_CUDA_CHECK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  ConvLayer c{};
+  c.mode = mode; c.B = B; c.Hin = Hin; c.Win = Win; c.Cin0 = Cin0; c.Cin1 = Cin1;
+  c.src0 = (const bf16*)src0; c.src1 = (const bf16*)src1; c.Cout = Cout; c.wpacked = dw; c.bias = bias;
+  c.scale = scale; c.shift = shift; c.act = act; c.slope = slope; c.res = (const bf16*)res;
+  c.out0 = (bf16*)out0; c.out1 = (bf16*)out1;
+  int rc = impl ? conv_ref_launch(c, (cudaStream_t)stream) : conv_tc_launch(c, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(dw);
+  if (rc) return rc;
+  if (e != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "yond_conv2d: kernel failed: %s", cudaGetErrorString(e));
+  return YOND_OK;
+}
+
+int yond_net_profile(yond_net_t* n, int enable) {
+  n->profile = enable;
+  if (enable && n->events.empty()) {
+    n->events.resize(8192);
+    for (auto& e : n->events) YOND_CUDA_CHECK(cudaEventCreate(&e));
+  }
+  return YOND_OK;
+}
+
+int yond_net_profile_read(yond_net_t* n, double* conv_ms, double* conv_flops, int* launches, int reset) {
+  if (n->ev_used) {
+    YOND_CUDA_CHECK(cudaEventSynchronize(n->events[n->ev_used - 1]));
+    for (size_t i = 0; i + 1 < n->ev_used; i += 2) {
+      float ms = 0;
+      YOND_CUDA_CHECK(cudaEventElapsedTime(&ms, n->events[i], n->events[i + 1]));
+      n->acc_ms += ms;
+    }
+    n->acc_launches += (int)(n->ev_used / 2);
+    n->acc_flops += n->pending_flops;
+    n->ev_used = 0;
+    n->pending_flops = 0;
+  }
+  if (conv_ms) *conv_ms = n->acc_ms;
+  if (conv_flops) *conv_flops = n->acc_flops;
+  if (launches) *launches = n->acc_launches;
+  if (reset) {
+    n->acc_ms = n->acc_flops = 0;
+    n->acc_launches = 0;
+  }
+  return YOND_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// CUDA-core kernels around the tensor-core conv stack: first layer (Cin=4), last layer (Cout=4),
+// 2x2 max-pool, the per-sample FiLM / SNR-gate vectors and NCHW<->NHWC4 layout converts.
+//   reference: archs/Unet.py:55-104,424-470; archs/modules.py:15-25 (data_normalize), :163-233 (blocks).
+#include "net_kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- first layer: 3x3, 4 -> 32*G channels, fp32 math on the fp32 network input (x = z / ub) ----------------
+// One thread = one pixel x 32 output channels.  Weights [tap][ci][co] in shared memory (broadcast reads).
+__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ z, const float* __restrict__ ub,
+                                                        const float* __restrict__ w, const float* __restrict__ bias, int B,
+                                                        int H, int W, int nf, float slope, bf16* __restrict__ out0,
+                                                        bf16* __restrict__ out1) {
+  extern __shared__ float sw[];  // [9*4*nf] + [nf]
+  for (int i = threadIdx.x; i < 36 * nf; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < nf; i += blockDim.x) sw[36 * nf + i] = bias[i];
+  __syncthreads();
+  const size_t npix = (size_t)B * H * W;
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int b = (int)(pix / ((size_t)W * H));
+    const float inv = ub ? 1.0f / __ldg(ub + b) : 1.0f;
+    float4 in[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int yy = y + r - 1, xx = x + s - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(z4 + ((size_t)b * H + yy) * W + xx);
+        // the reference divides first, then convolves: x = data / upper (modules.py:20)
+        in[r * 3 + s] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+      }
+    for (int g = 0; g < nf; g += 32) {
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = sw[36 * nf + g + j];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float* wt = sw + (t * 4) * nf + g;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          acc[j] = fmaf(in[t].x, wt[j], acc[j]);
+          acc[j] = fmaf(in[t].y, wt[nf + j], acc[j]);
+          acc[j] = fmaf(in[t].z, wt[2 * nf + j], acc[j]);
+          acc[j] = fmaf(in[t].w, wt[3 * nf + j], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * slope;
+      uint4* o = reinterpret_cast<uint4*>(out0 + pix * nf + g);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        o[q] = make_uint4(pack2(acc[q * 8], acc[q * 8 + 1]), pack2(acc[q * 8 + 2], acc[q * 8 + 3]),
+                          pack2(acc[q * 8 + 4], acc[q * 8 + 5]), pack2(acc[q * 8 + 6], acc[q * 8 + 7]));
+      if (out1) {
+        uint4* o1 = reinterpret_cast<uint4*>(out1 + pix * nf + g);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          o1[q] = make_uint4(pack2(silu_f(acc[q * 8]), silu_f(acc[q * 8 + 1])), pack2(silu_f(acc[q * 8 + 2]), silu_f(acc[q * 8 + 3])),
+                             pack2(silu_f(acc[q * 8 + 4]), silu_f(acc[q * 8 + 5])), pack2(silu_f(acc[q * 8 + 6]), silu_f(acc[q * 8 + 7])));
+      }
+    }
+  }
+}
+
+// ---- last layer: 1x1, nf -> 4, + input residual, x ub (data_inv_normalize); fp32 output NHWC4 ----------------
+__global__ void __launch_bounds__(256) tail_conv_kernel(const bf16* __restrict__ act, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ z,
+                                                        const float* __restrict__ ub, int res, size_t npix, size_t pix_per_img,
+                                                        int nf, float* __restrict__ y) {
+  extern __shared__ float sw[];  // [nf][4] + [4]
+  for (int i = threadIdx.x; i < nf * 4 + 4; i += blockDim.x) sw[i] = i < nf * 4 ? w[i] : bias[i - nf * 4];
+  __syncthreads();
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
+    float o0 = sw[nf * 4], o1 = sw[nf * 4 + 1], o2 = sw[nf * 4 + 2], o3 = sw[nf * 4 + 3];
+    const uint4* a4 = reinterpret_cast<const uint4*>(act + pix * nf);
+    for (int g = 0; g < nf / 8; ++g) {
+      const uint4 u = __ldg(a4 + g);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&uu[q]);
+        const float2 f = __bfloat1622float2(h);
+        const float* w0 = sw + (g * 8 + q * 2) * 4;
+        o0 = fmaf(f.x, w0[0], o0); o1 = fmaf(f.x, w0[1], o1); o2 = fmaf(f.x, w0[2], o2); o3 = fmaf(f.x, w0[3], o3);
+        o0 = fmaf(f.y, w0[4], o0); o1 = fmaf(f.y, w0[5], o1); o2 = fmaf(f.y, w0[6], o2); o3 = fmaf(f.y, w0[7], o3);
+      }
+    }
+    const float u_b = ub ? __ldg(ub + pix / pix_per_img) : 1.0f;
+    if (res) {
+      const float4 zi = __ldg(z4 + pix);
+      const float inv = 1.0f / u_b;
+      o0 += zi.x * inv; o1 += zi.y * inv; o2 += zi.z * inv; o3 += zi.w * inv;
+    }
+    y4[pix] = make_float4(o0 * u_b, o1 * u_b, o2 * u_b, o3 * u_b);
+  }
+}
+
+// ---- MaxPool2d(2) on NHWC bf16 (UNetSeeInDark); one thread = one output pixel x 8 channels ------------------
+__global__ void maxpool2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const size_t total = (size_t)B * Ho * Wo * C8;
+  const uint4* in4 = reinterpret_cast<const uint4*>(in);
+  uint4* out4 = reinterpret_cast<uint4*>(out);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8);
+    size_t p = idx / C8;
+    const int x = (int)(p % Wo);
+    const int y = (int)((p / Wo) % Ho);
+    const int b = (int)(p / ((size_t)Wo * Ho));
+    const size_t base = (((size_t)b * H + 2 * y) * W + 2 * x) * C8 + c;
+    const uint4 a = __ldg(in4 + base), bq = __ldg(in4 + base + C8);
+    const uint4 cq = __ldg(in4 + base + (size_t)W * C8), d = __ldg(in4 + base + (size_t)W * C8 + C8);
+    auto mx = [](uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
+      __nv_bfloat162 h0 = *reinterpret_cast<__nv_bfloat162*>(&p0), h1 = *reinterpret_cast<__nv_bfloat162*>(&p1);
+      __nv_bfloat162 h2 = *reinterpret_cast<__nv_bfloat162*>(&p2), h3 = *reinterpret_cast<__nv_bfloat162*>(&p3);
+      __nv_bfloat162 m = __hmax2(__hmax2(h0, h1), __hmax2(h2, h3));
+      return *reinterpret_cast<uint32_t*>(&m);
+    };
+    out4[idx] = make_uint4(mx(a.x, bq.x, cq.x, d.x), mx(a.y, bq.y, cq.y, d.y), mx(a.z, bq.z, cq.z, d.z), mx(a.w, bq.w, cq.w, d.w));
+  }
+}
+
+// ---- per-sample conditioning vectors (GuidedResidualBlock gamma/beta, SNR_Block sfm1/sfm2) -------------------
+// out_a = W2 * silu(w0 * t' + b0) + b2 ;  guided: out_b = Wb * silu(out_a) + bb ;  snr: out_b = second MLP(t').
+// t' = t[b] / ub[b] when the network normalises (archs/Unet.py:427-429).  One block per sample.
+__device__ __forceinline__ float warp_dot(const float* __restrict__ wrow, const float* v, int C, int lane) {
+  float s = 0.f;
+  for (int j = lane; j < C; j += 32) s = fmaf(__ldg(wrow + j), v[j], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+__global__ void __launch_bounds__(256) film_kernel(FilmWeights fw, const float* __restrict__ t, const float* __restrict__ ub,
+                                                   int C, int guided, float* __restrict__ out_a, float* __restrict__ out_b) {
+  extern __shared__ float sv[];  // [C] hidden, [C] out_a
+  float* hid = sv;
+  float* va = sv + C;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float tt = ub ? __ldg(t + b) / __ldg(ub + b) : __ldg(t + b);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) hid[i] = silu_f(fmaf(fw.w0[i], tt, fw.b0[i]));
+  __syncthreads();
+  for (int n = warp; n < C; n += nw) {
+    const float s = warp_dot(fw.w2 + (size_t)n * C, hid, C, lane) + fw.b2[n];
+    if (lane == 0) { va[n] = s; out_a[(size_t)b * C + n] = s; }
+  }
+  __syncthreads();
+  if (guided) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) hid[i] = silu_f(va[i]);
+    __syncthreads();
+    for (int n = warp; n < C; n += nw) {
+      const float s = warp_dot(fw.w3 + (size_t)n * C, hid, C, lane) + fw.b3[n];
+      if (lane == 0) out_b[(size_t)b * C + n] = s;
+    }
+  } else {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) hid[i] = silu_f(fmaf(fw.w3[i], tt, fw.b3[i]));
+    __syncthreads();
+    for (int n = warp; n < C; n += nw) {
+      const float s = warp_dot(fw.w4 + (size_t)n * C, hid, C, lane) + fw.b4[n];
+      if (lane == 0) out_b[(size_t)b * C + n] = s;
+    }
+  }
+}
+
+// ---- layout converts for the nn.Module-level surface (NCHW f32 <-> NHWC4 f32) + per-sample max ---------------
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__global__ void fill_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, float* __restrict__ z, float* __restrict__ ub, int HW) {
+  const int b = blockIdx.y;
+  const float* xb = x + (size_t)b * 4 * HW;
+  float4* zb = reinterpret_cast<float4*>(z) + (size_t)b * HW;
+  float m = -INFINITY;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float4 v = make_float4(xb[i], xb[HW + i], xb[2 * HW + i], xb[3 * HW + i]);
+    zb[i] = v;
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && ub) atomic_max_float(ub + b, m);
+}
+__global__ void nhwc4_to_nchw_kernel(const float* __restrict__ y, float* __restrict__ out, int HW) {
+  const int b = blockIdx.y;
+  const float4* yb = reinterpret_cast<const float4*>(y) + (size_t)b * HW;
+  float* ob = out + (size_t)b * 4 * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float4 v = yb[i];
+    ob[i] = v.x; ob[HW + i] = v.y; ob[2 * HW + i] = v.z; ob[3 * HW + i] = v.w;
+  }
+}
+
+inline int cap_grid(size_t blocks) {
+  const size_t cap = (size_t)yond_num_sms() * 16;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+
+int head_conv_launch(const float* z, const float* ub, const float* w, const float* bias, int B, int H, int W, int nf,
+                     float slope, bf16* out0, bf16* out1, cudaStream_t s) {
+  const size_t npix = (size_t)B * H * W;
+  const size_t smem = (size_t)(36 * nf + nf) * sizeof(float);
+  head_conv_kernel<<<cap_grid((npix + 127) / 128), 128, smem, s>>>(z, ub, w, bias, B, H, W, nf, slope, out0, out1);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+int tail_conv_launch(const bf16* act, const float* w, const float* bias, const float* z, const float* ub, int res, int B,
+                     int H, int W, int nf, float* y, cudaStream_t s) {
+  const size_t npix = (size_t)B * H * W;
+  tail_conv_kernel<<<cap_grid((npix + 255) / 256), 256, (size_t)(nf * 4 + 4) * sizeof(float), s>>>(
+      act, w, bias, z, ub, res, npix, (size_t)H * W, nf, y);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+int maxpool2_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s) {
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_kernel<<<cap_grid((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W, C);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+int film_launch(const FilmWeights& fw, const float* t, const float* ub, int B, int C, int guided, float* out_a, float* out_b,
+                cudaStream_t s) {
+  film_kernel<<<B, 256, (size_t)2 * C * sizeof(float), s>>>(fw, t, ub, C, guided, out_a, out_b);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+int nchw_to_nhwc4_launch(const float* x, float* z, float* ub, int B, int H, int W, cudaStream_t s) {
+  if (ub) {
+    fill_kernel<<<ceil_div(B, 256), 256, 0, s>>>(ub, B, -INFINITY);
+    YOND_LAUNCH_CHECK();
+  }
+  dim3 grid(cap_grid(((size_t)H * W + 255) / 256) / (B > 16 ? 16 : 1) + 1, B);
+  nchw_to_nhwc4_kernel<<<grid, 256, 0, s>>>(x, z, ub, H * W);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+int nhwc4_to_nchw_launch(const float* y, float* out, int B, int H, int W, cudaStream_t s) {
+  dim3 grid(cap_grid(((size_t)H * W + 255) / 256) / (B > 16 ? 16 : 1) + 1, B);
+  nhwc4_to_nchw_kernel<<<grid, 256, 0, s>>>(y, out, H * W);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}

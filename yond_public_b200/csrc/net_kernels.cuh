@@ -1,0 +1,20 @@
+// CUDA-core kernels around the tensor-core conv stack — host-side launchers.
+#pragma once
+#include "common.cuh"
+
+struct FilmWeights {
+  const float* w0; const float* b0;  // (C,1) , (C)      first 1x1 on the scalar t
+  const float* w2; const float* b2;  // (C,C) , (C)
+  const float* w3; const float* b3;  // guided: beta.1 (C,C),(C)   | snr: sfm2.0 (C,1),(C)
+  const float* w4; const float* b4;  // snr only: sfm2.2 (C,C),(C)
+};
+
+int head_conv_launch(const float* z, const float* ub, const float* w, const float* bias, int B, int H, int W, int nf,
+                     float slope, bf16* out0, bf16* out1, cudaStream_t s);
+int tail_conv_launch(const bf16* act, const float* w, const float* bias, const float* z, const float* ub, int res, int B,
+                     int H, int W, int nf, float* y, cudaStream_t s);
+int maxpool2_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s);
+int film_launch(const FilmWeights& fw, const float* t, const float* ub, int B, int C, int guided, float* out_a, float* out_b,
+                cudaStream_t s);
+int nchw_to_nhwc4_launch(const float* x, float* z, float* ub, int B, int H, int W, cudaStream_t s);
+int nhwc4_to_nchw_launch(const float* y, float* out, int B, int H, int W, cudaStream_t s);

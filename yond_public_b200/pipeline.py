@@ -1,0 +1,275 @@
+"""The YOND blind-denoise pipeline on B200, behind the reference driver's method surface
+(YOND_SIDD.py:136-483: Simple_Denoiser, VST_Denoiser, IterDenoise) plus a batched, device-resident engine.
+
+Per frame: pack -> noise-parameter estimate (SimpleNLF) -> bias LUT -> generalized-Anscombe VST -> normalise ->
+reflect-pad -> AWGN denoiser (tcgen05 conv stack) -> crop -> de-normalise -> inverse VST -> unpack.
+All per-pixel work runs in libyond_b200 kernels; the host keeps the reference's scalar logic and guards.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, archs, isp, nlf
+from ._lib import VstParams, check, ptr, stream_ptr
+
+SIGMA_CORR_PRE = 1.03  # YOND_SIDD.py:284
+
+
+def build_net(arch: dict, device="cuda"):
+    """globals()[arch['name']](arch) of the reference (YOND_SIDD.py:177)."""
+    cls = getattr(archs, arch["name"], None)
+    if cls is None:
+        raise NotImplementedError(f"arch '{arch['name']}' is outside the B200 hot path (UNetSeeInDark, GuidedResUnet, SNRnet)")
+    return cls(arch).to(device)
+
+
+class YondEngine:
+    """Batched VST-denoise of equally sized Bayer frames, device-resident."""
+
+    def __init__(self, net, arch, biaslut=None, chunk=None):
+        self.lib = _lib.load()
+        self.net = net
+        self.arch = arch
+        self.guided = "guided" in arch
+        self.biaslut = biaslut
+        self.chunk = chunk
+        self._bufs = {}
+
+    def _buf(self, name, shape, dtype, device):
+        n = int(np.prod(shape))
+        b = self._bufs.get(name)
+        if b is None or b.numel() < n or b.dtype != dtype or b.device != device:
+            b = torch.empty(n, device=device, dtype=dtype)
+            self._bufs[name] = b
+        return b[:n].view(*shape)
+
+    def default_chunk(self, B, hp, wp):
+        if self.chunk:
+            return min(B, int(self.chunk))
+        per = max(1, hp * wp * 800)  # ~bytes of activations per frame
+        return int(max(1, min(B, (6 << 30) // per, 128)))
+
+    # ------------------------------------------------------------------------------------------
+    def make_params(self, gains, sigmas, scale, bias_corr, vst_type, tables, device):
+        """Per-frame yond_vst_params + the bias rows they index.  `tables`: None (LUT / no bias) or a list of
+        (nodes, values) fallback tables, one per distinct (gain, sigma)."""
+        B = len(gains)
+        exact = 1 if (bias_corr is None and vst_type == "exact") else 0
+        uniq, row_of = {}, []
+        for k, s in zip(gains, sigmas):
+            key = (float(k), float(s))
+            if key not in uniq:
+                uniq[key] = len(uniq)
+            row_of.append(uniq[key])
+        stride = 1921
+        rows = xnodes = None
+        table_n = [0] * len(uniq)
+        if bias_corr is not None:
+            if self.biaslut is not None:
+                rows = torch.empty((len(uniq), stride), device=device, dtype=torch.float32)
+                for (k, s), i in uniq.items():
+                    if not self.biaslut.in_range(k, s):
+                        raise _lib.YondError(f"sigma/K = {s / k:.2f} e- is outside the BiasLUT range; pass fallback tables")
+                    self.biaslut.sigma_row(k, s, out=rows[i])
+                xnodes = self.biaslut.device_table()[1]
+            else:
+                assert tables is not None and len(tables) == len(uniq), "fallback bias tables required without a LUT"
+                stride = max(len(t[0]) for t in tables)
+                r = np.zeros((len(uniq), stride), np.float32)
+                xn = np.zeros((len(uniq), stride), np.float32)
+                for i, (nodes, vals) in enumerate(tables):
+                    r[i, :len(vals)], xn[i, :len(nodes)] = vals, nodes
+                    table_n[i] = len(nodes)
+                rows, xnodes = torch.from_numpy(r).to(device), torch.from_numpy(xn).to(device)
+        arr = (VstParams * B)()
+        t = np.zeros(B, np.float32)
+        for b, (k, s) in enumerate(zip(gains, sigmas)):
+            k, s = np.float64(k), np.float64(s)
+            lower = 2 / k * max((3 / 8) * k ** 2 + s ** 2, 0) ** 0.5  # VST(0)       YOND_SIDD.py:264
+            upper = 2 / k * max(k * scale + (3 / 8) * k ** 2 + s ** 2, 0) ** 0.5  # VST(scale)   :265
+            arr[b] = VstParams(float(k), float(s), float(scale), float(lower), float(upper),
+                               row_of[b] if bias_corr is not None else -1, table_n[row_of[b]], exact)
+            nsr = 1 / (upper - lower)  # :268
+            t[b] = nsr * (SIGMA_CORR_PRE if bias_corr == "pre" else 1.0)  # :284-285
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        return raw, rows, xnodes, stride, torch.from_numpy(t).to(device)
+
+    # ------------------------------------------------------------------------------------------
+    def vst_denoise(self, bayer, gains, sigmas, scale, bias_corr="pre", vst_type="exact", clip01=True, tables=None, out=None):
+        """VST_Denoiser (YOND_SIDD.py:250-299) for a batch: bayer (B,H,W) CUDA f32 -> (B,H,W) CUDA f32."""
+        B, H, W = bayer.shape
+        dev = bayer.device
+        h, w = H // 2, W // 2
+        pl, pr, pt, pb = isp.get_p2d((B, 4, h, w), base=32)
+        hp, wp = h + pt + pb, w + pl + pr
+        gains = np.broadcast_to(np.asarray(gains, np.float64), (B,))
+        sigmas = np.broadcast_to(np.asarray(sigmas, np.float64), (B,))
+        params, rows, xnodes, stride, t = self.make_params(gains, sigmas, float(scale), bias_corr, vst_type, tables, dev)
+        if out is None:
+            out = torch.empty_like(bayer)
+        cb = self.default_chunk(B, hp, wp)
+        z = self._buf("z", (cb, hp, wp, 4), torch.float32, dev)
+        y = self._buf("y", (cb, hp, wp, 4), torch.float32, dev)
+        ub = self._buf("ub", (cb,), torch.float32, dev)
+        psz = C.sizeof(VstParams)
+        st = stream_ptr()
+        for b0 in range(0, B, cb):
+            n = min(cb, B - b0)
+            pch = params[b0 * psz:]
+            check(self.lib.yond_vst_fwd(ptr(bayer[b0:b0 + n]), ptr(z[:n]), ptr(ub[:n]), n, H, W, pl, pr, pt, pb, ptr(pch),
+                                        ptr(rows), ptr(xnodes), stride, st))
+            self.net.forward_nhwc(z[:n], ub[:n], t[b0:b0 + n] if self.guided else None, out=y[:n])
+            check(self.lib.yond_vst_inv(ptr(y[:n]), ptr(out[b0:b0 + n]), n, H, W, pl, pr, pt, pb, ptr(pch), int(clip01), st))
+        return out
+
+    def simple_denoise(self, bayer, out=None):
+        """Simple_Denoiser (YOND_SIDD.py:238-248) for a batch (no VST; non-guided nets only, like the reference)."""
+        B, H, W = bayer.shape
+        dev = bayer.device
+        h, w = H // 2, W // 2
+        pl, pr, pt, pb = isp.get_p2d((B, 4, h, w), base=32)
+        hp, wp = h + pt + pb, w + pl + pr
+        if out is None:
+            out = torch.empty_like(bayer)
+        cb = self.default_chunk(B, hp, wp)
+        z = self._buf("z", (cb, hp, wp, 4), torch.float32, dev)
+        y = self._buf("y", (cb, hp, wp, 4), torch.float32, dev)
+        ub = self._buf("ub", (cb,), torch.float32, dev)
+        st = stream_ptr()
+        for b0 in range(0, B, cb):
+            n = min(cb, B - b0)
+            check(self.lib.yond_pack_pad(ptr(bayer[b0:b0 + n]), ptr(z[:n]), ptr(ub[:n]), n, H, W, pl, pr, pt, pb, st))
+            self.net.forward_nhwc(z[:n], ub[:n], None, out=y[:n])
+            check(self.lib.yond_crop_unpack(ptr(y[:n]), ptr(out[b0:b0 + n]), n, H, W, pl, pr, pt, pb, st))
+        return out
+
+
+class YOND_SIDD:
+    """Drop-in for the reference driver's pipeline methods.  Construct from the yml dicts:
+
+        drv = YOND_SIDD(arch=cfg['arch'], pipe=cfg['pipeline'], state_dict=torch.load(...))
+        res = drv.IterDenoise(data, {'p': p, 'img_id': k})          # same dict in / dict out as the reference
+    """
+
+    def __init__(self, arch, pipe, state_dict=None, net=None, biaslut="default", device="cuda", chunk=None, log=None):
+        self.arch = dict(arch)
+        self.pipe = dict(pipe)
+        if self.pipe.get("bias_corr") == "none":  # YOND_SIDD.py:164-165
+            self.pipe["bias_corr"] = None
+        self.device = torch.device(device)
+        self.net = net if net is not None else build_net(self.arch, self.device)
+        if state_dict is not None:
+            archs.load_weights(self.net, state_dict, by_name=False)  # YOND_SIDD.py:183-185
+        self.net.eval()
+        if biaslut == "default":  # the reference enables the LUT iff checkpoints/bias_lut_2d.npy exists (:171)
+            biaslut = isp.BiasLUT()
+        self.biaslut = biaslut
+        self.engine = YondEngine(self.net, self.arch, self.biaslut, chunk=chunk)
+        self.logfile = None
+        self._log = log or (lambda *a, **k: None)
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _bias_tables(self, upper_bound, gain, sigma, bias_func=None):
+        if self.biaslut is not None or self.pipe["bias_corr"] is None:
+            return None
+        if bias_func is not None:  # a (nodes, values) pair from a previous call, or a scipy interp1d-like object
+            return [bias_func if isinstance(bias_func, tuple) else (np.asarray(bias_func.x), np.asarray(bias_func.y))]
+        return [isp.get_bias_table(upper_bound, float(sigma), float(gain))]
+
+    # -- YOND_SIDD.py:238-248 ---------------------------------------------------------------------
+    def Simple_Denoiser(self, lr_raw, denoiser="unet", p=None, show=False):
+        x, np_in = isp.to_dev(lr_raw)
+        out = self.engine.simple_denoise(x[None])[0]
+        return out.cpu().numpy() if np_in else out
+
+    # -- YOND_SIDD.py:250-299 ---------------------------------------------------------------------
+    def VST_Denoiser(self, lr_raw, hr_raw=None, bias_corr="pre", bias_func=None, denoiser="net", p=None, show=False):
+        if denoiser in ("bm3d", "fbi"):
+            raise NotImplementedError("bm3d / fbi comparison denoisers are outside the B200 hot path (SURVEY §2)")
+        x, np_in = isp.to_dev(lr_raw)
+        tables = None
+        if bias_corr is not None and self.biaslut is None:
+            tables = self._bias_tables(float(x.max()) * p["scale"], p["gain"], p["sigma"], bias_func)
+        saved = self.pipe.get("bias_corr")
+        out = self.engine.vst_denoise(x[None], [p["gain"]], [p["sigma"]], p["scale"], bias_corr=bias_corr,
+                                      vst_type=self.pipe.get("vst_type", "exact"), clip01=False, tables=tables)[0]
+        self.pipe["bias_corr"] = saved
+        return out.cpu().numpy() if np_in else out
+
+    # -- YOND_SIDD.py:301-483 ---------------------------------------------------------------------
+    def IterDenoise(self, data, params):
+        lr = data["lr"]
+        p = params["p"]
+        np_in = isinstance(lr, np.ndarray)
+        blocks, _ = isp.to_dev(lr)
+        full = None
+        if data.get("lr_full") is not None:  # the reference loads data['lr_path_full'] from disk (:339-340)
+            full, _ = isp.to_dev(data["lr_full"])
+        res = self.iter_denoise_device(blocks, p, lr_full=full)
+        conv = (lambda t: t.cpu().numpy()) if np_in else (lambda t: t)
+        results = {"raw_dns": [conv(t) for t in res["raw_dns"]], "regs": res["regs"], "lr_raw": conv(res["lr_raw"])}
+        hr = data.get("hr")
+        results["hr_raw"] = (np.concatenate(list(hr), axis=-1) if isinstance(hr, np.ndarray) and hr.ndim == 3 else hr)
+        return results
+
+    def iter_denoise_device(self, blocks, p, lr_full=None):
+        """Device-resident IterDenoise.  `blocks`: (nblk,H,W) CUDA f32 (SIDD layout) or (H,W) frame.
+        Returns CUDA tensors in the reference's mosaic layout: (H, nblk*W)."""
+        pipe = self.pipe
+        p = p  # updated in place like the reference (p['gain'], p['sigma'])
+        scale_est = p["wp"] - p["bl"]
+        scale = p.get("scale", scale_est)
+        full_dn = bool(pipe["full_dn"])
+        single = blocks.dim() == 2
+        blk = blocks[None] if single else blocks
+        nblk, H, W = blk.shape
+        mosaic = blk[0] if nblk == 1 else blk.permute(1, 0, 2).reshape(H, nblk * W).contiguous()  # :315
+        k = pipe["k"]
+        sidd_256 = bool(pipe.get("sidd_256", nblk == 32))
+        bias_corr = pipe["bias_corr"]
+        vst_type = pipe.get("vst_type", "exact")
+        regs = []
+        if not pipe["full_est"]:
+            # :367-378 — no estimator configured: plain network pass per block, returned as-is (not clipped)
+            dn = self.engine.simple_denoise(blk)
+            dn = dn[0] if nblk == 1 else dn.permute(1, 0, 2).reshape(H, nblk * W)
+            return {"raw_dns": [dn], "regs": (0, 0), "lr_raw": mosaic}
+        if "simple" not in pipe["est_type"]:
+            raise NotImplementedError(f"est_type '{pipe['est_type']}' needs external estimate files / networks (YOND_SIDD.py:316-353)")
+        # ---- round 1: self-calibration (:338-341, :356)
+        raw4est = mosaic if lr_full is None else lr_full
+        reg = nlf.SimpleNLF(raw4est, k=k, setting={"mode": "self"})
+        regs.append(reg)
+        p["gain"], p["sigma"] = reg[0] * scale_est, np.sqrt(max(reg[1], 0)) * scale_est
+        self._log(f"Self Est: K={p['gain']:.4f}, b={p['sigma']:.4f} (beta1={reg[0]:.3e}, beta2={reg[1]:.3e})")
+
+        def denoise():
+            src = mosaic[None] if full_dn else blk
+            tables = None
+            if bias_corr is not None and self.biaslut is None:
+                tables = self._bias_tables(float(blk.max()) * scale_est, p["gain"], p["sigma"])  # :393-395 / :450-452
+            n = src.shape[0]
+            dn = self.engine.vst_denoise(src, [p["gain"]] * n, [p["sigma"]] * n, scale, bias_corr=bias_corr,
+                                         vst_type=vst_type, clip01=True, tables=tables)  # .clip(0,1): :389 / :406
+            return dn[0] if (full_dn or nblk == 1) else dn.permute(1, 0, 2).reshape(H, nblk * W).contiguous()  # :408
+
+        raw_dn = denoise()
+        raw_dns = [raw_dn]
+        # ---- round 2: iterative calibration (:419-472)
+        if pipe.get("iter") == "iter":
+            for _ in range(1, pipe["max_iter"] + 1):
+                reg = nlf.SimpleNLF(mosaic, raw_dn, k=k, setting={"mode": "collab", "SIDD_256": sidd_256})  # :431
+                if reg[1] < 0:  # :438-440
+                    self._log(f"Warning!!! b={reg[1]:.4f} is backup to {reg[0] ** 2:.4f}")
+                    reg = (reg[0], reg[0] ** 2)
+                p["gain"], p["sigma"] = reg[0] * scale_est, np.sqrt(reg[1]) * scale_est  # :442
+                if reg[0] < 0:  # :445-447
+                    self._log("Warning!!! Wrong noise level! Backup to iter_0 result.")
+                    break
+                raw_dn = denoise()
+                raw_dns.append(raw_dn)
+                regs.append(reg)
+        return {"raw_dns": raw_dns, "regs": regs, "lr_raw": mosaic}
