@@ -66,10 +66,11 @@ def run_conv_case(mode, impl, B, H, W, cin0, cin1, cout, act=0, use_res=False, u
     resd = res.permute(0, 2, 3, 1).contiguous().to(dev) if use_res else None
     wc = np.ascontiguousarray(w.numpy())
     p = _lib.ptr
+    bd = b.to(dev)  # keep device operands referenced until the (synchronous) call returns
+    scd = scale.to(dev).contiguous() if use_scale else None
+    shd = shift.to(dev).contiguous() if use_scale else None
     rc = lib.yond_conv2d(mode, impl, B, H, W, cin0, cin1, p(s0), p(s1), cout, wc.ctypes.data_as(C.c_void_p),
-                         p(b.to(dev)), p(scale.to(dev).contiguous()) if use_scale else None,
-                         p(shift.to(dev).contiguous()) if use_scale else None, act, 0.2, p(resd), p(out0), p(out1),
-                         _lib.stream_ptr())
+                         p(bd), p(scd), p(shd), act, 0.2, p(resd), p(out0), p(out1), _lib.stream_ptr())
     if rc:
         return f"rc={rc} {lib.yond_last_error().decode()}"
     got = out0.float().cpu().permute(0, 3, 1, 2)

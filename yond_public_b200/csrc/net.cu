@@ -559,7 +559,7 @@ int yond_conv2d(int mode, int impl, int B, int Hin, int Win, int Cin0, int Cin1,
 int yond_net_profile(yond_net_t* n, int enable) {
   n->profile = enable;
   if (enable && n->events.empty()) {
-    n->events.resize(8192);
+    n->events.resize(32768);
     for (auto& e : n->events) YOND_CUDA_CHECK(cudaEventCreate(&e));
   }
   return YOND_OK;

@@ -27,13 +27,14 @@ def _dev():
 
 def to_dev(a, dtype=torch.float32):
     """numpy / tensor -> contiguous CUDA tensor; returns (tensor, was_numpy)."""
+    dev = _dev()  # raises without CUDA: there is no CPU path
     if isinstance(a, np.ndarray):
         t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32 if dtype == torch.float32 else None))
-        return t.pin_memory().to(_dev(), non_blocking=True), True
+        return t.pin_memory().to(dev, non_blocking=True), True
     if not torch.is_tensor(a):
         a = torch.as_tensor(np.asarray(a, dtype=np.float32))
-        return a.to(_dev()), True
-    return a.to(device=_dev(), dtype=dtype).contiguous(), False
+        return a.to(dev), True
+    return a.to(device=dev, dtype=dtype).contiguous(), False
 
 
 def _back(t, was_numpy):
@@ -212,6 +213,8 @@ def get_bias_table(img_max, sigGs, K, pho_min=1, close_form=True):
     (`interp1d`) runs on the device inside yond_vst_fwd.  Device generation is a SURVEY §8(f) 'next' row."""
     from scipy.signal import convolve
     from scipy.stats import norm, poisson
+    # dtype flow of the reference call sites (YOND_SIDD.py:256,395,452): the bound is a float32 scalar, K and sigma float64
+    img_max, sigGs, K = np.float32(img_max), np.float64(sigGs), np.float64(K)
     lb, ub = 0, np.ceil(img_max) + 1
     if ub < 50:
         lams = np.linspace(lb, ub, int((ub - lb) / 0.1) + 2)

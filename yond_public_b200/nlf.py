@@ -58,7 +58,7 @@ class NlfEstimator:
         n = data.numel()
         q = np.asarray(quants, np.float64)
         qq = np.true_divide(q, 100)
-        vi = n * qq + (1 + qq * (1 - 1 - 1)) - 1  # NumPy's _compute_virtual_index with alpha = beta = 1 ('linear')
+        vi = (n - 1) * qq  # NumPy's virtual index for method='linear'
         lo = np.floor(vi).astype(np.int64)
         hi = np.minimum(lo + 1, n - 1)
         gamma = vi - lo

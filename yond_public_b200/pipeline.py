@@ -192,7 +192,7 @@ class YOND_SIDD:
         x, np_in = isp.to_dev(lr_raw)
         tables = None
         if bias_corr is not None and self.biaslut is None:
-            tables = self._bias_tables(float(x.max()) * p["scale"], p["gain"], p["sigma"], bias_func)
+            tables = self._bias_tables(np.float32(float(x.max())) * np.float32(p["scale"]), p["gain"], p["sigma"], bias_func)
         saved = self.pipe.get("bias_corr")
         out = self.engine.vst_denoise(x[None], [p["gain"]], [p["sigma"]], p["scale"], bias_corr=bias_corr,
                                       vst_type=self.pipe.get("vst_type", "exact"), clip01=False, tables=tables)[0]
@@ -250,7 +250,7 @@ class YOND_SIDD:
             src = mosaic[None] if full_dn else blk
             tables = None
             if bias_corr is not None and self.biaslut is None:
-                tables = self._bias_tables(float(blk.max()) * scale_est, p["gain"], p["sigma"])  # :393-395 / :450-452
+                tables = self._bias_tables(np.float32(float(blk.max())) * np.float32(scale_est), p["gain"], p["sigma"])  # :393-395 / :450-452
             n = src.shape[0]
             dn = self.engine.vst_denoise(src, [p["gain"]] * n, [p["sigma"]] * n, scale, bias_corr=bias_corr,
                                          vst_type=vst_type, clip01=True, tables=tables)  # .clip(0,1): :389 / :406
