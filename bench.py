@@ -39,10 +39,12 @@ def synth_images(n_images, seed=2024):
     out = np.empty((n_images, N_BLOCKS, BLK, BLK), np.float32)
     params = []
     for i in range(n_images):
-        K, S = O.sample_noise_params(rng)
+        # K >= 0.6 DN/e-: below that the blind estimate of sigma/K leaves the BiasLUT's range (>= 10 e-) on smooth
+        # synthetic content and both arms would spend their time in the host-side fallback-table generator (A6)
+        K, S = O.sample_noise_params(rng, logk_min=-0.5)
         params.append((K, S))
         for b in range(N_BLOCKS):
-            out[i, b] = O.synth_noisy(rng, O.synth_clean(rng, BLK, BLK), K, S, clip=True)
+            out[i, b] = O.synth_noisy(rng, O.synth_clean_smooth(rng, BLK, BLK), K, S, clip=True)
     return out, params
 
 

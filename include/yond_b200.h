@@ -59,15 +59,15 @@ typedef struct {
   float lower;     /* VST(0)                                      YOND_SIDD.py:264 */
   float upper;     /* VST(scale)                                  YOND_SIDD.py:265 */
   int32_t lut_row; /* row index into `rows` (−1: no bias correction, bias_corr=None) */
-  int32_t table_n; /* >0: `rows[lut_row]` is a generic piecewise-linear table with `table_n` nodes whose
-                      positions are at tables_x[lut_row] (fallback get_bias table, isp_algos.py:98-140) */
+  int32_t table_n; /* 0: `rows[lut_row]` is a sigma-interpolated BiasLUT row (1921 nodes, electrons);
+                      >0: a fallback get_bias table (isp_algos.py:98-140) with `table_n` nodes in DN */
   int32_t exact_inverse; /* 1: closed-form exact unbiased inverse (isp_algos.py:20-27) */
 } yond_vst_params;
 
 /* ---- A18 front half (YOND_SIDD.py:251-269,275,281-282,286): pack*scale -> bias -> VST-bias -> normalise ->
  * clamp(0,1) -> reflect-pad to (hp,wp) -> z (B,hp,wp,4) f32; also ub[b] = max(z[b]) (A14, modules.py:15-21).
- * `rows`: (nrows, row_stride) f32 bias tables; `xnodes`: node positions shared by all LUT rows (or per row when
- * table_n>0, same stride).  p2d = (left, right, top, bottom) in packed pixels (utils/utils.py:246-252). */
+ * `rows`: (nrows, row_stride) f32 bias tables; `xnodes`: (nrows, row_stride) node positions of each row (the BiasLUT
+ * x-grid in electrons for LUT rows, the get_bias nodes in DN for fallback tables).  p2d = (left, right, top, bottom) in packed pixels (utils/utils.py:246-252). */
 int yond_vst_fwd(const float* bayer, float* z, float* ub, int B, int H, int W, int pad_l, int pad_r, int pad_t,
                  int pad_b, const yond_vst_params* params_dev, const float* rows, const float* xnodes,
                  int row_stride, void* stream);

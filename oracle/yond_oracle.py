@@ -635,11 +635,11 @@ def synth_clean(rng, H, W):
     return np.clip(img, 0.02, 0.98).astype(np.float32)
 
 
-def sample_noise_params(rng):
+def sample_noise_params(rng, logk_min=-2.5):
     """yond_datasets.py:664-682: log K ~ U(-2.5, 3.5); log sigma ~ N((0.85187±0.2)·log K + (0.67991±1), 0.02921).
     Redrawn until sigma/K is inside the BiasLUT's sigma range (< 10 e-), where the LUT path (A5) applies."""
     while True:
-        logK = rng.uniform(-2.5, 3.5)
+        logK = rng.uniform(logk_min, 3.5)
         mu = (0.85187 + rng.uniform(-0.2, 0.2)) * logK + (0.67991 + rng.uniform(-1, 1))
         K = float(np.exp(logK))
         sigma = float(np.exp(rng.normal(mu, 0.02921)))
@@ -689,3 +689,19 @@ def smoother_state_dict(arch, alpha=1.0):
         for c in range(4):
             sd["conv10.weight"][c, c, 0, 0], sd["conv10.weight"][c, c + 4, 0, 0] = alpha * g, -alpha * g
     return sd
+
+
+def synth_clean_smooth(rng, H, W):
+    """Smooth clean Bayer field in [0.03,0.95]: low-frequency illumination with a per-frame level and a mild CFA
+    colour cast, no edges — so that, as in real photographs' flat regions, the 29x29 local statistics are dominated
+    by the noise and the blind estimator recovers (K, sigma).  Used by bench.py / smoke (the goldens keep synth_clean)."""
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    level = rng.uniform(0.08, 0.7)
+    amp = rng.uniform(0.2, 1.0) * 0.04 * (H / 256.0)  # gentle shading: ~0.03 across a 256-px block
+    f = rng.uniform(0.3, 1.2, size=3) * 2 * np.pi
+    ph = rng.uniform(0, 2 * np.pi, size=3)
+    field = (np.sin(f[0] * yy / H + ph[0]) * np.cos(f[1] * xx / W + ph[1]) + 0.5 * np.sin(f[2] * (xx / W + yy / H) + ph[2])) / 1.5
+    img = level + amp * field
+    cast = rng.uniform(0.85, 1.0, size=(2, 2)).astype(np.float32)  # per-CFA-site gain
+    img = img * np.tile(cast, (H // 2, W // 2))
+    return np.clip(img, 0.03, 0.95).astype(np.float32)

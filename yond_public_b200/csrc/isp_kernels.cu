@@ -116,16 +116,16 @@ __device__ __forceinline__ float bias_eval(float x_dn, const VstConst& c, const 
   if (c.lut_row < 0) return 0.f;
   const float xb = fmaxf(x_dn, 0.f);
   const float* row = rows + (size_t)c.lut_row * row_stride;
-  if (c.table_n > 0) {  // fallback get_bias table: nodes in DN, one node array per row
-    const float* nodes = xnodes + (size_t)c.lut_row * row_stride;
+  const float* nodes = xnodes + (size_t)c.lut_row * row_stride;  // every row carries its own node positions
+  if (c.table_n > 0) {  // fallback get_bias table (isp_algos.py:98-140): nodes in DN
     const float xc = fminf(xb, __ldg(nodes + c.table_n - 1));
     return table_eval(xc, row, nodes, c.table_n, false);
   }
-  const float xe = xb / c.K;  // electrons
+  const float xe = xb / c.K;  // BiasLUT row: nodes in electrons on the 1921-node lin+log grid
   const int nx = 1921;
-  const float last = __ldg(xnodes + nx - 1), prev = __ldg(xnodes + nx - 2);
+  const float last = __ldg(nodes + nx - 1), prev = __ldg(nodes + nx - 2);
   if (xe >= last + (last - prev)) return close_form_bias_f(xb, c);  // x_pos >= len(x_lut): isp_algos.py:228-230
-  return table_eval(xe, row, xnodes, nx, true);
+  return table_eval(xe, row, nodes, nx, true);
 }
 __device__ __forceinline__ float inverse_vst_f(float z, const VstConst& c) {
   float f;

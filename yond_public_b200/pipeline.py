@@ -37,6 +37,7 @@ class YondEngine:
         self.biaslut = biaslut
         self.chunk = chunk
         self._bufs = {}
+        self._tables = {}
 
     def _buf(self, name, shape, dtype, device):
         n = int(np.prod(shape))
@@ -53,52 +54,80 @@ class YondEngine:
         return int(max(1, min(B, (6 << 30) // per, 128)))
 
     # ------------------------------------------------------------------------------------------
-    def make_params(self, gains, sigmas, scale, bias_corr, vst_type, tables, device):
-        """Per-frame yond_vst_params + the bias rows they index.  `tables`: None (LUT / no bias) or a list of
-        (nodes, values) fallback tables, one per distinct (gain, sigma)."""
+    def make_params(self, gains, sigmas, scale, bias_corr, vst_type, frame_max, device, fixed_table=None):
+        """Per-frame yond_vst_params + the bias rows they index.
+
+        Bias source per frame, like the reference (YOND_SIDD.py:252-259, utils/isp_algos.py:196-231): the BiasLUT row
+        for this sigma/K when a LUT is loaded and sigma/K is inside its range, otherwise the fallback `get_bias`
+        table built on the host up to this frame's maximum (`frame_max`: callable returning per-frame max in DN)."""
         B = len(gains)
         exact = 1 if (bias_corr is None and vst_type == "exact") else 0
-        uniq, row_of = {}, []
-        for k, s in zip(gains, sigmas):
-            key = (float(k), float(s))
-            if key not in uniq:
-                uniq[key] = len(uniq)
-            row_of.append(uniq[key])
-        stride = 1921
-        rows = xnodes = None
-        table_n = [0] * len(uniq)
+        rows_np, nodes_np, table_n, key_row, row_of = [], [], [], {}, [-1] * B
+        lut_rows = []  # (row index, K, sigma) filled on device
         if bias_corr is not None:
-            if self.biaslut is not None:
-                rows = torch.empty((len(uniq), stride), device=device, dtype=torch.float32)
-                for (k, s), i in uniq.items():
-                    if not self.biaslut.in_range(k, s):
-                        raise _lib.YondError(f"sigma/K = {s / k:.2f} e- is outside the BiasLUT range; pass fallback tables")
-                    self.biaslut.sigma_row(k, s, out=rows[i])
-                xnodes = self.biaslut.device_table()[1]
-            else:
-                assert tables is not None and len(tables) == len(uniq), "fallback bias tables required without a LUT"
-                stride = max(len(t[0]) for t in tables)
-                r = np.zeros((len(uniq), stride), np.float32)
-                xn = np.zeros((len(uniq), stride), np.float32)
-                for i, (nodes, vals) in enumerate(tables):
-                    r[i, :len(vals)], xn[i, :len(nodes)] = vals, nodes
-                    table_n[i] = len(nodes)
-                rows, xnodes = torch.from_numpy(r).to(device), torch.from_numpy(xn).to(device)
+            fmax = None
+            for b, (k, s) in enumerate(zip(gains, sigmas)):
+                k, s = float(k), float(s)
+                if self.biaslut is not None and self.biaslut.in_range(k, s):
+                    key = ("lut", k, s)
+                    if key not in key_row:
+                        key_row[key] = len(rows_np)
+                        rows_np.append(None)
+                        nodes_np.append(self.biaslut.x_lut.astype(np.float32))
+                        table_n.append(0)
+                        lut_rows.append((key_row[key], k, s))
+                else:
+                    if fixed_table is not None:
+                        key = ("fixed",)
+                    else:
+                        if fmax is None:
+                            fmax = frame_max()
+                        ub = np.float32(fmax[b])
+                        key = ("tab", k, s, float(np.ceil(ub)))
+                    if key not in key_row:
+                        nodes, vals = fixed_table if fixed_table is not None else self.table_fn(ub, s, k)
+                        key_row[key] = len(rows_np)
+                        rows_np.append(np.asarray(vals, np.float32))
+                        nodes_np.append(np.asarray(nodes, np.float32))
+                        table_n.append(len(nodes))
+                row_of[b] = key_row[key]
+        rows = xnodes = None
+        stride = 1921
+        if rows_np:
+            stride = max(1921, max(len(n) for n in nodes_np))
+            r = np.zeros((len(rows_np), stride), np.float32)
+            xn = np.zeros((len(rows_np), stride), np.float32)
+            for i, (vals, nodes) in enumerate(zip(rows_np, nodes_np)):
+                xn[i, :len(nodes)] = nodes
+                if vals is not None:
+                    r[i, :len(vals)] = vals
+            rows, xnodes = torch.from_numpy(r).to(device), torch.from_numpy(xn).to(device)
+            for i, k, s in lut_rows:
+                self.biaslut.sigma_row(k, s, out=rows[i, :1921])
         arr = (VstParams * B)()
         t = np.zeros(B, np.float32)
         for b, (k, s) in enumerate(zip(gains, sigmas)):
             k, s = np.float64(k), np.float64(s)
             lower = 2 / k * max((3 / 8) * k ** 2 + s ** 2, 0) ** 0.5  # VST(0)       YOND_SIDD.py:264
             upper = 2 / k * max(k * scale + (3 / 8) * k ** 2 + s ** 2, 0) ** 0.5  # VST(scale)   :265
-            arr[b] = VstParams(float(k), float(s), float(scale), float(lower), float(upper),
-                               row_of[b] if bias_corr is not None else -1, table_n[row_of[b]], exact)
+            arr[b] = VstParams(float(k), float(s), float(scale), float(lower), float(upper), row_of[b],
+                               table_n[row_of[b]] if row_of[b] >= 0 else 0, exact)
             nsr = 1 / (upper - lower)  # :268
             t[b] = nsr * (SIGMA_CORR_PRE if bias_corr == "pre" else 1.0)  # :284-285
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
         return raw, rows, xnodes, stride, torch.from_numpy(t).to(device)
 
+    def table_fn(self, ub, sigma, gain):
+        """Fallback table generator; memoised because SIDD blocks of one image mostly share (max, K, sigma)."""
+        key = (float(ub), float(sigma), float(gain))
+        if key not in self._tables:
+            if len(self._tables) > 256:
+                self._tables.clear()
+            self._tables[key] = isp.get_bias_table(ub, sigma, gain)
+        return self._tables[key]
+
     # ------------------------------------------------------------------------------------------
-    def vst_denoise(self, bayer, gains, sigmas, scale, bias_corr="pre", vst_type="exact", clip01=True, tables=None, out=None):
+    def vst_denoise(self, bayer, gains, sigmas, scale, bias_corr="pre", vst_type="exact", clip01=True, table_bound=None, fixed_table=None, out=None):
         """VST_Denoiser (YOND_SIDD.py:250-299) for a batch: bayer (B,H,W) CUDA f32 -> (B,H,W) CUDA f32."""
         B, H, W = bayer.shape
         dev = bayer.device
@@ -107,7 +136,13 @@ class YondEngine:
         hp, wp = h + pt + pb, w + pl + pr
         gains = np.broadcast_to(np.asarray(gains, np.float64), (B,))
         sigmas = np.broadcast_to(np.asarray(sigmas, np.float64), (B,))
-        params, rows, xnodes, stride, t = self.make_params(gains, sigmas, float(scale), bias_corr, vst_type, tables, dev)
+        # upper bound of a fallback table: the caller's bound (YOND_SIDD.py:393-395: one table per image, up to the image
+        # max) or, like VST_Denoiser / BiasLUT.get_lut on their own, each frame's max in DN (float32 product)
+        if table_bound is not None:
+            frame_max = lambda: np.full(B, np.float32(table_bound), np.float32)
+        else:
+            frame_max = lambda: (bayer.amax(dim=(1, 2)).clamp_min(0).cpu().numpy().astype(np.float32) * np.float32(scale))
+        params, rows, xnodes, stride, t = self.make_params(gains, sigmas, float(scale), bias_corr, vst_type, frame_max, dev, fixed_table)
         if out is None:
             out = torch.empty_like(bayer)
         cb = self.default_chunk(B, hp, wp)
@@ -172,12 +207,14 @@ class YOND_SIDD:
         self._log = log or (lambda *a, **k: None)
 
     # -- helpers --------------------------------------------------------------------------------
-    def _bias_tables(self, upper_bound, gain, sigma, bias_func=None):
-        if self.biaslut is not None or self.pipe["bias_corr"] is None:
+    @staticmethod
+    def _as_table(bias_func):
+        """A reference-style `bias_func` (scipy interp1d from get_bias) or a (nodes, values) pair -> (nodes, values)."""
+        if bias_func is None:
             return None
-        if bias_func is not None:  # a (nodes, values) pair from a previous call, or a scipy interp1d-like object
-            return [bias_func if isinstance(bias_func, tuple) else (np.asarray(bias_func.x), np.asarray(bias_func.y))]
-        return [isp.get_bias_table(upper_bound, float(sigma), float(gain))]
+        if isinstance(bias_func, tuple):
+            return bias_func
+        return np.asarray(bias_func.x), np.asarray(bias_func.y)
 
     # -- YOND_SIDD.py:238-248 ---------------------------------------------------------------------
     def Simple_Denoiser(self, lr_raw, denoiser="unet", p=None, show=False):
@@ -190,13 +227,11 @@ class YOND_SIDD:
         if denoiser in ("bm3d", "fbi"):
             raise NotImplementedError("bm3d / fbi comparison denoisers are outside the B200 hot path (SURVEY §2)")
         x, np_in = isp.to_dev(lr_raw)
-        tables = None
-        if bias_corr is not None and self.biaslut is None:
-            tables = self._bias_tables(np.float32(float(x.max())) * np.float32(p["scale"]), p["gain"], p["sigma"], bias_func)
-        saved = self.pipe.get("bias_corr")
+        # bias: LUT when loaded and sigma/K in range, else the fallback table — the caller's `bias_func` when given
+        # (only consulted without a LUT, :254-257), else get_bias up to this frame's max (:256 / isp_algos.py:204-212)
+        fixed = self._as_table(bias_func) if self.biaslut is None else None
         out = self.engine.vst_denoise(x[None], [p["gain"]], [p["sigma"]], p["scale"], bias_corr=bias_corr,
-                                      vst_type=self.pipe.get("vst_type", "exact"), clip01=False, tables=tables)[0]
-        self.pipe["bias_corr"] = saved
+                                      vst_type=self.pipe.get("vst_type", "exact"), clip01=False, fixed_table=fixed)[0]
         return out.cpu().numpy() if np_in else out
 
     # -- YOND_SIDD.py:301-483 ---------------------------------------------------------------------
@@ -248,12 +283,13 @@ class YOND_SIDD:
 
         def denoise():
             src = mosaic[None] if full_dn else blk
-            tables = None
-            if bias_corr is not None and self.biaslut is None:
-                tables = self._bias_tables(np.float32(float(blk.max())) * np.float32(scale_est), p["gain"], p["sigma"])  # :393-395 / :450-452
+            bound = None
+            if bias_corr is not None and self.biaslut is None and not full_dn:
+                # one fallback table per image, up to the image max (:393-395 / :450-452), shared by its blocks
+                bound = np.float32(float(blk.max())) * np.float32(scale_est)
             n = src.shape[0]
             dn = self.engine.vst_denoise(src, [p["gain"]] * n, [p["sigma"]] * n, scale, bias_corr=bias_corr,
-                                         vst_type=vst_type, clip01=True, tables=tables)  # .clip(0,1): :389 / :406
+                                         vst_type=vst_type, clip01=True, table_bound=bound)  # .clip(0,1): :389 / :406
             return dn[0] if (full_dn or nblk == 1) else dn.permute(1, 0, 2).reshape(H, nblk * W).contiguous()  # :408
 
         raw_dn = denoise()
