@@ -1,0 +1,47 @@
+"""Profiling driver: warms up, then runs ONE SIDD-shaped image (32 blocks of 256x256) through iter_denoise_device
+between cudaProfilerStart/Stop (use with `ncu --profile-from-start off`).  `--batch N` profiles N blocks through the
+network only (conv-stack capture)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import yond_public_b200 as Y  # noqa: E402
+from oracle import yond_oracle as O  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--net-only", type=int, default=0, help="profile only the network forward on this many 128x128 packed blocks")
+ap.add_argument("--arch", default="gru")
+ap.add_argument("--frame", default=None, help="HxW packed frame for --net-only, e.g. 1536x2016")
+args = ap.parse_args()
+arch = bench.ARCH if args.arch == "gru" else {"name": "UNetSeeInDark", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
+sd = O.init_state_dict(arch, seed=0)
+drv = Y.YOND_SIDD(arch, bench.PIPE, state_dict=sd)
+if args.net_only:
+    B = args.net_only
+    H, W = (128, 128) if not args.frame else tuple(int(v) for v in args.frame.split("x"))
+    z = torch.rand((B, H, W, 4), device="cuda")
+    ub = z.amax(dim=(1, 2, 3)).contiguous()
+    t = torch.full((B,), 0.04, device="cuda")
+    for _ in range(3):
+        drv.net.forward_nhwc(z, ub, t if "guided" in arch else None)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    drv.net.forward_nhwc(z, ub, t if "guided" in arch else None)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+else:
+    imgs, _ = bench.synth_images(2)
+    dev_in = torch.from_numpy(imgs).cuda()
+    for i in range(3):
+        drv.iter_denoise_device(dev_in[i % 2], dict(bench.P0))
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    drv.iter_denoise_device(dev_in[0], dict(bench.P0))
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+print("profiled ok")

@@ -148,25 +148,56 @@ __global__ void __launch_bounds__(256) hist0_kernel(const float* __restrict__ d,
   for (int i = threadIdx.x; i < 2048; i += blockDim.x)
     if (h[i]) atomicAdd(&wk->hist0[i], (unsigned long long)h[i]);
 }
-// single block: resolve each query rank against a histogram level
-__global__ void select0_kernel(SelectWork* wk, const unsigned long long* __restrict__ ranks, int nranks) {
-  if (threadIdx.x != 0) return;
-  for (int i = 0; i < 2048; ++i) wk->slot1_of_prefix[i] = -1;
-  int ns = 0;
-  for (int q = 0; q < nranks; ++q) {
-    unsigned long long r = ranks[q], cum = 0;
-    int bin = 0;
-    for (; bin < 2048; ++bin) {
-      if (cum + wk->hist0[bin] > r) break;
-      cum += wk->hist0[bin];
+// Warp-cooperative search of the bin holding rank r in a histogram: returns the bin, *before = #elements below it.
+__device__ __forceinline__ int warp_find_bin(const unsigned long long* __restrict__ hist, int nbins, unsigned long long r,
+                                             unsigned long long* before) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long running = 0;
+  for (int base = 0; base < nbins; base += 32) {
+    const unsigned long long h = hist[base + lane];
+    unsigned long long incl = h;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    if (bin >= 2048) bin = 2047;
-    if (wk->slot1_of_prefix[bin] < 0) wk->slot1_of_prefix[bin] = ns++;
-    wk->q_slot1[q] = wk->slot1_of_prefix[bin];
-    wk->q_prefix[q] = (uint32_t)bin;
-    wk->rank_in[q] = r - cum;
+    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+    if (r < running + total) {
+      const unsigned int m = __ballot_sync(0xffffffffu, running + incl > r);
+      const int l = __ffs(m) - 1;
+      const unsigned long long excl = __shfl_sync(0xffffffffu, incl - h, l);
+      *before = running + excl;
+      return base + l;
+    }
+    running += total;
   }
-  wk->nslot1 = ns;
+  *before = running - hist[nbins - 1];
+  return nbins - 1;
+}
+
+// One block of 32 warps; warp w resolves queries w, w+32.  Thread 0 then assigns slots (deduplicated buckets).
+__global__ void __launch_bounds__(1024) select0_kernel(SelectWork* wk, const unsigned long long* __restrict__ ranks, int nranks) {
+  __shared__ int s_bin[kMaxRanks];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) wk->slot1_of_prefix[i] = -1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = warp; q < nranks; q += 32) {
+    unsigned long long before;
+    const int bin = warp_find_bin(wk->hist0, 2048, ranks[q], &before);
+    if (lane == 0) {
+      s_bin[q] = bin;
+      wk->q_prefix[q] = (uint32_t)bin;
+      wk->rank_in[q] = ranks[q] - before;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ns = 0;
+    for (int q = 0; q < nranks; ++q) {
+      const int bin = s_bin[q];
+      if (wk->slot1_of_prefix[bin] < 0) wk->slot1_of_prefix[bin] = ns++;
+      wk->q_slot1[q] = wk->slot1_of_prefix[bin];
+    }
+    wk->nslot1 = ns;
+  }
 }
 __global__ void __launch_bounds__(256) hist1_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -175,26 +206,30 @@ __global__ void __launch_bounds__(256) hist1_kernel(const float* __restrict__ d,
     if (s >= 0) atomicAdd(&wk->hist1[s][(k >> 10) & 2047u], 1ull);
   }
 }
-__global__ void select1_kernel(SelectWork* wk, int nranks) {
+__global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nranks) {
+  __shared__ int s_bin[kMaxRanks];
   for (int i = threadIdx.x; i < kMaxRanks * 2048; i += blockDim.x) (&wk->slot2_of[0][0])[i] = -1;
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  int ns = 0;
-  for (int q = 0; q < nranks; ++q) {
-    const int s1 = wk->q_slot1[q];
-    unsigned long long r = wk->rank_in[q], cum = 0;
-    int bin = 0;
-    for (; bin < 2048; ++bin) {
-      if (cum + wk->hist1[s1][bin] > r) break;
-      cum += wk->hist1[s1][bin];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = warp; q < nranks; q += 32) {
+    unsigned long long before;
+    const int bin = warp_find_bin(wk->hist1[wk->q_slot1[q]], 2048, wk->rank_in[q], &before);
+    __syncwarp();
+    if (lane == 0) {
+      s_bin[q] = bin;
+      wk->q_prefix[q] = (wk->q_prefix[q] << 11) | (uint32_t)bin;
+      wk->rank_in[q] -= before;
     }
-    if (bin >= 2048) bin = 2047;
-    if (wk->slot2_of[s1][bin] < 0) wk->slot2_of[s1][bin] = ns++;
-    wk->q_slot2[q] = wk->slot2_of[s1][bin];
-    wk->q_prefix[q] = (wk->q_prefix[q] << 11) | (uint32_t)bin;
-    wk->rank_in[q] = r - cum;
   }
-  wk->nslot2 = ns;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ns = 0;
+    for (int q = 0; q < nranks; ++q) {
+      const int s1 = wk->q_slot1[q], bin = s_bin[q];
+      if (wk->slot2_of[s1][bin] < 0) wk->slot2_of[s1][bin] = ns++;
+      wk->q_slot2[q] = wk->slot2_of[s1][bin];
+    }
+    wk->nslot2 = ns;
+  }
 }
 __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -205,18 +240,13 @@ __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d,
     if (s2 >= 0) atomicAdd(&wk->hist2[s2][k & 1023u], 1ull);
   }
 }
-__global__ void select2_kernel(SelectWork* wk, int nranks, float* __restrict__ out) {
-  const int q = threadIdx.x;
-  if (q >= nranks) return;
-  const int s2 = wk->q_slot2[q];
-  unsigned long long r = wk->rank_in[q], cum = 0;
-  int bin = 0;
-  for (; bin < 1024; ++bin) {
-    if (cum + wk->hist2[s2][bin] > r) break;
-    cum += wk->hist2[s2][bin];
+__global__ void __launch_bounds__(1024) select2_kernel(SelectWork* wk, int nranks, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = warp; q < nranks; q += 32) {
+    unsigned long long before;
+    const int bin = warp_find_bin(wk->hist2[wk->q_slot2[q]], 1024, wk->rank_in[q], &before);
+    if (lane == 0) out[q] = key2f((wk->q_prefix[q] << 10) | (uint32_t)bin);
   }
-  if (bin >= 1024) bin = 1023;
-  out[q] = key2f((wk->q_prefix[q] << 10) | (uint32_t)bin);
 }
 
 // ------------------------------------------------------------------ score3 bin occupancy
@@ -380,15 +410,15 @@ int yond_order_stats(const float* data, size_t n, const uint64_t* ranks_dev, int
   const int g = stream_grid(n);
   hist0_kernel<<<g, 256, 0, s>>>(data, n, wk);
   YOND_LAUNCH_CHECK();
-  select0_kernel<<<1, 32, 0, s>>>(wk, reinterpret_cast<const unsigned long long*>(ranks_dev), nranks);
+  select0_kernel<<<1, 1024, 0, s>>>(wk, reinterpret_cast<const unsigned long long*>(ranks_dev), nranks);
   YOND_LAUNCH_CHECK();
   hist1_kernel<<<g, 256, 0, s>>>(data, n, wk);
   YOND_LAUNCH_CHECK();
-  select1_kernel<<<1, 256, 0, s>>>(wk, nranks);
+  select1_kernel<<<1, 1024, 0, s>>>(wk, nranks);
   YOND_LAUNCH_CHECK();
   hist2_kernel<<<g, 256, 0, s>>>(data, n, wk);
   YOND_LAUNCH_CHECK();
-  select2_kernel<<<1, 64, 0, s>>>(wk, nranks, out_dev);
+  select2_kernel<<<1, 1024, 0, s>>>(wk, nranks, out_dev);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
