@@ -172,18 +172,17 @@ def run_b200(args):
     dev_out = torch.empty((N_IMAGES, BLK, N_BLOCKS * BLK), dtype=torch.float32, device=dev)
 
     def step_device():
-        for i in range(N_IMAGES):
-            res = drv.iter_denoise_device(dev_in[i], dict(P0))
-            dev_out[i].copy_(res["raw_dns"][-1])
+        res = drv.iter_denoise_batch(dev_in, dict(P0))
         if world > 1:
-            dist.gather(dev_out, gather_buf, dst=0)
+            dist.gather(res["raw_dns"][-1], gather_buf, dst=0)
+        return res
 
     def step_e2e():
-        for i in range(N_IMAGES):
-            x = host_in[i].to(dev, non_blocking=True)
-            res = drv.iter_denoise_device(x, dict(P0))
-            host_out[i].copy_(res["raw_dns"][-1], non_blocking=True)
+        x = host_in.to(dev, non_blocking=True)            # H2D of this step's inputs from pinned memory
+        res = drv.iter_denoise_batch(x, dict(P0))         # the batched form of the reference-facing IterDenoise
+        host_out.copy_(res["raw_dns"][-1], non_blocking=True)  # D2H of the denoised frames
         torch.cuda.synchronize()
+        return res
 
     def barrier():
         if world > 1:
@@ -205,8 +204,9 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
+    rounds = None
     for _ in range(args.warmup):
-        step_device()
+        rounds = step_device()["rounds"]
     net.set_profile(True)
     net.read_profile(reset=True)
     sampler = ClockSampler(local)
@@ -250,11 +250,12 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": "configs[1]: 1280 synthetic 256x256 Bayer blocks (40 images x 32), GuidedResUnet (GRU_5to50_norm_mix) random-init, "
                                    "SIDD_simple+full_pre pipeline: self estimate + VST denoise + collab estimate per image",
+                       "round2_denoise_images": int((rounds == 2).sum()) if rounds is not None else None,
                        "images_per_gpu": N_IMAGES, "blocks_per_image": N_BLOCKS, "block": [BLK, BLK],
                        "l2_policy": "inputs (335 MB per step) and activations exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"image-parallel x{world}, NCCL gather of denoised frames to rank 0" if world > 1 else "single GPU"},
             "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4),
-                    "ms_per_step": ms_e2e / args.steps, "api": "YOND_SIDD.iter_denoise_device on pinned host buffers (H2D + D2H per image)"},
+                    "ms_per_step": ms_e2e / args.steps, "api": "YOND_SIDD.iter_denoise_batch on pinned host buffers (H2D of the 40 images + D2H of the denoised frames per step)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,

@@ -93,21 +93,23 @@ size_t yond_nlf_work_bytes(int B, int h, int w, int C);
 int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float* lap, int B, int h, int w, int C,
                   int k, int mode, void* work, void* stream);
 
-/* ---- A9: get_threshold(mode='score3') — YOND_SIDD.py:22-49.
- * yond_order_stats: exact k-th smallest values (0-based ranks, ascending, nranks <= 64) of n floats by radix
- *   select; the host applies np.percentile's linear interpolation in float64.  `work`: yond_select_work_bytes().
- * yond_score3_bins: npeaks[i] = number of occupied bins of int(clip(mean,0,1)*1000) over {lap <= ths[i]} (:37-43),
- *   ths ascending (float64, nth <= 32).  `work`: >= 1001*4 bytes.  Results are written to device memory. */
-size_t yond_select_work_bytes(int nranks);
-int yond_order_stats(const float* data, size_t n, const uint64_t* ranks_dev, int nranks, float* out_dev, void* work,
-                     void* stream);
-int yond_score3_bins(const float* lap, const float* mean, size_t n, const double* ths_dev, int nth,
+/* ---- A9: get_threshold(mode='score3') — YOND_SIDD.py:22-49.  All three entry points are batched over `nseg`
+ * independent segments (one per image) of `seg_len` contiguous floats each.
+ * yond_order_stats: exact k-th smallest values (0-based ranks, shared by all segments, nranks <= 64) by radix select;
+ *   out (nseg, nranks).  The host applies np.percentile's linear interpolation in float64.
+ *   `work`: yond_select_work_bytes(nseg).
+ * yond_score3_bins: npeaks[s][i] = number of occupied bins of int(clip(mean,0,1)*1000) over {lap <= ths[s][i]} (:37-43),
+ *   ths ascending per segment (float64, (nseg, nth), nth <= 32).  `work`: >= nseg*1001*4 bytes. */
+size_t yond_select_work_bytes(int nseg);
+int yond_order_stats(const float* data, size_t seg_len, int nseg, const uint64_t* ranks_dev, int nranks, float* out_dev,
+                     void* work, void* stream);
+int yond_score3_bins(const float* lap, const float* mean, size_t seg_len, int nseg, const double* ths_dev, int nth,
                      int32_t* npeaks_dev, void* work, void* stream);
-/* ---- A10: masked line fit — YOND_SIDD.py:77-78 (strict lap<th), utils/isp_algos.py:345-365.
- * sums_dev[0..5]  = {N, Sx, Sy, Sxx, Sxy, Syy} over {lap < th};
- * sums_dev[6..11] = same over {lap < th, 1e-4 < mean < 0.8} (polyfit's non-saturated subset), float64. */
-int yond_masked_sums(const float* lap, const float* mean, const float* var, size_t n, double th, double* sums_dev,
-                     void* stream);
+/* ---- A10: masked line fit — YOND_SIDD.py:77-78 (strict lap<th), utils/isp_algos.py:345-365.  Per segment s:
+ * sums_dev[s][0..5]  = {N, Sx, Sy, Sxx, Sxy, Syy} over {lap < ths_dev[s]};
+ * sums_dev[s][6..11] = same over {lap < th, 1e-4 < mean < 0.8} (polyfit's non-saturated subset), float64. */
+int yond_masked_sums(const float* lap, const float* mean, const float* var, size_t seg_len, int nseg,
+                     const double* ths_dev, double* sums_dev, void* stream);
 
 /* ---- A14-A17, A20: denoiser networks — archs/Unet.py:4-104 (UNetSeeInDark), :380-470 (GuidedResUnet),
  * :288-378 (SNRnet); blocks archs/modules.py:117-125,163-233.  Plugin descriptor = the yml `arch:` block. */

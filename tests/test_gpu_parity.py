@@ -168,7 +168,7 @@ def _conv_cases():
     return G
 
 
-@pytest.mark.parametrize("idx", range(15))
+@pytest.mark.parametrize("idx", range(20))
 def test_conv_layer_tcgen05(Y, idx):
     G = _conv_cases()
     mode, B, H, W, c0, c1, co, act, res, sc, dual = G.CONV_CASES[idx]
@@ -287,6 +287,30 @@ def test_iterdenoise_golden_two_rounds(Y, golden, key):
     np.testing.assert_allclose(np.asarray(res["regs"][1]), g["regs"][1], rtol=2e-3)
     assert float(np.abs(res["raw_dns"][0][::8, ::8] - g["dn0_sub"]).max()) < TOL_ABS
     assert float(np.abs(res["raw_dns"][1][::8, ::8] - g["dn1_sub"]).max()) < TOL_ABS
+
+
+def test_batched_pipeline_equals_per_image(Y, lut_table):
+    """iter_denoise_batch (all images per stage, used by bench.py) == the per-image IterDenoise surface."""
+    rng = np.random.default_rng(11)
+    imgs = []
+    for K, S in ((2.0, 3.0), (9.0, 14.0), (5.0, 40.0)):
+        imgs.append(np.stack([O.synth_noisy(rng, O.synth_clean_smooth(rng, 128, 128), K, S) for _ in range(32)]))
+    imgs = np.stack(imgs)
+    for key, sd in (("gru", O.init_state_dict(ARCHS["gru"], seed=5)), ("gru", O.smoother_state_dict(ARCHS["gru"]))):
+        drv = Y.YOND_SIDD(ARCHS[key], PIPE, state_dict=sd)
+        p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+        res = drv.iter_denoise_batch(torch.from_numpy(imgs).cuda(), dict(p))
+        for i in range(len(imgs)):
+            one = drv.IterDenoise({"lr": imgs[i], "name": "x"}, {"p": dict(p), "img_id": i})
+            assert len(one["raw_dns"]) == int(res["rounds"][i])
+            for r in range(len(one["regs"])):
+                np.testing.assert_allclose(res["regs"][r][i], np.asarray(one["regs"][r]), rtol=1e-9)
+            np.testing.assert_allclose(res["raw_dns"][-1][i].cpu().numpy(), one["raw_dns"][-1], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(res["raw_dns"][0][i].cpu().numpy(), one["raw_dns"][0], rtol=0, atol=1e-6)
+        # and against the oracle for the first image
+        ref = O.IterDenoise(ARCHS[key], sd, imgs[0], dict(p), PIPE, biaslut=O.BiasLUT(lut_table))
+        np.testing.assert_allclose(res["regs"][0][0], np.asarray(ref["regs"][0]), rtol=TOL_EST)
+        assert float(np.abs(res["raw_dns"][0][0].cpu().numpy() - ref["raw_dns"][0]).max()) < TOL_ABS
 
 
 def test_full_frame_identity_roundtrip(Y):

@@ -101,6 +101,11 @@ CONV_CASES = [
     (1, 1, 16, 16, 64, 64, 64, 0, False, False, True),     # shortcut 1x1 on concat
     (0, 4, 128, 128, 32, 0, 32, 1, False, False, False),   # many tiles (persistent loop, phases)
     (0, 1, 4, 2, 512, 0, 512, 1, False, False, False),     # tiny maps (golden net fixture level 4)
+    (0, 4, 16, 16, 128, 0, 128, 2, True, True, False),     # T=2 sub-tiles along the batch, streamed weights
+    (0, 2, 64, 64, 64, 0, 64, 1, False, False, True),      # resident weights, T=2 along H
+    (0, 1, 40, 24, 128, 0, 128, 0, True, False, False),    # ragged super-tiles along H
+    (0, 3, 16, 16, 256, 0, 256, 1, False, False, False),   # odd batch with T=2 along the batch, two n tiles
+    (0, 1, 96, 126, 32, 32, 32, 2, False, True, False),    # full-frame-like ragged width, concat, T=4
 ]
 
 
@@ -194,7 +199,7 @@ def main():
         elif st == "nlf":
             stage_nlf()
         return
-    stages = [["isp"]] + [["conv", str(i)] for i in range(len(CONV_CASES))] + [["net", k] for k in ("unet", "gru", "snr")] + [["nlf"]]
+    stages = ([] if os.environ.get("STAGE_ONLY_CONV3") else [["isp"]]) + [["conv", str(i)] for i in (range(len(CONV_CASES)) if not os.environ.get("STAGE_ONLY_CONV3") else [i for i, c in enumerate(CONV_CASES) if c[0] == 0])] + ([] if os.environ.get("STAGE_ONLY_CONV3") else [["net", k] for k in ("unet", "gru", "snr")] + [["nlf"]])
     for st in stages:
         t0 = time.time()
         try:

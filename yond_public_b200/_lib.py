@@ -42,9 +42,9 @@ SIGNATURES = {
     "yond_nlf_work_bytes": (_SZ, [_I, _I, _I, _I]),
     "yond_nlf_maps": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "yond_select_work_bytes": (_SZ, [_I]),
-    "yond_order_stats": (_I, [_P, _SZ, _P, _I, _P, _P, _P]),
-    "yond_score3_bins": (_I, [_P, _P, _SZ, _P, _I, _P, _P, _P]),
-    "yond_masked_sums": (_I, [_P, _P, _P, _SZ, _D, _P, _P]),
+    "yond_order_stats": (_I, [_P, _SZ, _I, _P, _I, _P, _P, _P]),
+    "yond_score3_bins": (_I, [_P, _P, _SZ, _I, _P, _I, _P, _P, _P]),
+    "yond_masked_sums": (_I, [_P, _P, _P, _SZ, _I, _P, _P, _P]),
     "yond_net_create": (_I, [_I, _I, _I, _I, _I, _I, C.POINTER(_P)]),
     "yond_net_destroy": (None, [_P]),
     "yond_net_set_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),

@@ -4,30 +4,34 @@
 // archs/modules.py:117-125,163-233 (library kernels in the reference) with one persistent,
 // warp-specialised kernel:
 //
-//   warp 0   TMA producer  — activations: halo-extended NHWC tiles (cp.async.bulk.tensor.4d, OOB zero-fill
-//                            gives the conv's zero padding for free); weights: per-tap K-major tiles (2d)
-//   warp 1   MMA issuer    — one elected thread issues tcgen05.mma (M=128 pixels, N<=256 channels, K=16),
-//                            accumulating over taps x channel blocks into TMEM; tcgen05.commit frees stages
-//   warps 2-5 epilogue     — tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's MMAs
+//   warp 0    TMA producer — activations: halo-extended NHWC slabs (cp.async.bulk.tensor.4d; out-of-bounds
+//                            zero-fill is the conv's zero padding); weights: per-tap K-major tiles (2d)
+//   warp 1    MMA issuer   — one elected thread issues tcgen05.mma (M=128 pixels, N<=128 channels, K=16),
+//                            accumulating taps x channel blocks into TMEM; tcgen05.commit frees the stages
+//   warps 2-9 epilogue     — tcgen05.ld the accumulators (double-buffered in TMEM so the next tile's MMAs
 //                            overlap), bias / FiLM / activation / residual, bf16 NHWC stores
 //
-// GEMM view: M = output pixels (a tile is TH rows x NB images x TW columns = 128), N = Cout, K = taps*Cin.
-// A 3x3 stride-1 conv loads, per channel block, three W-shifted slabs of (TH+2) rows; the three vertical
-// taps of each slab are reached by advancing the UMMA descriptor start address by one image row
-// (NB*TW pixels = a whole number of 8-row swizzle atoms), so A traffic is 3 slabs instead of 9 tiles.
+// GEMM view: M = output pixels, N = Cout, K = taps*Cin.  A 3x3 stride-1 conv loads ONE halo slab per channel
+// block — (rows+2) x (8+2) pixels, 128 B (or 64 B) per pixel, hardware-swizzled by TMA — and reaches all nine
+// taps by moving the UMMA descriptor's start address by whole pixels (the swizzle XOR is a function of the
+// absolute shared-memory address, so any pixel-aligned start reads consistently).  T sub-tiles of 128 pixels
+// (stacked rows, or T images) share every weight tile, which cuts weight traffic from L2 by T.
 #include "conv_tc.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // 2 control warps + 8 epilogue warps
 constexpr int kMaxStagesA = 8;
 constexpr int kMaxStagesB = 8;
+constexpr int kMaxT = 4;
 
 struct TcParams {
   int B, H, W;  // tile-space dims (output dims; input dims for CONVT_2X2)
-  int TH, TW, NB;
+  int TW, TH, NB, T;  // sub-tile = TH rows x NB images x TW columns = 128 GEMM rows; T sub-tiles per CTA tile
+  int t_along_h;      // sub-tiles stacked along H (1) or along the batch (0)
   int tiles_h, tiles_w, tiles_b, tiles_n;
   int NT;     // N tile (UMMA N)
   int N;      // GEMM N total
@@ -35,9 +39,11 @@ struct TcParams {
   int CB;     // channel block (32 | 64)
   int ncb0, ncb1;
   int mode;
+  int slab;   // 3x3 stride-1: 1 = one halo slab per channel block (9 taps by descriptor offset); 0 = three W-shifted slabs
   int wres;   // weights resident in smem
   int SA, SB; // pipeline depths
-  uint32_t a_stage_bytes, b_stage_bytes;
+  uint32_t a_stage_bytes, a_tx_bytes, b_stage_bytes;  // stage pitch (1024-aligned), bytes one slab load writes, weight tile
+  uint32_t sub_off, sbo, tap_r_off;  // byte offsets inside an activation stage: next sub-tile, next 8-row group, next image row
   uint32_t smem_b_off, smem_bar_off;
   int tmem_cols;
   const float* bias;
@@ -90,7 +96,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
@@ -145,14 +150,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, K-major operand, 64B / 128B swizzle (rows of CB bf16, 8-row atoms).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t row_bytes) {
+// UMMA shared-memory descriptor, K-major operand, 64B / 128B swizzle (rows of CB bf16; `sbo` = byte distance
+// between consecutive 8-row groups of the M/N dimension).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t row_bytes, uint32_t sbo) {
   const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;  // SWIZZLE_128B : SWIZZLE_64B
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address, bits [0,14)
-  d |= 1ull << 16;                                 // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;    // stride byte offset: next 8-row group
-  d |= 1ull << 46;                                 // descriptor version (Blackwell)
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
+  d |= 1ull << 16;                             // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)((sbo & 0x3FFFFu) >> 4) << 32;  // stride byte offset
+  d |= 1ull << 46;                             // descriptor version (Blackwell)
   d |= layout << 61;
   return d;
 }
@@ -171,22 +177,31 @@ struct AStage {
   int map;       // index into TcMaps::a
   int c;         // channel coordinate
   int dw, dh;    // tile-origin offsets of the load
-  int ntaps;     // weight tiles consumed from this stage (3 for the slab mode, else 1)
-  int widx0;     // first weight-tile index; tap r uses widx0 + r*wstep
-  int wstep;
+  int ntaps;     // weight tiles consumed from this stage
+  int widx0;     // first weight-tile index
+  int sx;        // fixed horizontal tap of this stage (three-slab mode), else -1
 };
 __device__ __forceinline__ AStage decode_astage(const TcParams& p, int ai) {
   AStage s;
+  s.sx = -1;
   if (p.mode == CONV_3X3_S1) {
-    int cbg = ai / 3, sx = ai - cbg * 3;
-    int src = cbg >= p.ncb0;
+    int cbg, src;
+    if (p.slab) {
+      cbg = ai;
+      s.dw = -1;
+      s.ntaps = 9;
+      s.widx0 = cbg * 9;
+    } else {
+      cbg = ai / 3;
+      s.sx = ai - cbg * 3;
+      s.dw = s.sx - 1;
+      s.ntaps = 3;
+      s.widx0 = cbg * 9 + s.sx;  // tap = r*3 + sx
+    }
+    src = cbg >= p.ncb0;
     s.map = src;
     s.c = (src ? cbg - p.ncb0 : cbg) * p.CB;
-    s.dw = sx - 1;
     s.dh = -1;
-    s.ntaps = 3;
-    s.widx0 = cbg * 9 + sx;  // tap = r*3 + sx
-    s.wstep = 3;
   } else if (p.mode == CONV_3X3_S2) {
     int cbg = ai / 9, tap = ai - cbg * 9;
     int r = tap / 3, sx = tap - r * 3;
@@ -197,7 +212,6 @@ __device__ __forceinline__ AStage decode_astage(const TcParams& p, int ai) {
     s.dw = (sx == 0) ? -1 : 0;
     s.ntaps = 1;
     s.widx0 = cbg * 9 + tap;
-    s.wstep = 0;
   } else {
     int src = ai >= p.ncb0;
     s.map = src;
@@ -206,28 +220,44 @@ __device__ __forceinline__ AStage decode_astage(const TcParams& p, int ai) {
     s.dh = 0;
     s.ntaps = 1;
     s.widx0 = ai;
-    s.wstep = 0;
   }
   return s;
 }
 __device__ __forceinline__ int num_astages(const TcParams& p) {
   int ncb = p.ncb0 + p.ncb1;
-  return p.mode == CONV_3X3_S1 ? ncb * 3 : (p.mode == CONV_3X3_S2 ? ncb * 9 : ncb);
+  if (p.mode == CONV_3X3_S1) return p.slab ? ncb : ncb * 3;
+  return p.mode == CONV_3X3_S2 ? ncb * 9 : ncb;
 }
 __device__ __forceinline__ int num_wtiles(const TcParams& p) {
   int ncb = p.ncb0 + p.ncb1;
   return (p.mode == CONV_3X3_S1 || p.mode == CONV_3X3_S2) ? ncb * 9 : ncb;
 }
 
+struct TileCoord {
+  int n0, w0, h0, b0, n_idx;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
+  TileCoord t;
+  t.n_idx = tile % p.tiles_n;
+  int m = tile / p.tiles_n;
+  const int tw_i = m % p.tiles_w; m /= p.tiles_w;
+  const int th_i = m % p.tiles_h;
+  const int tb_i = m / p.tiles_h;
+  t.w0 = tw_i * p.TW;
+  t.h0 = th_i * p.TH * (p.t_along_h ? p.T : 1);
+  t.b0 = tb_i * p.NB * (p.t_along_h ? 1 : p.T);
+  t.n0 = t.n_idx * p.NT;
+  return t;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment: swizzle atoms (8 rows x 128 B) must start on their own boundary.
+  // 1024-byte alignment: swizzle atoms (8 rows x 128 B) are defined on absolute address bits.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + p.smem_b_off;
   const uint32_t bars = smem_base + p.smem_bar_off;
-  // barrier layout (8 bytes each)
   const uint32_t a_full = bars, a_empty = a_full + 8 * kMaxStagesA;
   const uint32_t b_full = a_empty + 8 * kMaxStagesA, b_empty = b_full + 8 * kMaxStagesB;
   const uint32_t acc_full = b_empty + 8 * kMaxStagesB, acc_empty = acc_full + 16;
@@ -243,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 8); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -269,24 +299,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
       int sa = 0, pa = 0, sb = 0, pb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_idx = tile % p.tiles_n;
-        int m = tile / p.tiles_n;
-        const int tw_i = m % p.tiles_w; m /= p.tiles_w;
-        const int th_i = m % p.tiles_h;
-        const int tb_i = m / p.tiles_h;
-        const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tb_i * p.NB, n0 = n_idx * p.NT;
+        const TileCoord tc = decode_tile(p, tile);
         for (int ai = 0; ai < n_ast; ++ai) {
           const AStage s = decode_astage(p, ai);
           mbar_wait(a_empty + 8 * sa, pa ^ 1);
-          mbar_expect_tx(a_full + 8 * sa, p.a_stage_bytes);
-          tma_load_4d(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full + 8 * sa, s.c, w0 + s.dw, b0, h0 + s.dh);
+          mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
+          tma_load_4d(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full + 8 * sa, s.c, tc.w0 + s.dw, tc.b0, tc.h0 + s.dh);
           if (++sa == p.SA) { sa = 0; pa ^= 1; }
           if (!p.wres) {
-            for (int r = 0; r < s.ntaps; ++r) {
+            for (int j = 0; j < s.ntaps; ++j) {
+              const int widx = s.widx0 + (s.sx >= 0 ? j * 3 : j);
               mbar_wait(b_empty + 8 * sb, pb ^ 1);
               mbar_expect_tx(b_full + 8 * sb, p.b_stage_bytes);
-              tma_load_2d(smem_b + sb * p.b_stage_bytes, &maps.w, b_full + 8 * sb, 0,
-                          (s.widx0 + r * s.wstep) * p.N + n0);
+              tma_load_2d(smem_b + sb * p.b_stage_bytes, &maps.w, b_full + 8 * sb, 0, widx * p.N + tc.n0);
               if (++sb == p.SB) { sb = 0; pb ^= 1; }
             }
           }
@@ -298,34 +323,41 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NT, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t row_shift_bytes = (uint32_t)(p.NB * p.TW) * row_bytes;  // one image row of the slab
       const int ksteps = p.CB / 16;
+      const uint32_t b_sbo = 8u * row_bytes;
       if (p.wres) mbar_wait(w_full, 0);
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(acc_empty + 8 * as, pacc ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.NT);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.T * p.NT);
         uint32_t accum = 0;
         for (int ai = 0; ai < n_ast; ++ai) {
           const AStage s = decode_astage(p, ai);
           mbar_wait(a_full + 8 * sa, pa);
           tc_fence_after();
           const uint32_t a_base = smem_a + sa * p.a_stage_bytes;
-          for (int r = 0; r < s.ntaps; ++r) {
+          for (int j = 0; j < s.ntaps; ++j) {
+            int r = 0, sx = 0, widx = s.widx0 + j;
+            if (p.mode == CONV_3X3_S1) {
+              if (s.sx >= 0) { r = j; widx = s.widx0 + j * 3; }       // three-slab mode: the stage fixes sx
+              else { r = j / 3; sx = j - r * 3; }                    // single slab: all nine taps
+            }
             uint32_t b_base;
             if (p.wres) {
-              b_base = smem_b + (uint32_t)(s.widx0 + r * s.wstep) * p.b_stage_bytes;
+              b_base = smem_b + (uint32_t)widx * p.b_stage_bytes;
             } else {
               mbar_wait(b_full + 8 * sb, pb);
               tc_fence_after();
               b_base = smem_b + sb * p.b_stage_bytes;
             }
-            const uint32_t a_tap = a_base + (p.mode == CONV_3X3_S1 ? r * row_shift_bytes : 0u);
-            for (int k = 0; k < ksteps; ++k) {
-              umma_bf16(d_tmem, umma_desc(a_tap + k * 32, row_bytes), umma_desc(b_base + k * 32, row_bytes), idesc, accum);
-              accum = 1;
+            const uint32_t a_tap = a_base + (uint32_t)r * p.tap_r_off + (uint32_t)sx * row_bytes;
+            for (int t = 0; t < p.T; ++t) {
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem + (uint32_t)(t * p.NT), umma_desc(a_tap + t * p.sub_off + k * 32, row_bytes, p.sbo),
+                          umma_desc(b_base + k * 32, row_bytes, b_sbo), idesc, accum | (uint32_t)(k > 0));
             }
+            accum = 1;
             if (!p.wres) {
               umma_commit(b_empty + 8 * sb);
               if (++sb == p.SB) { sb = 0; pb ^= 1; }
@@ -339,32 +371,30 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
+    // ===================== epilogue (warps 2..9) =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // two warps share a quarter and split the column chunks
+    const int row = q * 32 + lane;     // GEMM row inside a sub-tile
     const int w_i = row % p.TW;
-    const int b_i = (row / p.TW) % p.NB;
-    const int h_i = row / (p.TW * p.NB);
+    const int g_i = row / p.TW;        // (h, b) index inside the sub-tile, h-major
+    const int nchunk = p.NT / 32;
     int as = 0, pacc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_idx = tile % p.tiles_n;
-      int m = tile / p.tiles_n;
-      const int tw_i = m % p.tiles_w; m /= p.tiles_w;
-      const int th_i = m % p.tiles_h;
-      const int tb_i = m / p.tiles_h;
-      const int w = tw_i * p.TW + w_i, h = th_i * p.TH + h_i, b = tb_i * p.NB + b_i;
-      const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
+      const TileCoord tc = decode_tile(p, tile);
       mbar_wait(acc_full + 8 * as, pacc);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.NT);
-      for (int c = 0; c < p.NT; c += 32) {
+      for (int ci = half; ci < p.T * nchunk; ci += 2) {
+        const int t = ci / nchunk, c = (ci - t * nchunk) * 32;
+        int h = tc.h0 + g_i / p.NB, b = tc.b0 + g_i % p.NB;
+        if (p.t_along_h) h += t * p.TH; else b += t * p.NB;
+        const int w = tc.w0 + w_i;
+        const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
         uint32_t v[32];
-        tmem_ld32(t_base + c, v);
-        tmem_ld_wait();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.T + t) * p.NT + c), v);
+        const int n = tc.n0 + c;  // first GEMM column of this chunk
+        int co = n;
+        size_t pix = 0;
         if (valid) {
-          const int n = n_idx * p.NT + c;  // first GEMM column of this chunk
-          int co = n;
-          size_t pix;
           if (p.mode == CONVT_2X2) {
             const int quad = n / p.Cout;
             co = n - quad * p.Cout;
@@ -372,7 +402,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           } else {
             pix = ((size_t)b * p.H + h) * (size_t)p.W + w;
           }
-          const size_t off = pix * p.Cout + co;
+        }
+        const size_t off = pix * p.Cout + co;
+        uint4 rr[4];
+        if (valid && p.res) {  // issue the residual loads before waiting on TMEM
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rr[g] = __ldg(r4 + g);
+        }
+        tmem_ld_wait();
+        if (valid) {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + co + j);
@@ -394,36 +433,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
           }
           if (p.res) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              uint4 u = __ldg(r4 + g);
-              float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
               f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
               f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
             }
           }
           uint4* o4 = reinterpret_cast<uint4*>(p.out0 + off);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-            u.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-            u.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-            u.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-            o4[g] = u;
-          }
+          for (int g = 0; g < 4; ++g)
+            o4[g] = make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                               pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
           if (p.out1) {
             uint4* s4 = reinterpret_cast<uint4*>(p.out1 + off);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 u;
-              u.x = pack_bf16x2(silu_f(f[g * 8 + 0]), silu_f(f[g * 8 + 1]));
-              u.y = pack_bf16x2(silu_f(f[g * 8 + 2]), silu_f(f[g * 8 + 3]));
-              u.z = pack_bf16x2(silu_f(f[g * 8 + 4]), silu_f(f[g * 8 + 5]));
-              u.w = pack_bf16x2(silu_f(f[g * 8 + 6]), silu_f(f[g * 8 + 7]));
-              s4[g] = u;
-            }
+            for (int g = 0; g < 4; ++g)
+              s4[g] = make_uint4(pack_bf16x2(silu_f(f[g * 8 + 0]), silu_f(f[g * 8 + 1])), pack_bf16x2(silu_f(f[g * 8 + 2]), silu_f(f[g * 8 + 3])),
+                                 pack_bf16x2(silu_f(f[g * 8 + 4]), silu_f(f[g * 8 + 5])), pack_bf16x2(silu_f(f[g * 8 + 6]), silu_f(f[g * 8 + 7])));
           }
         }
       }
@@ -463,21 +490,21 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // Activation map over an NHWC bf16 tensor viewed as dims (C, W, B, H) so that a box lands in smem as
-// [h][b][w][c]: one image row of the tile (NB*TW pixels) is contiguous, whatever NB is.
+// [h][b][w][c]: one image row of the tile (all its images, all its columns) is contiguous.
 int make_act_map(CUtensorMap* m, const bf16* base, int C, int W, int B, int H, uint64_t strideW, uint64_t strideB,
-                 uint64_t strideH, int CB, int TW, int NB, int rows) {
+                 uint64_t strideH, int CB, int box_w, int box_b, int box_h) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return yond_set_error(YOND_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)B, (cuuint64_t)H};
   cuuint64_t strides[3] = {strideW, strideB, strideH};
-  cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)TW, (cuuint32_t)NB, (cuuint32_t)rows};
+  cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)box_w, (cuuint32_t)box_b, (cuuint32_t)box_h};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return yond_set_error(YOND_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d B=%d H=%d box=%d,%d,%d,%d)",
-                          (int)r, C, W, B, H, CB, TW, NB, rows);
+                          (int)r, C, W, B, H, CB, box_w, box_b, box_h);
   return YOND_OK;
 }
 
@@ -501,6 +528,13 @@ int pow2_ceil(int v) {
   return p;
 }
 
+// Debug / bring-up switches (environment): YOND_CONV_SLAB=0 selects the three-slab 3x3 path, YOND_CONV_T caps the
+// number of sub-tiles sharing a weight tile.
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 }  // namespace
 
 int conv_tc_channel_block(int Cin0, int Cin1) {
@@ -517,6 +551,8 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   YOND_REQUIRE(L.Cin0 % 32 == 0 && L.Cin1 % 32 == 0 && L.Cin0 > 0, "conv_tc: Cin must be a multiple of 32 (got %d,%d)",
                L.Cin0, L.Cin1);
   YOND_REQUIRE(L.Cout % 32 == 0, "conv_tc: Cout must be a multiple of 32 (got %d)", L.Cout);
+  static const int env_slab = env_int("YOND_CONV_SLAB", 1);
+  static const int env_T = env_int("YOND_CONV_T", kMaxT);
   TcParams p{};
   p.mode = L.mode;
   p.B = L.B;
@@ -533,44 +569,77 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.CB = conv_tc_channel_block(L.Cin0, L.Cin1);
   p.ncb0 = L.Cin0 / p.CB;
   p.ncb1 = L.Cin1 / p.CB;
-  p.NT = p.N < 256 ? p.N : 256;
+  p.NT = p.N < 128 ? p.N : 128;
   YOND_REQUIRE(p.N % p.NT == 0 && (p.NT & (p.NT - 1)) == 0, "conv_tc: unsupported N=%d", p.N);
   p.tiles_n = p.N / p.NT;
-  // tile shape: TH rows x NB images x TW columns = 128 GEMM rows
-  p.TW = p.W > 8 ? 16 : 8;
+  const uint32_t row_bytes = p.CB * 2;
+  const bool conv3 = L.mode == CONV_3X3_S1;
+  p.slab = conv3 ? env_slab : 0;
+
+  // sub-tile: TH rows x NB images x TW columns = 128 GEMM rows.  3x3 convs use 8-pixel-wide tiles so that every
+  // 8-row swizzle group is one image row of the slab (uniform stride between groups whatever the halo width).
+  p.TW = conv3 ? 8 : (p.W > 8 ? 16 : 8);
   const int rows = 128 / p.TW;
   p.TH = pow2_ceil(p.H) < rows ? pow2_ceil(p.H) : rows;
   p.NB = rows / p.TH;
-  p.tiles_w = ceil_div(p.W, p.TW);
-  p.tiles_h = ceil_div(p.H, p.TH);
-  p.tiles_b = ceil_div(p.B, p.NB);
-  const int slab_rows = (L.mode == CONV_3X3_S1) ? p.TH + 2 : p.TH;
-  const uint32_t row_bytes = p.CB * 2;
-  p.a_stage_bytes = (uint32_t)slab_rows * p.NB * p.TW * row_bytes;
-  p.b_stage_bytes = (uint32_t)p.NT * row_bytes;
-  YOND_REQUIRE(p.a_stage_bytes % 1024 == 0 && p.b_stage_bytes % 1024 == 0, "conv_tc: stage sizes not 1024-aligned");
-
   const int ncb = p.ncb0 + p.ncb1;
   const int nwt = ((L.mode == CONV_3X3_S1 || L.mode == CONV_3X3_S2) ? 9 : 1) * ncb;
   const size_t smem_budget = 227 * 1024 - 2048;  // dynamic smem minus alignment slack and barriers
+  p.b_stage_bytes = (uint32_t)p.NT * row_bytes;
+  YOND_REQUIRE(p.b_stage_bytes % 1024 == 0, "conv_tc: weight stage not 1024-aligned");
   const size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
-  p.wres = (p.tiles_n == 1 && wres_bytes <= 96 * 1024) ? 1 : 0;
+  p.wres = (p.tiles_n == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
   size_t b_region;
   if (p.wres) {
     p.SB = 1;
     b_region = wres_bytes;
   } else {
-    p.SB = 4;
-    while (p.SB > 2 && (size_t)p.SB * p.b_stage_bytes > 128 * 1024) --p.SB;
+    p.SB = 6;
+    while (p.SB > 2 && (size_t)p.SB * p.b_stage_bytes > 96 * 1024) --p.SB;
     b_region = (size_t)p.SB * p.b_stage_bytes;
   }
-  p.SA = (int)((smem_budget - b_region) / p.a_stage_bytes);
-  if (p.SA > kMaxStagesA) p.SA = kMaxStagesA;
+  // T sub-tiles share each weight tile (and one halo slab): stacked along H when the map is tall enough, else one
+  // image each.  T is bounded by TMEM (2 accumulator stages x T x NT columns <= 512) and by shared memory.
+  int T = 1;
+  if (conv3 && p.NB == 1) {
+    int tmax = 512 / (2 * p.NT);
+    if (tmax > env_T) tmax = env_T;
+    if (tmax > kMaxT) tmax = kMaxT;
+    while (T * 2 <= tmax && (p.H >= p.TH * T * 2 || p.B >= T * 2)) T *= 2;
+  }
+  int slab_w = 0, slab_h = 0, SBt = 0;
+  for (;; T /= 2) {
+    p.T = T;
+    p.t_along_h = (p.H >= p.TH * T) ? 1 : 0;
+    const int SH = p.TH * (p.t_along_h ? T : 1);
+    SBt = p.NB * (p.t_along_h ? 1 : T);
+    p.tiles_w = ceil_div(p.W, p.TW);
+    p.tiles_h = ceil_div(p.H, SH);
+    p.tiles_b = ceil_div(p.B, SBt);
+    slab_w = (conv3 && p.slab) ? p.TW + 2 : p.TW;
+    slab_h = conv3 ? SH + 2 : SH;
+    const uint32_t line = (uint32_t)slab_w * row_bytes;  // one image row of one image inside a stage
+    p.a_tx_bytes = (uint32_t)slab_h * SBt * line;
+    p.a_stage_bytes = (uint32_t)align_up((size_t)p.a_tx_bytes, 1024);
+    if (conv3) {
+      p.tap_r_off = (uint32_t)SBt * line;
+      p.sbo = (p.NB > 1 || p.t_along_h) ? line : (uint32_t)T * line;
+      p.sub_off = p.t_along_h ? (uint32_t)p.TH * line : line;
+    } else {
+      p.tap_r_off = 0;
+      p.sbo = 8u * row_bytes;
+      p.sub_off = 0;
+    }
+    p.SA = (int)((smem_budget - b_region) / p.a_stage_bytes);
+    if (p.SA > kMaxStagesA) p.SA = kMaxStagesA;
+    if (p.SA >= 3 || T == 1) break;
+  }
   YOND_REQUIRE(p.SA >= 2, "conv_tc: not enough shared memory for the activation pipeline");
   p.smem_b_off = (uint32_t)p.SA * p.a_stage_bytes;
   p.smem_bar_off = (uint32_t)align_up(p.smem_b_off + b_region, 1024);
   const size_t smem_bytes = p.smem_bar_off + 512 + 1024;  // barriers + alignment slack
-  p.tmem_cols = 2 * p.NT < 32 ? 32 : 2 * p.NT;
+  p.tmem_cols = 2 * p.T * p.NT < 32 ? 32 : 2 * p.T * p.NT;
+  YOND_REQUIRE(p.tmem_cols <= 512, "conv_tc: TMEM budget exceeded");
 
   p.bias = L.bias;
   p.scale = L.scale;
@@ -593,12 +662,12 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
         for (int pw = 0; pw < 2; ++pw) {
           const bf16* base = srcs[s] + ((size_t)ph * L.Win + pw) * C;
           int rc = make_act_map(&maps.a[s * 4 + ph * 2 + pw], base, C, L.Win / 2, L.B, L.Hin / 2, (uint64_t)2 * C * 2,
-                                (uint64_t)L.Hin * L.Win * C * 2, (uint64_t)2 * L.Win * C * 2, p.CB, p.TW, p.NB, slab_rows);
+                                (uint64_t)L.Hin * L.Win * C * 2, (uint64_t)2 * L.Win * C * 2, p.CB, slab_w, SBt, slab_h);
           if (rc) return rc;
         }
     } else {
       int rc = make_act_map(&maps.a[s], srcs[s], C, L.Win, L.B, L.Hin, (uint64_t)C * 2, (uint64_t)L.Hin * L.Win * C * 2,
-                            (uint64_t)L.Win * C * 2, p.CB, p.TW, p.NB, slab_rows);
+                            (uint64_t)L.Win * C * 2, p.CB, slab_w, SBt, slab_h);
       if (rc) return rc;
     }
   }
@@ -606,7 +675,6 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
     int rc = make_weight_map(&maps.w, L.wpacked, p.CB, (size_t)nwt * p.N, p.NT);
     if (rc) return rc;
   }
-
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {

@@ -133,41 +133,69 @@ __global__ void maxpool2_kernel(const bf16* __restrict__ in, bf16* __restrict__ 
 
 // ---- per-sample conditioning vectors (GuidedResidualBlock gamma/beta, SNR_Block sfm1/sfm2) -------------------
 // out_a = W2 * silu(w0 * t' + b0) + b2 ;  guided: out_b = Wb * silu(out_a) + bb ;  snr: out_b = second MLP(t').
-// t' = t[b] / ub[b] when the network normalises (archs/Unet.py:427-429).  One block per sample.
-__device__ __forceinline__ float warp_dot(const float* __restrict__ wrow, const float* v, int C, int lane) {
-  float s = 0.f;
-  for (int j = lane; j < C; j += 32) s = fmaf(__ldg(wrow + j), v[j], s);
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  return s;
-}
-__global__ void __launch_bounds__(256) film_kernel(FilmWeights fw, const float* __restrict__ t, const float* __restrict__ ub,
-                                                   int C, int guided, float* __restrict__ out_a, float* __restrict__ out_b) {
-  extern __shared__ float sv[];  // [C] hidden, [C] out_a
-  float* hid = sv;
-  float* va = sv + C;
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const float tt = ub ? __ldg(t + b) / __ldg(ub + b) : __ldg(t + b);
-  for (int i = threadIdx.x; i < C; i += blockDim.x) hid[i] = silu_f(fmaf(fw.w0[i], tt, fw.b0[i]));
-  __syncthreads();
+// t' = t[b] / ub[b] when the network normalises (archs/Unet.py:427-429).  One block handles kFilmS samples so each
+// weight row is read once per kFilmS dot products; a warp owns an output row.
+constexpr int kFilmS = 4;
+__device__ __forceinline__ void film_matvec(const float* __restrict__ Wm, const float* __restrict__ bias, const float* vin /*[S][C]*/,
+                                            int C, int ns, float* vout_smem /*[S][C] or null*/, float* __restrict__ out_g, int b0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int n = warp; n < C; n += nw) {
-    const float s = warp_dot(fw.w2 + (size_t)n * C, hid, C, lane) + fw.b2[n];
-    if (lane == 0) { va[n] = s; out_a[(size_t)b * C + n] = s; }
+    const float* wrow = Wm + (size_t)n * C;
+    float acc[kFilmS];
+#pragma unroll
+    for (int s = 0; s < kFilmS; ++s) acc[s] = 0.f;
+    for (int j = lane; j < C; j += 32) {
+      const float wv = __ldg(wrow + j);
+#pragma unroll
+      for (int s = 0; s < kFilmS; ++s) acc[s] = fmaf(wv, vin[s * C + j], acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < kFilmS; ++s)
+      for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+    if (lane == 0) {
+      const float bb = bias[n];
+#pragma unroll
+      for (int s = 0; s < kFilmS; ++s) {
+        if (s < ns) {
+          const float v = acc[s] + bb;
+          if (vout_smem) vout_smem[s * C + n] = v;
+          out_g[(size_t)(b0 + s) * C + n] = v;
+        }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(512) film_kernel(FilmWeights fw, const float* __restrict__ t, const float* __restrict__ ub,
+                                                   int B, int C, int guided, float* __restrict__ out_a, float* __restrict__ out_b) {
+  extern __shared__ float sv[];  // [S][C] hidden, [S][C] out_a
+  float* hid = sv;
+  float* va = sv + kFilmS * C;
+  const int b0 = blockIdx.x * kFilmS;
+  const int ns = min(kFilmS, B - b0);
+  __shared__ float tt[kFilmS];
+  if (threadIdx.x < kFilmS) {
+    const int b = min(b0 + (int)threadIdx.x, B - 1);
+    tt[threadIdx.x] = ub ? __ldg(t + b) / __ldg(ub + b) : __ldg(t + b);
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < kFilmS * C; i += blockDim.x) {
+    const int s = i / C, c = i - s * C;
+    hid[i] = silu_f(fmaf(fw.w0[c], tt[s], fw.b0[c]));
+  }
+  __syncthreads();
+  film_matvec(fw.w2, fw.b2, hid, C, ns, va, out_a, b0);
+  __syncthreads();
   if (guided) {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) hid[i] = silu_f(va[i]);
+    for (int i = threadIdx.x; i < kFilmS * C; i += blockDim.x) hid[i] = silu_f(va[i]);
     __syncthreads();
-    for (int n = warp; n < C; n += nw) {
-      const float s = warp_dot(fw.w3 + (size_t)n * C, hid, C, lane) + fw.b3[n];
-      if (lane == 0) out_b[(size_t)b * C + n] = s;
-    }
+    film_matvec(fw.w3, fw.b3, hid, C, ns, nullptr, out_b, b0);
   } else {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) hid[i] = silu_f(fmaf(fw.w3[i], tt, fw.b3[i]));
-    __syncthreads();
-    for (int n = warp; n < C; n += nw) {
-      const float s = warp_dot(fw.w4 + (size_t)n * C, hid, C, lane) + fw.b4[n];
-      if (lane == 0) out_b[(size_t)b * C + n] = s;
+    for (int i = threadIdx.x; i < kFilmS * C; i += blockDim.x) {
+      const int s = i / C, c = i - s * C;
+      hid[i] = silu_f(fmaf(fw.w3[c], tt[s], fw.b3[c]));
     }
+    __syncthreads();
+    film_matvec(fw.w4, fw.b4, hid, C, ns, nullptr, out_b, b0);
   }
 }
 
@@ -234,7 +262,7 @@ int maxpool2_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaS
 }
 int film_launch(const FilmWeights& fw, const float* t, const float* ub, int B, int C, int guided, float* out_a, float* out_b,
                 cudaStream_t s) {
-  film_kernel<<<B, 256, (size_t)2 * C * sizeof(float), s>>>(fw, t, ub, C, guided, out_a, out_b);
+  film_kernel<<<ceil_div(B, kFilmS), 512, (size_t)2 * kFilmS * C * sizeof(float), s>>>(fw, t, ub, B, C, guided, out_a, out_b);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

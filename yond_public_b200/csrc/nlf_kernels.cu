@@ -139,6 +139,8 @@ struct SelectWork {
 };
 
 __global__ void __launch_bounds__(256) hist0_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
+  d += (size_t)blockIdx.y * n;  // one segment (image) per blockIdx.y
+  wk += blockIdx.y;
   __shared__ unsigned int h[2048];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
   __syncthreads();
@@ -176,6 +178,7 @@ __device__ __forceinline__ int warp_find_bin(const unsigned long long* __restric
 
 // One block of 32 warps; warp w resolves queries w, w+32.  Thread 0 then assigns slots (deduplicated buckets).
 __global__ void __launch_bounds__(1024) select0_kernel(SelectWork* wk, const unsigned long long* __restrict__ ranks, int nranks) {
+  wk += blockIdx.x;
   __shared__ int s_bin[kMaxRanks];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) wk->slot1_of_prefix[i] = -1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,6 +203,8 @@ __global__ void __launch_bounds__(1024) select0_kernel(SelectWork* wk, const uns
   }
 }
 __global__ void __launch_bounds__(256) hist1_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
+  d += (size_t)blockIdx.y * n;
+  wk += blockIdx.y;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t k = f2key(d[i]);
     const int s = wk->slot1_of_prefix[k >> 21];
@@ -207,6 +212,7 @@ __global__ void __launch_bounds__(256) hist1_kernel(const float* __restrict__ d,
   }
 }
 __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nranks) {
+  wk += blockIdx.x;
   __shared__ int s_bin[kMaxRanks];
   for (int i = threadIdx.x; i < kMaxRanks * 2048; i += blockDim.x) (&wk->slot2_of[0][0])[i] = -1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,6 +238,8 @@ __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nrank
   }
 }
 __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
+  d += (size_t)blockIdx.y * n;
+  wk += blockIdx.y;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t k = f2key(d[i]);
     const int s1 = wk->slot1_of_prefix[k >> 21];
@@ -241,6 +249,8 @@ __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d,
   }
 }
 __global__ void __launch_bounds__(1024) select2_kernel(SelectWork* wk, int nranks, float* __restrict__ out) {
+  wk += blockIdx.x;
+  out += (size_t)blockIdx.x * nranks;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int q = warp; q < nranks; q += 32) {
     unsigned long long before;
@@ -253,6 +263,10 @@ __global__ void __launch_bounds__(1024) select2_kernel(SelectWork* wk, int nrank
 // minj[bin] = smallest threshold index i such that some pixel with lap <= ths[i] falls in `bin`
 __global__ void __launch_bounds__(256) score3_kernel(const float* __restrict__ lap, const float* __restrict__ mean, size_t n,
                                                      const double* __restrict__ ths, int nth, int* __restrict__ minj) {
+  lap += (size_t)blockIdx.y * n;
+  mean += (size_t)blockIdx.y * n;
+  ths += (size_t)blockIdx.y * nth;
+  minj += (size_t)blockIdx.y * 1001;
   __shared__ int smin[1001];
   __shared__ double sth[32];
   for (int i = threadIdx.x; i < 1001; i += blockDim.x) smin[i] = 0x7fffffff;
@@ -272,6 +286,8 @@ __global__ void __launch_bounds__(256) score3_kernel(const float* __restrict__ l
     if (smin[i] != 0x7fffffff) atomicMin(&minj[i], smin[i]);
 }
 __global__ void score3_count_kernel(const int* __restrict__ minj, int nth, int* __restrict__ npeaks) {
+  minj += (size_t)blockIdx.x * 1001;
+  npeaks += (size_t)blockIdx.x * nth;
   __shared__ int cnt[32];
   if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -295,8 +311,13 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 
 // ------------------------------------------------------------------ masked regression sums
 __global__ void __launch_bounds__(256) masked_sums_kernel(const float* __restrict__ lap, const float* __restrict__ mean,
-                                                          const float* __restrict__ var, size_t n, double th,
-                                                          double* __restrict__ sums) {
+                                                          const float* __restrict__ var, size_t n,
+                                                          const double* __restrict__ ths, double* __restrict__ sums) {
+  lap += (size_t)blockIdx.y * n;
+  mean += (size_t)blockIdx.y * n;
+  var += (size_t)blockIdx.y * n;
+  sums += (size_t)blockIdx.y * 12;
+  const double th = ths[blockIdx.y];
   double s[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) s[i] = 0.0;
@@ -395,53 +416,58 @@ int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float
   return YOND_OK;
 }
 
-size_t yond_select_work_bytes(int nranks) {
-  (void)nranks;
-  return sizeof(SelectWork) + 256;
-}
+size_t yond_select_work_bytes(int nseg) { return (size_t)(nseg < 1 ? 1 : nseg) * sizeof(SelectWork) + 256; }
 
-int yond_order_stats(const float* data, size_t n, const uint64_t* ranks_dev, int nranks, float* out_dev, void* work,
-                     void* stream) {
+int yond_order_stats(const float* data, size_t seg_len, int nseg, const uint64_t* ranks_dev, int nranks, float* out_dev,
+                     void* work, void* stream) {
   YOND_REQUIRE(nranks > 0 && nranks <= kMaxRanks, "yond_order_stats: 1..%d ranks (got %d)", kMaxRanks, nranks);
-  YOND_REQUIRE(n > 0, "yond_order_stats: empty input");
+  YOND_REQUIRE(seg_len > 0 && nseg > 0 && nseg <= 65535, "yond_order_stats: empty input");
   cudaStream_t s = (cudaStream_t)stream;
   SelectWork* wk = reinterpret_cast<SelectWork*>(work);
-  YOND_CUDA_CHECK(cudaMemsetAsync(wk, 0, offsetof(SelectWork, slot1_of_prefix), s));
-  const int g = stream_grid(n);
-  hist0_kernel<<<g, 256, 0, s>>>(data, n, wk);
+  for (int i = 0; i < nseg; ++i)
+    YOND_CUDA_CHECK(cudaMemsetAsync(wk + i, 0, offsetof(SelectWork, slot1_of_prefix), s));
+  dim3 g(stream_grid(seg_len), nseg);
+  if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
+  hist0_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
   YOND_LAUNCH_CHECK();
-  select0_kernel<<<1, 1024, 0, s>>>(wk, reinterpret_cast<const unsigned long long*>(ranks_dev), nranks);
+  select0_kernel<<<nseg, 1024, 0, s>>>(wk, reinterpret_cast<const unsigned long long*>(ranks_dev), nranks);
   YOND_LAUNCH_CHECK();
-  hist1_kernel<<<g, 256, 0, s>>>(data, n, wk);
+  hist1_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
   YOND_LAUNCH_CHECK();
-  select1_kernel<<<1, 1024, 0, s>>>(wk, nranks);
+  select1_kernel<<<nseg, 1024, 0, s>>>(wk, nranks);
   YOND_LAUNCH_CHECK();
-  hist2_kernel<<<g, 256, 0, s>>>(data, n, wk);
+  hist2_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
   YOND_LAUNCH_CHECK();
-  select2_kernel<<<1, 1024, 0, s>>>(wk, nranks, out_dev);
+  select2_kernel<<<nseg, 1024, 0, s>>>(wk, nranks, out_dev);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
 
-int yond_score3_bins(const float* lap, const float* mean, size_t n, const double* ths_dev, int nth, int32_t* npeaks_dev,
-                     void* work, void* stream) {
+int yond_score3_bins(const float* lap, const float* mean, size_t seg_len, int nseg, const double* ths_dev, int nth,
+                     int32_t* npeaks_dev, void* work, void* stream) {
   YOND_REQUIRE(nth > 0 && nth <= 32, "yond_score3_bins: 1..32 thresholds (got %d)", nth);
+  YOND_REQUIRE(nseg > 0 && nseg <= 65535, "yond_score3_bins: bad segment count");
   cudaStream_t s = (cudaStream_t)stream;
   int* minj = reinterpret_cast<int*>(work);
-  fill_int_kernel<<<ceil_div(1001, 256), 256, 0, s>>>(minj, 1001, 0x7fffffff);
+  fill_int_kernel<<<ceil_div(1001 * nseg, 256), 256, 0, s>>>(minj, 1001 * nseg, 0x7fffffff);
   YOND_LAUNCH_CHECK();
-  score3_kernel<<<stream_grid(n), 256, 0, s>>>(lap, mean, n, ths_dev, nth, minj);
+  dim3 g(stream_grid(seg_len), nseg);
+  if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
+  score3_kernel<<<g, 256, 0, s>>>(lap, mean, seg_len, ths_dev, nth, minj);
   YOND_LAUNCH_CHECK();
-  score3_count_kernel<<<1, 256, 0, s>>>(minj, nth, npeaks_dev);
+  score3_count_kernel<<<nseg, 256, 0, s>>>(minj, nth, npeaks_dev);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
 
-int yond_masked_sums(const float* lap, const float* mean, const float* var, size_t n, double th, double* sums_dev,
-                     void* stream) {
+int yond_masked_sums(const float* lap, const float* mean, const float* var, size_t seg_len, int nseg, const double* ths_dev,
+                     double* sums_dev, void* stream) {
+  YOND_REQUIRE(nseg > 0 && nseg <= 65535, "yond_masked_sums: bad segment count");
   cudaStream_t s = (cudaStream_t)stream;
-  YOND_CUDA_CHECK(cudaMemsetAsync(sums_dev, 0, 12 * sizeof(double), s));
-  masked_sums_kernel<<<stream_grid(n), 256, 0, s>>>(lap, mean, var, n, th, sums_dev);
+  YOND_CUDA_CHECK(cudaMemsetAsync(sums_dev, 0, (size_t)nseg * 12 * sizeof(double), s));
+  dim3 g(stream_grid(seg_len), nseg);
+  if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
+  masked_sums_kernel<<<g, 256, 0, s>>>(lap, mean, var, seg_len, ths_dev, sums_dev);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

@@ -28,24 +28,25 @@ def _percentiles_from_order_stats(lo_vals, hi_vals, gamma):
 
 
 class NlfEstimator:
-    """Reusable device scratch for the estimator."""
+    """Blind (beta1, beta2) estimation, batched over `nseg` images: every device stage runs once for the whole batch
+    and the host sees three small read-backs per batch (order statistics, bin counts, regression sums)."""
 
     def __init__(self):
         self.lib = _lib.load()
-        self._sel_work = None
-        self._small = None
+        self._scr = {}
 
-    def _scratch(self, dev):
-        if self._sel_work is None or self._sel_work.device != dev:
-            self._sel_work = torch.empty(self.lib.yond_select_work_bytes(64), device=dev, dtype=torch.uint8)
-            self._small = torch.empty(8192, device=dev, dtype=torch.uint8)
-        return self._sel_work, self._small
+    def _buf(self, name, nbytes, dev):
+        b = self._scr.get(name)
+        if b is None or b.numel() < nbytes or b.device != dev:
+            b = torch.empty(int(nbytes), device=dev, dtype=torch.uint8)
+            self._scr[name] = b
+        return b
 
     # -- maps -----------------------------------------------------------------------------------
     def maps(self, lr_rggb, hr_rggb=None, k=29):
         """lr_rggb / hr_rggb: (B,h,w,4) CUDA float32.  Returns var, mean, lap (same shape)."""
         B, h, w, _ = lr_rggb.shape
-        work = torch.empty(self.lib.yond_nlf_work_bytes(B, h, w, 4), device=lr_rggb.device, dtype=torch.uint8)
+        work = self._buf("maps", self.lib.yond_nlf_work_bytes(B, h, w, 4), lr_rggb.device)
         var, mean, lap = torch.empty_like(lr_rggb), torch.empty_like(lr_rggb), torch.empty_like(lr_rggb)
         mode = 0 if hr_rggb is None else 1
         check(self.lib.yond_nlf_maps(ptr(lr_rggb), ptr(hr_rggb), ptr(var), ptr(mean), ptr(lap), B, h, w, 4, int(k), mode,
@@ -53,62 +54,82 @@ class NlfEstimator:
         return var, mean, lap
 
     # -- percentiles ----------------------------------------------------------------------------
-    def percentiles(self, data, quants):
-        """np.percentile(data.reshape(-1), quants, method='linear') with exact device order statistics."""
-        n = data.numel()
-        q = np.asarray(quants, np.float64)
+    def percentiles(self, data, quants, nseg=1):
+        """np.percentile(segment.reshape(-1), quants, method='linear') for each of the `nseg` equal contiguous segments
+        of `data`, from exact device order statistics.  Returns (nseg, len(quants)) float64 ((len,) when nseg == 1)."""
+        n = data.numel() // nseg
+        q = np.atleast_1d(np.asarray(quants, np.float64))
         qq = np.true_divide(q, 100)
         vi = (n - 1) * qq  # NumPy's virtual index for method='linear'
         lo = np.floor(vi).astype(np.int64)
         hi = np.minimum(lo + 1, n - 1)
         gamma = vi - lo
         ranks = np.concatenate([lo, hi]).astype(np.uint64)
-        sel_work, _ = self._scratch(data.device)
+        sel_work = self._buf("select", self.lib.yond_select_work_bytes(nseg), data.device)
         ranks_dev = torch.from_numpy(ranks.view(np.int64)).to(data.device)
-        out = torch.empty(len(ranks), device=data.device, dtype=torch.float32)
-        check(self.lib.yond_order_stats(ptr(data), n, ptr(ranks_dev), len(ranks), ptr(out), ptr(sel_work), stream_ptr()))
+        out = torch.empty((nseg, len(ranks)), device=data.device, dtype=torch.float32)
+        check(self.lib.yond_order_stats(ptr(data), n, nseg, ptr(ranks_dev), len(ranks), ptr(out), ptr(sel_work), stream_ptr()))
         vals = out.cpu().numpy()
-        return _percentiles_from_order_stats(vals[:len(q)], vals[len(q):], gamma)
+        res = np.stack([_percentiles_from_order_stats(v[:len(q)], v[len(q):], gamma) for v in vals])
+        return res[0] if nseg == 1 else res
 
     # -- get_threshold(mode='score3'), YOND_SIDD.py:22-49 ----------------------------------------
-    def threshold_score3(self, lap, mean, step=5):
+    def threshold_score3(self, lap, mean, step=5, nseg=1):
         quants = np.linspace(step, 100, 100 // step, endpoint=True)
-        ths = self.percentiles(lap, quants)
-        _, small = self._scratch(lap.device)
-        ths_dev = torch.from_numpy(ths).to(lap.device)
-        npk = torch.empty(len(ths), device=lap.device, dtype=torch.int32)
-        check(self.lib.yond_score3_bins(ptr(lap), ptr(mean), lap.numel(), ptr(ths_dev), len(ths), ptr(npk), ptr(small),
+        ths = np.atleast_2d(self.percentiles(lap, quants, nseg))
+        n = lap.numel() // nseg
+        small = self._buf("bins", nseg * 1001 * 4 + 256, lap.device)
+        ths_dev = torch.from_numpy(np.ascontiguousarray(ths)).to(lap.device)
+        npk = torch.empty((nseg, ths.shape[1]), device=lap.device, dtype=torch.int32)
+        check(self.lib.yond_score3_bins(ptr(lap), ptr(mean), n, nseg, ptr(ths_dev), ths.shape[1], ptr(npk), ptr(small),
                                         stream_ptr()))
         npeaks = npk.cpu().numpy().astype(np.float64)
-        score = ths / (quants * npeaks)
-        i = int(np.argmin(score[1:]) + 1)  # start_pos = 1 skips the 5 % quantile (:46-47)
-        return ths[i], quants[i], dict(ths=ths, npeaks=npeaks, score=score)
+        score = ths / (quants[None] * npeaks)
+        idx = np.argmin(score[:, 1:], axis=1) + 1  # start_pos = 1 skips the 5 % quantile (:46-47)
+        th = ths[np.arange(nseg), idx]
+        info = dict(ths=ths, npeaks=npeaks, score=score)
+        if nseg == 1:
+            return th[0], quants[idx[0]], {k: v[0] for k, v in info.items()}
+        return th, quants[idx], info
 
     # -- masked fit, YOND_SIDD.py:77-86 + utils/isp_algos.py:345-365 ------------------------------
-    def masked_fit(self, var, mean, lap, th):
-        sums_dev = torch.empty(12, device=lap.device, dtype=torch.float64)
+    def masked_fit(self, var, mean, lap, th, nseg=1):
+        n = lap.numel() // nseg
+        th = np.atleast_1d(np.asarray(th, np.float64)).copy()
+        sums_dev = torch.empty((nseg, 12), device=lap.device, dtype=torch.float64)
 
         def sums(thr):
-            check(self.lib.yond_masked_sums(ptr(lap), ptr(mean), ptr(var), lap.numel(), float(thr), ptr(sums_dev), stream_ptr()))
+            thr_dev = torch.from_numpy(np.ascontiguousarray(thr)).to(lap.device)
+            check(self.lib.yond_masked_sums(ptr(lap), ptr(mean), ptr(var), n, nseg, ptr(thr_dev), ptr(sums_dev), stream_ptr()))
             return sums_dev.cpu().numpy()
         s = sums(th)
-        if s[0] == 0:  # "no flat area": fall back to the 25th percentile (:79-84)
-            th_backup = float(self.percentiles(lap, [25.0])[0])
-            if th != th_backup:
-                th = th_backup
-                s = sums(th)
-        use = s[6:12] if s[6] > 0.01 * s[0] else s[0:6]  # polyfit keeps 1e-4 < x < 0.8 when that is > 1 % (:348-350)
-        N, Sx, Sy, Sxx, Sxy = use[0], use[1], use[2], use[3], use[4]
-        det = N * Sxx - Sx * Sx
-        b1 = (N * Sxy - Sx * Sy) / det
-        b2 = (Sy - b1 * Sx) / N
-        return np.array([b1, b2], np.float64), th
+        empty = s[:, 0] == 0
+        if empty.any():  # "no flat area": fall back to the 25th percentile (:79-84)
+            th_backup = np.atleast_1d(self.percentiles(lap, [25.0], nseg)).reshape(nseg)
+            redo = empty & (th != th_backup)
+            if redo.any():
+                th[redo] = th_backup[redo]
+                s2 = sums(th)
+                s[redo] = s2[redo]
+        regs = np.zeros((nseg, 2), np.float64)
+        for i in range(nseg):
+            # polyfit keeps 1e-4 < x < 0.8 when that is > 1 % of the points (:348-350)
+            use = s[i, 6:12] if s[i, 6] > 0.01 * s[i, 0] else s[i, 0:6]
+            N, Sx, Sy, Sxx, Sxy = use[0], use[1], use[2], use[3], use[4]
+            det = N * Sxx - Sx * Sx
+            b1 = (N * Sxy - Sx * Sy) / det
+            regs[i] = (b1, (Sy - b1 * Sx) / N)
+        if nseg == 1:
+            return regs[0], th[0]
+        return regs, th
 
     # -- SelfNLF / CollabNLF ----------------------------------------------------------------------
-    def estimate(self, lr_rggb, hr_rggb=None, k=29, details=False):
+    def estimate(self, lr_rggb, hr_rggb=None, k=29, details=False, nseg=1):
+        """lr_rggb (and hr_rggb for collab): (B,h,w,4) with B = nseg * frames-per-image, image-major.  Returns the
+        (beta1, beta2) of every image: (2,) for nseg == 1, else (nseg, 2)."""
         var, mean, lap = self.maps(lr_rggb, hr_rggb, k)
-        th, pct, info = self.threshold_score3(lap, mean, step=5)
-        reg, th = self.masked_fit(var, mean, lap, th)
+        th, pct, info = self.threshold_score3(lap, mean, step=5, nseg=nseg)
+        reg, th = self.masked_fit(var, mean, lap, th, nseg=nseg)
         if details:
             return reg, dict(th=th, pct=pct, **info)
         return reg

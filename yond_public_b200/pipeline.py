@@ -250,6 +250,63 @@ class YOND_SIDD:
         results["hr_raw"] = (np.concatenate(list(hr), axis=-1) if isinstance(hr, np.ndarray) and hr.ndim == 3 else hr)
         return results
 
+    def iter_denoise_batch(self, blocks, p, log=None):
+        """IterDenoise for a BATCH of SIDD-shaped images at once: blocks (nimg, nblk, H, W) CUDA f32.  Same per-image
+        algorithm and guards as iter_denoise_device / the reference (YOND_SIDD.py:301-483), but every device stage
+        runs once for all images, so the host reads back three small arrays per estimate instead of per image.
+        Returns {'raw_dns': [round-1 (nimg,H,nblk*W), final (nimg,H,nblk*W)], 'regs': [(nimg,2) per round],
+        'rounds': (nimg,) number of denoise rounds each image completed}."""
+        pipe = self.pipe
+        assert pipe["full_est"] and "simple" in pipe["est_type"] and not pipe["full_dn"], "batched path = the SIDD configuration"
+        nimg, nblk, H, W = blocks.shape
+        scale_est = p["wp"] - p["bl"]
+        scale = p.get("scale", scale_est)
+        k, bias_corr, vst_type = pipe["k"], pipe["bias_corr"], pipe.get("vst_type", "exact")
+        est = nlf._estimator()
+        mosaic = blocks.permute(0, 2, 1, 3).reshape(nimg, H, nblk * W).contiguous()  # :315, per image
+        reg1 = np.atleast_2d(est.estimate(isp.bayer2rggb(mosaic), None, k, nseg=nimg))  # :338-341 (mode 'self')
+        gains = reg1[:, 0] * scale_est
+        sigmas = np.sqrt(np.maximum(reg1[:, 1], 0)) * scale_est  # :356
+        flat = blocks.reshape(nimg * nblk, H, W)
+
+        def denoise(g, s, sel=None):
+            src = flat if sel is None else blocks[sel].reshape(-1, H, W)
+            bound = None
+            gg, ss = np.repeat(g, nblk), np.repeat(s, nblk)
+            if bias_corr is not None and self.biaslut is None:
+                # one fallback table per image up to the image max (:393-395); expressed per frame for the engine
+                imax = (blocks if sel is None else blocks[sel]).amax(dim=(1, 2, 3)).cpu().numpy().astype(np.float32)
+                bound = np.repeat(imax * np.float32(scale_est), nblk)
+            dn = self.engine.vst_denoise(src, gg, ss, scale, bias_corr=bias_corr, vst_type=vst_type, clip01=True,
+                                         table_bound=bound)
+            n = dn.shape[0] // nblk
+            return dn.reshape(n, nblk, H, W).permute(0, 2, 1, 3).reshape(n, H, nblk * W).contiguous()  # :408
+
+        dn1 = denoise(gains, sigmas)
+        regs, rounds = [reg1], np.ones(nimg, np.int64)
+        final = dn1
+        if pipe.get("iter") == "iter" and pipe["max_iter"] >= 1:
+            assert pipe["max_iter"] == 1, "the shipped configurations use max_iter = 1"
+            sidd = bool(pipe.get("sidd_256", nblk == 32))
+            if sidd:  # blocks become separate images of the box filters (:91-93); segments stay per image
+                lr_b = isp.bayer2rggb(flat)
+                dn_b = isp.bayer2rggb(dn1.reshape(nimg, H, nblk, W).permute(0, 2, 1, 3).reshape(nimg * nblk, H, W).contiguous())
+            else:
+                lr_b, dn_b = isp.bayer2rggb(mosaic), isp.bayer2rggb(dn1)
+            reg2 = np.atleast_2d(est.estimate(lr_b, dn_b, k, nseg=nimg)).copy()  # :431 (mode 'collab')
+            neg_b = reg2[:, 1] < 0
+            reg2[neg_b, 1] = reg2[neg_b, 0] ** 2  # :438-440
+            ok = reg2[:, 0] >= 0  # :445-447: beta1 < 0 keeps the round-1 result
+            regs.append(reg2)
+            if ok.any():
+                sel = torch.from_numpy(np.nonzero(ok)[0]).to(blocks.device)
+                g2, s2 = reg2[ok, 0] * scale_est, np.sqrt(reg2[ok, 1]) * scale_est  # :442
+                dn2 = denoise(g2, s2, sel if not ok.all() else None)
+                final = dn1.clone()
+                final[sel] = dn2
+                rounds[ok] = 2
+        return {"raw_dns": [dn1, final], "regs": regs, "rounds": rounds, "lr_raw": mosaic}
+
     def iter_denoise_device(self, blocks, p, lr_full=None):
         """Device-resident IterDenoise.  `blocks`: (nblk,H,W) CUDA f32 (SIDD layout) or (H,W) frame.
         Returns CUDA tensors in the reference's mosaic layout: (H, nblk*W)."""
