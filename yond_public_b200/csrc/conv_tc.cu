@@ -95,6 +95,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// One lane of a converged warp (elect.sync); returns 1 on the elected lane.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred px;\n\t"
+      "elect.sync _|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -289,7 +299,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // Converged warp, one elected lane issues (keeps coordinates / addresses in uniform registers).
+    const uint32_t is_leader = elect_one();
+    if (is_leader) {
       tma_prefetch_desc(&maps.w);
       tma_prefetch_desc(&maps.a[0]);
       if (p.wres) {  // all weight tiles of this layer stay in smem for the kernel's lifetime
@@ -297,78 +309,101 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         mbar_expect_tx(w_full, nwt * p.b_stage_bytes);
         for (int i = 0; i < nwt; ++i) tma_load_2d(smem_b + i * p.b_stage_bytes, &maps.w, w_full, 0, i * p.N);
       }
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
-        for (int ai = 0; ai < n_ast; ++ai) {
-          const AStage s = decode_astage(p, ai);
-          mbar_wait(a_empty + 8 * sa, pa ^ 1);
+    }
+    __syncwarp();
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      for (int ai = 0; ai < n_ast; ++ai) {
+        const AStage s = decode_astage(p, ai);
+        mbar_wait(a_empty + 8 * sa, pa ^ 1);
+        if (is_leader) {
           mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
           tma_load_4d(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full + 8 * sa, s.c, tc.w0 + s.dw, tc.b0, tc.h0 + s.dh);
-          if (++sa == p.SA) { sa = 0; pa ^= 1; }
-          if (!p.wres) {
-            for (int j = 0; j < s.ntaps; ++j) {
-              const int widx = s.widx0 + (s.sx >= 0 ? j * 3 : j);
-              mbar_wait(b_empty + 8 * sb, pb ^ 1);
+        }
+        __syncwarp();
+        if (++sa == p.SA) { sa = 0; pa ^= 1; }
+        if (!p.wres) {
+          for (int j = 0; j < s.ntaps; ++j) {
+            const int widx = s.widx0 + (s.sx >= 0 ? j * 3 : j);
+            mbar_wait(b_empty + 8 * sb, pb ^ 1);
+            if (is_leader) {
               mbar_expect_tx(b_full + 8 * sb, p.b_stage_bytes);
               tma_load_2d(smem_b + sb * p.b_stage_bytes, &maps.w, b_full + 8 * sb, 0, widx * p.N + tc.n0);
-              if (++sb == p.SB) { sb = 0; pb ^= 1; }
             }
+            __syncwarp();
+            if (++sb == p.SB) { sb = 0; pb ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NT, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
-      const int ksteps = p.CB / 16;
-      const uint32_t b_sbo = 8u * row_bytes;
-      if (p.wres) mbar_wait(w_full, 0);
-      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(acc_empty + 8 * as, pacc ^ 1);
+    // The whole warp stays converged (so every value below is warp-uniform and lives in uniform registers);
+    // one elected lane issues the tcgen05 instructions.  Descriptors are (constant high word, running low word).
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+    const int ksteps = p.CB / 16;
+    const uint32_t layout = (row_bytes == 128) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
+    // high words: stride byte offset [32,46), version 1 at bit 46, layout type at [61,64)
+    const uint32_t a_hi = ((p.sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+    const uint32_t b_hi = (((8u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+    const uint32_t lo_flags = 1u << 16;  // leading byte offset field (ignored for swizzled K-major operands)
+    const uint32_t sub_step = p.sub_off >> 4;
+    const uint32_t is_leader = elect_one();
+    if (p.wres) mbar_wait(w_full, 0);
+    int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(acc_empty + 8 * as, pacc ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.T * p.NT);
+      uint32_t accum = 0;
+      for (int ai = 0; ai < n_ast; ++ai) {
+        const AStage s = decode_astage(p, ai);
+        mbar_wait(a_full + 8 * sa, pa);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.T * p.NT);
-        uint32_t accum = 0;
-        for (int ai = 0; ai < n_ast; ++ai) {
-          const AStage s = decode_astage(p, ai);
-          mbar_wait(a_full + 8 * sa, pa);
-          tc_fence_after();
-          const uint32_t a_base = smem_a + sa * p.a_stage_bytes;
-          for (int j = 0; j < s.ntaps; ++j) {
-            int r = 0, sx = 0, widx = s.widx0 + j;
-            if (p.mode == CONV_3X3_S1) {
-              if (s.sx >= 0) { r = j; widx = s.widx0 + j * 3; }       // three-slab mode: the stage fixes sx
-              else { r = j / 3; sx = j - r * 3; }                    // single slab: all nine taps
-            }
-            uint32_t b_base;
-            if (p.wres) {
-              b_base = smem_b + (uint32_t)widx * p.b_stage_bytes;
-            } else {
-              mbar_wait(b_full + 8 * sb, pb);
-              tc_fence_after();
-              b_base = smem_b + sb * p.b_stage_bytes;
-            }
-            const uint32_t a_tap = a_base + (uint32_t)r * p.tap_r_off + (uint32_t)sx * row_bytes;
-            for (int t = 0; t < p.T; ++t) {
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem + (uint32_t)(t * p.NT), umma_desc(a_tap + t * p.sub_off + k * 32, row_bytes, p.sbo),
-                          umma_desc(b_base + k * 32, row_bytes, b_sbo), idesc, accum | (uint32_t)(k > 0));
-            }
-            accum = 1;
-            if (!p.wres) {
-              umma_commit(b_empty + 8 * sb);
-              if (++sb == p.SB) { sb = 0; pb ^= 1; }
-            }
+        const uint32_t a_base = smem_a + sa * p.a_stage_bytes;
+        for (int j = 0; j < s.ntaps; ++j) {
+          int r = 0, sx = 0, widx = s.widx0 + j;
+          if (p.mode == CONV_3X3_S1) {
+            if (s.sx >= 0) { r = j; widx = s.widx0 + j * 3; }       // three-slab mode: the stage fixes sx
+            else { r = j / 3; sx = j - r * 3; }                    // single slab: all nine taps
           }
-          umma_commit(a_empty + 8 * sa);
-          if (++sa == p.SA) { sa = 0; pa ^= 1; }
+          uint32_t b_base;
+          if (p.wres) {
+            b_base = smem_b + (uint32_t)widx * p.b_stage_bytes;
+          } else {
+            mbar_wait(b_full + 8 * sb, pb);
+            tc_fence_after();
+            b_base = smem_b + sb * p.b_stage_bytes;
+          }
+          const uint32_t a_lo0 = (((a_base + (uint32_t)r * p.tap_r_off + (uint32_t)sx * row_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+          const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | lo_flags;
+          if (is_leader) {
+            for (int t = 0; t < p.T; ++t) {
+              const uint32_t dt = d_tmem + (uint32_t)(t * p.NT);
+              uint32_t a_lo = a_lo0 + t * sub_step, b_lo = b_lo0;
+              umma_bf16(dt, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, accum);
+              for (int k = 1; k < ksteps; ++k) {
+                a_lo += 2;  // +32 bytes along K inside the swizzle row
+                b_lo += 2;
+                umma_bf16(dt, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, 1u);
+              }
+            }
+            if (!p.wres) umma_commit(b_empty + 8 * sb);
+          }
+          __syncwarp();
+          accum = 1;
+          if (!p.wres) {
+            if (++sb == p.SB) { sb = 0; pb ^= 1; }
+          }
         }
-        umma_commit(acc_full + 8 * as);
-        if (++as == 2) { as = 0; pacc ^= 1; }
+        if (is_leader) umma_commit(a_empty + 8 * sa);
+        __syncwarp();
+        if (++sa == p.SA) { sa = 0; pa ^= 1; }
       }
+      if (is_leader) umma_commit(acc_full + 8 * as);
+      __syncwarp();
+      if (++as == 2) { as = 0; pacc ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================

@@ -15,7 +15,9 @@ struct D4 {
 };
 __device__ __forceinline__ void d4_add(D4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
 __device__ __forceinline__ void d4_sub(D4& a, const float4& v) { a.x -= v.x; a.y -= v.y; a.z -= v.z; a.w -= v.w; }
-__device__ __forceinline__ float4 sq4(const float4& v) { return make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w); }
+__device__ __forceinline__ float4 sq4(const float4& v) {
+  return make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w));
+}
 
 // Vertical pass: one thread owns one pixel column (4 channels) of a strip of `rows_per_strip` output rows and
 // slides a k-tall window down it.  Writes float64 column sums of x (and of fl32(x*x) when S2 != nullptr).
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(128) box_h_kernel(const D4* __restrict__ S1, c
   }
   const float4 m2 = make_float4((float)(q.x * inv), (float)(q.y * inv), (float)(q.z * inv), (float)(q.w * inv));
   // stdfilt (isp_algos.py:236-241): float32 square of the blurred image, float32 difference, sqrt
-  auto sd = [](float e2, float e1) { return sqrtf(fmaxf(e2 - e1 * e1, 0.f)); };
+  // explicit round-to-nearest mul/sub: an FMA contraction would skip the float32 rounding of mean^2 the reference has
+  auto sd = [](float e2, float e1) { return sqrtf(fmaxf(__fsub_rn(e2, __fmul_rn(e1, e1)), 0.f)); };
   const float4 st = make_float4(sd(m2.x, m.x), sd(m2.y, m.y), sd(m2.z, m.z), sd(m2.w, m.w));
   if (op == OP_MEAN_STD) {
     out0[rbase + c] = m;
@@ -106,10 +109,10 @@ __global__ void __launch_bounds__(128) box_h_kernel(const D4* __restrict__ S1, c
 __global__ void var_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ var, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float s = a[i];
-    float v = s * s;
+    float v = __fmul_rn(s, s);  // no FMA contraction: the reference rounds each square to float32 first
     if (b) {
       const float t = b[i];
-      v = v - t * t;
+      v = __fsub_rn(v, __fmul_rn(t, t));
     }
     var[i] = v;
   }
