@@ -16,6 +16,7 @@ from oracle import yond_oracle as O  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--net-only", type=int, default=0, help="profile only the network forward on this many 128x128 packed blocks")
 ap.add_argument("--arch", default="gru")
+ap.add_argument("--step", type=int, default=0, help="profile one batched pipeline step over this many images")
 ap.add_argument("--frame", default=None, help="HxW packed frame for --net-only, e.g. 1536x2016")
 args = ap.parse_args()
 arch = bench.ARCH if args.arch == "gru" else {"name": "UNetSeeInDark", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
@@ -32,6 +33,16 @@ if args.net_only:
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStart()
     drv.net.forward_nhwc(z, ub, t if "guided" in arch else None)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+elif args.step:
+    imgs, _ = bench.synth_images(args.step)
+    dev_in = torch.from_numpy(imgs).cuda()
+    for i in range(2):
+        drv.iter_denoise_batch(dev_in, dict(bench.P0))
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    drv.iter_denoise_batch(dev_in, dict(bench.P0))
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
 else:

@@ -158,6 +158,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&v)[NC]);
+template <>
+__device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, 64B / 128B swizzle (rows of CB bf16; `sbo` = byte distance
@@ -181,6 +196,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
 }
+
+__device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+struct TcParams;
+// Epilogue of NC accumulator columns of one GEMM row: bias, FiLM scale/shift, activation, residual, bf16 stores.
+template <int NC>
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t taddr, bool valid, int b, int co, size_t off);
 
 // One activation ("A") pipeline stage of the K loop, decoded identically by producer and MMA issuer.
 struct AStage {
@@ -258,6 +280,74 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
   t.b0 = tb_i * p.NB * (p.t_along_h ? 1 : p.T);
   t.n0 = t.n_idx * p.NT;
   return t;
+}
+
+template <int NC>
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t taddr, bool valid, int b, int co, size_t off) {
+  uint32_t v[NC];
+  tmem_ld_n<NC>(taddr, v);
+  uint4 rr[NC / 8];
+  if (valid && p.res) {  // issue the residual loads before waiting on TMEM
+    const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
+#pragma unroll
+    for (int g = 0; g < NC / 8; ++g) rr[g] = __ldg(r4 + g);
+  }
+  float f[NC];
+  if (valid) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + co);
+#pragma unroll
+    for (int g = 0; g < NC / 4; ++g) {
+      const float4 t = __ldg(b4 + g);
+      f[g * 4 + 0] = t.x; f[g * 4 + 1] = t.y; f[g * 4 + 2] = t.z; f[g * 4 + 3] = t.w;
+    }
+  }
+  tmem_ld_wait();
+  if (!valid) return;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) f[j] += __uint_as_float(v[j]);
+  if (p.scale) {
+    const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + co);
+#pragma unroll
+    for (int g = 0; g < NC / 4; ++g) {
+      const float4 t = __ldg(s4 + g);
+      f[g * 4 + 0] *= t.x; f[g * 4 + 1] *= t.y; f[g * 4 + 2] *= t.z; f[g * 4 + 3] *= t.w;
+    }
+  }
+  if (p.shift) {
+    const float4* s4 = reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + co);
+#pragma unroll
+    for (int g = 0; g < NC / 4; ++g) {
+      const float4 t = __ldg(s4 + g);
+      f[g * 4 + 0] += t.x; f[g * 4 + 1] += t.y; f[g * 4 + 2] += t.z; f[g * 4 + 3] += t.w;
+    }
+  }
+  if (p.act == ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+  } else if (p.act == ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = fast_silu(f[j]);
+  }
+  if (p.res) {
+#pragma unroll
+    for (int g = 0; g < NC / 8; ++g) {
+      const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
+      f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
+      f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
+    }
+  }
+  uint4* o4 = reinterpret_cast<uint4*>(p.out0 + off);
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g)
+    o4[g] = make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                       pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+  if (p.out1) {
+    uint4* s4 = reinterpret_cast<uint4*>(p.out1 + off);
+#pragma unroll
+    for (int g = 0; g < NC / 8; ++g)
+      s4[g] = make_uint4(pack_bf16x2(fast_silu(f[g * 8 + 0]), fast_silu(f[g * 8 + 1])), pack_bf16x2(fast_silu(f[g * 8 + 2]), fast_silu(f[g * 8 + 3])),
+                         pack_bf16x2(fast_silu(f[g * 8 + 4]), fast_silu(f[g * 8 + 5])), pack_bf16x2(fast_silu(f[g * 8 + 6]), fast_silu(f[g * 8 + 7])));
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -412,20 +502,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int row = q * 32 + lane;     // GEMM row inside a sub-tile
     const int w_i = row % p.TW;
     const int g_i = row / p.TW;        // (h, b) index inside the sub-tile, h-major
-    const int nchunk = p.NT / 32;
+    // column chunks of 32 (16 when N = 32, so that both warps of a quarter have work)
+    const int cw = p.NT == 32 ? 16 : 32;
+    const int nchunk = p.NT / cw;
     int as = 0, pacc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       mbar_wait(acc_full + 8 * as, pacc);
       tc_fence_after();
       for (int ci = half; ci < p.T * nchunk; ci += 2) {
-        const int t = ci / nchunk, c = (ci - t * nchunk) * 32;
+        const int t = ci / nchunk, c = (ci - t * nchunk) * cw;
         int h = tc.h0 + g_i / p.NB, b = tc.b0 + g_i % p.NB;
         if (p.t_along_h) h += t * p.TH; else b += t * p.NB;
         const int w = tc.w0 + w_i;
         const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.T + t) * p.NT + c), v);
         const int n = tc.n0 + c;  // first GEMM column of this chunk
         int co = n;
         size_t pix = 0;
@@ -439,55 +529,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         }
         const size_t off = pix * p.Cout + co;
-        uint4 rr[4];
-        if (valid && p.res) {  // issue the residual loads before waiting on TMEM
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rr[g] = __ldg(r4 + g);
-        }
-        tmem_ld_wait();
-        if (valid) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + co + j);
-          if (p.scale) {
-            const float* sc = p.scale + (size_t)b * p.Cout + co;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= __ldg(sc + j);
-          }
-          if (p.shift) {
-            const float* sh = p.shift + (size_t)b * p.Cout + co;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __ldg(sh + j);
-          }
-          if (p.act == ACT_LRELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
-          } else if (p.act == ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-          }
-          if (p.res) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
-              f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
-              f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
-            }
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(p.out0 + off);
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            o4[g] = make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
-                               pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
-          if (p.out1) {
-            uint4* s4 = reinterpret_cast<uint4*>(p.out1 + off);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              s4[g] = make_uint4(pack_bf16x2(silu_f(f[g * 8 + 0]), silu_f(f[g * 8 + 1])), pack_bf16x2(silu_f(f[g * 8 + 2]), silu_f(f[g * 8 + 3])),
-                                 pack_bf16x2(silu_f(f[g * 8 + 4]), silu_f(f[g * 8 + 5])), pack_bf16x2(silu_f(f[g * 8 + 6]), silu_f(f[g * 8 + 7])));
-          }
-        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.T + t) * p.NT + c);
+        if (cw == 16) epilogue_chunk<16>(p, taddr, valid, b, co, off);
+        else epilogue_chunk<32>(p, taddr, valid, b, co, off);
       }
       tc_fence_before();
       __syncwarp();

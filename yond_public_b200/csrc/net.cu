@@ -338,16 +338,18 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
   } else {
     const bool guided = n->arch == YOND_ARCH_GUIDED;
     if (!dry && t == nullptr) return yond_set_error(YOND_ERR_INVALID, "guided network needs the per-sample t vector");
-    // conditioning vectors of the 9 blocks
+    // conditioning vectors of the 9 blocks (one launch)
     float* va[10];
     float* vb[10];
+    FilmAll all{};
+    all.n = 9;
     for (int l = 1; l <= 9; ++l) {
       const int lv = l <= 5 ? l - 1 : 9 - l, C = n->ch(lv);
       va[l] = bump.take<float>((size_t)B * C);
       vb[l] = bump.take<float>((size_t)B * C);
-      if (!dry && rc == YOND_OK) {
+      if (!dry) {
         const std::string p = "conv" + std::to_string(l);
-        FilmWeights fw{};
+        FilmWeights& fw = all.fw[l - 1];
         if (guided) {
           fw.w0 = n->f32[p + ".gamma.0.weight"]; fw.b0 = n->f32[p + ".gamma.0.bias"];
           fw.w2 = n->f32[p + ".gamma.2.weight"]; fw.b2 = n->f32[p + ".gamma.2.bias"];
@@ -358,9 +360,12 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
           fw.w3 = n->f32[p + ".sfm2.0.weight"]; fw.b3 = n->f32[p + ".sfm2.0.bias"];
           fw.w4 = n->f32[p + ".sfm2.2.weight"]; fw.b4 = n->f32[p + ".sfm2.2.bias"];
         }
-        rc = film_launch(fw, t, ubn, B, C, guided ? 1 : 0, va[l], vb[l], s);
+        all.C[l - 1] = C;
+        all.out_a[l - 1] = va[l];
+        all.out_b[l - 1] = vb[l];
       }
     }
+    RUN(film_launch(all, t, ubn, B, guided ? 1 : 0, s));
     // One residual block: x (raw) and xs = SiLU(x) come from the producer's dual store.
     auto block = [&](int l, int lv, const bf16* x, const bf16* xs, bf16* out) {
       const int C = n->ch(lv), h = H >> lv, w = W >> lv;

@@ -11,61 +11,78 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // ---- first layer: 3x3, 4 -> 32*G channels, fp32 math on the fp32 network input (x = z / ub) ----------------
-// One thread = one pixel x 32 output channels.  Weights [tap][ci][co] in shared memory (broadcast reads).
+// One thread = two horizontally adjacent pixels x 32 output channels: every weight vector read from shared memory
+// (128-bit broadcast loads, layout [tap][ci][co]) feeds 8 FMAs, so the kernel is FMA-bound, not LDS-bound.
 __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ z, const float* __restrict__ ub,
                                                         const float* __restrict__ w, const float* __restrict__ bias, int B,
                                                         int H, int W, int nf, float slope, bf16* __restrict__ out0,
                                                         bf16* __restrict__ out1) {
-  extern __shared__ float sw[];  // [9*4*nf] + [nf]
+  extern __shared__ __align__(16) float sw[];  // [9*4*nf] + [nf]
   for (int i = threadIdx.x; i < 36 * nf; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < nf; i += blockDim.x) sw[36 * nf + i] = bias[i];
   __syncthreads();
-  const size_t npix = (size_t)B * H * W;
+  const int W2 = (W + 1) >> 1;
+  const size_t npair = (size_t)B * H * W2;
   const float4* z4 = reinterpret_cast<const float4*>(z);
-  for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(pix % W);
-    const int y = (int)((pix / W) % H);
-    const int b = (int)(pix / ((size_t)W * H));
+  for (size_t pr = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pr < npair; pr += (size_t)gridDim.x * blockDim.x) {
+    const int x0 = (int)(pr % W2) * 2;
+    const int y = (int)((pr / W2) % H);
+    const int b = (int)(pr / ((size_t)W2 * H));
     const float inv = ub ? 1.0f / __ldg(ub + b) : 1.0f;
-    float4 in[9];
+    float4 in[3][4];  // rows y-1..y+1, columns x0-1..x0+2
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int yy = y + r - 1, xx = x + s - 1;
+      for (int c = 0; c < 4; ++c) {
+        const int yy = y + r - 1, xx = x0 + c - 1;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(z4 + ((size_t)b * H + yy) * W + xx);
         // the reference divides first, then convolves: x = data / upper (modules.py:20)
-        in[r * 3 + s] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+        in[r][c] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
       }
+    const bool has1 = x0 + 1 < W;
+    const size_t pix0 = ((size_t)b * H + y) * W + x0;
     for (int g = 0; g < nf; g += 32) {
-      float acc[32];
+      float a0[32], a1[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = sw[36 * nf + g + j];
+      for (int j = 0; j < 32; ++j) a0[j] = a1[j] = sw[36 * nf + g + j];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float* wt = sw + (t * 4) * nf + g;
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          acc[j] = fmaf(in[t].x, wt[j], acc[j]);
-          acc[j] = fmaf(in[t].y, wt[nf + j], acc[j]);
-          acc[j] = fmaf(in[t].z, wt[2 * nf + j], acc[j]);
-          acc[j] = fmaf(in[t].w, wt[3 * nf + j], acc[j]);
+        for (int sx = 0; sx < 3; ++sx) {
+          const float i0[4] = {in[r][sx].x, in[r][sx].y, in[r][sx].z, in[r][sx].w};
+          const float i1[4] = {in[r][sx + 1].x, in[r][sx + 1].y, in[r][sx + 1].z, in[r][sx + 1].w};
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            const float4* wv = reinterpret_cast<const float4*>(sw + ((r * 3 + sx) * 4 + ci) * nf + g);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 ww = wv[q];
+              a0[q * 4 + 0] = fmaf(i0[ci], ww.x, a0[q * 4 + 0]); a1[q * 4 + 0] = fmaf(i1[ci], ww.x, a1[q * 4 + 0]);
+              a0[q * 4 + 1] = fmaf(i0[ci], ww.y, a0[q * 4 + 1]); a1[q * 4 + 1] = fmaf(i1[ci], ww.y, a1[q * 4 + 1]);
+              a0[q * 4 + 2] = fmaf(i0[ci], ww.z, a0[q * 4 + 2]); a1[q * 4 + 2] = fmaf(i1[ci], ww.z, a1[q * 4 + 2]);
+              a0[q * 4 + 3] = fmaf(i0[ci], ww.w, a0[q * 4 + 3]); a1[q * 4 + 3] = fmaf(i1[ci], ww.w, a1[q * 4 + 3]);
+            }
+          }
         }
-      }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * slope;
-      uint4* o = reinterpret_cast<uint4*>(out0 + pix * nf + g);
+      for (int px = 0; px < 2; ++px) {
+        if (px == 1 && !has1) break;
+        float* acc = px ? a1 : a0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        o[q] = make_uint4(pack2(acc[q * 8], acc[q * 8 + 1]), pack2(acc[q * 8 + 2], acc[q * 8 + 3]),
-                          pack2(acc[q * 8 + 4], acc[q * 8 + 5]), pack2(acc[q * 8 + 6], acc[q * 8 + 7]));
-      if (out1) {
-        uint4* o1 = reinterpret_cast<uint4*>(out1 + pix * nf + g);
+        for (int j = 0; j < 32; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * slope;
+        uint4* o = reinterpret_cast<uint4*>(out0 + (pix0 + px) * nf + g);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          o1[q] = make_uint4(pack2(silu_f(acc[q * 8]), silu_f(acc[q * 8 + 1])), pack2(silu_f(acc[q * 8 + 2]), silu_f(acc[q * 8 + 3])),
-                             pack2(silu_f(acc[q * 8 + 4]), silu_f(acc[q * 8 + 5])), pack2(silu_f(acc[q * 8 + 6]), silu_f(acc[q * 8 + 7])));
+          o[q] = make_uint4(pack2(acc[q * 8], acc[q * 8 + 1]), pack2(acc[q * 8 + 2], acc[q * 8 + 3]),
+                            pack2(acc[q * 8 + 4], acc[q * 8 + 5]), pack2(acc[q * 8 + 6], acc[q * 8 + 7]));
+        if (out1) {
+          uint4* o1 = reinterpret_cast<uint4*>(out1 + (pix0 + px) * nf + g);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o1[q] = make_uint4(pack2(silu_f(acc[q * 8]), silu_f(acc[q * 8 + 1])), pack2(silu_f(acc[q * 8 + 2]), silu_f(acc[q * 8 + 3])),
+                               pack2(silu_f(acc[q * 8 + 4]), silu_f(acc[q * 8 + 5])), pack2(silu_f(acc[q * 8 + 6]), silu_f(acc[q * 8 + 7])));
+        }
       }
     }
   }
@@ -165,8 +182,12 @@ __device__ __forceinline__ void film_matvec(const float* __restrict__ Wm, const 
     }
   }
 }
-__global__ void __launch_bounds__(512) film_kernel(FilmWeights fw, const float* __restrict__ t, const float* __restrict__ ub,
-                                                   int B, int C, int guided, float* __restrict__ out_a, float* __restrict__ out_b) {
+__global__ void __launch_bounds__(512) film_kernel(const __grid_constant__ FilmAll all, const float* __restrict__ t,
+                                                   const float* __restrict__ ub, int B, int guided) {
+  const FilmWeights& fw = all.fw[blockIdx.y];  // one conditioned block of the network per blockIdx.y
+  const int C = all.C[blockIdx.y];
+  float* __restrict__ out_a = all.out_a[blockIdx.y];
+  float* __restrict__ out_b = all.out_b[blockIdx.y];
   extern __shared__ float sv[];  // [S][C] hidden, [S][C] out_a
   float* hid = sv;
   float* va = sv + kFilmS * C;
@@ -240,9 +261,9 @@ inline int cap_grid(size_t blocks) {
 
 int head_conv_launch(const float* z, const float* ub, const float* w, const float* bias, int B, int H, int W, int nf,
                      float slope, bf16* out0, bf16* out1, cudaStream_t s) {
-  const size_t npix = (size_t)B * H * W;
+  const size_t npair = (size_t)B * H * ((W + 1) / 2);
   const size_t smem = (size_t)(36 * nf + nf) * sizeof(float);
-  head_conv_kernel<<<cap_grid((npix + 127) / 128), 128, smem, s>>>(z, ub, w, bias, B, H, W, nf, slope, out0, out1);
+  head_conv_kernel<<<cap_grid((npair + 127) / 128), 128, smem, s>>>(z, ub, w, bias, B, H, W, nf, slope, out0, out1);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
@@ -260,9 +281,11 @@ int maxpool2_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaS
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
-int film_launch(const FilmWeights& fw, const float* t, const float* ub, int B, int C, int guided, float* out_a, float* out_b,
-                cudaStream_t s) {
-  film_kernel<<<ceil_div(B, kFilmS), 512, (size_t)2 * kFilmS * C * sizeof(float), s>>>(fw, t, ub, B, C, guided, out_a, out_b);
+int film_launch(const FilmAll& all, const float* t, const float* ub, int B, int guided, cudaStream_t s) {
+  int cmax = 0;
+  for (int i = 0; i < all.n; ++i) cmax = all.C[i] > cmax ? all.C[i] : cmax;
+  dim3 grid(ceil_div(B, kFilmS), all.n);
+  film_kernel<<<grid, 512, (size_t)2 * kFilmS * cmax * sizeof(float), s>>>(all, t, ub, B, guided);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

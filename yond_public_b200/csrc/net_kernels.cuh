@@ -14,7 +14,13 @@ int head_conv_launch(const float* z, const float* ub, const float* w, const floa
 int tail_conv_launch(const bf16* act, const float* w, const float* bias, const float* z, const float* ub, int res, int B,
                      int H, int W, int nf, float* y, cudaStream_t s);
 int maxpool2_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s);
-int film_launch(const FilmWeights& fw, const float* t, const float* ub, int B, int C, int guided, float* out_a, float* out_b,
-                cudaStream_t s);
+struct FilmAll {  // every conditioned block of a network, evaluated by one launch
+  FilmWeights fw[9];
+  int C[9];
+  float* out_a[9];
+  float* out_b[9];
+  int n;
+};
+int film_launch(const FilmAll& all, const float* t, const float* ub, int B, int guided, cudaStream_t s);
 int nchw_to_nhwc4_launch(const float* x, float* z, float* ub, int B, int H, int W, cudaStream_t s);
 int nhwc4_to_nchw_launch(const float* y, float* out, int B, int H, int W, cudaStream_t s);
