@@ -45,6 +45,21 @@ elif args.step:
     drv.iter_denoise_batch(dev_in, dict(bench.P0))
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
+    import time
+    tm = {}
+    for _ in range(3):
+        tm.pop("_t", None)
+        drv.iter_denoise_batch(dev_in, dict(bench.P0), timings=tm)
+    print("stage ms/step:", {k: round(v / 3 * 1e3, 2) for k, v in tm.items() if k != "_t"})
+    for chunk in (32, 64, 128, 256):
+        drv.engine.chunk = chunk
+        drv.iter_denoise_batch(dev_in, dict(bench.P0))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            drv.iter_denoise_batch(dev_in, dict(bench.P0))
+        torch.cuda.synchronize()
+        print(f"chunk {chunk}: {(time.perf_counter() - t0) / 3 * 1e3:.2f} ms/step")
 else:
     imgs, _ = bench.synth_images(2)
     dev_in = torch.from_numpy(imgs).cuda()

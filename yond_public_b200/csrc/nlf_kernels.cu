@@ -56,52 +56,87 @@ __global__ void __launch_bounds__(128) box_v_kernel(const float4* __restrict__ x
   }
 }
 
-// Horizontal pass over the float64 column sums: block = one row segment of 128 pixels (+halo) staged in shared
-// memory, each thread sums its k neighbours.  Epilogue selected by `op`:
-//   0: out0 = mean                         1: out0 = mean, out1 = std = sqrt(max(m2 - mean^2, 0))
-//   2: out0 = std                          3: out1 (var) = std^2 - out1_in^2 ... see nlf_maps below
+// Horizontal pass over the float64 column sums.  A block stages kHCols pixels (+halo) of kHRows rows in shared
+// memory; each thread owns kSeg consecutive pixels of one row: one k-wide window sum, then it slides (add the
+// entering column, subtract the leaving one — exact in float64 for sums of float32 values).  Rows are padded by one
+// element per kSeg so that the threads of a warp hit different banks.  Epilogue selected by `op`:
+//   OP_MEAN: out0 = mean | OP_MEAN_STD: out0 = mean, out1 = std = sqrt(max(m2 - mean^2, 0)) | OP_STD: out0 = std
 enum { OP_MEAN = 0, OP_MEAN_STD = 1, OP_STD = 2 };
-__global__ void __launch_bounds__(128) box_h_kernel(const D4* __restrict__ S1, const D4* __restrict__ S2, float4* __restrict__ out0,
-                                                    float4* __restrict__ out1, int h, int w, int k, int op) {
-  __shared__ D4 t1[128 + kMaxK - 1];
-  __shared__ D4 t2[128 + kMaxK - 1];
+constexpr int kSeg = 8;
+constexpr int kHThreads = 64;
+constexpr int kHSpan = kHThreads * kSeg;                  // 512 pixels of output per block
+constexpr int kHStage = kHSpan + kMaxK - 1;               // + halo
+constexpr int kHPadded = kHStage + kHStage / kSeg + 1;    // one pad element every kSeg
+__device__ __forceinline__ int hpad(int i) { return i + i / kSeg; }
+__global__ void __launch_bounds__(kHThreads) box_h_kernel(const D4* __restrict__ S1, const D4* __restrict__ S2,
+                                                          float4* __restrict__ out0, float4* __restrict__ out1, int h, int w, int k,
+                                                          int op, int cols, int rows_per_block) {
+  __shared__ D4 t1[kHPadded];
+  __shared__ D4 t2[kHPadded];
   const int r = k / 2;
-  const int row = blockIdx.y, b = blockIdx.z;
-  const int c0 = blockIdx.x * 128;
-  const size_t rbase = ((size_t)b * h + row) * w;
-  for (int i = threadIdx.x; i < 128 + 2 * r; i += blockDim.x) {
-    const int c = reflect101(c0 + i - r, w);
-    t1[i] = S1[rbase + c];
-    if (S2) t2[i] = S2[rbase + c];
+  const int b = blockIdx.z;
+  const int row0 = blockIdx.y * rows_per_block;
+  const int c0 = blockIdx.x * cols;                 // first output column of this block
+  const int stage_w = cols + 2 * r;                 // staged columns per row
+  // stage: rows_per_block rows x stage_w columns, row-major in the padded index space
+  for (int i = threadIdx.x; i < rows_per_block * stage_w; i += blockDim.x) {
+    const int rr = i / stage_w, cc = i - rr * stage_w;
+    const int row = row0 + rr;
+    if (row < h) {
+      const int c = reflect101(c0 + cc - r, w);
+      const size_t g = ((size_t)b * h + row) * w + c;
+      t1[hpad(i)] = S1[g];
+      if (S2) t2[hpad(i)] = S2[g];
+    }
   }
   __syncthreads();
-  const int c = c0 + threadIdx.x;
-  if (c >= w) return;
+  const int segs_per_row = cols / kSeg;
+  const int rr = threadIdx.x / segs_per_row, sg = threadIdx.x - rr * segs_per_row;
+  const int row = row0 + rr;
+  if (rr >= rows_per_block || row >= h) return;
+  const int cfirst = c0 + sg * kSeg;
+  if (cfirst >= w) return;
+  const int base = rr * stage_w + sg * kSeg;        // staged index of the window start for the first pixel
   const double inv = 1.0 / ((double)k * (double)k);
   D4 a{0, 0, 0, 0}, q{0, 0, 0, 0};
   for (int j = 0; j < k; ++j) {
-    const D4 v = t1[threadIdx.x + j];
+    const D4 v = t1[hpad(base + j)];
     a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     if (S2) {
-      const D4 u = t2[threadIdx.x + j];
+      const D4 u = t2[hpad(base + j)];
       q.x += u.x; q.y += u.y; q.z += u.z; q.w += u.w;
     }
   }
-  const float4 m = make_float4((float)(a.x * inv), (float)(a.y * inv), (float)(a.z * inv), (float)(a.w * inv));
-  if (op == OP_MEAN) {
-    out0[rbase + c] = m;
-    return;
-  }
-  const float4 m2 = make_float4((float)(q.x * inv), (float)(q.y * inv), (float)(q.z * inv), (float)(q.w * inv));
-  // stdfilt (isp_algos.py:236-241): float32 square of the blurred image, float32 difference, sqrt
-  // explicit round-to-nearest mul/sub: an FMA contraction would skip the float32 rounding of mean^2 the reference has
+  const size_t rbase = ((size_t)b * h + row) * w;
+  // stdfilt (isp_algos.py:236-241): float32 square of the blurred image, float32 difference, sqrt; explicit
+  // round-to-nearest mul/sub: an FMA contraction would skip the float32 rounding of mean^2 the reference has
   auto sd = [](float e2, float e1) { return sqrtf(fmaxf(__fsub_rn(e2, __fmul_rn(e1, e1)), 0.f)); };
-  const float4 st = make_float4(sd(m2.x, m.x), sd(m2.y, m.y), sd(m2.z, m.z), sd(m2.w, m.w));
-  if (op == OP_MEAN_STD) {
-    out0[rbase + c] = m;
-    out1[rbase + c] = st;
-  } else {
-    out0[rbase + c] = st;
+#pragma unroll
+  for (int i = 0; i < kSeg; ++i) {
+    const int c = cfirst + i;
+    if (c < w) {
+      const float4 m = make_float4((float)(a.x * inv), (float)(a.y * inv), (float)(a.z * inv), (float)(a.w * inv));
+      if (op == OP_MEAN) {
+        out0[rbase + c] = m;
+      } else {
+        const float4 m2 = make_float4((float)(q.x * inv), (float)(q.y * inv), (float)(q.z * inv), (float)(q.w * inv));
+        const float4 st = make_float4(sd(m2.x, m.x), sd(m2.y, m.y), sd(m2.z, m.z), sd(m2.w, m.w));
+        if (op == OP_MEAN_STD) {
+          out0[rbase + c] = m;
+          out1[rbase + c] = st;
+        } else {
+          out0[rbase + c] = st;
+        }
+      }
+    }
+    if (i + 1 < kSeg) {  // slide the window one pixel to the right
+      const D4 vn = t1[hpad(base + i + k)], vo = t1[hpad(base + i)];
+      a.x += vn.x - vo.x; a.y += vn.y - vo.y; a.z += vn.z - vo.z; a.w += vn.w - vo.w;
+      if (S2) {
+        const D4 un = t2[hpad(base + i + k)], uo = t2[hpad(base + i)];
+        q.x += un.x - uo.x; q.y += un.y - uo.y; q.z += un.z - uo.z; q.w += un.w - uo.w;
+      }
+    }
   }
 }
 
@@ -364,8 +399,13 @@ int box_pass(const float* x, float* out0, float* out1, int B, int h, int w, int 
   dim3 gv(ceil_div(w, 128), ceil_div(h, rows_per_strip), B);
   box_v_kernel<<<gv, 128, 0, s>>>(reinterpret_cast<const float4*>(x), S1, S2, h, w, k, rows_per_strip, square_input);
   YOND_LAUNCH_CHECK();
-  dim3 gh(ceil_div(w, 128), h, B);
-  box_h_kernel<<<gh, 128, 0, s>>>(S1, S2, reinterpret_cast<float4*>(out0), reinterpret_cast<float4*>(out1), h, w, k, op);
+  // block = `cols` output columns (multiple of kSeg, <= kHSpan) x as many rows as fit in kHThreads threads
+  int cols = ceil_div(w, kSeg) * kSeg;
+  if (cols > kHSpan) cols = kHSpan;
+  int rpb = kHThreads / (cols / kSeg);
+  while (rpb > 1 && rpb * (cols + k - 1) > kHStage) --rpb;
+  dim3 gh(ceil_div(w, cols), ceil_div(h, rpb), B);
+  box_h_kernel<<<gh, kHThreads, 0, s>>>(S1, S2, reinterpret_cast<float4*>(out0), reinterpret_cast<float4*>(out1), h, w, k, op, cols, rpb);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

@@ -124,7 +124,7 @@ class NlfEstimator:
         return regs, th
 
     # -- SelfNLF / CollabNLF ----------------------------------------------------------------------
-    def estimate(self, lr_rggb, hr_rggb=None, k=29, details=False, nseg=1):
+    def estimate(self, lr_rggb, hr_rggb=None, k=29, details=False, nseg=1, timings=None):
         """lr_rggb (and hr_rggb for collab): (B,h,w,4) with B = nseg * frames-per-image, image-major.  Returns the
         (beta1, beta2) of every image: (2,) for nseg == 1, else (nseg, 2)."""
         var, mean, lap = self.maps(lr_rggb, hr_rggb, k)

@@ -250,7 +250,7 @@ class YOND_SIDD:
         results["hr_raw"] = (np.concatenate(list(hr), axis=-1) if isinstance(hr, np.ndarray) and hr.ndim == 3 else hr)
         return results
 
-    def iter_denoise_batch(self, blocks, p, log=None):
+    def iter_denoise_batch(self, blocks, p, log=None, timings=None):
         """IterDenoise for a BATCH of SIDD-shaped images at once: blocks (nimg, nblk, H, W) CUDA f32.  Same per-image
         algorithm and guards as iter_denoise_device / the reference (YOND_SIDD.py:301-483), but every device stage
         runs once for all images, so the host reads back three small arrays per estimate instead of per image.
@@ -263,8 +263,18 @@ class YOND_SIDD:
         scale = p.get("scale", scale_est)
         k, bias_corr, vst_type = pipe["k"], pipe["bias_corr"], pipe.get("vst_type", "exact")
         est = nlf._estimator()
+
+        def mark(name):  # optional stage timing (synchronising; for profiling only)
+            if timings is not None:
+                import time
+                torch.cuda.synchronize()
+                now = time.perf_counter()
+                timings[name] = timings.get(name, 0.0) + (now - timings.get("_t", now))
+                timings["_t"] = now
+        mark("start")
         mosaic = blocks.permute(0, 2, 1, 3).reshape(nimg, H, nblk * W).contiguous()  # :315, per image
         reg1 = np.atleast_2d(est.estimate(isp.bayer2rggb(mosaic), None, k, nseg=nimg))  # :338-341 (mode 'self')
+        mark("estimate_self")
         gains = reg1[:, 0] * scale_est
         sigmas = np.sqrt(np.maximum(reg1[:, 1], 0)) * scale_est  # :356
         flat = blocks.reshape(nimg * nblk, H, W)
@@ -283,6 +293,7 @@ class YOND_SIDD:
             return dn.reshape(n, nblk, H, W).permute(0, 2, 1, 3).reshape(n, H, nblk * W).contiguous()  # :408
 
         dn1 = denoise(gains, sigmas)
+        mark("denoise_round1")
         regs, rounds = [reg1], np.ones(nimg, np.int64)
         final = dn1
         if pipe.get("iter") == "iter" and pipe["max_iter"] >= 1:
@@ -294,6 +305,7 @@ class YOND_SIDD:
             else:
                 lr_b, dn_b = isp.bayer2rggb(mosaic), isp.bayer2rggb(dn1)
             reg2 = np.atleast_2d(est.estimate(lr_b, dn_b, k, nseg=nimg)).copy()  # :431 (mode 'collab')
+            mark("estimate_collab")
             neg_b = reg2[:, 1] < 0
             reg2[neg_b, 1] = reg2[neg_b, 0] ** 2  # :438-440
             ok = reg2[:, 0] >= 0  # :445-447: beta1 < 0 keeps the round-1 result
@@ -305,6 +317,7 @@ class YOND_SIDD:
                 final = dn1.clone()
                 final[sel] = dn2
                 rounds[ok] = 2
+                mark("denoise_round2")
         return {"raw_dns": [dn1, final], "regs": regs, "rounds": rounds, "lr_raw": mosaic}
 
     def iter_denoise_device(self, blocks, p, lr_full=None):
