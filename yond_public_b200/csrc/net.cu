@@ -2,6 +2,7 @@
 //   reference: archs/Unet.py:4-104, :288-378, :380-470; archs/modules.py:117-125, :163-233; archs/__init__.py:10-17.
 // The handle owns device copies of the weights, repacked once from the reference's state_dict layout
 // (utils/utils.py:160-209) into the tensor-core kernels' layout; activations live in a caller-provided workspace.
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -242,16 +243,16 @@ double layer_flops(const LayerW& L, int B, int Hin, int Win) {
 struct Runner {
   yond_net* n;
   cudaStream_t s;
-  int B;
   int rc = YOND_OK;
   double flops = 0;
-  bool dry;  // only count FLOPs / workspace
-  int conv(const std::string& name, int Hin, int Win, const bf16* src0, const bf16* src1, const float* scale,
-           const float* shift, int act, float slope, const bf16* res, bf16* out0, bf16* out1) {
+  bool dry = false;  // only count FLOPs / workspace
+  // One tensor-core conv layer on `B` images (pointers already offset to the first image).
+  void conv(const std::string& name, int B, int Hin, int Win, const bf16* src0, const bf16* src1, const float* scale,
+            const float* shift, int act, float slope, const bf16* res, bf16* out0, bf16* out1) {
     const LayerW& L = n->conv.at(name);
     const double f = layer_flops(L, B, Hin, Win);
     flops += f;
-    if (dry || rc) return rc;
+    if (dry || rc) return;
     ConvLayer c{};
     c.mode = L.mode;
     c.B = B;
@@ -279,68 +280,46 @@ struct Runner {
       n->ev_used += 2;
       n->pending_flops += f;
     }
-    return rc;
   }
 };
 
 // One forward pass; with ws == nullptr only measures workspace bytes and FLOPs.
+//
+// Schedule: the two full-resolution levels (0 and 1) hold ~85 % of the activation bytes, so they run in SUB-BATCHES
+// small enough for a producer's output to still be in the 126 MB L2 when its consumer reads it (encoder: first conv
+// .. second down-sampling; decoder: second up-sampling .. last 1x1).  The three coarse levels run once over the whole
+// batch so their (small) GEMMs fill all SMs.  Only the two skip tensors of levels 0/1 make a round trip to HBM.
 int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, float* y, int B, int H, int W, void* ws,
                  size_t* ws_bytes, double* flops, cudaStream_t s) {
   const bool dry = ws == nullptr;
   Bump bump(ws);
-  Runner R{n, s, B};
+  Runner R;
+  R.n = n;
+  R.s = s;
   R.dry = dry;
   const int nf = n->nf;
   const float* ubn = n->norm ? ub : nullptr;
-  auto act_buf = [&](int lvl, int C) { return bump.take<bf16>((size_t)B * (H >> lvl) * (W >> lvl) * C); };
+  const bool unet = n->arch == YOND_ARCH_UNET;
+  const bool guided = n->arch == YOND_ARCH_GUIDED;
+  if (!dry && !unet && t == nullptr) return yond_set_error(YOND_ERR_INVALID, "guided network needs the per-sample t vector");
   const double head_tail_flops = 2.0 * B * H * W * (36.0 * nf + 4.0 * nf);
-  int rc = YOND_OK;
-#define RUN(expr)                 \
-  do {                            \
-    if (!dry && rc == YOND_OK) rc = (expr); \
+  auto px = [&](int lv) { return (size_t)(H >> lv) * (W >> lv); };
+  // sub-batch of the full-resolution levels: one level-0 tensor (nf channels, bf16) of about 24 MB
+  static const int env_sub = getenv("YOND_SUB_BATCH") ? atoi(getenv("YOND_SUB_BATCH")) : 0;
+  int SBn = env_sub > 0 ? env_sub : (int)((24u << 20) / (px(0) * nf * 2));
+  if (SBn < 1) SBn = 1;
+  if (SBn > B) SBn = B;
+  auto buf = [&](int nb, int lv, int C) { return bump.take<bf16>((size_t)nb * px(lv) * C); };
+
+#define RUN(expr)                                       \
+  do {                                                  \
+    if (!dry && R.rc == YOND_OK) R.rc = (expr);         \
   } while (0)
 
-  if (n->arch == YOND_ARCH_UNET) {
-    bf16* a = act_buf(0, nf);
-    RUN(head_conv_launch(z, ubn, n->head_w, n->f32["conv1_1.bias"], B, H, W, nf, 0.2f, a, nullptr, s));
-    bf16* skip[5];
-    bf16* cur = a;
-    for (int l = 1; l <= 5; ++l) {
-      const int lv = l - 1, C = n->ch(lv), h = H >> lv, w = W >> lv;
-      const std::string p = "conv" + std::to_string(l);
-      if (l > 1) {
-        bf16* t1 = act_buf(lv, C);
-        rc = rc ? rc : R.conv(p + "_1", h, w, cur, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t1, nullptr);
-        cur = t1;
-      }
-      bf16* c2 = act_buf(lv, C);
-      rc = rc ? rc : R.conv(p + "_2", h, w, cur, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c2, nullptr);
-      skip[lv] = c2;
-      cur = c2;
-      if (l < 5) {
-        bf16* pl = act_buf(lv + 1, C);
-        RUN(maxpool2_launch(c2, pl, B, h, w, C, s));
-        cur = pl;
-      }
-    }
-    for (int i = 0; i < 4; ++i) {
-      const int lv = 3 - i, C = n->ch(lv), h = H >> lv, w = W >> lv;
-      const std::string l = std::to_string(6 + i);
-      bf16* up = act_buf(lv, C);
-      rc = rc ? rc : R.conv("upv" + l, h / 2, w / 2, cur, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, up, nullptr);
-      bf16* t1 = act_buf(lv, C);
-      rc = rc ? rc : R.conv("conv" + l + "_1", h, w, up, skip[lv], nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t1, nullptr);
-      bf16* c2 = act_buf(lv, C);
-      rc = rc ? rc : R.conv("conv" + l + "_2", h, w, t1, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c2, nullptr);
-      cur = c2;
-    }
-    RUN(tail_conv_launch(cur, n->tail_w, n->f32["conv10_1.bias"], z, ubn, n->res, B, H, W, nf, y, s));
-  } else {
-    const bool guided = n->arch == YOND_ARCH_GUIDED;
-    if (!dry && t == nullptr) return yond_set_error(YOND_ERR_INVALID, "guided network needs the per-sample t vector");
-    // conditioning vectors of the 9 blocks (one launch)
-    float* va[10];
-    float* vb[10];
+  // ---- conditioning vectors of the 9 blocks (one launch, whole batch) ----
+  float* va[10] = {nullptr};
+  float* vb[10] = {nullptr};
+  if (!unet) {
     FilmAll all{};
     all.n = 9;
     for (int l = 1; l <= 9; ++l) {
@@ -366,53 +345,129 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
       }
     }
     RUN(film_launch(all, t, ubn, B, guided ? 1 : 0, s));
-    // One residual block: x (raw) and xs = SiLU(x) come from the producer's dual store.
-    auto block = [&](int l, int lv, const bf16* x, const bf16* xs, bf16* out) {
-      const int C = n->ch(lv), h = H >> lv, w = W >> lv;
-      const std::string p = "conv" + std::to_string(l);
-      bf16* zb = act_buf(lv, C);
-      if (guided) {  // z = SiLU(conv1(SiLU(x)) * tk + tb); out = conv2(z) + x
-        rc = rc ? rc : R.conv(p + ".conv1", h, w, xs, nullptr, va[l], vb[l], ACT_SILU, 0.f, nullptr, zb, nullptr);
-        rc = rc ? rc : R.conv(p + ".conv2", h, w, zb, nullptr, nullptr, nullptr, ACT_NONE, 0.f, x, out, nullptr);
-      } else {  // z = SiLU(conv1(SiLU(x)) * a1); out = conv2(z) * a2 + x
-        rc = rc ? rc : R.conv(p + ".conv1", h, w, xs, nullptr, va[l], nullptr, ACT_SILU, 0.f, nullptr, zb, nullptr);
-        rc = rc ? rc : R.conv(p + ".conv2", h, w, zb, nullptr, vb[l], nullptr, ACT_NONE, 0.f, x, out, nullptr);
-      }
-    };
-    bf16* x = act_buf(0, nf);
-    bf16* xs = act_buf(0, nf);
-    RUN(head_conv_launch(z, ubn, n->head_w, n->f32["conv_in.bias"], B, H, W, nf, 0.01f, x, xs, s));
-    bf16* skip[5];
-    for (int l = 1; l <= 5; ++l) {
-      const int lv = l - 1, C = n->ch(lv), h = H >> lv, w = W >> lv;
-      bf16* c = act_buf(lv, C);
-      block(l, lv, x, xs, c);
-      skip[lv] = c;
-      if (l < 5) {  // stride-2 conv, no activation (modules.py:117-125); dual store feeds the next block
-        x = act_buf(lv + 1, 2 * C);
-        xs = act_buf(lv + 1, 2 * C);
-        rc = rc ? rc : R.conv("pool" + std::to_string(l) + ".conv", h, w, c, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x, xs);
-      }
+  }
+  // One residual block on `nb` images starting at image b0 (FiLM rows are per image): x raw, xs = SiLU(x).
+  auto block = [&](int l, int lv, int b0, int nb, const bf16* x, const bf16* xs, bf16* zb, bf16* out) {
+    const int C = n->ch(lv), h = H >> lv, w = W >> lv;
+    const std::string p = "conv" + std::to_string(l);
+    const float* a = va[l] ? va[l] + (size_t)b0 * C : nullptr;
+    const float* bb = vb[l] ? vb[l] + (size_t)b0 * C : nullptr;
+    if (guided) {  // z = SiLU(conv1(SiLU(x)) * tk + tb); out = conv2(z) + x
+      R.conv(p + ".conv1", nb, h, w, xs, nullptr, a, bb, ACT_SILU, 0.f, nullptr, zb, nullptr);
+      R.conv(p + ".conv2", nb, h, w, zb, nullptr, nullptr, nullptr, ACT_NONE, 0.f, x, out, nullptr);
+    } else {  // SNR: z = SiLU(conv1(SiLU(x)) * a1); out = conv2(z) * a2 + x
+      R.conv(p + ".conv1", nb, h, w, xs, nullptr, a, nullptr, ACT_SILU, 0.f, nullptr, zb, nullptr);
+      R.conv(p + ".conv2", nb, h, w, zb, nullptr, bb, nullptr, ACT_NONE, 0.f, x, out, nullptr);
     }
-    bf16* cur = skip[4];
-    for (int i = 0; i < 4; ++i) {
-      const int lv = 3 - i, C = n->ch(lv), h = H >> lv, w = W >> lv, l = 6 + i;
-      bf16* up = act_buf(lv, C);
-      rc = rc ? rc : R.conv("upv" + std::to_string(l), h / 2, w / 2, cur, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, up, nullptr);
-      x = act_buf(lv, C);
-      xs = act_buf(lv, C);
-      rc = rc ? rc : R.conv("conv" + std::to_string(l) + ".short_cut.0", h, w, up, skip[lv], nullptr, nullptr, ACT_NONE, 0.f, nullptr, x, xs);
-      bf16* c = act_buf(lv, C);
-      block(l, lv, x, xs, c);
-      cur = c;
+  };
+  const int C0 = n->ch(0), C1 = n->ch(1), C2 = n->ch(2), C3 = n->ch(3), C4 = n->ch(4);
+  const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2, H3 = H >> 3, W3 = W >> 3, H4 = H >> 4, W4 = W >> 4;
+  // skips of the full-resolution levels (whole batch) and the level-2 hand-over tensors
+  bf16* skip0 = buf(B, 0, C0);
+  bf16* skip1 = buf(B, 1, C1);
+
+  if (unet) {
+    bf16* p2 = buf(B, 2, C1);  // pooled level-1 output
+    // sub-batch temporaries
+    bf16* a0 = buf(SBn, 0, C0);
+    bf16* p1 = buf(SBn, 1, C0);
+    bf16* a1 = buf(SBn, 1, C1);
+    for (int b0 = 0; b0 < B; b0 += SBn) {
+      const int nb = B - b0 < SBn ? B - b0 : SBn;
+      bf16* s0 = skip0 + (size_t)b0 * px(0) * C0;
+      bf16* s1 = skip1 + (size_t)b0 * px(1) * C1;
+      RUN(head_conv_launch(z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->head_w, n->f32["conv1_1.bias"], nb, H, W, nf, 0.2f, a0, nullptr, s));
+      R.conv("conv1_2", nb, H, W, a0, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, s0, nullptr);
+      RUN(maxpool2_launch(s0, p1, nb, H, W, C0, s));
+      R.conv("conv2_1", nb, H1, W1, p1, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, a1, nullptr);
+      R.conv("conv2_2", nb, H1, W1, a1, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, s1, nullptr);
+      RUN(maxpool2_launch(s1, p2 + (size_t)b0 * px(2) * C1, nb, H1, W1, C1, s));
     }
-    RUN(tail_conv_launch(cur, n->tail_w, n->f32["conv10.bias"], z, ubn, n->res, B, H, W, nf, y, s));
+    // coarse levels, whole batch
+    bf16* a2 = buf(B, 2, C2); bf16* c3 = buf(B, 2, C2); bf16* p3 = buf(B, 3, C2);
+    bf16* a3 = buf(B, 3, C3); bf16* c4 = buf(B, 3, C3); bf16* p4 = buf(B, 4, C3);
+    bf16* a4 = buf(B, 4, C4); bf16* c5 = buf(B, 4, C4);
+    R.conv("conv3_1", B, H2, W2, p2, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, a2, nullptr);
+    R.conv("conv3_2", B, H2, W2, a2, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c3, nullptr);
+    RUN(maxpool2_launch(c3, p3, B, H2, W2, C2, s));
+    R.conv("conv4_1", B, H3, W3, p3, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, a3, nullptr);
+    R.conv("conv4_2", B, H3, W3, a3, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c4, nullptr);
+    RUN(maxpool2_launch(c4, p4, B, H3, W3, C3, s));
+    R.conv("conv5_1", B, H4, W4, p4, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, a4, nullptr);
+    R.conv("conv5_2", B, H4, W4, a4, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c5, nullptr);
+    bf16* u6 = buf(B, 3, C3); bf16* t6 = buf(B, 3, C3); bf16* c6 = buf(B, 3, C3);
+    R.conv("upv6", B, H4, W4, c5, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u6, nullptr);
+    R.conv("conv6_1", B, H3, W3, u6, c4, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t6, nullptr);
+    R.conv("conv6_2", B, H3, W3, t6, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c6, nullptr);
+    bf16* u7 = buf(B, 2, C2); bf16* t7 = buf(B, 2, C2); bf16* c7 = buf(B, 2, C2);
+    R.conv("upv7", B, H3, W3, c6, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u7, nullptr);
+    R.conv("conv7_1", B, H2, W2, u7, c3, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t7, nullptr);
+    R.conv("conv7_2", B, H2, W2, t7, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c7, nullptr);
+    // decoder of the full-resolution levels, per sub-batch
+    bf16* u8 = buf(SBn, 1, C1); bf16* t8 = buf(SBn, 1, C1); bf16* c8 = buf(SBn, 1, C1);
+    bf16* u9 = buf(SBn, 0, C0); bf16* t9 = buf(SBn, 0, C0); bf16* c9 = buf(SBn, 0, C0);
+    for (int b0 = 0; b0 < B; b0 += SBn) {
+      const int nb = B - b0 < SBn ? B - b0 : SBn;
+      R.conv("upv8", nb, H2, W2, c7 + (size_t)b0 * px(2) * C2, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u8, nullptr);
+      R.conv("conv8_1", nb, H1, W1, u8, skip1 + (size_t)b0 * px(1) * C1, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t8, nullptr);
+      R.conv("conv8_2", nb, H1, W1, t8, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c8, nullptr);
+      R.conv("upv9", nb, H1, W1, c8, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u9, nullptr);
+      R.conv("conv9_1", nb, H, W, u9, skip0 + (size_t)b0 * px(0) * C0, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t9, nullptr);
+      R.conv("conv9_2", nb, H, W, t9, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c9, nullptr);
+      RUN(tail_conv_launch(c9, n->tail_w, n->f32["conv10_1.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->res, nb,
+                           H, W, nf, y + (size_t)b0 * px(0) * 4, s));
+    }
+  } else {
+    bf16* x2 = buf(B, 2, C2);   // pool2 output (raw) and its SiLU: inputs of the level-2 block
+    bf16* x2s = buf(B, 2, C2);
+    bf16* x0 = buf(SBn, 0, C0); bf16* x0s = buf(SBn, 0, C0); bf16* z0 = buf(SBn, 0, C0);
+    bf16* x1 = buf(SBn, 1, C1); bf16* x1s = buf(SBn, 1, C1); bf16* z1 = buf(SBn, 1, C1);
+    for (int b0 = 0; b0 < B; b0 += SBn) {
+      const int nb = B - b0 < SBn ? B - b0 : SBn;
+      bf16* s0 = skip0 + (size_t)b0 * px(0) * C0;
+      bf16* s1 = skip1 + (size_t)b0 * px(1) * C1;
+      RUN(head_conv_launch(z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->head_w, n->f32["conv_in.bias"], nb, H, W, nf, 0.01f, x0, x0s, s));
+      block(1, 0, b0, nb, x0, x0s, z0, s0);
+      // stride-2 conv, no activation (modules.py:117-125); the dual store feeds the next block
+      R.conv("pool1.conv", nb, H, W, s0, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x1, x1s);
+      block(2, 1, b0, nb, x1, x1s, z1, s1);
+      R.conv("pool2.conv", nb, H1, W1, s1, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x2 + (size_t)b0 * px(2) * C2,
+             x2s + (size_t)b0 * px(2) * C2);
+    }
+    bf16* zb2 = buf(B, 2, C2); bf16* c3 = buf(B, 2, C2);
+    bf16* x3 = buf(B, 3, C3); bf16* x3s = buf(B, 3, C3); bf16* zb3 = buf(B, 3, C3); bf16* c4 = buf(B, 3, C3);
+    bf16* x4 = buf(B, 4, C4); bf16* x4s = buf(B, 4, C4); bf16* zb4 = buf(B, 4, C4); bf16* c5 = buf(B, 4, C4);
+    block(3, 2, 0, B, x2, x2s, zb2, c3);
+    R.conv("pool3.conv", B, H2, W2, c3, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x3, x3s);
+    block(4, 3, 0, B, x3, x3s, zb3, c4);
+    R.conv("pool4.conv", B, H3, W3, c4, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x4, x4s);
+    block(5, 4, 0, B, x4, x4s, zb4, c5);
+    bf16* u6 = buf(B, 3, C3); bf16* c6 = buf(B, 3, C3);
+    R.conv("upv6", B, H4, W4, c5, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u6, nullptr);
+    R.conv("conv6.short_cut.0", B, H3, W3, u6, c4, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x3, x3s);  // x3/x3s are free again
+    block(6, 3, 0, B, x3, x3s, zb3, c6);
+    bf16* u7 = buf(B, 2, C2); bf16* c7 = buf(B, 2, C2);
+    R.conv("upv7", B, H3, W3, c6, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u7, nullptr);
+    R.conv("conv7.short_cut.0", B, H2, W2, u7, c3, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x2, x2s);
+    block(7, 2, 0, B, x2, x2s, zb2, c7);
+    bf16* u8 = buf(SBn, 1, C1); bf16* c8 = buf(SBn, 1, C1);
+    bf16* u9 = buf(SBn, 0, C0); bf16* c9 = buf(SBn, 0, C0);
+    for (int b0 = 0; b0 < B; b0 += SBn) {
+      const int nb = B - b0 < SBn ? B - b0 : SBn;
+      R.conv("upv8", nb, H2, W2, c7 + (size_t)b0 * px(2) * C2, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u8, nullptr);
+      R.conv("conv8.short_cut.0", nb, H1, W1, u8, skip1 + (size_t)b0 * px(1) * C1, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x1, x1s);
+      block(8, 1, b0, nb, x1, x1s, z1, c8);
+      R.conv("upv9", nb, H1, W1, c8, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u9, nullptr);
+      R.conv("conv9.short_cut.0", nb, H, W, u9, skip0 + (size_t)b0 * px(0) * C0, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x0, x0s);
+      block(9, 0, b0, nb, x0, x0s, z0, c9);
+      RUN(tail_conv_launch(c9, n->tail_w, n->f32["conv10.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->res, nb, H, W,
+                           nf, y + (size_t)b0 * px(0) * 4, s));
+    }
   }
 #undef RUN
-  if (R.rc) rc = R.rc;
   if (ws_bytes) *ws_bytes = align_up(bump.off, 1024);
   if (flops) *flops = R.flops + head_tail_flops;
-  return rc;
+  return R.rc;
 }
 
 }  // namespace

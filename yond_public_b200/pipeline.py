@@ -51,7 +51,7 @@ class YondEngine:
         if self.chunk:
             return min(B, int(self.chunk))
         per = max(1, hp * wp * 800)  # ~bytes of activations per frame
-        return int(max(1, min(B, (6 << 30) // per, 128)))
+        return int(max(1, min(B, (8 << 30) // per, 256)))
 
     # ------------------------------------------------------------------------------------------
     def make_params(self, gains, sigmas, scale, bias_corr, vst_type, frame_max, device, fixed_table=None):
@@ -60,23 +60,30 @@ class YondEngine:
         Bias source per frame, like the reference (YOND_SIDD.py:252-259, utils/isp_algos.py:196-231): the BiasLUT row
         for this sigma/K when a LUT is loaded and sigma/K is inside its range, otherwise the fallback `get_bias`
         table built on the host up to this frame's maximum (`frame_max`: callable returning per-frame max in DN)."""
+        gains = np.asarray(gains, np.float64)
+        sigmas = np.asarray(sigmas, np.float64)
         B = len(gains)
         exact = 1 if (bias_corr is None and vst_type == "exact") else 0
-        rows_np, nodes_np, table_n, key_row, row_of = [], [], [], {}, [-1] * B
+        rows_np, nodes_np, table_n, key_row = [], [], [], {}
+        row_of = np.full(B, -1, np.int32)
         lut_rows = []  # (row index, K, sigma) filled on device
         if bias_corr is not None:
+            # frames come in runs sharing (K, sigma) (the 32 blocks of an image): resolve each distinct pair once
+            pairs, inverse = np.unique(np.stack([gains, sigmas], 1), axis=0, return_inverse=True)
+            inverse = np.asarray(inverse).reshape(-1)
             fmax = None
-            for b, (k, s) in enumerate(zip(gains, sigmas)):
+            for u, (k, s) in enumerate(pairs):
                 k, s = float(k), float(s)
+                idx = np.nonzero(inverse == u)[0]
                 if self.biaslut is not None and self.biaslut.in_range(k, s):
-                    key = ("lut", k, s)
-                    if key not in key_row:
-                        key_row[key] = len(rows_np)
-                        rows_np.append(None)
-                        nodes_np.append(self.biaslut.x_lut.astype(np.float32))
-                        table_n.append(0)
-                        lut_rows.append((key_row[key], k, s))
-                else:
+                    key_row[("lut", k, s)] = len(rows_np)
+                    lut_rows.append((len(rows_np), k, s))
+                    row_of[idx] = len(rows_np)
+                    rows_np.append(None)
+                    nodes_np.append(self.biaslut.x_lut.astype(np.float32))
+                    table_n.append(0)
+                    continue
+                for b in idx:
                     if fixed_table is not None:
                         key = ("fixed",)
                     else:
@@ -90,7 +97,7 @@ class YondEngine:
                         rows_np.append(np.asarray(vals, np.float32))
                         nodes_np.append(np.asarray(nodes, np.float32))
                         table_n.append(len(nodes))
-                row_of[b] = key_row[key]
+                    row_of[b] = key_row[key]
         rows = xnodes = None
         stride = 1921
         if rows_np:
@@ -104,17 +111,20 @@ class YondEngine:
             rows, xnodes = torch.from_numpy(r).to(device), torch.from_numpy(xn).to(device)
             for i, k, s in lut_rows:
                 self.biaslut.sigma_row(k, s, out=rows[i, :1921])
-        arr = (VstParams * B)()
-        t = np.zeros(B, np.float32)
-        for b, (k, s) in enumerate(zip(gains, sigmas)):
-            k, s = np.float64(k), np.float64(s)
-            lower = 2 / k * max((3 / 8) * k ** 2 + s ** 2, 0) ** 0.5  # VST(0)       YOND_SIDD.py:264
-            upper = 2 / k * max(k * scale + (3 / 8) * k ** 2 + s ** 2, 0) ** 0.5  # VST(scale)   :265
-            arr[b] = VstParams(float(k), float(s), float(scale), float(lower), float(upper), row_of[b],
-                               table_n[row_of[b]] if row_of[b] >= 0 else 0, exact)
-            nsr = 1 / (upper - lower)  # :268
-            t[b] = nsr * (SIGMA_CORR_PRE if bias_corr == "pre" else 1.0)  # :284-285
-        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        # VST(0) / VST(scale) / nsr in float64 on the host (YOND_SIDD.py:264-268), vectorised over the batch
+        c0 = (3 / 8) * gains ** 2 + sigmas ** 2
+        lower = 2 / gains * np.sqrt(np.maximum(c0, 0))
+        upper = 2 / gains * np.sqrt(np.maximum(gains * scale + c0, 0))
+        rec = np.zeros(B, dtype=np.dtype([("gain", "<f4"), ("sigma", "<f4"), ("scale", "<f4"), ("lower", "<f4"), ("upper", "<f4"),
+                                          ("lut_row", "<i4"), ("table_n", "<i4"), ("exact", "<i4")]))
+        assert rec.dtype.itemsize == C.sizeof(VstParams)
+        rec["gain"], rec["sigma"], rec["scale"], rec["lower"], rec["upper"] = gains, sigmas, scale, lower, upper
+        rec["lut_row"] = row_of
+        tn = np.asarray(table_n + [0], np.int32)
+        rec["table_n"] = np.where(row_of >= 0, tn[np.maximum(row_of, 0)], 0)
+        rec["exact"] = exact
+        t = (1 / (upper - lower) * (SIGMA_CORR_PRE if bias_corr == "pre" else 1.0)).astype(np.float32)  # :268, :284-285
+        raw = torch.from_numpy(rec.view(np.uint8).copy()).to(device)
         return raw, rows, xnodes, stride, torch.from_numpy(t).to(device)
 
     def table_fn(self, ub, sigma, gain):
