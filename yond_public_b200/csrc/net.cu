@@ -285,10 +285,10 @@ struct Runner {
 
 // One forward pass; with ws == nullptr only measures workspace bytes and FLOPs.
 //
-// Schedule: the two full-resolution levels (0 and 1) hold ~85 % of the activation bytes, so they run in SUB-BATCHES
+// Schedule: the two full-resolution levels (0 and 1) hold ~85 % of the activation bytes; they CAN run in sub-batches
 // small enough for a producer's output to still be in the 126 MB L2 when its consumer reads it (encoder: first conv
-// .. second down-sampling; decoder: second up-sampling .. last 1x1).  The three coarse levels run once over the whole
-// batch so their (small) GEMMs fill all SMs.  Only the two skip tensors of levels 0/1 make a round trip to HBM.
+// .. second down-sampling; decoder: second up-sampling .. last 1x1) while the three coarse levels run once over the
+// whole batch.  See the measurement note at SBn below: the split is off by default.
 int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, float* y, int B, int H, int W, void* ws,
                  size_t* ws_bytes, double* flops, cudaStream_t s) {
   const bool dry = ws == nullptr;
@@ -304,9 +304,11 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
   if (!dry && !unet && t == nullptr) return yond_set_error(YOND_ERR_INVALID, "guided network needs the per-sample t vector");
   const double head_tail_flops = 2.0 * B * H * W * (36.0 * nf + 4.0 * nf);
   auto px = [&](int lv) { return (size_t)(H >> lv) * (W >> lv); };
-  // sub-batch of the full-resolution levels: one level-0 tensor (nf channels, bf16) of about 24 MB
+  // Sub-batch of the full-resolution levels.  Measured on B200 (bench.py, 1280 blocks): splitting costs more in
+  // launch tails than L2 residency returns (43.7 ms/step unsplit vs 49-60 ms at 16-48 blocks), so the default is the
+  // whole batch; YOND_SUB_BATCH=n re-enables the split for experiments.
   static const int env_sub = getenv("YOND_SUB_BATCH") ? atoi(getenv("YOND_SUB_BATCH")) : 0;
-  int SBn = env_sub > 0 ? env_sub : (int)((24u << 20) / (px(0) * nf * 2));
+  int SBn = env_sub > 0 ? env_sub : B;
   if (SBn < 1) SBn = 1;
   if (SBn > B) SBn = B;
   auto buf = [&](int nb, int lv, int C) { return bump.take<bf16>((size_t)nb * px(lv) * C); };
