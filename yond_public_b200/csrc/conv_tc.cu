@@ -46,6 +46,7 @@ struct TcParams {
   uint32_t sub_off, sbo, tap_r_off;  // byte offsets inside an activation stage: next sub-tile, next 8-row group, next image row
   uint32_t smem_b_off, smem_bar_off;
   int tmem_cols;
+  int dbg;    // bring-up switches (YOND_CONV_DBG): 1 = skip global stores, 2 = skip the epilogue math, 4 = skip residual loads
   const float* bias;
   const float* scale;
   const float* shift;
@@ -287,6 +288,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t taddr
   uint32_t v[NC];
   tmem_ld_n<NC>(taddr, v);
   uint4 rr[NC / 8];
+  if (p.dbg & 2) { tmem_ld_wait(); return; }
   if (valid && p.res) {  // issue the residual loads before waiting on TMEM
     const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
 #pragma unroll
@@ -335,6 +337,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t taddr
       f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
       f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
     }
+  }
+  if (p.dbg & 1) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc += f[j];
+    if (acc == 123.456f) p.out0[0] = __float2bfloat16_rn(acc);  // keep the math alive
+    return;
   }
   uint4* o4 = reinterpret_cast<uint4*>(p.out0 + off);
 #pragma unroll
@@ -402,11 +411,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     __syncwarp();
     int sa = 0, pa = 0, sb = 0, pb = 0;
+    long long t_wait = 0, t_begin = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       for (int ai = 0; ai < n_ast; ++ai) {
         const AStage s = decode_astage(p, ai);
+        const long long tw0 = clock64();
         mbar_wait(a_empty + 8 * sa, pa ^ 1);
+        t_wait += clock64() - tw0;
         if (is_leader) {
           mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
           tma_load_4d(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full + 8 * sa, s.c, tc.w0 + s.dw, tc.b0, tc.h0 + s.dh);
@@ -427,6 +439,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       }
     }
+    if ((p.dbg & 8) && blockIdx.x == 0 && is_leader)
+      printf("[conv dbg] producer: total %lld cyc, waiting for a free A stage %lld cyc\n", clock64() - t_begin, t_wait);
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // The whole warp stays converged (so every value below is warp-uniform and lives in uniform registers);
@@ -442,14 +456,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const uint32_t is_leader = elect_one();
     if (p.wres) mbar_wait(w_full, 0);
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    long long t_acc = 0, t_a = 0, t_b = 0, t_begin = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      long long tw0 = clock64();
       mbar_wait(acc_empty + 8 * as, pacc ^ 1);
+      t_acc += clock64() - tw0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.T * p.NT);
       uint32_t accum = 0;
       for (int ai = 0; ai < n_ast; ++ai) {
         const AStage s = decode_astage(p, ai);
+        tw0 = clock64();
         mbar_wait(a_full + 8 * sa, pa);
+        t_a += clock64() - tw0;
         tc_fence_after();
         const uint32_t a_base = smem_a + sa * p.a_stage_bytes;
         for (int j = 0; j < s.ntaps; ++j) {
@@ -462,7 +481,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           if (p.wres) {
             b_base = smem_b + (uint32_t)widx * p.b_stage_bytes;
           } else {
+            tw0 = clock64();
             mbar_wait(b_full + 8 * sb, pb);
+            t_b += clock64() - tw0;
             tc_fence_after();
             b_base = smem_b + sb * p.b_stage_bytes;
           }
@@ -495,6 +516,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       __syncwarp();
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
+    if ((p.dbg & 8) && blockIdx.x == 0 && is_leader)
+      printf("[conv dbg] issuer: total %lld cyc; waiting: accumulator %lld, activations %lld, weights %lld; tiles %d, A stages/tile %d, SA %d SB %d T %d NT %d\n",
+             clock64() - t_begin, t_acc, t_a, t_b, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
@@ -632,6 +656,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   YOND_REQUIRE(L.Cout % 32 == 0, "conv_tc: Cout must be a multiple of 32 (got %d)", L.Cout);
   static const int env_slab = env_int("YOND_CONV_SLAB", 1);
   static const int env_T = env_int("YOND_CONV_T", kMaxT);
+  static const int env_dbg = env_int("YOND_CONV_DBG", 0);
   TcParams p{};
   p.mode = L.mode;
   p.B = L.B;
@@ -648,7 +673,8 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.CB = conv_tc_channel_block(L.Cin0, L.Cin1);
   p.ncb0 = L.Cin0 / p.CB;
   p.ncb1 = L.Cin1 / p.CB;
-  p.NT = p.N < 128 ? p.N : 128;
+  static const int env_nt = env_int("YOND_CONV_NT", 256);
+  p.NT = p.N < env_nt ? p.N : env_nt;
   YOND_REQUIRE(p.N % p.NT == 0 && (p.NT & (p.NT - 1)) == 0, "conv_tc: unsupported N=%d", p.N);
   p.tiles_n = p.N / p.NT;
   const uint32_t row_bytes = p.CB * 2;
@@ -674,7 +700,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
     b_region = wres_bytes;
   } else {
     p.SB = 6;
-    while (p.SB > 2 && (size_t)p.SB * p.b_stage_bytes > 96 * 1024) --p.SB;
+    while (p.SB > 3 && (size_t)p.SB * p.b_stage_bytes > 96 * 1024) --p.SB;
     b_region = (size_t)p.SB * p.b_stage_bytes;
   }
   // T sub-tiles share each weight tile (and one halo slab): stacked along H when the map is tall enough, else one
@@ -720,6 +746,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.tmem_cols = 2 * p.T * p.NT < 32 ? 32 : 2 * p.T * p.NT;
   YOND_REQUIRE(p.tmem_cols <= 512, "conv_tc: TMEM budget exceeded");
 
+  p.dbg = env_dbg;
   p.bias = L.bias;
   p.scale = L.scale;
   p.shift = L.shift;

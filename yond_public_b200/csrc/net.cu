@@ -611,6 +611,23 @@ int yond_conv2d(int mode, int impl, int B, int Hin, int Win, int Cin0, int Cin1,
   c.scale = scale; c.shift = shift; c.act = act; c.slope = slope; c.res = (const bf16*)res;
   c.out0 = (bf16*)out0; c.out1 = (bf16*)out1;
   int rc = impl ? conv_ref_launch(c, (cudaStream_t)stream) : conv_tc_launch(c, (cudaStream_t)stream);
+  if (const char* reps_s = getenv("YOND_CONV_REPS")) {  // bring-up micro-benchmark: time back-to-back launches
+    const int reps = atoi(reps_s);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3 && !rc; ++i) rc = conv_tc_launch(c, (cudaStream_t)stream);
+    cudaEventRecord(e0, (cudaStream_t)stream);
+    for (int i = 0; i < reps && !rc; ++i) rc = conv_tc_launch(c, (cudaStream_t)stream);
+    cudaEventRecord(e1, (cudaStream_t)stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "conv2d_bench mode=%d B=%d HxW=%dx%d Cin=%d+%d Cout=%d: %.2f us/launch\n", mode, B, Hin, Win, Cin0, Cin1, Cout,
+            1e3 * ms / (reps > 0 ? reps : 1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(dw);
   if (rc) return rc;

@@ -5,84 +5,72 @@
 
 namespace {
 
+__device__ __forceinline__ float fsilu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // ---- first layer: 3x3, 4 -> 32*G channels, fp32 math on the fp32 network input (x = z / ub) ----------------
-// One thread = two horizontally adjacent pixels x 32 output channels: every weight vector read from shared memory
-// (128-bit broadcast loads, layout [tap][ci][co]) feeds 8 FMAs, so the kernel is FMA-bound, not LDS-bound.
-__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ z, const float* __restrict__ ub,
-                                                        const float* __restrict__ w, const float* __restrict__ bias, int B,
-                                                        int H, int W, int nf, float slope, bf16* __restrict__ out0,
-                                                        bf16* __restrict__ out1) {
+// One thread = one pixel x 32 output channels.  Weights [tap][ci][co] sit in shared memory and are read as 128-bit
+// broadcasts (one LDS per 4 FMAs), so the kernel is bound by the FP32 pipe and by its 64-128 B/pixel of stores.
+__global__ void __launch_bounds__(256, 2) head_conv_kernel(const float* __restrict__ z, const float* __restrict__ ub,
+                                                           const float* __restrict__ w, const float* __restrict__ bias, int B,
+                                                           int H, int W, int nf, float slope, bf16* __restrict__ out0,
+                                                           bf16* __restrict__ out1) {
   extern __shared__ __align__(16) float sw[];  // [9*4*nf] + [nf]
   for (int i = threadIdx.x; i < 36 * nf; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < nf; i += blockDim.x) sw[36 * nf + i] = bias[i];
   __syncthreads();
-  const int W2 = (W + 1) >> 1;
-  const size_t npair = (size_t)B * H * W2;
+  const size_t npix = (size_t)B * H * W;
   const float4* z4 = reinterpret_cast<const float4*>(z);
-  for (size_t pr = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pr < npair; pr += (size_t)gridDim.x * blockDim.x) {
-    const int x0 = (int)(pr % W2) * 2;
-    const int y = (int)((pr / W2) % H);
-    const int b = (int)(pr / ((size_t)W2 * H));
+  for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int b = (int)(pix / ((size_t)W * H));
     const float inv = ub ? 1.0f / __ldg(ub + b) : 1.0f;
-    float4 in[3][4];  // rows y-1..y+1, columns x0-1..x0+2
+    float in[36];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int yy = y + r - 1, xx = x0 + c - 1;
+      for (int s = 0; s < 3; ++s) {
+        const int yy = y + r - 1, xx = x + s - 1;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(z4 + ((size_t)b * H + yy) * W + xx);
         // the reference divides first, then convolves: x = data / upper (modules.py:20)
-        in[r][c] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+        const int t = (r * 3 + s) * 4;
+        in[t] = v.x * inv; in[t + 1] = v.y * inv; in[t + 2] = v.z * inv; in[t + 3] = v.w * inv;
       }
-    const bool has1 = x0 + 1 < W;
-    const size_t pix0 = ((size_t)b * H + y) * W + x0;
     for (int g = 0; g < nf; g += 32) {
-      float a0[32], a1[32];
+      float acc[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a0[j] = a1[j] = sw[36 * nf + g + j];
+      for (int j = 0; j < 32; ++j) acc[j] = sw[36 * nf + g + j];
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int t = 0; t < 36; ++t) {
+        const float4* wv = reinterpret_cast<const float4*>(sw + t * nf + g);
+        const float xv = in[t];
 #pragma unroll
-        for (int sx = 0; sx < 3; ++sx) {
-          const float i0[4] = {in[r][sx].x, in[r][sx].y, in[r][sx].z, in[r][sx].w};
-          const float i1[4] = {in[r][sx + 1].x, in[r][sx + 1].y, in[r][sx + 1].z, in[r][sx + 1].w};
-#pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
-            const float4* wv = reinterpret_cast<const float4*>(sw + ((r * 3 + sx) * 4 + ci) * nf + g);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 ww = wv[q];
-              a0[q * 4 + 0] = fmaf(i0[ci], ww.x, a0[q * 4 + 0]); a1[q * 4 + 0] = fmaf(i1[ci], ww.x, a1[q * 4 + 0]);
-              a0[q * 4 + 1] = fmaf(i0[ci], ww.y, a0[q * 4 + 1]); a1[q * 4 + 1] = fmaf(i1[ci], ww.y, a1[q * 4 + 1]);
-              a0[q * 4 + 2] = fmaf(i0[ci], ww.z, a0[q * 4 + 2]); a1[q * 4 + 2] = fmaf(i1[ci], ww.z, a1[q * 4 + 2]);
-              a0[q * 4 + 3] = fmaf(i0[ci], ww.w, a0[q * 4 + 3]); a1[q * 4 + 3] = fmaf(i1[ci], ww.w, a1[q * 4 + 3]);
-            }
-          }
+        for (int q = 0; q < 8; ++q) {
+          const float4 ww = wv[q];
+          acc[q * 4 + 0] = fmaf(xv, ww.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(xv, ww.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(xv, ww.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(xv, ww.w, acc[q * 4 + 3]);
         }
+      }
 #pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        if (px == 1 && !has1) break;
-        float* acc = px ? a1 : a0;
+      for (int j = 0; j < 32; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * slope;
+      uint4* o = reinterpret_cast<uint4*>(out0 + pix * nf + g);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * slope;
-        uint4* o = reinterpret_cast<uint4*>(out0 + (pix0 + px) * nf + g);
+      for (int q = 0; q < 4; ++q)
+        o[q] = make_uint4(pack2(acc[q * 8], acc[q * 8 + 1]), pack2(acc[q * 8 + 2], acc[q * 8 + 3]),
+                          pack2(acc[q * 8 + 4], acc[q * 8 + 5]), pack2(acc[q * 8 + 6], acc[q * 8 + 7]));
+      if (out1) {
+        uint4* o1 = reinterpret_cast<uint4*>(out1 + pix * nf + g);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          o[q] = make_uint4(pack2(acc[q * 8], acc[q * 8 + 1]), pack2(acc[q * 8 + 2], acc[q * 8 + 3]),
-                            pack2(acc[q * 8 + 4], acc[q * 8 + 5]), pack2(acc[q * 8 + 6], acc[q * 8 + 7]));
-        if (out1) {
-          uint4* o1 = reinterpret_cast<uint4*>(out1 + (pix0 + px) * nf + g);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            o1[q] = make_uint4(pack2(silu_f(acc[q * 8]), silu_f(acc[q * 8 + 1])), pack2(silu_f(acc[q * 8 + 2]), silu_f(acc[q * 8 + 3])),
-                               pack2(silu_f(acc[q * 8 + 4]), silu_f(acc[q * 8 + 5])), pack2(silu_f(acc[q * 8 + 6]), silu_f(acc[q * 8 + 7])));
-        }
+          o1[q] = make_uint4(pack2(fsilu(acc[q * 8]), fsilu(acc[q * 8 + 1])), pack2(fsilu(acc[q * 8 + 2]), fsilu(acc[q * 8 + 3])),
+                             pack2(fsilu(acc[q * 8 + 4]), fsilu(acc[q * 8 + 5])), pack2(fsilu(acc[q * 8 + 6]), fsilu(acc[q * 8 + 7])));
       }
     }
   }
@@ -261,9 +249,9 @@ inline int cap_grid(size_t blocks) {
 
 int head_conv_launch(const float* z, const float* ub, const float* w, const float* bias, int B, int H, int W, int nf,
                      float slope, bf16* out0, bf16* out1, cudaStream_t s) {
-  const size_t npair = (size_t)B * H * ((W + 1) / 2);
+  const size_t npix = (size_t)B * H * W;
   const size_t smem = (size_t)(36 * nf + nf) * sizeof(float);
-  head_conv_kernel<<<cap_grid((npair + 127) / 128), 128, smem, s>>>(z, ub, w, bias, B, H, W, nf, slope, out0, out1);
+  head_conv_kernel<<<cap_grid((npix + 255) / 256), 256, smem, s>>>(z, ub, w, bias, B, H, W, nf, slope, out0, out1);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
