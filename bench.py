@@ -30,6 +30,8 @@ PIPE = {"data_type": "SIDD", "full_est": True, "est_type": "simple+full", "k": 2
 P0 = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
 N_IMAGES, N_BLOCKS, BLK = 40, 32, 256
 METRIC = "raw_MP_per_s_end_to_end_YOND_denoise"
+WORKLOAD = ("configs[1]: 1280 synthetic 256x256 Bayer blocks (40 images x 32), GuidedResUnet (GRU_5to50_norm_mix) random-init, "
+            "SIDD_simple+full_pre pipeline: self estimate + VST denoise + collab estimate per image")
 
 
 def synth_images(n_images, seed=2024):
@@ -133,8 +135,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SIDD-shaped synthetic 256x256 Bayer blocks, GuidedResUnet random-init, simple+full_pre pipeline (configs[1])",
-                       "sample": sample},
+            "config": {"workload": WORKLOAD, "sample": sample},
             "cpu_baseline": {"value": val, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                              "os_cpu_count": os.cpu_count(), "cv2_threads": cvt},
             "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -248,8 +249,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: 1280 synthetic 256x256 Bayer blocks (40 images x 32), GuidedResUnet (GRU_5to50_norm_mix) random-init, "
-                                   "SIDD_simple+full_pre pipeline: self estimate + VST denoise + collab estimate per image",
+            "config": {"workload": WORKLOAD,
                        "round2_denoise_images": int((rounds == 2).sum()) if rounds is not None else None,
                        "images_per_gpu": N_IMAGES, "blocks_per_image": N_BLOCKS, "block": [BLK, BLK],
                        "l2_policy": "inputs (335 MB per step) and activations exceed the 126 MB L2; no explicit flush",

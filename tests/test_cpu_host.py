@@ -147,10 +147,19 @@ def _gloo_worker(rank, world, port, q):
     from yond_public_b200.parallel import run_sharded
     units = torch.arange(7 * 6, dtype=torch.float32).reshape(7, 2, 3)  # 7 units: ragged shares (4 + 3)
     out = run_sharded(units, lambda u: u * 2 + 1, dst=0)
-    if rank == 0:
-        q.put(bool(torch.equal(out, units * 2 + 1)))
-    else:
-        q.put(out is None)
+    ok = bool(torch.equal(out, units * 2 + 1)) if rank == 0 else out is None
+    # tile-sharded frame: disjoint supports assembled by a SUM reduction
+    from yond_public_b200.parallel import gather_disjoint, shard_range
+    from yond_public_b200.pipeline import YondEngine
+    grid = YondEngine.tile_grid(96, 160, 64)  # 2 x 3 tiles, ragged last column
+    full = torch.arange(96 * 160 * 4, dtype=torch.float32).reshape(1, 96, 160, 4) + 1
+    part = torch.zeros_like(full)
+    a, b = shard_range(len(grid), rank, world)
+    for (y0, x0, ch, cw) in grid[a:b]:
+        part[:, y0:y0 + ch, x0:x0 + cw] = full[:, y0:y0 + ch, x0:x0 + cw]
+    got = gather_disjoint(part, dst=0)
+    ok = ok and (bool(torch.equal(got, full)) if rank == 0 else got is None)
+    q.put(ok)
     dist.destroy_process_group()
 
 

@@ -313,6 +313,46 @@ def test_batched_pipeline_equals_per_image(Y, lut_table):
         assert float(np.abs(res["raw_dns"][0][0].cpu().numpy() - ref["raw_dns"][0]).max()) < TOL_ABS
 
 
+def test_halo_tiling_equals_whole_frame(Y):
+    """Halo-overlapped tiling (128-px halo, origins on multiples of 16, global ub / t) reproduces the whole-frame forward
+    of the reference semantics; checked on a frame with ragged tile edges for both architectures."""
+    rng = np.random.default_rng(21)
+    H, W = 2 * 600, 2 * 840  # packed 600x840 -> padded 608x864
+    noisy = torch.from_numpy(O.synth_noisy(rng, O.synth_clean(rng, H, W), 4.0, 6.0)).cuda()
+    for key in ("gru", "unet"):
+        arch = ARCHS[key]
+        net = Y.build_net(arch)
+        net.load_state_dict(O.init_state_dict(arch, seed=5, weight_scale=3.0))  # scaled up so distant pixels matter
+        eng = Y.YondEngine(net, arch, Y.BiasLUT())
+        whole = eng.vst_denoise(noisy[None], [4.1], [6.2], 959.0)[0]
+        tiled = eng.vst_denoise_tiled(noisy, 4.1, 6.2, 959.0, core=256)
+        assert float((whole - tiled).abs().max()) < 1e-6, key
+
+
+def test_full_frame_12mp_vs_oracle(Y, lut_table):
+    """Config C3 geometry: a 4032x3024 frame (packed 1512x2016, reflect-padded to 1536x2016) through estimate + VST +
+    network + inverse, whole-frame and tiled, against the oracle's fp32 path."""
+    rng = np.random.default_rng(31)
+    H, W = 3024, 4032
+    clean = O.synth_clean_smooth(rng, H, W)
+    noisy = O.synth_noisy(rng, clean, 3.0, 5.0)
+    arch = ARCHS["gru"]
+    sd = O.init_state_dict(arch, seed=5)
+    pipe = dict(PIPE, full_dn=True, iter="once")
+    drv = Y.YOND_SIDD(arch, pipe, state_dict=sd)
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+    res = drv.IterDenoise({"lr": noisy, "name": "frame"}, {"p": dict(p), "img_id": 0})
+    ref = O.IterDenoise(arch, sd, noisy, dict(p), pipe, biaslut=O.BiasLUT(lut_table))
+    np.testing.assert_allclose(np.asarray(res["regs"][0]), np.asarray(ref["regs"][0]), rtol=TOL_EST)
+    out, refo = res["raw_dns"][0], ref["raw_dns"][0]
+    assert out.shape == (H, W)
+    assert float(np.abs(out - refo).max()) < TOL_ABS
+    assert abs(psnr(out, clean) - psnr(refo, clean)) < TOL_PSNR
+    reg = np.asarray(res["regs"][0])
+    tiled = drv.engine.vst_denoise_tiled(torch.from_numpy(noisy).cuda(), reg[0] * 959, np.sqrt(max(reg[1], 0)) * 959, 959.0, core=512)
+    assert float(np.abs(tiled.cpu().numpy() - out).max()) < 1e-6
+
+
 def test_full_frame_identity_roundtrip(Y):
     """Size-independent property at the 12 MP size (C3): with an identity network (zero weights, res=True) and
     bias_corr=None, VST -> normalise -> pad -> net -> crop -> de-normalise -> algebraic inverse is the identity."""

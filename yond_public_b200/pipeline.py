@@ -38,6 +38,7 @@ class YondEngine:
         self.chunk = chunk
         self._bufs = {}
         self._tables = {}
+        self.tile_batch = 4
 
     def _buf(self, name, shape, dtype, device):
         n = int(np.prod(shape))
@@ -168,6 +169,69 @@ class YondEngine:
                                         ptr(rows), ptr(xnodes), stride, st))
             self.net.forward_nhwc(z[:n], ub[:n], t[b0:b0 + n] if self.guided else None, out=y[:n])
             check(self.lib.yond_vst_inv(ptr(y[:n]), ptr(out[b0:b0 + n]), n, H, W, pl, pr, pt, pb, ptr(pch), int(clip01), st))
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # Halo-overlapped tiling of one full-resolution frame (new design; the reference forwards whole frames,
+    # YOND_SIDD.py:281-290).  The receptive field of the networks is 107 (UNetSeeInDark) / 123 (GuidedResUnet, SNRnet)
+    # packed pixels, so a 128-pixel halo with tile origins on multiples of 16 reproduces the whole-frame
+    # forward; the frame-global quantities (per-sample max `ub`, guidance `t`, VST constants) are computed on the whole
+    # frame BEFORE tiling and handed to every tile.
+    HALO = 128
+
+    @staticmethod
+    def tile_grid(hp, wp, core):
+        """Tile cores (y0, x0, ch, cw) covering the padded frame; `core` is a multiple of 16."""
+        assert core % 16 == 0
+        return [(y0, x0, min(core, hp - y0), min(core, wp - x0)) for y0 in range(0, hp, core) for x0 in range(0, wp, core)]
+
+    def net_forward_tiled(self, z, ub, t, core=512, tiles=None, y=None):
+        """z: (1,hp,wp,4) padded frame on device -> y (1,hp,wp,4).  Only `tiles` (default: all) are computed — a rank
+        of a tile-sharded run passes its own share and the cores are gathered afterwards."""
+        _, hp, wp, _ = z.shape
+        halo = self.HALO
+        grid = self.tile_grid(hp, wp, core)
+        tiles = list(range(len(grid))) if tiles is None else list(tiles)
+        if y is None:
+            y = torch.zeros_like(z)
+        th = tw = core + 2 * halo
+        st = stream_ptr()
+        tb = self.tile_batch
+        zt = self._buf("tile_in", (tb, th, tw, 4), torch.float32, z.device)
+        yt = self._buf("tile_out", (tb, th, tw, 4), torch.float32, z.device)
+        for i0 in range(0, len(tiles), tb):
+            part = tiles[i0:i0 + tb]
+            n = len(part)
+            for j, ti in enumerate(part):
+                y0, x0, _, _ = grid[ti]
+                check(self.lib.yond_tile_extract(ptr(z[0]), ptr(zt[j]), hp, wp, y0 - halo, x0 - halo, th, tw, st))
+            ubn = ub.expand(n).contiguous()
+            tn = t.expand(n).contiguous() if t is not None else None
+            self.net.forward_nhwc(zt[:n], ubn, tn, out=yt[:n])
+            for j, ti in enumerate(part):
+                y0, x0, ch, cw = grid[ti]
+                check(self.lib.yond_tile_insert(ptr(yt[j]), ptr(y[0]), hp, wp, y0 - halo, x0 - halo, th, tw, halo, halo, ch, cw, st))
+        return y
+
+    def vst_denoise_tiled(self, frame, gain, sigma, scale, bias_corr="pre", vst_type="exact", clip01=True, core=512,
+                          tiles=None, return_padded=False):
+        """VST_Denoiser on one full-resolution Bayer frame (H,W) with halo tiling of the network stage."""
+        H, W = frame.shape
+        dev = frame.device
+        h, w = H // 2, W // 2
+        pl, pr, pt, pb = isp.get_p2d((1, 4, h, w), base=32)
+        hp, wp = h + pt + pb, w + pl + pr
+        fmax = lambda: (frame.amax().clamp_min(0).reshape(1).cpu().numpy().astype(np.float32) * np.float32(scale))
+        params, rows, xnodes, stride, t = self.make_params([gain], [sigma], float(scale), bias_corr, vst_type, fmax, dev)
+        z = torch.empty((1, hp, wp, 4), device=dev, dtype=torch.float32)
+        ub = torch.empty(1, device=dev, dtype=torch.float32)
+        st = stream_ptr()
+        check(self.lib.yond_vst_fwd(ptr(frame), ptr(z), ptr(ub), 1, H, W, pl, pr, pt, pb, ptr(params), ptr(rows), ptr(xnodes), stride, st))
+        y = self.net_forward_tiled(z, ub, t if self.guided else None, core=core, tiles=tiles)
+        if return_padded:  # a rank of a sharded run returns its partial padded output for the gather
+            return y, (params, (pl, pr, pt, pb))
+        out = torch.empty_like(frame)
+        check(self.lib.yond_vst_inv(ptr(y), ptr(out), 1, H, W, pl, pr, pt, pb, ptr(params), int(clip01), st))
         return out
 
     def simple_denoise(self, bayer, out=None):
