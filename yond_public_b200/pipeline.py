@@ -187,30 +187,29 @@ class YondEngine:
 
     def net_forward_tiled(self, z, ub, t, core=512, tiles=None, y=None):
         """z: (1,hp,wp,4) padded frame on device -> y (1,hp,wp,4).  Only `tiles` (default: all) are computed — a rank
-        of a tile-sharded run passes its own share and the cores are gathered afterwards."""
+        of a tile-sharded run passes its own share and the cores are gathered afterwards.
+
+        A tile is its core plus a halo that is CUT at the frame border: the network zero-pads every feature map at the
+        true border, so nothing outside the frame may be fed to it (zeros at the input would become non-zero features
+        after the first bias).  Tiles therefore differ in shape and are forwarded one at a time (a 768x768 tile is as
+        much work as 36 SIDD blocks)."""
         _, hp, wp, _ = z.shape
         halo = self.HALO
         grid = self.tile_grid(hp, wp, core)
         tiles = list(range(len(grid))) if tiles is None else list(tiles)
         if y is None:
             y = torch.zeros_like(z)
-        th = tw = core + 2 * halo
         st = stream_ptr()
-        tb = self.tile_batch
-        zt = self._buf("tile_in", (tb, th, tw, 4), torch.float32, z.device)
-        yt = self._buf("tile_out", (tb, th, tw, 4), torch.float32, z.device)
-        for i0 in range(0, len(tiles), tb):
-            part = tiles[i0:i0 + tb]
-            n = len(part)
-            for j, ti in enumerate(part):
-                y0, x0, _, _ = grid[ti]
-                check(self.lib.yond_tile_extract(ptr(z[0]), ptr(zt[j]), hp, wp, y0 - halo, x0 - halo, th, tw, st))
-            ubn = ub.expand(n).contiguous()
-            tn = t.expand(n).contiguous() if t is not None else None
-            self.net.forward_nhwc(zt[:n], ubn, tn, out=yt[:n])
-            for j, ti in enumerate(part):
-                y0, x0, ch, cw = grid[ti]
-                check(self.lib.yond_tile_insert(ptr(yt[j]), ptr(y[0]), hp, wp, y0 - halo, x0 - halo, th, tw, halo, halo, ch, cw, st))
+        for ti in tiles:
+            y0, x0, ch, cw = grid[ti]
+            ty0, tx0 = max(0, y0 - halo), max(0, x0 - halo)
+            ty1, tx1 = min(hp, y0 + ch + halo), min(wp, x0 + cw + halo)
+            th, tw = ty1 - ty0, tx1 - tx0
+            zt = self._buf("tile_in", (1, th, tw, 4), torch.float32, z.device)
+            yt = self._buf("tile_out", (1, th, tw, 4), torch.float32, z.device)
+            check(self.lib.yond_tile_extract(ptr(z[0]), ptr(zt[0]), hp, wp, ty0, tx0, th, tw, st))
+            self.net.forward_nhwc(zt, ub, t, out=yt)
+            check(self.lib.yond_tile_insert(ptr(yt[0]), ptr(y[0]), hp, wp, ty0, tx0, th, tw, y0 - ty0, x0 - tx0, ch, cw, st))
         return y
 
     def vst_denoise_tiled(self, frame, gain, sigma, scale, bias_corr="pre", vst_type="exact", clip01=True, core=512,
