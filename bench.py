@@ -231,6 +231,14 @@ def run_b200(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     ach_tf = prof["conv_flops"] / (prof["conv_ms"] / 1e3) / 1e12 if prof["conv_ms"] > 0 else 0.0
 
+    traffic, traffic_note = None, None
+    try:  # ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the conv launches of one 256-block chunk
+        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_note = "profiles/r01_conv_traffic.json: mean DRAM bytes per conv_tc_kernel launch (ncu, cold cache, 256-block chunk)"
+    except Exception:
+        pass
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         lut = O.BiasLUT(drv.biaslut.bias_lut)
@@ -259,7 +267,11 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-                         "traffic": None, "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv stack)", "peak_source": peak_src + " bf16_tflops_sustained",
+                         "traffic": traffic, "traffic_note": traffic_note,
+                         "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv stack)",
+                         "flops_per_launch": prof["conv_flops"] / max(prof["launches"], 1),
+                         "ms_per_launch": prof["conv_ms"] / max(prof["launches"], 1),
+                         "share_of_step": (prof["conv_ms"] / args.steps) / (ms / args.steps), "peak_source": peak_src + " bf16_tflops_sustained",
                          "conv_ms_per_step": prof["conv_ms"] / args.steps, "conv_launches": prof["launches"],
                          "algorithmic_flops_per_step": prof["conv_flops"] / args.steps},
             "cpu_baseline": cpu_base,
