@@ -110,7 +110,7 @@ def test_blur_stdfilt_golden(Y, golden):
     np.testing.assert_allclose(Y.stdfilt(g["img"], 5), g["std5"], rtol=0, atol=5e-7)
 
 
-@pytest.mark.parametrize("n", [1000, 65537, 3_000_001])
+@pytest.mark.parametrize("n", [1000, 65536, 3_000_004])
 def test_order_stats_and_percentiles_exact(Y, n):
     from yond_public_b200.nlf import NlfEstimator
     rng = np.random.default_rng(n)
@@ -351,6 +351,20 @@ def test_full_frame_12mp_vs_oracle(Y, lut_table):
     reg = np.asarray(res["regs"][0])
     tiled = drv.engine.vst_denoise_tiled(torch.from_numpy(noisy).cuda(), reg[0] * 959, np.sqrt(max(reg[1], 0)) * 959, 959.0, core=512)
     assert float(np.abs(tiled.cpu().numpy() - out).max()) < 1e-6
+
+
+def test_host_pipelined_path_equals_batched(Y):
+    """iter_denoise_host (pinned host buffers, copies overlapped on side streams; bench.py's e2e) == iter_denoise_batch."""
+    rng = np.random.default_rng(13)
+    imgs = np.stack([np.stack([O.synth_noisy(rng, O.synth_clean_smooth(rng, 64, 64), 4.0, 6.0 + i) for _ in range(32)]) for i in range(5)])
+    drv = Y.YOND_SIDD(ARCHS["gru"], PIPE, state_dict=O.init_state_dict(ARCHS["gru"], seed=5))
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+    ref = drv.iter_denoise_batch(torch.from_numpy(imgs).cuda(), dict(p))
+    hin = torch.from_numpy(imgs).pin_memory()
+    hout = torch.empty((5, 64, 32 * 64)).pin_memory()
+    res = drv.iter_denoise_host(hin, hout, dict(p), group=2)
+    assert torch.equal(hout, ref["raw_dns"][-1].cpu())
+    assert np.array_equal(res["rounds"], ref["rounds"])
 
 
 def test_full_frame_identity_roundtrip(Y):

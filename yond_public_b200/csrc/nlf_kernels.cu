@@ -19,124 +19,97 @@ __device__ __forceinline__ float4 sq4(const float4& v) {
   return make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w));
 }
 
-// Vertical pass: one thread owns one pixel column (4 channels) of a strip of `rows_per_strip` output rows and
-// slides a k-tall window down it.  Writes float64 column sums of x (and of fl32(x*x) when S2 != nullptr).
-__global__ void __launch_bounds__(128) box_v_kernel(const float4* __restrict__ x, D4* __restrict__ S1, D4* __restrict__ S2,
-                                                    int h, int w, int k, int rows_per_strip, int square_input) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.z;
-  if (col >= w) return;
+// Fused box statistics: one kernel, no float64 scratch in HBM.
+// A block of 256 threads owns 256 consecutive columns (output columns + a halo of k/2 on each side) of a strip of rows.
+// Every thread slides a k-tall window down its column (float64 sums of x and of fl32(x*x), 4 channels).  For each row
+// the k-wide horizontal sums come from a block-wide inclusive prefix scan of the column sums (warp shuffles + one
+// shared-memory hop): window(c) = P[c+r] - P[c-r-1].  All sums are of float32 values in float64, i.e. exact, so the
+// result equals cv2.blur's float64 accumulation rounded to float32, whatever the summation order.
+enum { OP_MEAN = 0, OP_MEAN_STD = 1, OP_STD = 2 };
+constexpr int kBoxThreads = 256;
+template <bool kSq>
+__global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(const float4* __restrict__ x, float4* __restrict__ out0,
+                                                                float4* __restrict__ out1, int h, int w, int k, int op,
+                                                                int rows_per_strip) {
+  constexpr int NQ = kSq ? 8 : 4;
+  __shared__ double tot[kBoxThreads / 32][NQ];
+  __shared__ double P[NQ][kBoxThreads + 1];  // P[q][0] = 0, P[q][c+1] = inclusive prefix at thread c
   const int r = k / 2;
+  const int outc = kBoxThreads - 2 * r;
+  const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+  const int b = blockIdx.z;
+  const int col_out = blockIdx.x * outc + (c - r);          // image column this thread's window is centred on
+  const int col_src = reflect101(col_out, w);               // BORDER_REFLECT_101
   const int i0 = blockIdx.y * rows_per_strip;
   const int i1 = min(h, i0 + rows_per_strip);
   const float4* xb = x + (size_t)b * h * w;
-  D4 s1{0, 0, 0, 0}, s2{0, 0, 0, 0};
-  auto ld = [&](int i) {
-    float4 v = __ldg(xb + (size_t)reflect101(i, h) * w + col);
-    return square_input ? sq4(v) : v;
+  double s[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) s[q] = 0.0;
+  auto add = [&](int i, double sign) {
+    const float4 v = __ldg(xb + (size_t)reflect101(i, h) * w + col_src);
+    s[0] += sign * v.x; s[1] += sign * v.y; s[2] += sign * v.z; s[3] += sign * v.w;
+    if (kSq) {
+      const float4 q2 = sq4(v);
+      s[4] += sign * q2.x; s[5] += sign * q2.y; s[6] += sign * q2.z; s[7] += sign * q2.w;
+    }
   };
-  for (int i = i0 - r; i <= i0 + r; ++i) {
-    const float4 v = ld(i);
-    d4_add(s1, v);
-    if (S2) d4_add(s2, sq4(v));
+  for (int i = i0 - r; i <= i0 + r; ++i) add(i, 1.0);
+  if (c == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) P[q][0] = 0.0;
   }
-  for (int i = i0; i < i1; ++i) {
-    const size_t o = ((size_t)b * h + i) * w + col;
-    S1[o] = s1;
-    if (S2) S2[o] = s2;
-    if (i + 1 < i1) {
-      const float4 vn = ld(i + 1 + r), vo = ld(i - r);
-      d4_add(s1, vn);
-      d4_sub(s1, vo);
-      if (S2) {
-        d4_add(s2, sq4(vn));
-        d4_sub(s2, sq4(vo));
-      }
-    }
-  }
-}
-
-// Horizontal pass over the float64 column sums.  A block stages kHCols pixels (+halo) of kHRows rows in shared
-// memory; each thread owns kSeg consecutive pixels of one row: one k-wide window sum, then it slides (add the
-// entering column, subtract the leaving one — exact in float64 for sums of float32 values).  Rows are padded by one
-// element per kSeg so that the threads of a warp hit different banks.  Epilogue selected by `op`:
-//   OP_MEAN: out0 = mean | OP_MEAN_STD: out0 = mean, out1 = std = sqrt(max(m2 - mean^2, 0)) | OP_STD: out0 = std
-enum { OP_MEAN = 0, OP_MEAN_STD = 1, OP_STD = 2 };
-constexpr int kSeg = 8;
-constexpr int kHThreads = 64;
-constexpr int kHSpan = kHThreads * kSeg;                  // 512 pixels of output per block
-constexpr int kHStage = kHSpan + kMaxK - 1;               // + halo
-constexpr int kHPadded = kHStage + kHStage / kSeg + 1;    // one pad element every kSeg
-__device__ __forceinline__ int hpad(int i) { return i + i / kSeg; }
-__global__ void __launch_bounds__(kHThreads) box_h_kernel(const D4* __restrict__ S1, const D4* __restrict__ S2,
-                                                          float4* __restrict__ out0, float4* __restrict__ out1, int h, int w, int k,
-                                                          int op, int cols, int rows_per_block) {
-  __shared__ D4 t1[kHPadded];
-  __shared__ D4 t2[kHPadded];
-  const int r = k / 2;
-  const int b = blockIdx.z;
-  const int row0 = blockIdx.y * rows_per_block;
-  const int c0 = blockIdx.x * cols;                 // first output column of this block
-  const int stage_w = cols + 2 * r;                 // staged columns per row
-  // stage: rows_per_block rows x stage_w columns, row-major in the padded index space
-  for (int i = threadIdx.x; i < rows_per_block * stage_w; i += blockDim.x) {
-    const int rr = i / stage_w, cc = i - rr * stage_w;
-    const int row = row0 + rr;
-    if (row < h) {
-      const int c = reflect101(c0 + cc - r, w);
-      const size_t g = ((size_t)b * h + row) * w + c;
-      t1[hpad(i)] = S1[g];
-      if (S2) t2[hpad(i)] = S2[g];
-    }
-  }
-  __syncthreads();
-  const int segs_per_row = cols / kSeg;
-  const int rr = threadIdx.x / segs_per_row, sg = threadIdx.x - rr * segs_per_row;
-  const int row = row0 + rr;
-  if (rr >= rows_per_block || row >= h) return;
-  const int cfirst = c0 + sg * kSeg;
-  if (cfirst >= w) return;
-  const int base = rr * stage_w + sg * kSeg;        // staged index of the window start for the first pixel
   const double inv = 1.0 / ((double)k * (double)k);
-  D4 a{0, 0, 0, 0}, q{0, 0, 0, 0};
-  for (int j = 0; j < k; ++j) {
-    const D4 v = t1[hpad(base + j)];
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    if (S2) {
-      const D4 u = t2[hpad(base + j)];
-      q.x += u.x; q.y += u.y; q.z += u.z; q.w += u.w;
-    }
-  }
-  const size_t rbase = ((size_t)b * h + row) * w;
   // stdfilt (isp_algos.py:236-241): float32 square of the blurred image, float32 difference, sqrt; explicit
   // round-to-nearest mul/sub: an FMA contraction would skip the float32 rounding of mean^2 the reference has
   auto sd = [](float e2, float e1) { return sqrtf(fmaxf(__fsub_rn(e2, __fmul_rn(e1, e1)), 0.f)); };
+  const bool writer = (c >= r) && (c < r + outc) && (col_out < w);
+  for (int i = i0; i < i1; ++i) {
+    // inclusive scan of the column sums across the 256 threads
+    double p[NQ];
 #pragma unroll
-  for (int i = 0; i < kSeg; ++i) {
-    const int c = cfirst + i;
-    if (c < w) {
-      const float4 m = make_float4((float)(a.x * inv), (float)(a.y * inv), (float)(a.z * inv), (float)(a.w * inv));
-      if (op == OP_MEAN) {
-        out0[rbase + c] = m;
+    for (int q = 0; q < NQ; ++q) {
+      double v = s[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      p[q] = v;
+      if (lane == 31) tot[warp][q] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double off = 0.0;
+      for (int ww = 0; ww < warp; ++ww) off += tot[ww][q];
+      P[q][c + 1] = p[q] + off;
+    }
+    __syncthreads();
+    if (writer) {
+      double a[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) a[q] = P[q][c + r + 1] - P[q][c - r];
+      const size_t o = ((size_t)b * h + i) * w + col_out;
+      const float4 m = make_float4((float)(a[0] * inv), (float)(a[1] * inv), (float)(a[2] * inv), (float)(a[3] * inv));
+      if (!kSq || op == OP_MEAN) {
+        out0[o] = m;
       } else {
-        const float4 m2 = make_float4((float)(q.x * inv), (float)(q.y * inv), (float)(q.z * inv), (float)(q.w * inv));
+        const float4 m2 = make_float4((float)(a[4] * inv), (float)(a[5] * inv), (float)(a[6] * inv), (float)(a[7] * inv));
         const float4 st = make_float4(sd(m2.x, m.x), sd(m2.y, m.y), sd(m2.z, m.z), sd(m2.w, m.w));
         if (op == OP_MEAN_STD) {
-          out0[rbase + c] = m;
-          out1[rbase + c] = st;
+          out0[o] = m;
+          out1[o] = st;
         } else {
-          out0[rbase + c] = st;
+          out0[o] = st;
         }
       }
     }
-    if (i + 1 < kSeg) {  // slide the window one pixel to the right
-      const D4 vn = t1[hpad(base + i + k)], vo = t1[hpad(base + i)];
-      a.x += vn.x - vo.x; a.y += vn.y - vo.y; a.z += vn.z - vo.z; a.w += vn.w - vo.w;
-      if (S2) {
-        const D4 un = t2[hpad(base + i + k)], uo = t2[hpad(base + i)];
-        q.x += un.x - uo.x; q.y += un.y - uo.y; q.z += un.z - uo.z; q.w += un.w - uo.w;
-      }
+    if (i + 1 < i1) {
+      add(i + 1 + r, 1.0);
+      add(i - r, -1.0);
     }
+    // the next iteration's first __syncthreads orders these reads of P before its rewrite
   }
 }
 
@@ -182,8 +155,14 @@ __global__ void __launch_bounds__(256) hist0_kernel(const float* __restrict__ d,
   __shared__ unsigned int h[2048];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
   __syncthreads();
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    atomicAdd(&h[f2key(d[i]) >> 21], 1u);
+  const float4* d4 = reinterpret_cast<const float4*>(d);  // segments hold 4-channel pixels: n % 4 == 0, 16-byte aligned
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream_f4(d4 + i);
+    atomicAdd(&h[f2key(v.x) >> 21], 1u);
+    atomicAdd(&h[f2key(v.y) >> 21], 1u);
+    atomicAdd(&h[f2key(v.z) >> 21], 1u);
+    atomicAdd(&h[f2key(v.w) >> 21], 1u);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += blockDim.x)
     if (h[i]) atomicAdd(&wk->hist0[i], (unsigned long long)h[i]);
@@ -243,10 +222,16 @@ __global__ void __launch_bounds__(1024) select0_kernel(SelectWork* wk, const uns
 __global__ void __launch_bounds__(256) hist1_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
   d += (size_t)blockIdx.y * n;
   wk += blockIdx.y;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t k = f2key(d[i]);
-    const int s = wk->slot1_of_prefix[k >> 21];
-    if (s >= 0) atomicAdd(&wk->hist1[s][(k >> 10) & 2047u], 1ull);
+  const float4* d4 = reinterpret_cast<const float4*>(d);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream_f4(d4 + i);
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t k = f2key(e[j]);
+      const int s = wk->slot1_of_prefix[k >> 21];
+      if (s >= 0) atomicAdd(&wk->hist1[s][(k >> 10) & 2047u], 1ull);
+    }
   }
 }
 __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nranks) {
@@ -278,12 +263,18 @@ __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nrank
 __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
   d += (size_t)blockIdx.y * n;
   wk += blockIdx.y;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t k = f2key(d[i]);
-    const int s1 = wk->slot1_of_prefix[k >> 21];
-    if (s1 < 0) continue;
-    const int s2 = wk->slot2_of[s1][(k >> 10) & 2047u];
-    if (s2 >= 0) atomicAdd(&wk->hist2[s2][k & 1023u], 1ull);
+  const float4* d4 = reinterpret_cast<const float4*>(d);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream_f4(d4 + i);
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t k = f2key(e[j]);
+      const int s1 = wk->slot1_of_prefix[k >> 21];
+      if (s1 < 0) continue;
+      const int s2 = wk->slot2_of[s1][(k >> 10) & 2047u];
+      if (s2 >= 0) atomicAdd(&wk->hist2[s2][k & 1023u], 1ull);
+    }
   }
 }
 __global__ void __launch_bounds__(1024) select2_kernel(SelectWork* wk, int nranks, float* __restrict__ out) {
@@ -310,13 +301,20 @@ __global__ void __launch_bounds__(256) score3_kernel(const float* __restrict__ l
   for (int i = threadIdx.x; i < 1001; i += blockDim.x) smin[i] = 0x7fffffff;
   if (threadIdx.x < nth) sth[threadIdx.x] = ths[threadIdx.x];
   __syncthreads();
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const double l = (double)lap[i];
-    int j = 0;
-    while (j < nth && !(l <= sth[j])) ++j;  // ths ascending: first threshold that admits this pixel
-    if (j < nth) {
-      const int bin = (int)(fminf(fmaxf(mean[i], 0.f), 1.f) * 1000.f);
-      if (smin[bin] > j) atomicMin(&smin[bin], j);
+  const float4* l4 = reinterpret_cast<const float4*>(lap);
+  const float4* m4 = reinterpret_cast<const float4*>(mean);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 lv = ldg_stream_f4(l4 + i), mv = ldg_stream_f4(m4 + i);
+    const float le[4] = {lv.x, lv.y, lv.z, lv.w}, me[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double l = (double)le[e];
+      int j = 0;
+      while (j < nth && !(l <= sth[j])) ++j;  // ths ascending: first threshold that admits this pixel
+      if (j < nth) {
+        const int bin = (int)__fmul_rn(fminf(fmaxf(me[e], 0.f), 1.f), 1000.f);
+        if (smin[bin] > j) atomicMin(&smin[bin], j);
+      }
     }
   }
   __syncthreads();
@@ -359,13 +357,21 @@ __global__ void __launch_bounds__(256) masked_sums_kernel(const float* __restric
   double s[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) s[i] = 0.0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    if ((double)lap[i] < th) {
-      const float xf = mean[i];
-      const double x = xf, y = var[i];
-      s[0] += 1.0; s[1] += x; s[2] += y; s[3] += x * x; s[4] += x * y; s[5] += y * y;
-      if (xf > 1e-4f && xf < 0.8f) {
-        s[6] += 1.0; s[7] += x; s[8] += y; s[9] += x * x; s[10] += x * y; s[11] += y * y;
+  const float4* l4 = reinterpret_cast<const float4*>(lap);
+  const float4* m4 = reinterpret_cast<const float4*>(mean);
+  const float4* v4 = reinterpret_cast<const float4*>(var);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 lv = ldg_stream_f4(l4 + i), mv = ldg_stream_f4(m4 + i), vv = ldg_stream_f4(v4 + i);
+    const float le[4] = {lv.x, lv.y, lv.z, lv.w}, me[4] = {mv.x, mv.y, mv.z, mv.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if ((double)le[e] < th) {
+        const float xf = me[e];
+        const double x = xf, y = ve[e];
+        s[0] += 1.0; s[1] += x; s[2] += y; s[3] += x * x; s[4] += x * y; s[5] += y * y;
+        if (xf > 1e-4f && xf < 0.8f) {
+          s[6] += 1.0; s[7] += x; s[8] += y; s[9] += x * x; s[10] += x * y; s[11] += y * y;
+        }
       }
     }
   }
@@ -385,27 +391,24 @@ __global__ void __launch_bounds__(256) masked_sums_kernel(const float* __restric
 }
 
 inline int stream_grid(size_t n) {
-  size_t g = (n + 256 * 8 - 1) / (256 * 8);
+  size_t g = (n + 256 * 16 - 1) / (256 * 16);
   const size_t cap = (size_t)yond_num_sms() * 8;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
 int box_pass(const float* x, float* out0, float* out1, int B, int h, int w, int k, int square_input, bool with_sq, int op,
              void* work, cudaStream_t s) {
-  const size_t npix = (size_t)B * h * w;
-  D4* S1 = reinterpret_cast<D4*>(work);
-  D4* S2 = with_sq ? S1 + npix : nullptr;
+  (void)work;
+  (void)square_input;
+  const int outc = kBoxThreads - 2 * (k / 2);
   const int rows_per_strip = 64;
-  dim3 gv(ceil_div(w, 128), ceil_div(h, rows_per_strip), B);
-  box_v_kernel<<<gv, 128, 0, s>>>(reinterpret_cast<const float4*>(x), S1, S2, h, w, k, rows_per_strip, square_input);
-  YOND_LAUNCH_CHECK();
-  // block = `cols` output columns (multiple of kSeg, <= kHSpan) x as many rows as fit in kHThreads threads
-  int cols = ceil_div(w, kSeg) * kSeg;
-  if (cols > kHSpan) cols = kHSpan;
-  int rpb = kHThreads / (cols / kSeg);
-  while (rpb > 1 && rpb * (cols + k - 1) > kHStage) --rpb;
-  dim3 gh(ceil_div(w, cols), ceil_div(h, rpb), B);
-  box_h_kernel<<<gh, kHThreads, 0, s>>>(S1, S2, reinterpret_cast<float4*>(out0), reinterpret_cast<float4*>(out1), h, w, k, op, cols, rpb);
+  dim3 g(ceil_div(w, outc), ceil_div(h, rows_per_strip), B);
+  if (with_sq)
+    box_fused_kernel<true><<<g, kBoxThreads, 0, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out0),
+                                                    reinterpret_cast<float4*>(out1), h, w, k, op, rows_per_strip);
+  else
+    box_fused_kernel<false><<<g, kBoxThreads, 0, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out0),
+                                                     reinterpret_cast<float4*>(out1), h, w, k, OP_MEAN, rows_per_strip);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
@@ -417,15 +420,16 @@ extern "C" {
 size_t yond_nlf_work_bytes(int B, int h, int w, int C) {
   (void)C;
   const size_t npix = (size_t)B * h * w;
-  // two float64x4 column-sum planes + two float32x4 temporaries (blur_k2(x), std of the second input)
-  return 2 * npix * sizeof(D4) + 2 * npix * sizeof(float4) + 4096;
+  // two float32x4 temporaries (blur_k2(x) / std of the first input)
+  return 2 * npix * sizeof(float4) + 4096;
 }
 
 int yond_box_blur(const float* x, float* out, int B, int h, int w, int C, int k, int square_input, void* work, void* stream) {
   YOND_REQUIRE(C == 4, "yond_box_blur: packed 4-channel frames only (pass SIDD block stacks as a batch)");
   YOND_REQUIRE(k % 2 == 1 && k >= 1 && k <= kMaxK, "yond_box_blur: odd k <= %d required (got %d)", kMaxK, k);
   YOND_REQUIRE(h > k / 2 && w > k / 2, "yond_box_blur: frame smaller than the filter radius");
-  return box_pass(x, out, nullptr, B, h, w, k, square_input, false, OP_MEAN, work, (cudaStream_t)stream);
+  YOND_REQUIRE(square_input == 0, "yond_box_blur: square_input is not supported");
+  return box_pass(x, out, nullptr, B, h, w, k, 0, false, OP_MEAN, work, (cudaStream_t)stream);
 }
 
 int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float* lap, int B, int h, int w, int C, int k,
@@ -437,7 +441,7 @@ int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float
   cudaStream_t s = (cudaStream_t)stream;
   const size_t npix = (size_t)B * h * w, n = npix * 4;
   uint8_t* wb = reinterpret_cast<uint8_t*>(work);
-  float* tmpA = reinterpret_cast<float*>(wb + 2 * npix * sizeof(D4));
+  float* tmpA = reinterpret_cast<float*>(wb);
   float* tmpB = tmpA + n;
   int rc;
   if (mode == 0) {
@@ -465,6 +469,7 @@ int yond_order_stats(const float* data, size_t seg_len, int nseg, const uint64_t
                      void* work, void* stream) {
   YOND_REQUIRE(nranks > 0 && nranks <= kMaxRanks, "yond_order_stats: 1..%d ranks (got %d)", kMaxRanks, nranks);
   YOND_REQUIRE(seg_len > 0 && nseg > 0 && nseg <= 65535, "yond_order_stats: empty input");
+  YOND_REQUIRE(seg_len % 4 == 0 && (uintptr_t)data % 16 == 0, "yond_order_stats: segments must hold whole 4-channel pixels (16-byte aligned)");
   cudaStream_t s = (cudaStream_t)stream;
   SelectWork* wk = reinterpret_cast<SelectWork*>(work);
   for (int i = 0; i < nseg; ++i)
@@ -490,6 +495,7 @@ int yond_score3_bins(const float* lap, const float* mean, size_t seg_len, int ns
                      int32_t* npeaks_dev, void* work, void* stream) {
   YOND_REQUIRE(nth > 0 && nth <= 32, "yond_score3_bins: 1..32 thresholds (got %d)", nth);
   YOND_REQUIRE(nseg > 0 && nseg <= 65535, "yond_score3_bins: bad segment count");
+  YOND_REQUIRE(seg_len % 4 == 0 && (uintptr_t)lap % 16 == 0 && (uintptr_t)mean % 16 == 0, "yond_score3_bins: 4-channel pixel segments required");
   cudaStream_t s = (cudaStream_t)stream;
   int* minj = reinterpret_cast<int*>(work);
   fill_int_kernel<<<ceil_div(1001 * nseg, 256), 256, 0, s>>>(minj, 1001 * nseg, 0x7fffffff);
@@ -506,6 +512,7 @@ int yond_score3_bins(const float* lap, const float* mean, size_t seg_len, int ns
 int yond_masked_sums(const float* lap, const float* mean, const float* var, size_t seg_len, int nseg, const double* ths_dev,
                      double* sums_dev, void* stream) {
   YOND_REQUIRE(nseg > 0 && nseg <= 65535, "yond_masked_sums: bad segment count");
+  YOND_REQUIRE(seg_len % 4 == 0, "yond_masked_sums: 4-channel pixel segments required");
   cudaStream_t s = (cudaStream_t)stream;
   YOND_CUDA_CHECK(cudaMemsetAsync(sums_dev, 0, (size_t)nseg * 12 * sizeof(double), s));
   dim3 g(stream_grid(seg_len), nseg);

@@ -393,6 +393,60 @@ class YOND_SIDD:
                 mark("denoise_round2")
         return {"raw_dns": [dn1, final], "regs": regs, "rounds": rounds, "lr_raw": mosaic}
 
+    def iter_denoise_host(self, host_in, host_out, p, group=8):
+        """End-to-end batched IterDenoise on HOST buffers: host_in (nimg,nblk,H,W) f32 pinned -> host_out
+        (nimg,H,nblk*W) f32 pinned (final round of every image).  Images are processed in groups; the H2D copy of the next
+        group and the D2H copy of the previous one run on their own streams while the current group computes
+        (double-buffered device staging, event-ordered)."""
+        assert host_in.is_pinned() and host_out.is_pinned(), "pinned host buffers required for asynchronous copies"
+        nimg = host_in.shape[0]
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_io"):
+            self._io = dict(s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), bufs={})
+        s_in, s_out = self._io["s_in"], self._io["s_out"]
+        key = (tuple(host_in.shape[1:]), group)
+        if key not in self._io["bufs"]:
+            self._io["bufs"] = {key: ([torch.empty((group,) + tuple(host_in.shape[1:]), device=dev) for _ in range(2)],
+                                      [torch.empty((group,) + tuple(host_out.shape[1:]), device=dev) for _ in range(2)])}
+        din, dout = self._io["bufs"][key]
+        groups = [(a, min(a + group, nimg)) for a in range(0, nimg, group)]
+        in_ready, comp_done, out_done = {}, {}, {}
+
+        def stage_in(g):
+            a, b = groups[g]
+            if g >= 2:
+                s_in.wait_event(comp_done[g - 2])  # the staging buffer is free once group g-2 has been consumed
+            else:
+                s_in.wait_stream(cur)
+            with torch.cuda.stream(s_in):
+                din[g % 2][:b - a].copy_(host_in[a:b], non_blocking=True)
+                in_ready[g] = torch.cuda.Event()
+                in_ready[g].record(s_in)
+
+        regs, rounds = [], []
+        stage_in(0)
+        for g, (a, b) in enumerate(groups):
+            if g + 1 < len(groups):
+                stage_in(g + 1)
+            cur.wait_event(in_ready[g])
+            if g >= 2:
+                cur.wait_event(out_done[g - 2])
+            res = self.iter_denoise_batch(din[g % 2][:b - a], dict(p))
+            dout[g % 2][:b - a].copy_(res["raw_dns"][-1])
+            comp_done[g] = torch.cuda.Event()
+            comp_done[g].record(cur)
+            s_out.wait_event(comp_done[g])
+            with torch.cuda.stream(s_out):
+                host_out[a:b].copy_(dout[g % 2][:b - a], non_blocking=True)
+                out_done[g] = torch.cuda.Event()
+                out_done[g].record(s_out)
+            regs.append(res["regs"])
+            rounds.append(res["rounds"])
+        cur.wait_stream(s_out)
+        torch.cuda.synchronize(dev)
+        return {"regs": regs, "rounds": np.concatenate(rounds)}
+
     def iter_denoise_device(self, blocks, p, lr_full=None):
         """Device-resident IterDenoise.  `blocks`: (nblk,H,W) CUDA f32 (SIDD layout) or (H,W) frame.
         Returns CUDA tensors in the reference's mosaic layout: (H, nblk*W)."""
