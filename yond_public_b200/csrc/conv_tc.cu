@@ -23,7 +23,8 @@
 
 namespace {
 
-constexpr int kThreads = 320;  // 2 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 16;                 // four per TMEM lane quarter, splitting the column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // 2 control warps + the epilogue warps
 constexpr int kMaxStagesA = 8;
 constexpr int kMaxStagesB = 8;
 constexpr int kMaxT = 4;
@@ -96,6 +97,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Copies a kernel parameter into a register the compiler cannot rematerialise from the constant bank: inside the MMA
+// issue loop every re-load of a parameter (LDCU) sits on the critical path of the next tcgen05.mma.
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
 // One lane of a converged warp (elect.sync); returns 1 on the elected lane.
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred = 0;
@@ -142,6 +150,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// Same MMA with the two shared-memory descriptors given as (low, high) 32-bit halves and packed inside the asm
+// block: the running low words are then plain 32-bit uniform adds (no 64-bit carry chains between MMAs).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// A operand in TMEM (lanes = rows, 8 columns per K=16 step), B from shared memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -198,7 +228,14 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(h);
 }
 
-__device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU(v) = v * sigmoid(v) = 0.5 v (1 + tanh(v / 2)): one MUFU (tanh.approx, ~2^-11 relative) instead of exp + rcp;
+// the result is stored as bf16 (2^-9), so the approximation is below the storage rounding.
+__device__ __forceinline__ float fast_silu(float v) {
+  float t;
+  const float h = 0.5f * v;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 struct TcParams;
 // Epilogue of NC accumulator columns of one GEMM row: bias, FiLM scale/shift, activation, residual, bf16 stores.
@@ -281,6 +318,53 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
   t.b0 = tb_i * p.NB * (p.t_along_h ? 1 : p.T);
   t.n0 = t.n_idx * p.NT;
   return t;
+}
+
+// All MMAs of one tap (weight tile): TT sub-tile accumulators x KS steps of K=16, fully unrolled so that every
+// descriptor is `running low word + immediate` (two uniform adds per MMA; the B200 tensor pipe retires an
+// M=128,N=32 SS MMA every 40 cycles, N=64 every 48, N=128 every 64 — tools/mma_rate.cu — so the issue stream must
+// stay well below that).
+// MMA + in-place advance of both descriptor low words by one K=16 step (32 bytes = 2 units of 16 B).
+__device__ __forceinline__ void umma_step(uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t& b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%0, %2};\n\t"
+      "mov.b64 db, {%1, %3};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%4], da, db, %5, p;\n\t"
+      "add.u32 %0, %0, 2;\n\t"
+      "add.u32 %1, %1, 2;\n\t}"
+      : "+r"(a_lo), "+r"(b_lo)
+      : "r"(a_hi), "r"(b_hi), "r"(tmem_d), "r"(idesc), "r"(accum)
+      : "memory");
+}
+template <int KS, int TT>
+__device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t nt, uint32_t a_lo0, uint32_t sub_step, uint32_t b_lo0,
+                                          uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t accum) {
+  uint32_t al = a_lo0, dt = d_tmem;
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    uint32_t bl = b_lo0;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) umma_step(dt, al, a_hi, bl, b_hi, idesc, k ? 1u : accum);
+    al += sub_step - 2u * KS;  // next sub-tile, back to K step 0
+    dt += nt;
+  }
+}
+
+// All nine taps of one halo slab as straight-line code (resident weights): the only run-time inputs are a handful of
+// uniform bases and strides, everything else is an immediate.
+template <int KS, int TT>
+__device__ __forceinline__ void issue_slab_resident(uint32_t d_tmem, uint32_t nt, uint32_t a_stage_lo, uint32_t tap_r16, uint32_t px16,
+                                                    uint32_t sub_step, uint32_t b_lo_first, uint32_t b_step16, uint32_t a_hi,
+                                                    uint32_t b_hi, uint32_t idesc, uint32_t first_accum) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int sx = 0; sx < 3; ++sx)
+      issue_tap<KS, TT>(d_tmem, nt, a_stage_lo + (uint32_t)r * tap_r16 + (uint32_t)sx * px16, sub_step,
+                        b_lo_first + (uint32_t)(r * 3 + sx) * b_step16, a_hi, b_hi, idesc, (r | sx) ? 1u : first_accum);
 }
 
 template <int NC>
@@ -382,7 +466,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kEpiWarps); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -420,8 +504,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         mbar_wait(a_empty + 8 * sa, pa ^ 1);
         t_wait += clock64() - tw0;
         if (is_leader) {
-          mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
-          tma_load_4d(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full + 8 * sa, s.c, tc.w0 + s.dw, tc.b0, tc.h0 + s.dh);
+          if (p.dbg & 16) {  // bring-up: no activation loads (MMA-rate experiment; results are garbage)
+            mbar_arrive(a_full + 8 * sa);
+          } else {
+            mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
+            tma_load_4d(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full + 8 * sa, s.c, tc.w0 + s.dw, tc.b0, tc.h0 + s.dh);
+          }
         }
         __syncwarp();
         if (++sa == p.SA) { sa = 0; pa ^= 1; }
@@ -443,8 +531,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       printf("[conv dbg] producer: total %lld cyc, waiting for a free A stage %lld cyc\n", clock64() - t_begin, t_wait);
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The whole warp stays converged (so every value below is warp-uniform and lives in uniform registers);
-    // one elected lane issues the tcgen05 instructions.  Descriptors are (constant high word, running low word).
+    // The whole warp stays converged and ONE elected lane issues the tcgen05 instructions.  tcgen05.mma takes its
+    // descriptors from UNIFORM registers, so every value on the issue path must be provably warp-uniform for the
+    // compiler: values read through inline asm / shared memory (TMEM base, smem base) are laundered through a
+    // warp reduction (REDUX writes a uniform register), loop state is only updated in converged code, and the elected
+    // region derives everything from that state.  Otherwise each tap pays ~9 R2UR moves (~375 cycles, measured)
+    // — far more than its MMAs (40/48/64 cycles each for N = 32/64/128, tools/mma_rate.cu).
+    const uint32_t u_tmem = __reduce_max_sync(0xffffffffu, tmem_base);
+    const uint32_t u_smem_a = __reduce_max_sync(0xffffffffu, smem_a);
+    const uint32_t u_smem_b = __reduce_max_sync(0xffffffffu, smem_b);
+    const uint32_t u_bars = __reduce_max_sync(0xffffffffu, bars);
+    const uint32_t ua_full = u_bars, ua_empty = ua_full + 8 * kMaxStagesA;
+    const uint32_t ub_full = ua_empty + 8 * kMaxStagesA, ub_empty = ub_full + 8 * kMaxStagesB;
+    const uint32_t uacc_full = ub_empty + 8 * kMaxStagesB, uacc_empty = uacc_full + 16;
+    const uint32_t uw_full = uacc_empty + 16;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
     const int ksteps = p.CB / 16;
     const uint32_t layout = (row_bytes == 128) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
@@ -453,88 +553,109 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const uint32_t b_hi = (((8u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
     const uint32_t lo_flags = 1u << 16;  // leading byte offset field (ignored for swizzled K-major operands)
     const uint32_t sub_step = p.sub_off >> 4;
-    const uint32_t is_leader = elect_one();
-    if (p.wres) mbar_wait(w_full, 0);
+    const uint32_t tap_r16 = p.tap_r_off >> 4, px16 = row_bytes >> 4;
+    const uint32_t nt = (uint32_t)p.NT;
+    const bool leader = elect_one() != 0;
+    if (p.wres) mbar_wait(uw_full, 0);
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-    long long t_acc = 0, t_a = 0, t_b = 0, t_begin = clock64();
+    long long t_acc = 0, t_a = 0, t_issue = 0, t_begin = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       long long tw0 = clock64();
-      mbar_wait(acc_empty + 8 * as, pacc ^ 1);
+      mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
       t_acc += clock64() - tw0;
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.T * p.NT);
-      uint32_t accum = 0;
+      const uint32_t d_tmem = u_tmem + (uint32_t)(as * p.T) * nt;
       for (int ai = 0; ai < n_ast; ++ai) {
         const AStage s = decode_astage(p, ai);
         tw0 = clock64();
-        mbar_wait(a_full + 8 * sa, pa);
+        mbar_wait(ua_full + 8 * sa, pa);
         t_a += clock64() - tw0;
         tc_fence_after();
-        const uint32_t a_base = smem_a + sa * p.a_stage_bytes;
-        for (int j = 0; j < s.ntaps; ++j) {
-          int r = 0, sx = 0, widx = s.widx0 + j;
-          if (p.mode == CONV_3X3_S1) {
-            if (s.sx >= 0) { r = j; widx = s.widx0 + j * 3; }       // three-slab mode: the stage fixes sx
-            else { r = j / 3; sx = j - r * 3; }                    // single slab: all nine taps
-          }
-          uint32_t b_base;
-          if (p.wres) {
-            b_base = smem_b + (uint32_t)widx * p.b_stage_bytes;
+        const uint32_t a_stage_lo = (((u_smem_a + (uint32_t)sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+        const long long ti0 = clock64();
+        if (leader && p.wres && p.slab && p.mode == CONV_3X3_S1 && !(p.dbg & 32)) {
+          // resident weights, single slab: 9 taps x T sub-tiles x K steps as one straight-line burst
+          const uint32_t b_first = (((u_smem_b + (uint32_t)s.widx0 * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+          const uint32_t b_step16 = p.b_stage_bytes >> 4;
+          const uint32_t acc0 = ai ? 1u : 0u;
+          if (ksteps == 4) {
+            if (p.T == 1) issue_slab_resident<4, 1>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else if (p.T == 2) issue_slab_resident<4, 2>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else issue_slab_resident<4, 4>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
           } else {
-            tw0 = clock64();
-            mbar_wait(b_full + 8 * sb, pb);
-            t_b += clock64() - tw0;
-            tc_fence_after();
-            b_base = smem_b + sb * p.b_stage_bytes;
+            if (p.T == 1) issue_slab_resident<2, 1>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else if (p.T == 2) issue_slab_resident<2, 2>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else issue_slab_resident<2, 4>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
           }
-          const uint32_t a_lo0 = (((a_base + (uint32_t)r * p.tap_r_off + (uint32_t)sx * row_bytes) & 0x3FFFFu) >> 4) | lo_flags;
-          const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | lo_flags;
-          if (is_leader) {
-            for (int t = 0; t < p.T; ++t) {
-              const uint32_t dt = d_tmem + (uint32_t)(t * p.NT);
-              uint32_t a_lo = a_lo0 + t * sub_step, b_lo = b_lo0;
-              umma_bf16(dt, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, accum);
-              for (int k = 1; k < ksteps; ++k) {
-                a_lo += 2;  // +32 bytes along K inside the swizzle row
-                b_lo += 2;
-                umma_bf16(dt, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, 1u);
+          umma_commit(ua_empty + 8 * sa);
+        } else if (leader) {
+          int lsb = sb, lpb = pb;  // weight-ring position of this stage's first tap (uniform on entry)
+          for (int j = 0; j < s.ntaps; ++j) {
+            uint32_t r = 0, sx = 0, widx = (uint32_t)(s.widx0 + j);
+            if (p.mode == CONV_3X3_S1) {
+              if (s.sx >= 0) { r = j; widx = (uint32_t)(s.widx0 + j * 3); }   // three-slab mode: the stage fixes sx
+              else { r = (j >= 3) + (j >= 6); sx = j - r * 3; }             // single slab: all nine taps
+            }
+            uint32_t b_base;
+            if (p.wres) {
+              b_base = u_smem_b + widx * p.b_stage_bytes;
+            } else {
+              mbar_wait(ub_full + 8 * lsb, lpb);
+              tc_fence_after();
+              b_base = u_smem_b + (uint32_t)lsb * p.b_stage_bytes;
+            }
+            const uint32_t a_lo0 = a_stage_lo + r * tap_r16 + sx * px16;
+            const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | lo_flags;
+            const uint32_t accum = (ai | j) ? 1u : 0u;
+            if (!(p.dbg & 32)) {  // dbg 32: no MMAs (TMA-rate experiment)
+              if (ksteps == 4) {
+                if (p.T == 1) issue_tap<4, 1>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+                else if (p.T == 2) issue_tap<4, 2>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+                else issue_tap<4, 4>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+              } else {
+                if (p.T == 1) issue_tap<2, 1>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+                else if (p.T == 2) issue_tap<2, 2>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+                else issue_tap<2, 4>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
               }
             }
-            if (!p.wres) umma_commit(b_empty + 8 * sb);
+            if (!p.wres) {
+              umma_commit(ub_empty + 8 * lsb);
+              if (++lsb == p.SB) { lsb = 0; lpb ^= 1; }
+            }
           }
-          __syncwarp();
-          accum = 1;
-          if (!p.wres) {
-            if (++sb == p.SB) { sb = 0; pb ^= 1; }
-          }
+          umma_commit(ua_empty + 8 * sa);
         }
-        if (is_leader) umma_commit(a_empty + 8 * sa);
         __syncwarp();
+        t_issue += clock64() - ti0;
+        if (!p.wres) {  // advance the weight ring by this stage's taps, in converged code
+          sb += s.ntaps;
+          while (sb >= p.SB) { sb -= p.SB; pb ^= 1; }
+        }
         if (++sa == p.SA) { sa = 0; pa ^= 1; }
       }
-      if (is_leader) umma_commit(acc_full + 8 * as);
+      if (leader) umma_commit(uacc_full + 8 * as);
       __syncwarp();
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
-    if ((p.dbg & 8) && blockIdx.x == 0 && is_leader)
-      printf("[conv dbg] issuer: total %lld cyc; waiting: accumulator %lld, activations %lld, weights %lld; tiles %d, A stages/tile %d, SA %d SB %d T %d NT %d\n",
-             clock64() - t_begin, t_acc, t_a, t_b, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
+    if ((p.dbg & 8) && blockIdx.x == 0 && leader)
+      printf("[conv dbg] issuer: total %lld cyc; issue regions %lld; waiting: accumulator %lld, activations %lld; tiles %d, A stages/tile %d, SA %d SB %d T %d NT %d\n",
+             clock64() - t_begin, t_issue, t_acc, t_a, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..2+kEpiWarps) =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // two warps share a quarter and split the column chunks
+    const int part = (warp - 2) >> 2;  // kEpiWarps/4 warps share a quarter and split the column chunks
     const int row = q * 32 + lane;     // GEMM row inside a sub-tile
     const int w_i = row % p.TW;
     const int g_i = row / p.TW;        // (h, b) index inside the sub-tile, h-major
-    // column chunks of 32 (16 when N = 32, so that both warps of a quarter have work)
-    const int cw = p.NT == 32 ? 16 : 32;
+    // column chunks of 16 accumulator columns (keeps the per-thread register footprint small with 18 warps resident)
+    constexpr int cw = 16;
     const int nchunk = p.NT / cw;
     int as = 0, pacc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       mbar_wait(acc_full + 8 * as, pacc);
       tc_fence_after();
-      for (int ci = half; ci < p.T * nchunk; ci += 2) {
+      for (int ci = part; ci < p.T * nchunk && !(p.dbg & 128); ci += kEpiWarps / 4) {  // dbg 128: the epilogue does not touch TMEM
         const int t = ci / nchunk, c = (ci - t * nchunk) * cw;
         int h = tc.h0 + g_i / p.NB, b = tc.b0 + g_i % p.NB;
         if (p.t_along_h) h += t * p.TH; else b += t * p.NB;
@@ -554,8 +675,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         const size_t off = pix * p.Cout + co;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.T + t) * p.NT + c);
-        if (cw == 16) epilogue_chunk<16>(p, taddr, valid, b, co, off);
-        else epilogue_chunk<32>(p, taddr, valid, b, co, off);
+        epilogue_chunk<cw>(p, taddr, valid, b, co, off);
       }
       tc_fence_before();
       __syncwarp();
@@ -744,6 +864,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.smem_bar_off = (uint32_t)align_up(p.smem_b_off + b_region, 1024);
   const size_t smem_bytes = p.smem_bar_off + 512 + 1024;  // barriers + alignment slack
   p.tmem_cols = 2 * p.T * p.NT < 32 ? 32 : 2 * p.T * p.NT;
+  if ((env_dbg & 64) && p.tmem_cols <= 256) p.tmem_cols = 512;
   YOND_REQUIRE(p.tmem_cols <= 512, "conv_tc: TMEM budget exceeded");
 
   p.dbg = env_dbg;
