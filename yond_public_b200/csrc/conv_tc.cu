@@ -588,6 +588,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             else issue_slab_resident<2, 4>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
           }
           umma_commit(ua_empty + 8 * sa);
+        } else if (leader && p.wres && p.mode != CONV_3X3_S1 && !(p.dbg & 32)) {
+          // resident weights, one tap per stage (stride-2 / 1x1 / transposed): one straight-line burst
+          const uint32_t b_lo0 = (((u_smem_b + (uint32_t)s.widx0 * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+          const uint32_t acc0 = ai ? 1u : 0u;
+          if (ksteps == 4) {
+            if (p.T == 1) issue_tap<4, 1>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
+            else if (p.T == 2) issue_tap<4, 2>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
+            else issue_tap<4, 4>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
+          } else {
+            if (p.T == 1) issue_tap<2, 1>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
+            else if (p.T == 2) issue_tap<2, 2>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
+            else issue_tap<2, 4>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
+          }
+          umma_commit(ua_empty + 8 * sa);
         } else if (leader) {
           int lsb = sb, lpb = pb;  // weight-ring position of this stage's first tap (uniform on entry)
           for (int j = 0; j < s.ntaps; ++j) {
@@ -825,12 +839,13 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   }
   // T sub-tiles share each weight tile (and one halo slab): stacked along H when the map is tall enough, else one
   // image each.  T is bounded by TMEM (2 accumulator stages x T x NT columns <= 512) and by shared memory.
+  // Stride-2 / 1x1 / transposed layers stack their sub-tiles along H only (a taller box of whole 128-row tiles).
   int T = 1;
-  if (conv3 && p.NB == 1) {
+  if (p.NB == 1) {
     int tmax = 512 / (2 * p.NT);
     if (tmax > env_T) tmax = env_T;
     if (tmax > kMaxT) tmax = kMaxT;
-    while (T * 2 <= tmax && (p.H >= p.TH * T * 2 || p.B >= T * 2)) T *= 2;
+    while (T * 2 <= tmax && (p.H >= p.TH * T * 2 || (conv3 && p.B >= T * 2))) T *= 2;
   }
   int slab_w = 0, slab_h = 0, SBt = 0;
   for (;; T /= 2) {
@@ -853,7 +868,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
     } else {
       p.tap_r_off = 0;
       p.sbo = 8u * row_bytes;
-      p.sub_off = 0;
+      p.sub_off = (uint32_t)p.TH * line;  // = 128 rows: sub-tile t is the t-th whole tile of the box
     }
     p.SA = (int)((smem_budget - b_region) / p.a_stage_bytes);
     if (p.SA > kMaxStagesA) p.SA = kMaxStagesA;

@@ -50,6 +50,9 @@ struct yond_net {
   size_t ev_used = 0;
   double acc_ms = 0, acc_flops = 0, pending_flops = 0;
   int acc_launches = 0;
+  // side stream for the conditioning vectors: they depend only on t and run beside the first layer
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int ch(int lvl) const { return nf << lvl; }
 };
 
@@ -318,7 +321,15 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
     if (!dry && R.rc == YOND_OK) R.rc = (expr);         \
   } while (0)
 
-  // ---- conditioning vectors of the 9 blocks (one launch, whole batch) ----
+  // ---- conditioning vectors of the 9 blocks (one launch, whole batch, on the side stream) ----
+  bool film_pending = false;
+  auto film_join = [&]() {
+    if (film_pending) {
+      film_pending = false;
+      if (cudaStreamWaitEvent(s, n->ev_join, 0) != cudaSuccess && R.rc == YOND_OK)
+        R.rc = yond_set_error(YOND_ERR_CUDA, "cudaStreamWaitEvent(film) failed");
+    }
+  };
   float* va[10] = {nullptr};
   float* vb[10] = {nullptr};
   if (!unet) {
@@ -346,7 +357,18 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
         all.out_b[l - 1] = vb[l];
       }
     }
-    RUN(film_launch(all, t, ubn, B, guided ? 1 : 0, s));
+    if (!dry && R.rc == YOND_OK) {
+      if (!n->side) {
+        YOND_CUDA_CHECK(cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking));
+        YOND_CUDA_CHECK(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
+        YOND_CUDA_CHECK(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
+      }
+      YOND_CUDA_CHECK(cudaEventRecord(n->ev_fork, s));
+      YOND_CUDA_CHECK(cudaStreamWaitEvent(n->side, n->ev_fork, 0));
+      R.rc = film_launch(all, t, ubn, B, guided ? 1 : 0, n->side);
+      YOND_CUDA_CHECK(cudaEventRecord(n->ev_join, n->side));
+      film_pending = true;
+    }
   }
   // One residual block on `nb` images starting at image b0 (FiLM rows are per image): x raw, xs = SiLU(x).
   auto block = [&](int l, int lv, int b0, int nb, const bf16* x, const bf16* xs, bf16* zb, bf16* out) {
@@ -429,6 +451,7 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
       bf16* s0 = skip0 + (size_t)b0 * px(0) * C0;
       bf16* s1 = skip1 + (size_t)b0 * px(1) * C1;
       RUN(head_conv_launch(z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->head_w, n->f32["conv_in.bias"], nb, H, W, nf, 0.01f, x0, x0s, s));
+      film_join();
       block(1, 0, b0, nb, x0, x0s, z0, s0);
       // stride-2 conv, no activation (modules.py:117-125); the dual store feeds the next block
       R.conv("pool1.conv", nb, H, W, s0, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x1, x1s);
@@ -466,6 +489,7 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
                            nf, y + (size_t)b0 * px(0) * 4, s));
     }
   }
+  film_join();
 #undef RUN
   if (ws_bytes) *ws_bytes = align_up(bump.off, 1024);
   if (flops) *flops = R.flops + head_tail_flops;
@@ -497,6 +521,9 @@ void yond_net_destroy(yond_net_t* n) {
   if (!n) return;
   free_device(n);
   for (auto e : n->events) cudaEventDestroy(e);
+  if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+  if (n->ev_join) cudaEventDestroy(n->ev_join);
+  if (n->side) cudaStreamDestroy(n->side);
   delete n;
 }
 

@@ -76,6 +76,149 @@ __global__ void __launch_bounds__(256, 2) head_conv_kernel(const float* __restri
   }
 }
 
+// ---- first layer on the (legacy, warp-level) tensor path: nf = 32 ---------------------------------------------
+// The layer is HBM-bound (16 B in, 64-128 B out per pixel) but 1152 FMAs per pixel keep the FP32 pipe busy for 3x
+// the memory time, so the products run as mma.sync m16n8k16 bf16 with fp32 accumulation.  To keep the fp32 accuracy
+// the layer has in the reference, input and weights are split x = xh + xl, w = wh + wl (bf16 pairs, 16 mantissa
+// bits) and the three leading terms xh*wh + xl*wh + xh*wl are accumulated (the dropped xl*wl is < 2^-16 relative).
+// K layout: k = tap*4 + channel; taps 0-7 fill two k-steps (three fragment products each), tap 8 carries its three
+// terms in one k-step: k 0-3 xh*wh, k 4-7 xl*wh, k 8-11 xh*wl, k 12-15 zero  ->  28 HMMAs per 16 pixels x 32 channels.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const float2 hf = __bfloat1622float2(h);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = pack2(x - hf.x, y - hf.y);
+}
+
+constexpr int kHeadTile = 16;               // 16 x 16 pixels per block iteration: 8 warps x 2 rows of 16 pixels
+constexpr int kHeadPitch = kHeadTile + 2;   // halo tile pitch in pixels
+
+__global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __restrict__ z, const float* __restrict__ ub,
+                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                               int B, int H, int W, float slope, bf16* __restrict__ out0,
+                                                               bf16* __restrict__ out1) {
+  constexpr int nf = 32;
+  __shared__ __align__(16) float4 tile[kHeadPitch * kHeadPitch];
+  __shared__ __align__(16) uint32_t stage[8][2][16 * 16];  // per warp: out0 / out1 staging, 16 pixels x 32 bf16
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  // weight fragments (B operand, "col" layout: b0 = k 2t,2t+1; b1 = k 2t+8,2t+9; n = g)
+  uint32_t bh[2][4][2], bl[2][4][2], bs[4][2];
+  float bv[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int n = nt * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int k = 2 * t + 8 * half;
+        const int tap = ks * 4 + (k >> 2), ci = k & 3;
+        split2(__ldg(w + (tap * 4 + ci) * nf + n), __ldg(w + (tap * 4 + ci + 1) * nf + n), bh[ks][nt][half], bl[ks][nt][half]);
+      }
+    uint32_t h8, l8;
+    const int ci = 2 * (t & 1);
+    split2(__ldg(w + (32 + ci) * nf + n), __ldg(w + (32 + ci + 1) * nf + n), h8, l8);
+    bs[nt][0] = h8;
+    bs[nt][1] = t < 2 ? l8 : 0u;
+    bv[nt][0] = __ldg(bias + nt * 8 + 2 * t);
+    bv[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
+  }
+
+  const int tiles_x = (W + kHeadTile - 1) / kHeadTile, tiles_y = (H + kHeadTile - 1) / kHeadTile;
+  const int ntiles = B * tiles_x * tiles_y;
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  const float2* tile2 = reinterpret_cast<const float2*>(tile);
+  for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+    const int b = ti / (tiles_x * tiles_y), rem = ti % (tiles_x * tiles_y);
+    const int y0 = (rem / tiles_x) * kHeadTile, x0 = (rem % tiles_x) * kHeadTile;
+    const float inv = ub ? 1.0f / __ldg(ub + b) : 1.0f;  // the reference divides first, then convolves (modules.py:20)
+    __syncthreads();  // previous iteration's readers are done with the tile
+    for (int i = threadIdx.x; i < kHeadPitch * kHeadPitch; i += 256) {
+      const int yy = y0 + i / kHeadPitch - 1, xx = x0 + i % kHeadPitch - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(z4 + ((size_t)b * H + yy) * W + xx);
+      tile[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = warp * 2 + rr;  // tile row of this m-tile: 16 pixels along x
+      if (y0 + row >= H) break;
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][2] = bv[nt][0]; acc[nt][1] = acc[nt][3] = bv[nt][1]; }
+      const int cp = t & 1;  // channel pair inside the pixel (float2 index)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int tap = ks * 4 + half * 2 + (t >> 1);
+          const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+          for (int rs = 0; rs < 2; ++rs) {
+            const float2 v = tile2[((row + dy) * kHeadPitch + g + 8 * rs + dx) * 2 + cp];
+            split2(v.x, v.y, ah[half * 2 + rs], al[half * 2 + rs]);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma16816(acc[nt], ah, bh[ks][nt][0], bh[ks][nt][1]);
+          mma16816(acc[nt], ah, bl[ks][nt][0], bl[ks][nt][1]);
+          mma16816(acc[nt], al, bh[ks][nt][0], bh[ks][nt][1]);
+        }
+      }
+      {  // tap 8 (dy = dx = 2): all three terms in one k-step
+        uint32_t a[4], h0, l0, h1, l1;
+        const float2 v0 = tile2[((row + 2) * kHeadPitch + g + 2) * 2 + cp];
+        const float2 v1 = tile2[((row + 2) * kHeadPitch + g + 8 + 2) * 2 + cp];
+        split2(v0.x, v0.y, h0, l0);
+        split2(v1.x, v1.y, h1, l1);
+        a[0] = t < 2 ? h0 : l0;
+        a[1] = t < 2 ? h1 : l1;
+        a[2] = t < 2 ? h0 : 0u;
+        a[3] = t < 2 ? h1 : 0u;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma16816(acc[nt], a, bs[nt][0], bs[nt][1]);
+      }
+      // epilogue: LeakyReLU (+ SiLU copy), staged through shared memory so that every lane stores 16 contiguous bytes
+      uint32_t* st0 = stage[warp][0];
+      uint32_t* st1 = stage[warp][1];
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          const int px = g + 8 * rs;
+          float v0 = acc[nt][rs * 2], v1 = acc[nt][rs * 2 + 1];
+          v0 = v0 > 0.f ? v0 : v0 * slope;
+          v1 = v1 > 0.f ? v1 : v1 * slope;
+          const int word = px * 16 + ((nt ^ ((px >> 1) & 3)) << 2) + t;  // 16-byte chunks XOR-swizzled: conflict-free
+          st0[word] = pack2(v0, v1);
+          if (out1) st1[word] = pack2(fsilu(v0), fsilu(v1));
+        }
+      __syncwarp();
+      const size_t pix0 = ((size_t)b * H + y0 + row) * W + x0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int j = lane + 32 * i, px = j >> 2, c = j & 3;
+        if (x0 + px < W) {
+          const int src = px * 4 + (c ^ ((px >> 1) & 3));
+          reinterpret_cast<uint4*>(out0 + (pix0 + px) * nf)[c] = reinterpret_cast<const uint4*>(st0)[src];
+          if (out1) reinterpret_cast<uint4*>(out1 + (pix0 + px) * nf)[c] = reinterpret_cast<const uint4*>(st1)[src];
+        }
+      }
+    }
+  }
+}
+
 // ---- last layer: 1x1, nf -> 4, + input residual, x ub (data_inv_normalize); fp32 output NHWC4 ----------------
 __global__ void __launch_bounds__(256) tail_conv_kernel(const bf16* __restrict__ act, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const float* __restrict__ z,
@@ -250,6 +393,12 @@ inline int cap_grid(size_t blocks) {
 int head_conv_launch(const float* z, const float* ub, const float* w, const float* bias, int B, int H, int W, int nf,
                      float slope, bf16* out0, bf16* out1, cudaStream_t s) {
   const size_t npix = (size_t)B * H * W;
+  if (nf == 32) {
+    const size_t tiles = (size_t)B * ((H + kHeadTile - 1) / kHeadTile) * ((W + kHeadTile - 1) / kHeadTile);
+    head_conv_mma_kernel<<<cap_grid(tiles), 256, 0, s>>>(z, ub, w, bias, B, H, W, slope, out0, out1);
+    YOND_LAUNCH_CHECK();
+    return YOND_OK;
+  }
   const size_t smem = (size_t)(36 * nf + nf) * sizeof(float);
   head_conv_kernel<<<cap_grid((npix + 255) / 256), 256, smem, s>>>(z, ub, w, bias, B, H, W, nf, slope, out0, out1);
   YOND_LAUNCH_CHECK();
