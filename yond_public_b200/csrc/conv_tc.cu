@@ -47,6 +47,8 @@ struct TcParams {
   uint32_t sub_off, sbo, tap_r_off;  // byte offsets inside an activation stage: next sub-tile, next 8-row group, next image row
   uint32_t smem_b_off, smem_bar_off;
   int tmem_cols;
+  int acc_stages;  // accumulator stages in TMEM: 2 (epilogue of tile i overlaps the MMAs of tile i+1) or 1 (T*NT = 512 columns)
+  int epi_fixed;  // every visit of an epilogue warp covers the same 16 channels of the same image (see epilogue_loop)
   int dbg;    // bring-up switches (YOND_CONV_DBG): 1 = skip global stores, 2 = skip the epilogue math, 4 = skip residual loads
   const float* bias;
   const float* scale;
@@ -237,11 +239,6 @@ __device__ __forceinline__ float fast_silu(float v) {
   return fmaf(h, t, h);
 }
 
-struct TcParams;
-// Epilogue of NC accumulator columns of one GEMM row: bias, FiLM scale/shift, activation, residual, bf16 stores.
-template <int NC>
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t taddr, bool valid, int b, int co, size_t off);
-
 // One activation ("A") pipeline stage of the K loop, decoded identically by producer and MMA issuer.
 struct AStage {
   int map;       // index into TcMaps::a
@@ -367,79 +364,173 @@ __device__ __forceinline__ void issue_slab_resident(uint32_t d_tmem, uint32_t nt
                         b_lo_first + (uint32_t)(r * 3 + sx) * b_step16, a_hi, b_hi, idesc, (r | sx) ? 1u : first_accum);
 }
 
-template <int NC>
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t taddr, bool valid, int b, int co, size_t off) {
-  uint32_t v[NC];
-  tmem_ld_n<NC>(taddr, v);
-  uint4 rr[NC / 8];
-  if (p.dbg & 2) { tmem_ld_wait(); return; }
-  if (valid && p.res) {  // issue the residual loads before waiting on TMEM
-    const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
+// 256-bit global accesses (sm_100): one lane moves a whole 32-byte sector per instruction, so a pixel-per-lane store of
+// 16 bf16 channels is one full-sector write instead of two half-sector partial writes.
+struct __align__(32) U8 { uint32_t v[8]; };
+__device__ __forceinline__ void stg256(void* ptr, const U8& u) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(u.v[0]), "r"(u.v[1]), "r"(u.v[2]), "r"(u.v[3]),
+               "r"(u.v[4]), "r"(u.v[5]), "r"(u.v[6]), "r"(u.v[7])
+               : "memory");
+}
+__device__ __forceinline__ U8 ldg256(const void* ptr) {
+  U8 u;
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u.v[0]), "=r"(u.v[1]), "=r"(u.v[2]), "=r"(u.v[3]), "=r"(u.v[4]), "=r"(u.v[5]), "=r"(u.v[6]), "=r"(u.v[7])
+               : "l"(ptr));
+  return u;
+}
+
+// Epilogue warps: bias, FiLM scale/shift, activation, residual, bf16 stores of the finished accumulators.
+// A warp owns one TMEM lane quarter (32 GEMM rows = 32 pixels) and every fourth 16-column chunk of the tile: at most
+// four "visits" per tile.  Per visit the work is ~150 instructions, so the loop is latency-, not throughput-bound:
+// everything with a long latency is issued BEFORE the wait on the accumulator barrier, while the tile's MMAs run:
+//   - the residual (one 256-bit load per visit, kept in registers),
+//   - when the layer is narrow (NT <= 64, one image per tile) a warp's visits all cover the same 16 channels of the
+//     same image, so bias / scale / shift collapse to out = act(acc * A + Bc) with A, Bc loaded once per tile
+//     (`epi_fixed`); wider layers load them per visit.
+template <bool kScale, bool kRes>
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, int warp,
+                                              int lane, int total_tiles) {
+  const int q = warp & 3;            // TMEM lane quarter this warp may access
+  const int part = (warp - 2) >> 2;  // kEpiWarps/4 warps share a quarter and split the column chunks
+  const int row = q * 32 + lane;     // GEMM row inside a sub-tile
+  const int w_i = row % p.TW;
+  const int g_i = row / p.TW;        // (h, b) index inside the sub-tile, h-major
+  const int dh = g_i / p.NB, db = g_i % p.NB;
+  const int nchunk = p.NT / 16, nvis = p.T * nchunk;
+  const bool fixed = p.epi_fixed != 0 && !(kScale && kRes);  // both at once would not fit the register budget
+  const int cfix = (part % nchunk) * 16;
+  float A[16], Bc[16];
+  if (fixed) {
 #pragma unroll
-    for (int g = 0; g < NC / 8; ++g) rr[g] = __ldg(r4 + g);
+    for (int j = 0; j < 16; ++j) { A[j] = 1.f; Bc[j] = __ldg(p.bias + cfix + j); }
   }
-  float f[NC];
-  if (valid) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + co);
+  int as = 0, pacc = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const TileCoord tc = decode_tile(p, tile);
+    // visits in groups of four (one group unless T * NT = 512)
+    for (int k0 = 0; part + 4 * k0 < nvis; k0 += 4) {
+    // ---- before the accumulator is ready: addresses, residual loads, per-tile parameters ----
+    uint32_t off[4];
+    uint32_t vmask = 0;
+    U8 rr[4];
 #pragma unroll
-    for (int g = 0; g < NC / 4; ++g) {
-      const float4 t = __ldg(b4 + g);
-      f[g * 4 + 0] = t.x; f[g * 4 + 1] = t.y; f[g * 4 + 2] = t.z; f[g * 4 + 3] = t.w;
+    for (int k = 0; k < 4; ++k) {
+      const int ci = part + 4 * (k0 + k);
+      off[k] = 0;
+      if (ci < nvis) {
+        const int t = ci / nchunk, c = (ci - t * nchunk) * 16;
+        int h = tc.h0 + dh, b = tc.b0 + db;
+        if (p.t_along_h) h += t * p.TH; else b = tc.b0 + db * p.T + t;  // sub-tile t = images t, t+T, ... of the tile
+        const int w = tc.w0 + w_i;
+        if ((w < p.W) && (h < p.H) && (b < p.B)) {
+          const int n = tc.n0 + c;
+          size_t e;
+          if (p.mode == CONVT_2X2) {
+            const int quad = n / p.Cout;
+            e = (((size_t)b * (2 * p.H) + (2 * h + (quad >> 1))) * (size_t)(2 * p.W) + (2 * w + (quad & 1))) * p.Cout + (n - quad * p.Cout);
+          } else {
+            e = (((size_t)b * p.H + h) * (size_t)p.W + w) * p.Cout + n;
+          }
+          off[k] = (uint32_t)e;  // element offsets fit 32 bits (checked on the host)
+          vmask |= 1u << k;
+          if (kRes) rr[k] = ldg256(p.res + e);
+        }
+      }
     }
-  }
-  tmem_ld_wait();
-  if (!valid) return;
+    if (kScale && fixed && k0 == 0) {
+      int b = tc.b0 + db;
+      if (b > p.B - 1) b = p.B - 1;
+      const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + cfix);
+      const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + cfix) : nullptr;
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + cfix);
 #pragma unroll
-  for (int j = 0; j < NC; ++j) f[j] += __uint_as_float(v[j]);
-  if (p.scale) {
-    const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + co);
-#pragma unroll
-    for (int g = 0; g < NC / 4; ++g) {
-      const float4 t = __ldg(s4 + g);
-      f[g * 4 + 0] *= t.x; f[g * 4 + 1] *= t.y; f[g * 4 + 2] *= t.z; f[g * 4 + 3] *= t.w;
+      for (int g = 0; g < 4; ++g) {
+        const float4 sc = __ldg(s4 + g), sh = h4 ? __ldg(h4 + g) : make_float4(0.f, 0.f, 0.f, 0.f), bi = __ldg(b4 + g);
+        A[g * 4 + 0] = sc.x; A[g * 4 + 1] = sc.y; A[g * 4 + 2] = sc.z; A[g * 4 + 3] = sc.w;
+        Bc[g * 4 + 0] = fmaf(bi.x, sc.x, sh.x); Bc[g * 4 + 1] = fmaf(bi.y, sc.y, sh.y);
+        Bc[g * 4 + 2] = fmaf(bi.z, sc.z, sh.z); Bc[g * 4 + 3] = fmaf(bi.w, sc.w, sh.w);
+      }
     }
-  }
-  if (p.shift) {
-    const float4* s4 = reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + co);
-#pragma unroll
-    for (int g = 0; g < NC / 4; ++g) {
-      const float4 t = __ldg(s4 + g);
-      f[g * 4 + 0] += t.x; f[g * 4 + 1] += t.y; f[g * 4 + 2] += t.z; f[g * 4 + 3] += t.w;
+    if (k0 == 0) {
+      mbar_wait(acc_full + 8 * as, pacc);
+      tc_fence_after();
     }
-  }
-  if (p.act == ACT_LRELU) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
-  } else if (p.act == ACT_SILU) {
+    for (int k = 0; k < 4; ++k) {
+      const int ci = part + 4 * (k0 + k);
+      if (ci < nvis && !(p.dbg & 128)) {  // dbg 128: the epilogue does not touch TMEM
+        const int t = ci / nchunk, c = (ci - t * nchunk) * 16;
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.T + t) * p.NT + c), v);
+        tmem_ld_wait();
+        if (!(p.dbg & 2) && ((vmask >> k) & 1u)) {
+          float f[16];
+          if (fixed) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = fast_silu(f[j]);
-  }
-  if (p.res) {
+            for (int j = 0; j < 16; ++j) f[j] = kScale ? fmaf(__uint_as_float(v[j]), A[j], Bc[j]) : __uint_as_float(v[j]) + Bc[j];
+          } else {
+            const int n = tc.n0 + c;
+            const int co = p.mode == CONVT_2X2 ? n % p.Cout : n;
+            int b = p.t_along_h ? tc.b0 + db : tc.b0 + db * p.T + t;
+            if (b > p.B - 1) b = p.B - 1;
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + co);
 #pragma unroll
-    for (int g = 0; g < NC / 8; ++g) {
-      const float2 a0 = unpack_bf16x2(rr[g].x), a1 = unpack_bf16x2(rr[g].y), a2 = unpack_bf16x2(rr[g].z), a3 = unpack_bf16x2(rr[g].w);
-      f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
-      f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
+            for (int g = 0; g < 4; ++g) {
+              const float4 bi = __ldg(b4 + g);
+              f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + bi.x; f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + bi.y;
+              f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + bi.z; f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + bi.w;
+            }
+            if (kScale) {
+              const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + co);
+              const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + co) : nullptr;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 sc = __ldg(s4 + g), sh = h4 ? __ldg(h4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+                f[g * 4 + 0] = fmaf(f[g * 4 + 0], sc.x, sh.x); f[g * 4 + 1] = fmaf(f[g * 4 + 1], sc.y, sh.y);
+                f[g * 4 + 2] = fmaf(f[g * 4 + 2], sc.z, sh.z); f[g * 4 + 3] = fmaf(f[g * 4 + 3], sc.w, sh.w);
+              }
+            }
+          }
+          if (p.act == ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+          } else if (p.act == ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fast_silu(f[j]);
+          }
+          if (kRes) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 a = unpack_bf16x2(rr[k].v[j]);
+              f[2 * j] += a.x;
+              f[2 * j + 1] += a.y;
+            }
+          }
+          if (p.dbg & 1) {  // dbg 1: no global stores (keep the math alive)
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc += f[j];
+            if (acc == 123.456f) p.out0[0] = __float2bfloat16_rn(acc);
+          } else {
+            U8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            stg256(p.out0 + off[k], o);
+            if (p.out1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16x2(fast_silu(f[2 * j]), fast_silu(f[2 * j + 1]));
+              stg256(p.out1 + off[k], o);
+            }
+          }
+        }
+      }
     }
-  }
-  if (p.dbg & 1) {
-    float acc = 0.f;
-#pragma unroll
-    for (int j = 0; j < NC; ++j) acc += f[j];
-    if (acc == 123.456f) p.out0[0] = __float2bfloat16_rn(acc);  // keep the math alive
-    return;
-  }
-  uint4* o4 = reinterpret_cast<uint4*>(p.out0 + off);
-#pragma unroll
-  for (int g = 0; g < NC / 8; ++g)
-    o4[g] = make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
-                       pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
-  if (p.out1) {
-    uint4* s4 = reinterpret_cast<uint4*>(p.out1 + off);
-#pragma unroll
-    for (int g = 0; g < NC / 8; ++g)
-      s4[g] = make_uint4(pack_bf16x2(fast_silu(f[g * 8 + 0]), fast_silu(f[g * 8 + 1])), pack_bf16x2(fast_silu(f[g * 8 + 2]), fast_silu(f[g * 8 + 3])),
-                         pack_bf16x2(fast_silu(f[g * 8 + 4]), fast_silu(f[g * 8 + 5])), pack_bf16x2(fast_silu(f[g * 8 + 6]), fast_silu(f[g * 8 + 7])));
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+    if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
   }
 }
 
@@ -649,53 +740,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
       if (leader) umma_commit(uacc_full + 8 * as);
       __syncwarp();
-      if (++as == 2) { as = 0; pacc ^= 1; }
+      if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
     }
     if ((p.dbg & 8) && blockIdx.x == 0 && leader)
       printf("[conv dbg] issuer: total %lld cyc; issue regions %lld; waiting: accumulator %lld, activations %lld; tiles %d, A stages/tile %d, SA %d SB %d T %d NT %d\n",
              clock64() - t_begin, t_issue, t_acc, t_a, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
   } else {
     // ===================== epilogue (warps 2..2+kEpiWarps) =====================
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int part = (warp - 2) >> 2;  // kEpiWarps/4 warps share a quarter and split the column chunks
-    const int row = q * 32 + lane;     // GEMM row inside a sub-tile
-    const int w_i = row % p.TW;
-    const int g_i = row / p.TW;        // (h, b) index inside the sub-tile, h-major
-    // column chunks of 16 accumulator columns (keeps the per-thread register footprint small with 18 warps resident)
-    constexpr int cw = 16;
-    const int nchunk = p.NT / cw;
-    int as = 0, pacc = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      mbar_wait(acc_full + 8 * as, pacc);
-      tc_fence_after();
-      for (int ci = part; ci < p.T * nchunk && !(p.dbg & 128); ci += kEpiWarps / 4) {  // dbg 128: the epilogue does not touch TMEM
-        const int t = ci / nchunk, c = (ci - t * nchunk) * cw;
-        int h = tc.h0 + g_i / p.NB, b = tc.b0 + g_i % p.NB;
-        if (p.t_along_h) h += t * p.TH; else b += t * p.NB;
-        const int w = tc.w0 + w_i;
-        const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
-        const int n = tc.n0 + c;  // first GEMM column of this chunk
-        int co = n;
-        size_t pix = 0;
-        if (valid) {
-          if (p.mode == CONVT_2X2) {
-            const int quad = n / p.Cout;
-            co = n - quad * p.Cout;
-            pix = ((size_t)b * (2 * p.H) + (2 * h + (quad >> 1))) * (size_t)(2 * p.W) + (2 * w + (quad & 1));
-          } else {
-            pix = ((size_t)b * p.H + h) * (size_t)p.W + w;
-          }
-        }
-        const size_t off = pix * p.Cout + co;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.T + t) * p.NT + c);
-        epilogue_chunk<cw>(p, taddr, valid, b, co, off);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + 8 * as);
-      if (++as == 2) { as = 0; pacc ^= 1; }
-    }
+    if (p.scale && p.res) epilogue_loop<true, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles);
+    else if (p.scale) epilogue_loop<true, false>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles);
+    else if (p.res) epilogue_loop<false, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles);
+    else epilogue_loop<false, false>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles);
   }
 
   tc_fence_before();
@@ -791,6 +846,9 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   static const int env_slab = env_int("YOND_CONV_SLAB", 1);
   static const int env_T = env_int("YOND_CONV_T", kMaxT);
   static const int env_dbg = env_int("YOND_CONV_DBG", 0);
+  YOND_REQUIRE((double)L.B * L.Hin * L.Win * (L.mode == CONVT_2X2 ? 4.0 : 1.0) * L.Cout < 4294967296.0,
+               "conv_tc: output of %d x %d x %d x %d elements exceeds the 32-bit offset range; split the batch", L.B, L.Hin, L.Win, L.Cout);
+  YOND_REQUIRE(L.scale != nullptr || L.shift == nullptr, "conv_tc: a shift vector needs a scale vector");
   TcParams p{};
   p.mode = L.mode;
   p.B = L.B;
@@ -828,26 +886,27 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   YOND_REQUIRE(p.b_stage_bytes % 1024 == 0, "conv_tc: weight stage not 1024-aligned");
   const size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
   p.wres = (p.tiles_n == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
-  size_t b_region;
-  if (p.wres) {
-    p.SB = 1;
-    b_region = wres_bytes;
-  } else {
-    p.SB = 6;
-    while (p.SB > 3 && (size_t)p.SB * p.b_stage_bytes > 96 * 1024) --p.SB;
-    b_region = (size_t)p.SB * p.b_stage_bytes;
-  }
-  // T sub-tiles share each weight tile (and one halo slab): stacked along H when the map is tall enough, else one
-  // image each.  T is bounded by TMEM (2 accumulator stages x T x NT columns <= 512) and by shared memory.
+  // T sub-tiles share each weight tile (and one halo slab): stacked along H when the map is tall enough, else along
+  // the batch (sub-tile t = images t, t+T, ... of the tile, so that the 8-row groups keep a uniform stride).  T is
+  // bounded by TMEM and by shared memory.  Resident-weight layers keep two accumulator stages (2 T NT <= 512 columns);
+  // layers that stream their weights take T NT = 512 with a single stage when they can: the serialised epilogue
+  // costs a few percent, re-streaming the whole weight set for half as many pixels costs L2 bandwidth, which is what
+  // bounds them (measured: 256/512-channel layers moved ~7.7 TB/s of weights through L2 at T = 1).
   // Stride-2 / 1x1 / transposed layers stack their sub-tiles along H only (a taller box of whole 128-row tiles).
   int T = 1;
-  if (p.NB == 1) {
-    int tmax = 512 / (2 * p.NT);
+  {
+    static const int env_acc1 = env_int("YOND_CONV_ACC1", 1);  // 0: never trade the second accumulator stage for a larger T
+    int tmax = (p.wres || !env_acc1) ? 512 / (2 * p.NT) : 512 / p.NT;
     if (tmax > env_T) tmax = env_T;
     if (tmax > kMaxT) tmax = kMaxT;
-    while (T * 2 <= tmax && (p.H >= p.TH * T * 2 || (conv3 && p.B >= T * 2))) T *= 2;
+    if (p.NB == 1) {
+      while (T * 2 <= tmax && (p.H >= p.TH * T * 2 || (conv3 && p.B >= T * 2))) T *= 2;
+    } else if (conv3) {
+      while (T * 2 <= tmax && p.B >= p.NB * T * 2) T *= 2;
+    }
   }
   int slab_w = 0, slab_h = 0, SBt = 0;
+  size_t b_region = 0;
   for (;; T /= 2) {
     p.T = T;
     p.t_along_h = (p.H >= p.TH * T) ? 1 : 0;
@@ -863,26 +922,46 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
     p.a_stage_bytes = (uint32_t)align_up((size_t)p.a_tx_bytes, 1024);
     if (conv3) {
       p.tap_r_off = (uint32_t)SBt * line;
-      p.sbo = (p.NB > 1 || p.t_along_h) ? line : (uint32_t)T * line;
+      p.sbo = p.t_along_h ? line : (uint32_t)T * line;
       p.sub_off = p.t_along_h ? (uint32_t)p.TH * line : line;
     } else {
       p.tap_r_off = 0;
       p.sbo = 8u * row_bytes;
       p.sub_off = (uint32_t)p.TH * line;  // = 128 rows: sub-tile t is the t-th whole tile of the box
     }
-    p.SA = (int)((smem_budget - b_region) / p.a_stage_bytes);
-    if (p.SA > kMaxStagesA) p.SA = kMaxStagesA;
-    if (p.SA >= 3 || T == 1) break;
+    if (p.wres) {
+      p.SB = 1;
+      b_region = wres_bytes;
+      p.SA = (int)((smem_budget - b_region) / p.a_stage_bytes);
+      if (p.SA > kMaxStagesA) p.SA = kMaxStagesA;
+      if (p.SA >= 3 || T == 1) break;
+    } else {
+      // streamed weights: two activation stages (one stage feeds 9 taps x T sub-tiles of MMAs), the rest of the
+      // shared memory goes to the weight ring, what is left after that back to the activations
+      const size_t rest = smem_budget > 2 * (size_t)p.a_stage_bytes ? smem_budget - 2 * (size_t)p.a_stage_bytes : 0;
+      p.SB = (int)(rest / p.b_stage_bytes);
+      if (p.SB > kMaxStagesB) p.SB = kMaxStagesB;
+      b_region = (size_t)p.SB * p.b_stage_bytes;
+      p.SA = p.SB > 0 ? (int)((smem_budget - b_region) / p.a_stage_bytes) : 0;
+      if (p.SA > kMaxStagesA) p.SA = kMaxStagesA;
+      if ((p.SB >= 3 && p.SA >= 2) || T == 1) break;
+    }
   }
+  YOND_REQUIRE(p.SB >= 1, "conv_tc: not enough shared memory for the weight ring");
   YOND_REQUIRE(p.SA >= 2, "conv_tc: not enough shared memory for the activation pipeline");
   p.smem_b_off = (uint32_t)p.SA * p.a_stage_bytes;
   p.smem_bar_off = (uint32_t)align_up(p.smem_b_off + b_region, 1024);
   const size_t smem_bytes = p.smem_bar_off + 512 + 1024;  // barriers + alignment slack
-  p.tmem_cols = 2 * p.T * p.NT < 32 ? 32 : 2 * p.T * p.NT;
+  p.acc_stages = 2 * p.T * p.NT <= 512 ? 2 : 1;
+  p.tmem_cols = p.acc_stages * p.T * p.NT < 32 ? 32 : p.acc_stages * p.T * p.NT;
   if ((env_dbg & 64) && p.tmem_cols <= 256) p.tmem_cols = 512;
   YOND_REQUIRE(p.tmem_cols <= 512, "conv_tc: TMEM budget exceeded");
 
   p.dbg = env_dbg;
+  {
+    const int nchunk = p.NT / 16;
+    p.epi_fixed = (p.tiles_n == 1 && nchunk <= 4 && p.NB == 1 && (p.T == 1 || p.t_along_h) && L.mode != CONVT_2X2) ? 1 : 0;
+  }
   p.bias = L.bias;
   p.scale = L.scale;
   p.shift = L.shift;

@@ -95,15 +95,23 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
   lo = pack2(x - hf.x, y - hf.y);
 }
 
-constexpr int kHeadTile = 16;               // 16 x 16 pixels per block iteration: 8 warps x 2 rows of 16 pixels
-constexpr int kHeadPitch = kHeadTile + 2;   // halo tile pitch in pixels
+constexpr int kHeadTW = 16, kHeadTH = 32;   // pixels per block iteration: 8 warps x 4 rows of 16 pixels
+constexpr int kHeadPW = kHeadTW + 2, kHeadPH = kHeadTH + 2;
+constexpr int kHeadLoads = (kHeadPW * kHeadPH + 255) / 256;  // halo pixels per thread
+
+__device__ __forceinline__ float head_silu(float v) {  // same tanh form as the conv epilogue
+  float t;
+  const float h = 0.5f * v;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __restrict__ z, const float* __restrict__ ub,
                                                                const float* __restrict__ w, const float* __restrict__ bias,
                                                                int B, int H, int W, float slope, bf16* __restrict__ out0,
                                                                bf16* __restrict__ out1) {
   constexpr int nf = 32;
-  __shared__ __align__(16) float4 tile[kHeadPitch * kHeadPitch];
+  __shared__ __align__(16) float4 tile[kHeadPW * kHeadPH];
   __shared__ __align__(16) uint32_t stage[8][2][16 * 16];  // per warp: out0 / out1 staging, 16 pixels x 32 bf16
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -131,25 +139,39 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
     bv[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
   }
 
-  const int tiles_x = (W + kHeadTile - 1) / kHeadTile, tiles_y = (H + kHeadTile - 1) / kHeadTile;
+  const int tiles_x = (W + kHeadTW - 1) / kHeadTW, tiles_y = (H + kHeadTH - 1) / kHeadTH;
   const int ntiles = B * tiles_x * tiles_y;
   const float4* z4 = reinterpret_cast<const float4*>(z);
   const float2* tile2 = reinterpret_cast<const float2*>(tile);
+  // software pipeline: the next tile's halo pixels are in flight (registers) while this tile is computed
+  float4 pre[kHeadLoads];
+  auto prefetch = [&](int ti) {
+    const int b = ti / (tiles_x * tiles_y), rem = ti % (tiles_x * tiles_y);
+    const int y0 = (rem / tiles_x) * kHeadTH, x0 = (rem % tiles_x) * kHeadTW;
+#pragma unroll
+    for (int k = 0; k < kHeadLoads; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int yy = y0 + i / kHeadPW - 1, xx = x0 + i % kHeadPW - 1;
+      pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < kHeadPW * kHeadPH && yy >= 0 && yy < H && xx >= 0 && xx < W) pre[k] = __ldg(z4 + ((size_t)b * H + yy) * W + xx);
+    }
+  };
+  if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x);
   for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
     const int b = ti / (tiles_x * tiles_y), rem = ti % (tiles_x * tiles_y);
-    const int y0 = (rem / tiles_x) * kHeadTile, x0 = (rem % tiles_x) * kHeadTile;
+    const int y0 = (rem / tiles_x) * kHeadTH, x0 = (rem % tiles_x) * kHeadTW;
     const float inv = ub ? 1.0f / __ldg(ub + b) : 1.0f;  // the reference divides first, then convolves (modules.py:20)
     __syncthreads();  // previous iteration's readers are done with the tile
-    for (int i = threadIdx.x; i < kHeadPitch * kHeadPitch; i += 256) {
-      const int yy = y0 + i / kHeadPitch - 1, xx = x0 + i % kHeadPitch - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(z4 + ((size_t)b * H + yy) * W + xx);
-      tile[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+#pragma unroll
+    for (int k = 0; k < kHeadLoads; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      if (i < kHeadPW * kHeadPH) tile[i] = make_float4(pre[k].x * inv, pre[k].y * inv, pre[k].z * inv, pre[k].w * inv);
     }
     __syncthreads();
+    if (ti + (int)gridDim.x < ntiles) prefetch(ti + gridDim.x);
 #pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {
-      const int row = warp * 2 + rr;  // tile row of this m-tile: 16 pixels along x
+    for (int rr = 0; rr < kHeadTH / 8; ++rr) {
+      const int row = warp * (kHeadTH / 8) + rr;  // tile row of this m-tile: 16 pixels along x
       if (y0 + row >= H) break;
       float acc[4][4];
 #pragma unroll
@@ -164,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
           const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
           for (int rs = 0; rs < 2; ++rs) {
-            const float2 v = tile2[((row + dy) * kHeadPitch + g + 8 * rs + dx) * 2 + cp];
+            const float2 v = tile2[((row + dy) * kHeadPW + g + 8 * rs + dx) * 2 + cp];
             split2(v.x, v.y, ah[half * 2 + rs], al[half * 2 + rs]);
           }
         }
@@ -177,8 +199,8 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
       }
       {  // tap 8 (dy = dx = 2): all three terms in one k-step
         uint32_t a[4], h0, l0, h1, l1;
-        const float2 v0 = tile2[((row + 2) * kHeadPitch + g + 2) * 2 + cp];
-        const float2 v1 = tile2[((row + 2) * kHeadPitch + g + 8 + 2) * 2 + cp];
+        const float2 v0 = tile2[((row + 2) * kHeadPW + g + 2) * 2 + cp];
+        const float2 v1 = tile2[((row + 2) * kHeadPW + g + 8 + 2) * 2 + cp];
         split2(v0.x, v0.y, h0, l0);
         split2(v1.x, v1.y, h1, l1);
         a[0] = t < 2 ? h0 : l0;
@@ -202,7 +224,7 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
           v1 = v1 > 0.f ? v1 : v1 * slope;
           const int word = px * 16 + ((nt ^ ((px >> 1) & 3)) << 2) + t;  // 16-byte chunks XOR-swizzled: conflict-free
           st0[word] = pack2(v0, v1);
-          if (out1) st1[word] = pack2(fsilu(v0), fsilu(v1));
+          if (out1) st1[word] = pack2(head_silu(v0), head_silu(v1));
         }
       __syncwarp();
       const size_t pix0 = ((size_t)b * H + y0 + row) * W + x0;
@@ -394,8 +416,9 @@ int head_conv_launch(const float* z, const float* ub, const float* w, const floa
                      float slope, bf16* out0, bf16* out1, cudaStream_t s) {
   const size_t npix = (size_t)B * H * W;
   if (nf == 32) {
-    const size_t tiles = (size_t)B * ((H + kHeadTile - 1) / kHeadTile) * ((W + kHeadTile - 1) / kHeadTile);
-    head_conv_mma_kernel<<<cap_grid(tiles), 256, 0, s>>>(z, ub, w, bias, B, H, W, slope, out0, out1);
+    const size_t tiles = (size_t)B * ((H + kHeadTH - 1) / kHeadTH) * ((W + kHeadTW - 1) / kHeadTW);
+    const size_t resident = (size_t)yond_num_sms() * 2;  // persistent: two blocks per SM walk the tiles
+    head_conv_mma_kernel<<<(int)(tiles < resident ? tiles : resident), 256, 0, s>>>(z, ub, w, bias, B, H, W, slope, out0, out1);
     YOND_LAUNCH_CHECK();
     return YOND_OK;
   }
