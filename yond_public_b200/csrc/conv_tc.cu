@@ -29,6 +29,24 @@ constexpr int kMaxStagesA = 8;
 constexpr int kMaxStagesB = 8;
 constexpr int kMaxT = 4;
 
+// Division by a run-time constant as multiply-high + shift (n < 2^31): the epilogue and the tile decode run once per
+// tile in every warp, and a 32-bit integer division is ~20 instructions.
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+__host__ FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{0u, 0u, d};
+  if (d > 1) {
+    uint32_t lg = 0;
+    while ((1u << lg) < d) ++lg;
+    const uint32_t pw = 31 + lg;
+    f.mul = (uint32_t)(((1ull << pw) + d - 1) / d);
+    f.shr = pw - 32;
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
+
 struct TcParams {
   int B, H, W;  // tile-space dims (output dims; input dims for CONVT_2X2)
   int TW, TH, NB, T;  // sub-tile = TH rows x NB images x TW columns = 128 GEMM rows; T sub-tiles per CTA tile
@@ -48,6 +66,9 @@ struct TcParams {
   uint32_t smem_b_off, smem_bar_off;
   int tmem_cols;
   int acc_stages;  // accumulator stages in TMEM: 2 (epilogue of tile i overlaps the MMAs of tile i+1) or 1 (T*NT = 512 columns)
+  FastDiv fd_tiles_n, fd_tiles_w, fd_tiles_h, fd_cout;
+  int lg_nchunk;       // log2(NT / 16)
+  uint32_t t_off;      // output element offset between consecutive sub-tiles
   int epi_fixed;  // every visit of an epilogue warp covers the same 16 channels of the same image (see epilogue_loop)
   int dbg;    // bring-up switches (YOND_CONV_DBG): 1 = skip global stores, 2 = skip the epilogue math, 4 = skip residual loads
   const float* bias;
@@ -305,11 +326,13 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
   TileCoord t;
-  t.n_idx = tile % p.tiles_n;
-  int m = tile / p.tiles_n;
-  const int tw_i = m % p.tiles_w; m /= p.tiles_w;
-  const int th_i = m % p.tiles_h;
-  const int tb_i = m / p.tiles_h;
+  uint32_t m = fdiv((uint32_t)tile, p.fd_tiles_n);
+  t.n_idx = tile - (int)m * p.tiles_n;
+  uint32_t m2 = fdiv(m, p.fd_tiles_w);
+  const int tw_i = (int)(m - m2 * p.tiles_w);
+  const uint32_t m3 = fdiv(m2, p.fd_tiles_h);
+  const int th_i = (int)(m2 - m3 * p.tiles_h);
+  const int tb_i = (int)m3;
   t.w0 = tw_i * p.TW;
   t.h0 = th_i * p.TH * (p.t_along_h ? p.T : 1);
   t.b0 = tb_i * p.NB * (p.t_along_h ? 1 : p.T);
@@ -381,25 +404,32 @@ __device__ __forceinline__ U8 ldg256(const void* ptr) {
 }
 
 // Epilogue warps: bias, FiLM scale/shift, activation, residual, bf16 stores of the finished accumulators.
-// A warp owns one TMEM lane quarter (32 GEMM rows = 32 pixels) and every fourth 16-column chunk of the tile: at most
-// four "visits" per tile.  Per visit the work is ~150 instructions, so the loop is latency-, not throughput-bound:
-// everything with a long latency is issued BEFORE the wait on the accumulator barrier, while the tile's MMAs run:
+// A warp owns one TMEM lane quarter (32 GEMM rows = 32 pixels) and every fourth 16-column chunk of the tile ("visits":
+// 2 to 8 per tile).  16 warps x visits x instructions-per-visit has to fit under the tile's MMA time on 4 issue ports
+// (an N=32 tile of 512 pixels is only ~2900 cycles of MMAs), so the loop is written for instruction count:
+// no integer divisions (shifts / multiply-high), 32-bit element offsets from one per-tile base, activation and the
+// presence of scale / residual resolved at compile time.  Everything with a long latency is issued BEFORE the wait on
+// the accumulator barrier, while the tile's MMAs run:
 //   - the residual (one 256-bit load per visit, kept in registers),
 //   - when the layer is narrow (NT <= 64, one image per tile) a warp's visits all cover the same 16 channels of the
 //     same image, so bias / scale / shift collapse to out = act(acc * A + Bc) with A, Bc loaded once per tile
 //     (`epi_fixed`); wider layers load them per visit.
-template <bool kScale, bool kRes>
+template <bool kScale, bool kRes, bool kSilu>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, int warp,
                                               int lane, int total_tiles) {
   const int q = warp & 3;            // TMEM lane quarter this warp may access
   const int part = (warp - 2) >> 2;  // kEpiWarps/4 warps share a quarter and split the column chunks
   const int row = q * 32 + lane;     // GEMM row inside a sub-tile
-  const int w_i = row % p.TW;
+  const int w_i = row & (p.TW - 1);  // TW, NB are powers of two
   const int g_i = row / p.TW;        // (h, b) index inside the sub-tile, h-major
-  const int dh = g_i / p.NB, db = g_i % p.NB;
-  const int nchunk = p.NT / 16, nvis = p.T * nchunk;
+  const int dh = g_i / p.NB, db = g_i & (p.NB - 1);
+  const int nchunk_m1 = (1 << p.lg_nchunk) - 1, nvis = p.T << p.lg_nchunk;
   const bool fixed = p.epi_fixed != 0 && !(kScale && kRes);  // both at once would not fit the register budget
-  const int cfix = (part % nchunk) * 16;
+  const bool convt = p.mode == CONVT_2X2;
+  const int cfix = (part & nchunk_m1) * 16;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+  const bool lrelu = p.act == ACT_LRELU;
+  const float slope = p.slope;
   float A[16], Bc[16];
   if (fixed) {
 #pragma unroll
@@ -408,124 +438,126 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   int as = 0, pacc = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const TileCoord tc = decode_tile(p, tile);
+    const int w = tc.w0 + w_i, h0 = tc.h0 + dh;
+    const int bb = tc.b0 + (p.t_along_h ? db : db * p.T);  // along the batch: sub-tile t = images t, t+T, ... of the tile
+    const bool wv = (w < p.W) && (h0 < p.H) && (bb < p.B);
+    // element offset of this thread's pixel in sub-tile 0 (+ first column of the tile unless transposed conv)
+    const uint32_t e0 = convt ? (((uint32_t)bb * (2 * p.H) + 2 * h0) * (uint32_t)(2 * p.W) + 2 * w) * (uint32_t)p.Cout
+                              : (((uint32_t)bb * p.H + h0) * (uint32_t)p.W + w) * (uint32_t)p.Cout + tc.n0;
     // visits in groups of four (one group unless T * NT = 512)
     for (int k0 = 0; part + 4 * k0 < nvis; k0 += 4) {
-    // ---- before the accumulator is ready: addresses, residual loads, per-tile parameters ----
-    uint32_t off[4];
-    uint32_t vmask = 0;
-    U8 rr[4];
+      // ---- before the accumulator is ready: addresses, residual loads, per-tile parameters ----
+      uint32_t off[4];
+      uint32_t vmask = 0;
+      U8 rr[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int ci = part + 4 * (k0 + k);
-      off[k] = 0;
-      if (ci < nvis) {
-        const int t = ci / nchunk, c = (ci - t * nchunk) * 16;
-        int h = tc.h0 + dh, b = tc.b0 + db;
-        if (p.t_along_h) h += t * p.TH; else b = tc.b0 + db * p.T + t;  // sub-tile t = images t, t+T, ... of the tile
-        const int w = tc.w0 + w_i;
-        if ((w < p.W) && (h < p.H) && (b < p.B)) {
-          const int n = tc.n0 + c;
-          size_t e;
-          if (p.mode == CONVT_2X2) {
-            const int quad = n / p.Cout;
-            e = (((size_t)b * (2 * p.H) + (2 * h + (quad >> 1))) * (size_t)(2 * p.W) + (2 * w + (quad & 1))) * p.Cout + (n - quad * p.Cout);
+      for (int k = 0; k < 4; ++k) {
+        const int ci = part + 4 * (k0 + k);
+        off[k] = 0;
+        if (ci < nvis) {
+          const int t = ci >> p.lg_nchunk, c = (ci & nchunk_m1) << 4;
+          const bool ok = wv && (p.t_along_h ? (h0 + t * p.TH < p.H) : (bb + t < p.B));
+          uint32_t e = e0 + (uint32_t)t * p.t_off;
+          if (convt) {
+            const uint32_t n = (uint32_t)(tc.n0 + c), quad = fdiv(n, p.fd_cout);
+            e += ((quad >> 1) * (uint32_t)(2 * p.W) + (quad & 1u)) * (uint32_t)p.Cout + (n - quad * p.Cout);
           } else {
-            e = (((size_t)b * p.H + h) * (size_t)p.W + w) * p.Cout + n;
+            e += (uint32_t)c;
           }
-          off[k] = (uint32_t)e;  // element offsets fit 32 bits (checked on the host)
-          vmask |= 1u << k;
-          if (kRes) rr[k] = ldg256(p.res + e);
+          off[k] = e;
+          if (ok) {
+            vmask |= 1u << k;
+            if (kRes) rr[k] = ldg256(p.res + e);
+          }
         }
       }
-    }
-    if (kScale && fixed && k0 == 0) {
-      int b = tc.b0 + db;
-      if (b > p.B - 1) b = p.B - 1;
-      const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + cfix);
-      const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + cfix) : nullptr;
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + cfix);
+      if (k0 == 0) {
+        if (kScale && fixed) {
+          const int b = bb < p.B ? bb : p.B - 1;
+          const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + cfix);
+          const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + cfix) : nullptr;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + cfix);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float4 sc = __ldg(s4 + g), sh = h4 ? __ldg(h4 + g) : make_float4(0.f, 0.f, 0.f, 0.f), bi = __ldg(b4 + g);
-        A[g * 4 + 0] = sc.x; A[g * 4 + 1] = sc.y; A[g * 4 + 2] = sc.z; A[g * 4 + 3] = sc.w;
-        Bc[g * 4 + 0] = fmaf(bi.x, sc.x, sh.x); Bc[g * 4 + 1] = fmaf(bi.y, sc.y, sh.y);
-        Bc[g * 4 + 2] = fmaf(bi.z, sc.z, sh.z); Bc[g * 4 + 3] = fmaf(bi.w, sc.w, sh.w);
+          for (int g = 0; g < 4; ++g) {
+            const float4 sc = __ldg(s4 + g), sh = h4 ? __ldg(h4 + g) : make_float4(0.f, 0.f, 0.f, 0.f), bi = __ldg(b4 + g);
+            A[g * 4 + 0] = sc.x; A[g * 4 + 1] = sc.y; A[g * 4 + 2] = sc.z; A[g * 4 + 3] = sc.w;
+            Bc[g * 4 + 0] = fmaf(bi.x, sc.x, sh.x); Bc[g * 4 + 1] = fmaf(bi.y, sc.y, sh.y);
+            Bc[g * 4 + 2] = fmaf(bi.z, sc.z, sh.z); Bc[g * 4 + 3] = fmaf(bi.w, sc.w, sh.w);
+          }
+        }
+        mbar_wait(acc_full + 8 * as, pacc);
+        tc_fence_after();
       }
-    }
-    if (k0 == 0) {
-      mbar_wait(acc_full + 8 * as, pacc);
-      tc_fence_after();
-    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int ci = part + 4 * (k0 + k);
-      if (ci < nvis && !(p.dbg & 128)) {  // dbg 128: the epilogue does not touch TMEM
-        const int t = ci / nchunk, c = (ci - t * nchunk) * 16;
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.T + t) * p.NT + c), v);
-        tmem_ld_wait();
-        if (!(p.dbg & 2) && ((vmask >> k) & 1u)) {
-          float f[16];
-          if (fixed) {
+      for (int k = 0; k < 4; ++k) {
+        const int ci = part + 4 * (k0 + k);
+        if (ci < nvis && !(p.dbg & 128)) {  // dbg 128: the epilogue does not touch TMEM
+          const int t = ci >> p.lg_nchunk, c = (ci & nchunk_m1) << 4;
+          uint32_t v[16];
+          tmem_ld16(tmem_row + (uint32_t)((as * p.T + t) * p.NT + c), v);
+          tmem_ld_wait();
+          if (!(p.dbg & 2) && ((vmask >> k) & 1u)) {
+            float f[16];
+            if (fixed) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = kScale ? fmaf(__uint_as_float(v[j]), A[j], Bc[j]) : __uint_as_float(v[j]) + Bc[j];
-          } else {
-            const int n = tc.n0 + c;
-            const int co = p.mode == CONVT_2X2 ? n % p.Cout : n;
-            int b = p.t_along_h ? tc.b0 + db : tc.b0 + db * p.T + t;
-            if (b > p.B - 1) b = p.B - 1;
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + co);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 bi = __ldg(b4 + g);
-              f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + bi.x; f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + bi.y;
-              f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + bi.z; f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + bi.w;
-            }
-            if (kScale) {
-              const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + co);
-              const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + co) : nullptr;
+              for (int j = 0; j < 16; ++j) f[j] = kScale ? fmaf(__uint_as_float(v[j]), A[j], Bc[j]) : __uint_as_float(v[j]) + Bc[j];
+            } else {
+              const uint32_t n = (uint32_t)(tc.n0 + c);
+              const uint32_t co = convt ? n - fdiv(n, p.fd_cout) * p.Cout : n;
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + co);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                const float4 sc = __ldg(s4 + g), sh = h4 ? __ldg(h4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-                f[g * 4 + 0] = fmaf(f[g * 4 + 0], sc.x, sh.x); f[g * 4 + 1] = fmaf(f[g * 4 + 1], sc.y, sh.y);
-                f[g * 4 + 2] = fmaf(f[g * 4 + 2], sc.z, sh.z); f[g * 4 + 3] = fmaf(f[g * 4 + 3], sc.w, sh.w);
+                const float4 bi = __ldg(b4 + g);
+                f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + bi.x; f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + bi.y;
+                f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + bi.z; f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + bi.w;
+              }
+              if (kScale) {
+                int b = p.t_along_h ? bb : bb + t;
+                if (b > p.B - 1) b = p.B - 1;
+                const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + co);
+                const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + co) : nullptr;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const float4 sc = __ldg(s4 + g), sh = h4 ? __ldg(h4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  f[g * 4 + 0] = fmaf(f[g * 4 + 0], sc.x, sh.x); f[g * 4 + 1] = fmaf(f[g * 4 + 1], sc.y, sh.y);
+                  f[g * 4 + 2] = fmaf(f[g * 4 + 2], sc.z, sh.z); f[g * 4 + 3] = fmaf(f[g * 4 + 3], sc.w, sh.w);
+                }
+              }
+            }
+            if (kSilu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fast_silu(f[j]);
+            } else if (lrelu) {  // slope < 1: LeakyReLU(x) = max(x, slope * x)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * slope);
+            }
+            if (kRes) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 a = unpack_bf16x2(rr[k].v[j]);
+                f[2 * j] += a.x;
+                f[2 * j + 1] += a.y;
+              }
+            }
+            if (p.dbg & 1) {  // dbg 1: no global stores (keep the math alive)
+              float acc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc += f[j];
+              if (acc == 123.456f) p.out0[0] = __float2bfloat16_rn(acc);
+            } else {
+              U8 o;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+              stg256(p.out0 + off[k], o);
+              if (p.out1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16x2(fast_silu(f[2 * j]), fast_silu(f[2 * j + 1]));
+                stg256(p.out1 + off[k], o);
               }
             }
           }
-          if (p.act == ACT_LRELU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
-          } else if (p.act == ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fast_silu(f[j]);
-          }
-          if (kRes) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 a = unpack_bf16x2(rr[k].v[j]);
-              f[2 * j] += a.x;
-              f[2 * j + 1] += a.y;
-            }
-          }
-          if (p.dbg & 1) {  // dbg 1: no global stores (keep the math alive)
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc += f[j];
-            if (acc == 123.456f) p.out0[0] = __float2bfloat16_rn(acc);
-          } else {
-            U8 o;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-            stg256(p.out0 + off[k], o);
-            if (p.out1) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16x2(fast_silu(f[2 * j]), fast_silu(f[2 * j + 1]));
-              stg256(p.out1 + off[k], o);
-            }
-          }
         }
       }
-    }
     }
     tc_fence_before();
     __syncwarp();
@@ -747,10 +779,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
              clock64() - t_begin, t_issue, t_acc, t_a, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
   } else {
     // ===================== epilogue (warps 2..2+kEpiWarps) =====================
-    if (p.scale && p.res) epilogue_loop<true, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles);
-    else if (p.scale) epilogue_loop<true, false>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles);
-    else if (p.res) epilogue_loop<false, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles);
-    else epilogue_loop<false, false>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles);
+    const bool silu = p.act == ACT_SILU;
+#define YOND_EPI(S, R, A) epilogue_loop<S, R, A>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles)
+    if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true); else YOND_EPI(true, true, false); }
+    else if (p.scale) { if (silu) YOND_EPI(true, false, true); else YOND_EPI(true, false, false); }
+    else if (p.res) { if (silu) YOND_EPI(false, true, true); else YOND_EPI(false, true, false); }
+    else { if (silu) YOND_EPI(false, false, true); else YOND_EPI(false, false, false); }
+#undef YOND_EPI
   }
 
   tc_fence_before();
@@ -958,6 +993,15 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   YOND_REQUIRE(p.tmem_cols <= 512, "conv_tc: TMEM budget exceeded");
 
   p.dbg = env_dbg;
+  p.fd_tiles_n = make_fastdiv((uint32_t)p.tiles_n);
+  p.fd_tiles_w = make_fastdiv((uint32_t)p.tiles_w);
+  p.fd_tiles_h = make_fastdiv((uint32_t)p.tiles_h);
+  p.fd_cout = make_fastdiv((uint32_t)p.Cout);
+  p.lg_nchunk = 0;
+  while ((16 << p.lg_nchunk) < p.NT) ++p.lg_nchunk;
+  if (L.mode == CONVT_2X2) p.t_off = (uint32_t)p.TH * 4u * p.W * p.Cout;  // TH input rows = 2 TH output rows of 2 W pixels
+  else p.t_off = (p.t_along_h ? (uint32_t)p.TH * p.W : (uint32_t)p.H * p.W) * (uint32_t)p.Cout;
+  YOND_REQUIRE(L.act != ACT_LRELU || (L.slope >= 0.f && L.slope <= 1.f), "conv_tc: LeakyReLU slope must be in [0, 1]");
   {
     const int nchunk = p.NT / 16;
     p.epi_fixed = (p.tiles_n == 1 && nchunk <= 4 && p.NB == 1 && (p.T == 1 || p.t_along_h) && L.mode != CONVT_2X2) ? 1 : 0;
