@@ -63,7 +63,7 @@ struct TcParams {
   int SA, SB; // pipeline depths
   uint32_t a_stage_bytes, a_tx_bytes, b_stage_bytes;  // stage pitch (1024-aligned), bytes one slab load writes, weight tile
   uint32_t sub_off, sbo, tap_r_off;  // byte offsets inside an activation stage: next sub-tile, next 8-row group, next image row
-  uint32_t smem_b_off, smem_bar_off;
+  uint32_t smem_b_off, smem_bar_off, smem_epi_off;  // weights, barriers, epilogue parameter rows (128 B per epilogue warp)
   int tmem_cols;
   int acc_stages;  // accumulator stages in TMEM: 2 (epilogue of tile i overlaps the MMAs of tile i+1) or 1 (T*NT = 512 columns)
   FastDiv fd_tiles_n, fd_tiles_w, fd_tiles_h, fd_cout;
@@ -414,9 +414,16 @@ __device__ __forceinline__ U8 ldg256(const void* ptr) {
 //   - when the layer is narrow (NT <= 64, one image per tile) a warp's visits all cover the same 16 channels of the
 //     same image, so bias / scale / shift collapse to out = act(acc * A + Bc) with A, Bc loaded once per tile
 //     (`epi_fixed`); wider layers load them per visit.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
 template <bool kScale, bool kRes, bool kSilu>
-__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, int warp,
-                                              int lane, int total_tiles) {
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, uint32_t ptab,
+                                              int warp, int lane, int total_tiles) {
   const int q = warp & 3;            // TMEM lane quarter this warp may access
   const int part = (warp - 2) >> 2;  // kEpiWarps/4 warps share a quarter and split the column chunks
   const int row = q * 32 + lane;     // GEMM row inside a sub-tile
@@ -430,11 +437,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
   const bool lrelu = p.act == ACT_LRELU;
   const float slope = p.slope;
-  float A[16], Bc[16];
-  if (fixed) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { A[j] = 1.f; Bc[j] = __ldg(p.bias + cfix + j); }
+  // `fixed`: A[16] | Bc[16] of this warp's channels live in a 128-byte shared-memory row (registers are short: 18
+  // warps leave 96 per thread, and spilled values miss the ~28 KB of L1 that 227 KB of shared memory leaves)
+  const float bias_l = (fixed && lane < 16) ? __ldg(p.bias + cfix + lane) : 0.f;
+  if (fixed && lane < 16) {
+    sts_f32(ptab + 4 * lane, 1.f);
+    sts_f32(ptab + 64 + 4 * lane, bias_l);
   }
+  __syncwarp();
   int as = 0, pacc = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const TileCoord tc = decode_tile(p, tile);
@@ -474,16 +484,13 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
       if (k0 == 0) {
         if (kScale && fixed) {
           const int b = bb < p.B ? bb : p.B - 1;
-          const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + cfix);
-          const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + cfix) : nullptr;
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + cfix);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 sc = __ldg(s4 + g), sh = h4 ? __ldg(h4 + g) : make_float4(0.f, 0.f, 0.f, 0.f), bi = __ldg(b4 + g);
-            A[g * 4 + 0] = sc.x; A[g * 4 + 1] = sc.y; A[g * 4 + 2] = sc.z; A[g * 4 + 3] = sc.w;
-            Bc[g * 4 + 0] = fmaf(bi.x, sc.x, sh.x); Bc[g * 4 + 1] = fmaf(bi.y, sc.y, sh.y);
-            Bc[g * 4 + 2] = fmaf(bi.z, sc.z, sh.z); Bc[g * 4 + 3] = fmaf(bi.w, sc.w, sh.w);
+          if (lane < 16) {
+            const float sc = __ldg(p.scale + (size_t)b * p.Cout + cfix + lane);
+            const float sh = p.shift ? __ldg(p.shift + (size_t)b * p.Cout + cfix + lane) : 0.f;
+            sts_f32(ptab + 4 * lane, sc);
+            sts_f32(ptab + 64 + 4 * lane, fmaf(bias_l, sc, sh));
           }
+          __syncwarp();
         }
         mbar_wait(acc_full + 8 * as, pacc);
         tc_fence_after();
@@ -500,7 +507,17 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
             float f[16];
             if (fixed) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = kScale ? fmaf(__uint_as_float(v[j]), A[j], Bc[j]) : __uint_as_float(v[j]) + Bc[j];
+              for (int g = 0; g < 4; ++g) {
+                const float4 bc = lds_f4(ptab + 64 + 16 * g);
+                if (kScale) {
+                  const float4 a = lds_f4(ptab + 16 * g);
+                  f[g * 4 + 0] = fmaf(__uint_as_float(v[g * 4 + 0]), a.x, bc.x); f[g * 4 + 1] = fmaf(__uint_as_float(v[g * 4 + 1]), a.y, bc.y);
+                  f[g * 4 + 2] = fmaf(__uint_as_float(v[g * 4 + 2]), a.z, bc.z); f[g * 4 + 3] = fmaf(__uint_as_float(v[g * 4 + 3]), a.w, bc.w);
+                } else {
+                  f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + bc.x; f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + bc.y;
+                  f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + bc.z; f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + bc.w;
+                }
+              }
             } else {
               const uint32_t n = (uint32_t)(tc.n0 + c);
               const uint32_t co = convt ? n - fdiv(n, p.fd_cout) * p.Cout : n;
@@ -780,7 +797,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   } else {
     // ===================== epilogue (warps 2..2+kEpiWarps) =====================
     const bool silu = p.act == ACT_SILU;
-#define YOND_EPI(S, R, A) epilogue_loop<S, R, A>(p, tmem_base, acc_full, acc_empty, warp, lane, total_tiles)
+    const uint32_t ptab = smem_base + p.smem_epi_off + (uint32_t)(warp - 2) * 128u;
+#define YOND_EPI(S, R, A) epilogue_loop<S, R, A>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles)
     if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true); else YOND_EPI(true, true, false); }
     else if (p.scale) { if (silu) YOND_EPI(true, false, true); else YOND_EPI(true, false, false); }
     else if (p.res) { if (silu) YOND_EPI(false, true, true); else YOND_EPI(false, true, false); }
@@ -916,7 +934,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.NB = rows / p.TH;
   const int ncb = p.ncb0 + p.ncb1;
   const int nwt = ((L.mode == CONV_3X3_S1 || L.mode == CONV_3X3_S2) ? 9 : 1) * ncb;
-  const size_t smem_budget = 227 * 1024 - 2048;  // dynamic smem minus alignment slack and barriers
+  const size_t smem_budget = 227 * 1024 - 2048 - kEpiWarps * 128;  // dynamic smem minus alignment slack, barriers, parameter rows
   p.b_stage_bytes = (uint32_t)p.NT * row_bytes;
   YOND_REQUIRE(p.b_stage_bytes % 1024 == 0, "conv_tc: weight stage not 1024-aligned");
   const size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
@@ -986,7 +1004,8 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   YOND_REQUIRE(p.SA >= 2, "conv_tc: not enough shared memory for the activation pipeline");
   p.smem_b_off = (uint32_t)p.SA * p.a_stage_bytes;
   p.smem_bar_off = (uint32_t)align_up(p.smem_b_off + b_region, 1024);
-  const size_t smem_bytes = p.smem_bar_off + 512 + 1024;  // barriers + alignment slack
+  p.smem_epi_off = p.smem_bar_off + 512;
+  const size_t smem_bytes = p.smem_epi_off + kEpiWarps * 128 + 1024;  // barriers, parameter rows, alignment slack
   p.acc_stages = 2 * p.T * p.NT <= 512 ? 2 : 1;
   p.tmem_cols = p.acc_stages * p.T * p.NT < 32 ? 32 : p.acc_stages * p.T * p.NT;
   if ((env_dbg & 64) && p.tmem_cols <= 256) p.tmem_cols = 512;
