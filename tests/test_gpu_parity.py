@@ -354,7 +354,7 @@ def test_full_frame_12mp_vs_oracle(Y, lut_table):
 
 
 def test_host_pipelined_path_equals_batched(Y):
-    """iter_denoise_host (pinned host buffers, copies overlapped on side streams; bench.py's e2e) == iter_denoise_batch."""
+    """iter_denoise_host (pinned host buffers, copies and estimator read-backs overlapped; bench.py's e2e) == iter_denoise_batch."""
     rng = np.random.default_rng(13)
     imgs = np.stack([np.stack([O.synth_noisy(rng, O.synth_clean_smooth(rng, 64, 64), 4.0, 6.0 + i) for _ in range(32)]) for i in range(5)])
     drv = Y.YOND_SIDD(ARCHS["gru"], PIPE, state_dict=O.init_state_dict(ARCHS["gru"], seed=5))
@@ -362,9 +362,12 @@ def test_host_pipelined_path_equals_batched(Y):
     ref = drv.iter_denoise_batch(torch.from_numpy(imgs).cuda(), dict(p))
     hin = torch.from_numpy(imgs).pin_memory()
     hout = torch.empty((5, 64, 32 * 64)).pin_memory()
-    res = drv.iter_denoise_host(hin, hout, dict(p), group=2)
-    assert torch.equal(hout, ref["raw_dns"][-1].cpu())
-    assert np.array_equal(res["rounds"], ref["rounds"])
+    for lanes in (1, 2):  # one host thread with copy streams; two host threads, each with its own stream and driver clone
+        hout.zero_()
+        res = drv.iter_denoise_host(hin, hout, dict(p), group=2, lanes=lanes)
+        assert torch.equal(hout, ref["raw_dns"][-1].cpu()), lanes
+        assert np.array_equal(res["rounds"], ref["rounds"])
+        assert np.allclose(np.concatenate([np.atleast_2d(r[0]) for r in res["regs"]]), ref["regs"][0], rtol=1e-12)
 
 
 def test_full_frame_identity_roundtrip(Y):

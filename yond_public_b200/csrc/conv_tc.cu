@@ -421,7 +421,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
-template <bool kScale, bool kRes, bool kSilu>
+template <bool kScale, bool kRes, bool kSilu, int kV>  // kV: visits per group (residual registers held at once)
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, uint32_t ptab,
                                               int warp, int lane, int total_tiles) {
   const int q = warp & 3;            // TMEM lane quarter this warp may access
@@ -454,14 +454,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
     // element offset of this thread's pixel in sub-tile 0 (+ first column of the tile unless transposed conv)
     const uint32_t e0 = convt ? (((uint32_t)bb * (2 * p.H) + 2 * h0) * (uint32_t)(2 * p.W) + 2 * w) * (uint32_t)p.Cout
                               : (((uint32_t)bb * p.H + h0) * (uint32_t)p.W + w) * (uint32_t)p.Cout + tc.n0;
-    // visits in groups of four (one group unless T * NT = 512)
-    for (int k0 = 0; part + 4 * k0 < nvis; k0 += 4) {
+    // visits in groups of kV
+    for (int k0 = 0; part + 4 * k0 < nvis; k0 += kV) {
       // ---- before the accumulator is ready: addresses, residual loads, per-tile parameters ----
-      uint32_t off[4];
+      uint32_t off[kV];
       uint32_t vmask = 0;
-      U8 rr[4];
+      U8 rr[kV];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kV; ++k) {
         const int ci = part + 4 * (k0 + k);
         off[k] = 0;
         if (ci < nvis) {
@@ -496,7 +496,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         tc_fence_after();
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kV; ++k) {
         const int ci = part + 4 * (k0 + k);
         if (ci < nvis && !(p.dbg & 128)) {  // dbg 128: the epilogue does not touch TMEM
           const int t = ci >> p.lg_nchunk, c = (ci & nchunk_m1) << 4;
@@ -798,11 +798,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // ===================== epilogue (warps 2..2+kEpiWarps) =====================
     const bool silu = p.act == ACT_SILU;
     const uint32_t ptab = smem_base + p.smem_epi_off + (uint32_t)(warp - 2) * 128u;
-#define YOND_EPI(S, R, A) epilogue_loop<S, R, A>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles)
-    if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true); else YOND_EPI(true, true, false); }
-    else if (p.scale) { if (silu) YOND_EPI(true, false, true); else YOND_EPI(true, false, false); }
-    else if (p.res) { if (silu) YOND_EPI(false, true, true); else YOND_EPI(false, true, false); }
-    else { if (silu) YOND_EPI(false, false, true); else YOND_EPI(false, false, false); }
+#define YOND_EPI(S, R, A, V) epilogue_loop<S, R, A, V>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles)
+    const bool few = p.T * (p.NT / 16) <= 8;  // at most two visits per warp and tile: hold two residual rows, not four
+    if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true, 2); else YOND_EPI(true, true, false, 2); }
+    else if (p.scale) { if (silu) YOND_EPI(true, false, true, 4); else YOND_EPI(true, false, false, 4); }
+    else if (p.res) {
+      if (few) { if (silu) YOND_EPI(false, true, true, 2); else YOND_EPI(false, true, false, 2); }
+      else { if (silu) YOND_EPI(false, true, true, 4); else YOND_EPI(false, true, false, 4); }
+    }
+    else { if (silu) YOND_EPI(false, false, true, 4); else YOND_EPI(false, false, false, 4); }
 #undef YOND_EPI
   }
 

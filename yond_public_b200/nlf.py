@@ -7,6 +7,8 @@ and the 2x2 least-squares solve.
 """
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 import torch
 
@@ -135,14 +137,15 @@ class NlfEstimator:
         return reg
 
 
-_EST = None
+_EST = threading.local()
 
 
 def _estimator():
-    global _EST
-    if _EST is None:
-        _EST = NlfEstimator()
-    return _EST
+    """One estimator (and its device scratch) per host thread: the host-pipelined path runs two lanes concurrently."""
+    est = getattr(_EST, "est", None)
+    if est is None:
+        est = _EST.est = NlfEstimator()
+    return est
 
 
 def _rggb_batch(raw, sidd_256):

@@ -393,11 +393,18 @@ class YOND_SIDD:
                 mark("denoise_round2")
         return {"raw_dns": [dn1, final], "regs": regs, "rounds": rounds, "lr_raw": mosaic}
 
-    def iter_denoise_host(self, host_in, host_out, p, group=8):
+    def iter_denoise_host(self, host_in, host_out, p, group=8, lanes=2):
         """End-to-end batched IterDenoise on HOST buffers: host_in (nimg,nblk,H,W) f32 pinned -> host_out
-        (nimg,H,nblk*W) f32 pinned (final round of every image).  Images are processed in groups; the H2D copy of the next
-        group and the D2H copy of the previous one run on their own streams while the current group computes
-        (double-buffered device staging, event-ordered)."""
+        (nimg,H,nblk*W) f32 pinned (final round of every image).  Images are processed in groups.
+
+        lanes >= 2 (default): the groups are dealt to `lanes` host threads, each with its own CUDA stream, driver clone
+        (network handle + workspace) and staging buffers.  A lane's H2D copy, compute and D2H copy are ordered on its
+        stream; across lanes they overlap, and — what a single host thread cannot do — the read-backs of the noise
+        estimator (three small synchronisations per group) of one lane are covered by the other lane's kernels.
+        lanes = 1: one host thread; the H2D copy of the next group and the D2H copy of the previous one run on their own
+        streams while the current group computes (double-buffered device staging, event-ordered)."""
+        if lanes > 1 and host_in.shape[0] > group:
+            return self._iter_denoise_host_lanes(host_in, host_out, p, group, lanes)
         assert host_in.is_pinned() and host_out.is_pinned(), "pinned host buffers required for asynchronous copies"
         nimg = host_in.shape[0]
         dev = self.device
@@ -446,6 +453,55 @@ class YOND_SIDD:
         cur.wait_stream(s_out)
         torch.cuda.synchronize(dev)
         return {"regs": regs, "rounds": np.concatenate(rounds)}
+
+    def _iter_denoise_host_lanes(self, host_in, host_out, p, group, lanes):
+        import threading
+        assert host_in.is_pinned() and host_out.is_pinned(), "pinned host buffers required for asynchronous copies"
+        nimg = host_in.shape[0]
+        dev = self.device
+        key = (tuple(host_in.shape[1:]), tuple(host_out.shape[1:]), group, lanes)
+        if getattr(self, "_lanes_key", None) != key:
+            sd = self.net.state_dict()
+            self._lanes = []
+            for i in range(lanes):
+                drv = self if i == 0 else YOND_SIDD(self.arch, self.pipe, state_dict=sd, biaslut=self.biaslut, device=dev,
+                                                     chunk=self.engine.chunk)
+                self._lanes.append(dict(drv=drv, stream=torch.cuda.Stream(dev),
+                                        din=torch.empty((group,) + tuple(host_in.shape[1:]), device=dev),
+                                        dout=torch.empty((group,) + tuple(host_out.shape[1:]), device=dev)))
+            self._lanes_key = key
+        groups = [(a, min(a + group, nimg)) for a in range(0, nimg, group)]
+        results = [None] * len(groups)
+        errors = []
+        start = torch.cuda.Event()
+        start.record(torch.cuda.current_stream(dev))
+
+        def work(li):
+            lane = self._lanes[li]
+            try:
+                with torch.cuda.device(dev), torch.cuda.stream(lane["stream"]):
+                    lane["stream"].wait_event(start)
+                    for g in range(li, len(groups), lanes):
+                        a, b = groups[g]
+                        lane["din"][:b - a].copy_(host_in[a:b], non_blocking=True)
+                        res = lane["drv"].iter_denoise_batch(lane["din"][:b - a], dict(p))
+                        lane["dout"][:b - a].copy_(res["raw_dns"][-1])
+                        host_out[a:b].copy_(lane["dout"][:b - a], non_blocking=True)
+                        results[g] = (res["regs"], res["rounds"])
+                    lane["stream"].synchronize()
+            except BaseException as e:  # surfaced on the calling thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(li,)) for li in range(1, lanes)]
+        for t in threads:
+            t.start()
+        work(0)
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        torch.cuda.current_stream(dev).wait_stream(self._lanes[0]["stream"])
+        return {"regs": [r[0] for r in results], "rounds": np.concatenate([r[1] for r in results])}
 
     def iter_denoise_device(self, blocks, p, lr_full=None):
         """Device-resident IterDenoise.  `blocks`: (nblk,H,W) CUDA f32 (SIDD layout) or (H,W) frame.
