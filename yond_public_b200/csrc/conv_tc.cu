@@ -65,6 +65,7 @@ struct TcParams {
   uint32_t sub_off, sbo, tap_r_off;  // byte offsets inside an activation stage: next sub-tile, next 8-row group, next image row
   uint32_t smem_b_off, smem_bar_off, smem_epi_off;  // weights, barriers, epilogue parameter rows (128 B per epilogue warp)
   int tmem_cols;
+  int cta2;        // CTA pair: cta_group::2 MMAs (M = 256 over two SMs), each CTA loads its own tile and half of every weight tile
   int acc_stages;  // accumulator stages in TMEM: 2 (epilogue of tile i overlaps the MMAs of tile i+1) or 1 (T*NT = 512 columns)
   FastDiv fd_tiles_n, fd_tiles_w, fd_tiles_h, fd_cout;
   int lg_nchunk;       // log2(NT / 16)
@@ -200,6 +201,56 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pair (cta_group::2): two SMs of one TPC run one M=256 MMA; each holds its own 128 rows of A and of the
+// accumulator and HALF of the B tile, so per-SM shared-memory reads and weight traffic halve.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in this CTA's shared memory, the transaction bytes are counted on `bar`, a
+// shared::cluster address (the leader CTA's barrier).
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -340,6 +391,36 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
   return t;
 }
 
+// Persistent tile schedule.  Single CTA: tile = blockIdx.x, += gridDim.x.  CTA pair: the pair walks "units" = (pair of
+// consecutive M tiles, n tile); rank r of the pair owns M tile 2 m + r (an M tile past the end decodes to images >= B:
+// its loads are zero-filled and its stores masked, but it takes part in the pair's MMAs).
+struct TileSched {
+  int first, step, n_units, rank, cta2;
+};
+template <bool kPair>
+__device__ __forceinline__ TileSched make_sched(const TcParams& p, int total_tiles) {
+  TileSched s;
+  s.cta2 = kPair ? 1 : 0;
+  if (kPair) {
+    s.rank = (int)cluster_ctarank();
+    s.first = (int)blockIdx.x >> 1;
+    s.step = (int)gridDim.x >> 1;
+    const int m_tiles = total_tiles / p.tiles_n;
+    s.n_units = ((m_tiles + 1) >> 1) * p.tiles_n;
+  } else {
+    s.rank = 0;
+    s.first = (int)blockIdx.x;
+    s.step = (int)gridDim.x;
+    s.n_units = total_tiles;
+  }
+  return s;
+}
+__device__ __forceinline__ int sched_tile(const TcParams& p, const TileSched& s, int u) {
+  if (!s.cta2) return u;
+  const int m2 = (int)fdiv((uint32_t)u, p.fd_tiles_n);
+  return (2 * m2 + s.rank) * p.tiles_n + (u - m2 * p.tiles_n);
+}
+
 // All MMAs of one tap (weight tile): TT sub-tile accumulators x KS steps of K=16, fully unrolled so that every
 // descriptor is `running low word + immediate` (two uniform adds per MMA; the B200 tensor pipe retires an
 // M=128,N=32 SS MMA every 40 cycles, N=64 every 48, N=128 every 64 — tools/mma_rate.cu — so the issue stream must
@@ -358,6 +439,33 @@ __device__ __forceinline__ void umma_step(uint32_t tmem_d, uint32_t& a_lo, uint3
       : "+r"(a_lo), "+r"(b_lo)
       : "r"(a_hi), "r"(b_hi), "r"(tmem_d), "r"(idesc), "r"(accum)
       : "memory");
+}
+__device__ __forceinline__ void umma_step_pair(uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t& b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%0, %2};\n\t"
+      "mov.b64 db, {%1, %3};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%4], da, db, %5, p;\n\t"
+      "add.u32 %0, %0, 2;\n\t"
+      "add.u32 %1, %1, 2;\n\t}"
+      : "+r"(a_lo), "+r"(b_lo)
+      : "r"(a_hi), "r"(b_hi), "r"(tmem_d), "r"(idesc), "r"(accum)
+      : "memory");
+}
+template <int KS, int TT>
+__device__ __forceinline__ void issue_tap_pair(uint32_t d_tmem, uint32_t nt, uint32_t a_lo0, uint32_t sub_step, uint32_t b_lo0,
+                                               uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t accum) {
+  uint32_t al = a_lo0, dt = d_tmem;
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    uint32_t bl = b_lo0;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) umma_step_pair(dt, al, a_hi, bl, b_hi, idesc, k ? 1u : accum);
+    al += sub_step - 2u * KS;
+    dt += nt;
+  }
 }
 template <int KS, int TT>
 __device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t nt, uint32_t a_lo0, uint32_t sub_step, uint32_t b_lo0,
@@ -421,9 +529,12 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
-template <bool kScale, bool kRes, bool kSilu, int kV>  // kV: visits per group (residual registers held at once)
+template <bool kScale, bool kRes, bool kSilu, int kV, bool kPair>  // kV: visits per group (residual registers held at once)
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, uint32_t ptab,
                                               int warp, int lane, int total_tiles) {
+  const TileSched sched = make_sched<kPair>(p, total_tiles);
+  // the MMA issuer that waits for "accumulator drained" lives in the pair's leader CTA
+  const uint32_t acc_empty_remote = kPair ? mapa_shared(acc_empty, 0) : acc_empty;
   const int q = warp & 3;            // TMEM lane quarter this warp may access
   const int part = (warp - 2) >> 2;  // kEpiWarps/4 warps share a quarter and split the column chunks
   const int row = q * 32 + lane;     // GEMM row inside a sub-tile
@@ -446,8 +557,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   }
   __syncwarp();
   int as = 0, pacc = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const TileCoord tc = decode_tile(p, tile);
+  for (int u = sched.first; u < sched.n_units; u += sched.step) {
+    const TileCoord tc = decode_tile(p, sched_tile(p, sched, u));
     const int w = tc.w0 + w_i, h0 = tc.h0 + dh;
     const int bb = tc.b0 + (p.t_along_h ? db : db * p.T);  // along the batch: sub-tile t = images t, t+T, ... of the tile
     const bool wv = (w < p.W) && (h0 < p.H) && (bb < p.B);
@@ -578,11 +689,15 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+    if (lane == 0) {
+      if (kPair) mbar_arrive_cluster(acc_empty_remote + 8 * as);
+      else mbar_arrive(acc_empty + 8 * as);
+    }
     if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
   }
 }
 
+template <bool kPair>  // kPair: CTA-pair build (cluster of 2, cta_group::2 instructions); launched with a cluster dimension
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -606,17 +721,28 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kEpiWarps); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + 8 * i, 1);
+      mbar_init(acc_empty + 8 * i, kPair ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogue warps report to the leader
+    }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(tmem_slot, p.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
+  const TileSched sched = make_sched<kPair>(p, total_tiles);
+  const bool pair_leader = sched.rank == 0;
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -636,8 +762,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     __syncwarp();
     int sa = 0, pa = 0, sb = 0, pb = 0;
     long long t_wait = 0, t_begin = clock64();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+    // CTA pair: "data landed" is counted on the LEADER's barriers (its MMA consumes both CTAs' stages); the leader
+    // expects the bytes of both CTAs, the peer only issues its loads.  "Stage free" arrives on each CTA's own barrier
+    // through the multicast commit.
+    const uint32_t a_full_sig = kPair ? mapa_shared(a_full, 0) : a_full;
+    const uint32_t b_full_sig = kPair ? mapa_shared(b_full, 0) : b_full;
+    const uint32_t b_half = kPair ? (uint32_t)(sched.rank * (p.NT / 2)) : 0u;  // this CTA's rows of every weight tile
+    for (int u = sched.first; u < sched.n_units; u += sched.step) {
+      const TileCoord tc = decode_tile(p, sched_tile(p, sched, u));
       for (int ai = 0; ai < n_ast; ++ai) {
         const AStage s = decode_astage(p, ai);
         const long long tw0 = clock64();
@@ -646,6 +778,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (is_leader) {
           if (p.dbg & 16) {  // bring-up: no activation loads (MMA-rate experiment; results are garbage)
             mbar_arrive(a_full + 8 * sa);
+          } else if (kPair) {
+            if (pair_leader) mbar_expect_tx(a_full + 8 * sa, 2 * p.a_tx_bytes);
+            tma_load_4d_pair(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full_sig + 8 * sa, s.c, tc.w0 + s.dw, tc.b0, tc.h0 + s.dh);
           } else {
             mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
             tma_load_4d(smem_a + sa * p.a_stage_bytes, &maps.a[s.map], a_full + 8 * sa, s.c, tc.w0 + s.dw, tc.b0, tc.h0 + s.dh);
@@ -658,8 +793,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const int widx = s.widx0 + (s.sx >= 0 ? j * 3 : j);
             mbar_wait(b_empty + 8 * sb, pb ^ 1);
             if (is_leader) {
-              mbar_expect_tx(b_full + 8 * sb, p.b_stage_bytes);
-              tma_load_2d(smem_b + sb * p.b_stage_bytes, &maps.w, b_full + 8 * sb, 0, widx * p.N + tc.n0);
+              if (kPair) {
+                if (pair_leader) mbar_expect_tx(b_full + 8 * sb, 2 * p.b_stage_bytes);
+                tma_load_2d_pair(smem_b + sb * p.b_stage_bytes, &maps.w, b_full_sig + 8 * sb, 0, widx * p.N + tc.n0 + (int)b_half);
+              } else {
+                mbar_expect_tx(b_full + 8 * sb, p.b_stage_bytes);
+                tma_load_2d(smem_b + sb * p.b_stage_bytes, &maps.w, b_full + 8 * sb, 0, widx * p.N + tc.n0);
+              }
             }
             __syncwarp();
             if (++sb == p.SB) { sb = 0; pb ^= 1; }
@@ -685,7 +825,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const uint32_t ub_full = ua_empty + 8 * kMaxStagesA, ub_empty = ub_full + 8 * kMaxStagesB;
     const uint32_t uacc_full = ub_empty + 8 * kMaxStagesB, uacc_empty = uacc_full + 16;
     const uint32_t uw_full = uacc_empty + 16;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
     const int ksteps = p.CB / 16;
     const uint32_t layout = (row_bytes == 128) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     // high words: stride byte offset [32,46), version 1 at bit 46, layout type at [61,64)
@@ -699,7 +839,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (p.wres) mbar_wait(uw_full, 0);
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     long long t_acc = 0, t_a = 0, t_issue = 0, t_begin = clock64();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // CTA pair: only the leader CTA issues (its MMAs drive both SMs' tensor cores); the peer's warp 1 idles
+    for (int u = (kPair && !pair_leader) ? sched.n_units : sched.first; u < sched.n_units; u += sched.step) {
       long long tw0 = clock64();
       mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
       t_acc += clock64() - tw0;
@@ -742,6 +883,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             else issue_tap<2, 4>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
           }
           umma_commit(ua_empty + 8 * sa);
+        } else if (leader && kPair) {
+          // CTA pair, streamed weights, single slab, 64-channel blocks: nine taps, each waits for both halves of its
+          // weight tile (counted on this CTA's barrier) and frees the stage in both CTAs
+          int lsb = sb, lpb = pb;
+          for (int j = 0; j < 9; ++j) {
+            const uint32_t r = (j >= 3) + (j >= 6), sx = j - r * 3;
+            mbar_wait(ub_full + 8 * lsb, lpb);
+            tc_fence_after();
+            const uint32_t a_lo0 = a_stage_lo + r * tap_r16 + sx * px16;
+            const uint32_t b_lo0 = (((u_smem_b + (uint32_t)lsb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+            const uint32_t accum = (ai | j) ? 1u : 0u;
+            if (p.T == 1) issue_tap_pair<4, 1>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+            else if (p.T == 2) issue_tap_pair<4, 2>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+            else issue_tap_pair<4, 4>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+            umma_commit_pair(ub_empty + 8 * lsb);
+            if (++lsb == p.SB) { lsb = 0; lpb ^= 1; }
+          }
+          umma_commit_pair(ua_empty + 8 * sa);
         } else if (leader) {
           int lsb = sb, lpb = pb;  // weight-ring position of this stage's first tap (uniform on entry)
           for (int j = 0; j < s.ntaps; ++j) {
@@ -787,7 +946,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         if (++sa == p.SA) { sa = 0; pa ^= 1; }
       }
-      if (leader) umma_commit(uacc_full + 8 * as);
+      if (leader) {
+        if (kPair) umma_commit_pair(uacc_full + 8 * as);
+        else umma_commit(uacc_full + 8 * as);
+      }
       __syncwarp();
       if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
     }
@@ -798,7 +960,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // ===================== epilogue (warps 2..2+kEpiWarps) =====================
     const bool silu = p.act == ACT_SILU;
     const uint32_t ptab = smem_base + p.smem_epi_off + (uint32_t)(warp - 2) * 128u;
-#define YOND_EPI(S, R, A, V) epilogue_loop<S, R, A, V>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles)
+#define YOND_EPI(S, R, A, V) epilogue_loop<S, R, A, V, kPair>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles)
     const bool few = p.T * (p.NT / 16) <= 8;  // at most two visits per warp and tile: hold two residual rows, not four
     if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true, 2); else YOND_EPI(true, true, false, 2); }
     else if (p.scale) { if (silu) YOND_EPI(true, false, true, 4); else YOND_EPI(true, false, false, 4); }
@@ -812,9 +974,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer's shared memory / barriers stay valid until both CTAs are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (kPair) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -943,6 +1107,11 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   YOND_REQUIRE(p.b_stage_bytes % 1024 == 0, "conv_tc: weight stage not 1024-aligned");
   const size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
   p.wres = (p.tiles_n == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
+  // CTA pairs for the layers that stream their weights (>= 128 channels): halves the per-SM weight traffic and the
+  // shared-memory reads of the B operand, which is what bounds those layers with single-CTA MMAs.
+  static const int env_cta2 = env_int("YOND_CONV_CTA2", 256);  // smallest N tile that runs as a CTA pair (0: never)
+  p.cta2 = (conv3 && p.slab && !p.wres && p.CB == 64 && p.NT >= env_cta2 && env_cta2 > 0 && yond_num_sms() >= 2) ? 1 : 0;
+  if (p.cta2) p.b_stage_bytes /= 2;  // each CTA of the pair holds NT/2 rows of every weight tile
   // T sub-tiles share each weight tile (and one halo slab): stacked along H when the map is tall enough, else along
   // the batch (sub-tile t = images t, t+T, ... of the tile, so that the 8-row groups keep a uniform stride).  T is
   // bounded by TMEM and by shared memory.  Resident-weight layers keep two accumulator stages (2 T NT <= 512 columns);
@@ -1060,21 +1229,45 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
     }
   }
   {
-    int rc = make_weight_map(&maps.w, L.wpacked, p.CB, (size_t)nwt * p.N, p.NT);
+    int rc = make_weight_map(&maps.w, L.wpacked, p.CB, (size_t)nwt * p.N, p.cta2 ? p.NT / 2 : p.NT);
     if (rc) return rc;
   }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess)
     return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_kernel) failed: %s", cudaGetErrorString(attr_err));
 
   const int total_tiles = p.tiles_b * p.tiles_h * p.tiles_w * p.tiles_n;
+  if (p.cta2) {
+    const int m_tiles = total_tiles / p.tiles_n;
+    const int units = ((m_tiles + 1) / 2) * p.tiles_n;
+    int grid = yond_num_sms() & ~1;
+    if (grid > 2 * units) grid = 2 * units;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, maps, p);
+    if (e != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "conv_tc: cluster launch failed: %s", cudaGetErrorString(e));
+    yond_count_launch(1);
+    return YOND_OK;
+  }
   int grid = yond_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(maps, p);
+  conv_tc_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(maps, p);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -52,7 +54,8 @@ class YondEngine:
         if self.chunk:
             return min(B, int(self.chunk))
         per = max(1, hp * wp * 800)  # ~bytes of activations per frame
-        return int(max(1, min(B, (8 << 30) // per, 256)))
+        cap = int(os.environ.get("YOND_CHUNK", "640"))
+        return int(max(1, min(B, (8 << 30) // per, cap)))
 
     # ------------------------------------------------------------------------------------------
     def make_params(self, gains, sigmas, scale, bias_corr, vst_type, frame_max, device, fixed_table=None):
