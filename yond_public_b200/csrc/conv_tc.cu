@@ -883,24 +883,33 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             else issue_tap<2, 4>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
           }
           umma_commit(ua_empty + 8 * sa);
-        } else if (leader && kPair) {
-          // CTA pair, streamed weights, single slab, 64-channel blocks: nine taps, each waits for both halves of its
-          // weight tile (counted on this CTA's barrier) and frees the stage in both CTAs
+        } else if (leader && !p.wres && p.slab && p.mode == CONV_3X3_S1 && ksteps == 4 && !(p.dbg & 32)) {
+          // streamed weights, single slab, 64-channel blocks: nine taps with a compile-time trip count; each waits for
+          // its weight tile (CTA pair: both halves, counted on this CTA's barrier) and frees the stage (in both CTAs)
           int lsb = sb, lpb = pb;
+#pragma unroll
           for (int j = 0; j < 9; ++j) {
-            const uint32_t r = (j >= 3) + (j >= 6), sx = j - r * 3;
+            const uint32_t r = j / 3, sx = j % 3;
             mbar_wait(ub_full + 8 * lsb, lpb);
             tc_fence_after();
             const uint32_t a_lo0 = a_stage_lo + r * tap_r16 + sx * px16;
             const uint32_t b_lo0 = (((u_smem_b + (uint32_t)lsb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
             const uint32_t accum = (ai | j) ? 1u : 0u;
-            if (p.T == 1) issue_tap_pair<4, 1>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
-            else if (p.T == 2) issue_tap_pair<4, 2>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
-            else issue_tap_pair<4, 4>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
-            umma_commit_pair(ub_empty + 8 * lsb);
+            if (kPair) {
+              if (p.T == 1) issue_tap_pair<4, 1>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+              else if (p.T == 2) issue_tap_pair<4, 2>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+              else issue_tap_pair<4, 4>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+              umma_commit_pair(ub_empty + 8 * lsb);
+            } else {
+              if (p.T == 1) issue_tap<4, 1>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+              else if (p.T == 2) issue_tap<4, 2>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+              else issue_tap<4, 4>(d_tmem, nt, a_lo0, sub_step, b_lo0, a_hi, b_hi, idesc, accum);
+              umma_commit(ub_empty + 8 * lsb);
+            }
             if (++lsb == p.SB) { lsb = 0; lpb ^= 1; }
           }
-          umma_commit_pair(ua_empty + 8 * sa);
+          if (kPair) umma_commit_pair(ua_empty + 8 * sa);
+          else umma_commit(ua_empty + 8 * sa);
         } else if (leader) {
           int lsb = sb, lpb = pb;  // weight-ring position of this stage's first tap (uniform on entry)
           for (int j = 0; j < s.ntaps; ++j) {
@@ -1109,7 +1118,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.wres = (p.tiles_n == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
   // CTA pairs for the layers that stream their weights (>= 128 channels): halves the per-SM weight traffic and the
   // shared-memory reads of the B operand, which is what bounds those layers with single-CTA MMAs.
-  static const int env_cta2 = env_int("YOND_CONV_CTA2", 256);  // smallest N tile that runs as a CTA pair (0: never)
+  static const int env_cta2 = env_int("YOND_CONV_CTA2", 128);  // smallest N tile that runs as a CTA pair (0: never)
   p.cta2 = (conv3 && p.slab && !p.wres && p.CB == 64 && p.NT >= env_cta2 && env_cta2 > 0 && yond_num_sms() >= 2) ? 1 : 0;
   if (p.cta2) p.b_stage_bytes /= 2;  // each CTA of the pair holds NT/2 rows of every weight tile
   // T sub-tiles share each weight tile (and one halo slab): stacked along H when the map is tall enough, else along
@@ -1121,8 +1130,10 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   // Stride-2 / 1x1 / transposed layers stack their sub-tiles along H only (a taller box of whole 128-row tiles).
   int T = 1;
   {
+    static const int env_pair_double = env_int("YOND_CONV_PAIR_DOUBLE", 1);
     static const int env_acc1 = env_int("YOND_CONV_ACC1", 1);  // 0: never trade the second accumulator stage for a larger T
-    int tmax = (p.wres || !env_acc1) ? 512 / (2 * p.NT) : 512 / p.NT;
+    // (a CTA pair already halves the weight traffic per SM: it keeps both accumulator stages)
+    int tmax = (p.wres || !env_acc1 || (p.cta2 && env_pair_double)) ? 512 / (2 * p.NT) : 512 / p.NT;
     if (tmax > env_T) tmax = env_T;
     if (tmax > kMaxT) tmax = kMaxT;
     if (p.NB == 1) {
