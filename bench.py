@@ -35,7 +35,7 @@ WORKLOAD = ("configs[1]: 1280 synthetic 256x256 Bayer blocks (40 images x 32), G
 
 
 E2E_GROUP = int(os.environ.get("YOND_E2E_GROUP", "8"))
-E2E_LANES = int(os.environ.get("YOND_E2E_LANES", "3"))
+E2E_LANES = int(os.environ.get("YOND_E2E_LANES", "5"))
 
 
 def synth_images(n_images, seed=2024):

@@ -478,6 +478,10 @@ class YOND_SIDD:
         errors = []
         start = torch.cuda.Event()
         start.record(torch.cuda.current_stream(dev))
+        # H2D copies are chained in group order (each waits for the previous group's copy): the first group then arrives
+        # at full PCIe rate and its lane starts computing while the later groups are still on the wire
+        h2d_done = [torch.cuda.Event() for _ in groups]
+        h2d_issued = [threading.Event() for _ in groups]
 
         def work(li):
             lane = self._lanes[li]
@@ -486,7 +490,12 @@ class YOND_SIDD:
                     lane["stream"].wait_event(start)
                     for g in range(li, len(groups), lanes):
                         a, b = groups[g]
+                        if g > 0:
+                            h2d_issued[g - 1].wait()
+                            lane["stream"].wait_event(h2d_done[g - 1])
                         lane["din"][:b - a].copy_(host_in[a:b], non_blocking=True)
+                        h2d_done[g].record(lane["stream"])
+                        h2d_issued[g].set()
                         res = lane["drv"].iter_denoise_batch(lane["din"][:b - a], dict(p))
                         lane["dout"][:b - a].copy_(res["raw_dns"][-1])
                         host_out[a:b].copy_(lane["dout"][:b - a], non_blocking=True)
@@ -494,6 +503,8 @@ class YOND_SIDD:
                     lane["stream"].synchronize()
             except BaseException as e:  # surfaced on the calling thread
                 errors.append(e)
+                for ev in h2d_issued:  # never leave the other lanes waiting
+                    ev.set()
 
         threads = [threading.Thread(target=work, args=(li,)) for li in range(1, lanes)]
         for t in threads:
