@@ -366,9 +366,9 @@ class YOND_SIDD:
             dn = self.engine.vst_denoise(src, gg, ss, scale, bias_corr=bias_corr, vst_type=vst_type, clip01=True,
                                          table_bound=bound)
             n = dn.shape[0] // nblk
-            return dn.reshape(n, nblk, H, W).permute(0, 2, 1, 3).reshape(n, H, nblk * W).contiguous()  # :408
+            return dn.reshape(n, nblk, H, W).permute(0, 2, 1, 3).reshape(n, H, nblk * W).contiguous(), dn  # :408 (+ block layout)
 
-        dn1 = denoise(gains, sigmas)
+        dn1, dn1_blocks = denoise(gains, sigmas)
         mark("denoise_round1")
         regs, rounds = [reg1], np.ones(nimg, np.int64)
         final = dn1
@@ -377,7 +377,7 @@ class YOND_SIDD:
             sidd = bool(pipe.get("sidd_256", nblk == 32))
             if sidd:  # blocks become separate images of the box filters (:91-93); segments stay per image
                 lr_b = isp.bayer2rggb(flat)
-                dn_b = isp.bayer2rggb(dn1.reshape(nimg, H, nblk, W).permute(0, 2, 1, 3).reshape(nimg * nblk, H, W).contiguous())
+                dn_b = isp.bayer2rggb(dn1_blocks)  # the denoised blocks as they left the network (no mosaic round trip)
             else:
                 lr_b, dn_b = isp.bayer2rggb(mosaic), isp.bayer2rggb(dn1)
             reg2 = np.atleast_2d(est.estimate(lr_b, dn_b, k, nseg=nimg)).copy()  # :431 (mode 'collab')
@@ -389,7 +389,7 @@ class YOND_SIDD:
             if ok.any():
                 sel = torch.from_numpy(np.nonzero(ok)[0]).to(blocks.device)
                 g2, s2 = reg2[ok, 0] * scale_est, np.sqrt(reg2[ok, 1]) * scale_est  # :442
-                dn2 = denoise(g2, s2, sel if not ok.all() else None)
+                dn2, _ = denoise(g2, s2, sel if not ok.all() else None)
                 final = dn1.clone()
                 final[sel] = dn2
                 rounds[ok] = 2
