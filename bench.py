@@ -234,11 +234,11 @@ def run_b200(args):
     ach_tf = prof["conv_flops"] / (prof["conv_ms"] / 1e3) / 1e12 if prof["conv_ms"] > 0 else 0.0
 
     traffic, traffic_note = None, None
-    try:  # ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the conv launches of one 256-block chunk
+    try:  # ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the conv launches of one 640-block chunk
         with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
             tj = json.load(f)
         traffic = tj["dram_bytes_per_launch"]
-        traffic_note = "profiles/r01_conv_traffic.json: mean DRAM bytes per conv_tc_kernel launch (ncu, cold cache, 256-block chunk)"
+        traffic_note = "profiles/r01_conv_traffic.json: mean DRAM bytes per conv_tc_kernel launch (ncu, cold cache, one 640-block chunk = half a step)"
     except Exception:
         pass
     cpu_base = None
@@ -265,7 +265,7 @@ def run_b200(args):
                        "l2_policy": "inputs (335 MB per step) and activations exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"image-parallel x{world}, NCCL gather of denoised frames to rank 0" if world > 1 else "single GPU"},
             "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4),
-                    "ms_per_step": ms_e2e / args.steps, "api": f"YOND_SIDD.iter_denoise_host: pinned host buffers in/out, groups of {E2E_GROUP} images dealt to {E2E_LANES} host threads (own stream + driver clone each); copies and estimator read-backs of one lane overlap the other lane's kernels"},
+                    "ms_per_step": ms_e2e / args.steps, "api": f"YOND_SIDD.iter_denoise_host: pinned host buffers in/out, groups of {E2E_GROUP} images dealt to {E2E_LANES} host threads (own stream + driver clone each); H2D copies chained in group order; copies and estimator read-backs of one lane overlap the other lanes' kernels"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
