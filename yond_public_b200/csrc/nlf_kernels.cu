@@ -4,6 +4,8 @@
 //              YOND_SIDD.py:22-49 (get_threshold 'score3'), :62-115 (SelfNLF / CollabNLF).
 // cv2.blur on float32 = normalised box, BORDER_REFLECT_101, float64 running sums, result rounded to float32;
 // the kernels below keep float64 sums (vertical pass -> float64 scratch -> horizontal pass) to match it.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -238,9 +240,18 @@ __global__ void __launch_bounds__(1024) select0_kernel(SelectWork* wk, const uns
     wk->nslot1 = ns;
   }
 }
-__global__ void __launch_bounds__(256) hist1_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
+// Second radix level.  The queried ranks (percentiles 5..95) sit in a handful of top-11-bit buckets that together
+// hold most of the data, so nearly every element increments a counter: the counters of the first kHist1Slots buckets
+// are privatised in shared memory (32-bit, flushed once per block), later buckets fall back to global atomics.
+constexpr int kHist1Slots = 16;
+constexpr int kHist1Threads = 1024;
+__global__ void __launch_bounds__(kHist1Threads) hist1_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
+  extern __shared__ unsigned int hs[];  // [kHist1Slots][2048]
   d += (size_t)blockIdx.y * n;
   wk += blockIdx.y;
+  const int nsh = min(wk->nslot1, kHist1Slots);
+  for (int i = threadIdx.x; i < nsh * 2048; i += blockDim.x) hs[i] = 0u;
+  __syncthreads();
   const float4* d4 = reinterpret_cast<const float4*>(d);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = ldg_stream_f4(d4 + i);
@@ -248,10 +259,17 @@ __global__ void __launch_bounds__(256) hist1_kernel(const float* __restrict__ d,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t k = f2key(e[j]);
-      const int s = wk->slot1_of_prefix[k >> 21];
-      if (s >= 0) atomicAdd(&wk->hist1[s][(k >> 10) & 2047u], 1ull);
+      const int s = __ldg(&wk->slot1_of_prefix[k >> 21]);
+      if (s >= 0) {
+        const uint32_t mid = (k >> 10) & 2047u;
+        if (s < kHist1Slots) atomicAdd(&hs[s * 2048 + mid], 1u);
+        else atomicAdd(&wk->hist1[s][mid], 1ull);
+      }
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nsh * 2048; i += blockDim.x)
+    if (hs[i]) atomicAdd(&wk->hist1[i >> 11][i & 2047], (unsigned long long)hs[i]);
 }
 __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nranks) {
   wk += blockIdx.x;
@@ -316,9 +334,18 @@ __global__ void __launch_bounds__(256) score3_kernel(const float* __restrict__ l
   ths += (size_t)blockIdx.y * nth;
   minj += (size_t)blockIdx.y * 1001;
   __shared__ int smin[1001];
-  __shared__ double sth[32];
+  __shared__ float sthf[32];
   for (int i = threadIdx.x; i < 1001; i += blockDim.x) smin[i] = 0x7fffffff;
-  if (threadIdx.x < nth) sth[threadIdx.x] = ths[threadIdx.x];
+  if (threadIdx.x < 32) {
+    // lap is float32: (double)l <= t  <=>  l <= the largest float32 not above t, so the comparison runs in float32
+    float f = __int_as_float(0x7f800000);  // +inf pads the table
+    if ((int)threadIdx.x < nth) {
+      const double t = ths[threadIdx.x];
+      f = __double2float_rn(t);
+      if ((double)f > t) f = nextafterf(f, -__int_as_float(0x7f800000));
+    }
+    sthf[threadIdx.x] = f;
+  }
   __syncthreads();
   const float4* l4 = reinterpret_cast<const float4*>(lap);
   const float4* m4 = reinterpret_cast<const float4*>(mean);
@@ -327,9 +354,14 @@ __global__ void __launch_bounds__(256) score3_kernel(const float* __restrict__ l
     const float le[4] = {lv.x, lv.y, lv.z, lv.w}, me[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const double l = (double)le[e];
+      const float l = le[e];
+      // ths ascending: j = number of thresholds that do not admit this pixel = index of the first that does
       int j = 0;
-      while (j < nth && !(l <= sth[j])) ++j;  // ths ascending: first threshold that admits this pixel
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const int m = j + step;
+        if (m <= nth && !(l <= sthf[m - 1])) j = m;
+      }
       if (j < nth) {
         const int bin = (int)__fmul_rn(fminf(fmaxf(me[e], 0.f), 1.f), 1000.f);
         if (smin[bin] > j) atomicMin(&smin[bin], j);
@@ -498,16 +530,27 @@ int yond_order_stats(const float* data, size_t seg_len, int nseg, const uint64_t
   YOND_REQUIRE(seg_len % 4 == 0 && (uintptr_t)data % 16 == 0, "yond_order_stats: segments must hold whole 4-channel pixels (16-byte aligned)");
   cudaStream_t s = (cudaStream_t)stream;
   SelectWork* wk = reinterpret_cast<SelectWork*>(work);
-  for (int i = 0; i < nseg; ++i)
-    YOND_CUDA_CHECK(cudaMemsetAsync(wk + i, 0, offsetof(SelectWork, slot1_of_prefix), s));
+  // one memset for all segments (the slot tables behind the histograms are rewritten by the select kernels anyway)
+  YOND_CUDA_CHECK(cudaMemsetAsync(wk, 0, (size_t)nseg * sizeof(SelectWork), s));
   dim3 g(stream_grid(seg_len), nseg);
   if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
   hist0_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
   YOND_LAUNCH_CHECK();
   select0_kernel<<<nseg, 1024, 0, s>>>(wk, reinterpret_cast<const unsigned long long*>(ranks_dev), nranks);
   YOND_LAUNCH_CHECK();
-  hist1_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
-  YOND_LAUNCH_CHECK();
+  {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    const size_t smem = (size_t)kHist1Slots * 2048 * sizeof(unsigned int);
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(hist1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    if (attr_err != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(hist1_kernel) failed: %s", cudaGetErrorString(attr_err));
+    int bx = yond_num_sms() / nseg;  // one 128 KB block per SM
+    if (bx < 1) bx = 1;
+    const size_t need = (seg_len / 4 + kHist1Threads - 1) / kHist1Threads;
+    if ((size_t)bx > need) bx = (int)need;
+    hist1_kernel<<<dim3(bx, nseg), kHist1Threads, smem, s>>>(data, seg_len, wk);
+    YOND_LAUNCH_CHECK();
+  }
   select1_kernel<<<nseg, 1024, 0, s>>>(wk, nranks);
   YOND_LAUNCH_CHECK();
   hist2_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
