@@ -34,7 +34,8 @@ WORKLOAD = ("configs[1]: 1280 synthetic 256x256 Bayer blocks (40 images x 32), G
             "SIDD_simple+full_pre pipeline: self estimate + VST denoise + collab estimate per image")
 
 
-E2E_GROUP = int(os.environ.get("YOND_E2E_GROUP", "8"))
+E2E_GROUP = os.environ.get("YOND_E2E_GROUP", "8")
+E2E_GROUP = int(E2E_GROUP) if "," not in E2E_GROUP else [int(v) for v in E2E_GROUP.split(",")]
 E2E_LANES = int(os.environ.get("YOND_E2E_LANES", "5"))
 
 

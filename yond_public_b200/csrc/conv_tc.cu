@@ -65,6 +65,7 @@ struct TcParams {
   uint32_t sub_off, sbo, tap_r_off;  // byte offsets inside an activation stage: next sub-tile, next 8-row group, next image row
   uint32_t smem_b_off, smem_bar_off, smem_epi_off;  // weights, barriers, epilogue parameter rows (128 B per epilogue warp)
   int tmem_cols;
+  uint32_t b2_stage_bytes, b2_off;  // CONV_UPSC: skip-part weight tile (Cout rows) and where those tiles start in the weight region
   int cta2;        // CTA pair: cta_group::2 MMAs (M = 256 over two SMs), each CTA loads its own tile and half of every weight tile
   int acc_stages;  // accumulator stages in TMEM: 2 (epilogue of tile i overlaps the MMAs of tile i+1) or 1 (T*NT = 512 columns)
   FastDiv fd_tiles_n, fd_tiles_w, fd_tiles_h, fd_cout;
@@ -85,6 +86,7 @@ struct TcParams {
 struct TcMaps {
   CUtensorMap a[8];
   CUtensorMap w;
+  CUtensorMap w2;  // CONV_UPSC: skip-part weight tiles
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -351,6 +353,22 @@ __device__ __forceinline__ AStage decode_astage(const TcParams& p, int ai) {
     s.dw = (sx == 0) ? -1 : 0;
     s.ntaps = 1;
     s.widx0 = cbg * 9 + tap;
+  } else if (p.mode == CONV_UPSC) {
+    s.dw = 0;
+    s.dh = 0;
+    s.ntaps = 1;
+    if (ai < p.ncb0) {  // folded up-sampling part: low-resolution source, all four parities at once (N = 4 Cout)
+      s.map = 0;
+      s.c = ai * p.CB;
+      s.widx0 = ai;
+    } else {            // skip part: one stage per (parity, channel block), N = Cout into that parity's columns
+      const int j = ai - p.ncb0;
+      const int q = j / p.ncb1, cb = j - q * p.ncb1;
+      s.map = 4 + q;
+      s.c = cb * p.CB;
+      s.widx0 = cb;
+      s.sx = q;
+    }
   } else {
     int src = ai >= p.ncb0;
     s.map = src;
@@ -365,6 +383,7 @@ __device__ __forceinline__ AStage decode_astage(const TcParams& p, int ai) {
 __device__ __forceinline__ int num_astages(const TcParams& p) {
   int ncb = p.ncb0 + p.ncb1;
   if (p.mode == CONV_3X3_S1) return p.slab ? ncb : ncb * 3;
+  if (p.mode == CONV_UPSC) return p.ncb0 + 4 * p.ncb1;
   return p.mode == CONV_3X3_S2 ? ncb * 9 : ncb;
 }
 __device__ __forceinline__ int num_wtiles(const TcParams& p) {
@@ -543,7 +562,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   const int dh = g_i / p.NB, db = g_i & (p.NB - 1);
   const int nchunk_m1 = (1 << p.lg_nchunk) - 1, nvis = p.T << p.lg_nchunk;
   const bool fixed = p.epi_fixed != 0 && !(kScale && kRes);  // both at once would not fit the register budget
-  const bool convt = p.mode == CONVT_2X2;
+  const bool convt = p.mode == CONVT_2X2 || p.mode == CONV_UPSC;  // output pixel (2h+a, 2w+b), n = (a*2+b)*Cout + co
   const int cfix = (part & nchunk_m1) * 16;
   const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
   const bool lrelu = p.act == ACT_LRELU;
@@ -753,7 +772,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (is_leader) {
       tma_prefetch_desc(&maps.w);
       tma_prefetch_desc(&maps.a[0]);
-      if (p.wres) {  // all weight tiles of this layer stay in smem for the kernel's lifetime
+      if (p.wres && p.mode == CONV_UPSC) {
+        mbar_expect_tx(w_full, p.ncb0 * p.b_stage_bytes + p.ncb1 * p.b2_stage_bytes);
+        for (int i = 0; i < p.ncb0; ++i) tma_load_2d(smem_b + i * p.b_stage_bytes, &maps.w, w_full, 0, i * p.N);
+        for (int i = 0; i < p.ncb1; ++i) tma_load_2d(smem_b + p.b2_off + i * p.b2_stage_bytes, &maps.w2, w_full, 0, i * p.Cout);
+      } else if (p.wres) {  // all weight tiles of this layer stay in smem for the kernel's lifetime
         const int nwt = num_wtiles(p);
         mbar_expect_tx(w_full, nwt * p.b_stage_bytes);
         for (int i = 0; i < nwt; ++i) tma_load_2d(smem_b + i * p.b_stage_bytes, &maps.w, w_full, 0, i * p.N);
@@ -826,6 +849,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const uint32_t uacc_full = ub_empty + 8 * kMaxStagesB, uacc_empty = uacc_full + 16;
     const uint32_t uw_full = uacc_empty + 16;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
+    const uint32_t idesc_full = idesc;
     const int ksteps = p.CB / 16;
     const uint32_t layout = (row_bytes == 128) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     // high words: stride byte offset [32,46), version 1 at bit 46, layout type at [61,64)
@@ -846,6 +870,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       t_acc += clock64() - tw0;
       tc_fence_after();
       const uint32_t d_tmem = u_tmem + (uint32_t)(as * p.T) * nt;
+      const uint32_t d_tmem_tile = d_tmem;
       for (int ai = 0; ai < n_ast; ++ai) {
         const AStage s = decode_astage(p, ai);
         tw0 = clock64();
@@ -870,9 +895,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
           umma_commit(ua_empty + 8 * sa);
         } else if (leader && p.wres && p.mode != CONV_3X3_S1 && !(p.dbg & 32)) {
-          // resident weights, one tap per stage (stride-2 / 1x1 / transposed): one straight-line burst
-          const uint32_t b_lo0 = (((u_smem_b + (uint32_t)s.widx0 * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+          // resident weights, one tap per stage (stride-2 / 1x1 / transposed / fused up-sampling): one straight-line burst
+          uint32_t b_lo0 = (((u_smem_b + (uint32_t)s.widx0 * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
           const uint32_t acc0 = ai ? 1u : 0u;
+          uint32_t idesc = idesc_full, d_tmem = d_tmem_tile;
+          if (p.mode == CONV_UPSC && s.sx >= 0) {  // skip part: N = Cout, accumulate into parity s.sx's columns
+            b_lo0 = (((u_smem_b + p.b2_off + (uint32_t)s.widx0 * p.b2_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+            idesc = (idesc_full & ~(0x3Fu << 17)) | ((uint32_t)(p.Cout >> 3) << 17);
+            d_tmem = d_tmem_tile + (uint32_t)(s.sx * p.Cout);
+          }
           if (ksteps == 4) {
             if (p.T == 1) issue_tap<4, 1>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
             else if (p.T == 2) issue_tap<4, 2>(d_tmem, nt, a_stage_lo, sub_step, b_lo0, a_hi, b_hi, idesc, acc0);
@@ -1064,6 +1095,7 @@ int conv_tc_channel_block(int Cin0, int Cin1) {
 }
 
 size_t conv_tc_packed_elems(int mode, int Cin_total, int Cout) {
+  if (mode == CONV_UPSC) return (size_t)(Cin_total - Cout) * 4 * Cout + (size_t)Cout * Cout;  // folded part + skip part
   int taps = (mode == CONV_3X3_S1 || mode == CONV_3X3_S2) ? 9 : 1;
   int N = (mode == CONVT_2X2) ? 4 * Cout : Cout;
   return (size_t)taps * Cin_total * N;
@@ -1076,7 +1108,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   static const int env_slab = env_int("YOND_CONV_SLAB", 1);
   static const int env_T = env_int("YOND_CONV_T", kMaxT);
   static const int env_dbg = env_int("YOND_CONV_DBG", 0);
-  YOND_REQUIRE((double)L.B * L.Hin * L.Win * (L.mode == CONVT_2X2 ? 4.0 : 1.0) * L.Cout < 4294967296.0,
+  YOND_REQUIRE((double)L.B * L.Hin * L.Win * ((L.mode == CONVT_2X2 || L.mode == CONV_UPSC) ? 4.0 : 1.0) * L.Cout < 4294967296.0,
                "conv_tc: output of %d x %d x %d x %d elements exceeds the 32-bit offset range; split the batch", L.B, L.Hin, L.Win, L.Cout);
   YOND_REQUIRE(L.scale != nullptr || L.shift == nullptr, "conv_tc: a shift vector needs a scale vector");
   TcParams p{};
@@ -1091,7 +1123,8 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
     p.W = L.Win;
   }
   p.Cout = L.Cout;
-  p.N = (L.mode == CONVT_2X2) ? 4 * L.Cout : L.Cout;
+  const bool convt_like = L.mode == CONVT_2X2 || L.mode == CONV_UPSC;
+  p.N = convt_like ? 4 * L.Cout : L.Cout;
   p.CB = conv_tc_channel_block(L.Cin0, L.Cin1);
   p.ncb0 = L.Cin0 / p.CB;
   p.ncb1 = L.Cin1 / p.CB;
@@ -1114,7 +1147,15 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   const size_t smem_budget = 227 * 1024 - 2048 - kEpiWarps * 128;  // dynamic smem minus alignment slack, barriers, parameter rows
   p.b_stage_bytes = (uint32_t)p.NT * row_bytes;
   YOND_REQUIRE(p.b_stage_bytes % 1024 == 0, "conv_tc: weight stage not 1024-aligned");
-  const size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
+  size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
+  if (L.mode == CONV_UPSC) {
+    YOND_REQUIRE(L.Cin1 == L.Cout && L.src1 != nullptr, "conv_tc: fused up-sampling needs a skip source with Cout channels");
+    p.b2_stage_bytes = (uint32_t)L.Cout * row_bytes;
+    p.b2_off = (uint32_t)p.ncb0 * p.b_stage_bytes;
+    wres_bytes = (size_t)p.b2_off + (size_t)p.ncb1 * p.b2_stage_bytes;
+    YOND_REQUIRE(p.tiles_n == 1 && wres_bytes <= 80 * 1024 && p.b2_stage_bytes % 1024 == 0,
+                 "conv_tc: fused up-sampling is built for resident weights (Cout <= 64); got Cout=%d", L.Cout);
+  }
   p.wres = (p.tiles_n == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
   // CTA pairs for the layers that stream their weights (>= 128 channels): halves the per-SM weight traffic and the
   // shared-memory reads of the B operand, which is what bounds those layers with single-CTA MMAs.
@@ -1202,12 +1243,12 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.fd_cout = make_fastdiv((uint32_t)p.Cout);
   p.lg_nchunk = 0;
   while ((16 << p.lg_nchunk) < p.NT) ++p.lg_nchunk;
-  if (L.mode == CONVT_2X2) p.t_off = (uint32_t)p.TH * 4u * p.W * p.Cout;  // TH input rows = 2 TH output rows of 2 W pixels
+  if (convt_like) p.t_off = (uint32_t)p.TH * 4u * p.W * p.Cout;  // TH input rows = 2 TH output rows of 2 W pixels
   else p.t_off = (p.t_along_h ? (uint32_t)p.TH * p.W : (uint32_t)p.H * p.W) * (uint32_t)p.Cout;
   YOND_REQUIRE(L.act != ACT_LRELU || (L.slope >= 0.f && L.slope <= 1.f), "conv_tc: LeakyReLU slope must be in [0, 1]");
   {
     const int nchunk = p.NT / 16;
-    p.epi_fixed = (p.tiles_n == 1 && nchunk <= 4 && p.NB == 1 && (p.T == 1 || p.t_along_h) && L.mode != CONVT_2X2) ? 1 : 0;
+    p.epi_fixed = (p.tiles_n == 1 && nchunk <= 4 && p.NB == 1 && (p.T == 1 || p.t_along_h) && !convt_like) ? 1 : 0;
   }
   p.bias = L.bias;
   p.scale = L.scale;
@@ -1225,7 +1266,16 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   for (int s = 0; s < 2; ++s) {
     if (cins[s] == 0) continue;
     const int C = cins[s];
-    if (L.mode == CONV_3X3_S2) {
+    if (L.mode == CONV_UPSC && s == 1) {  // skip tensor at twice the tile-space resolution: one map per output parity
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const int Wh = 2 * L.Win, Hh = 2 * L.Hin;
+          const bf16* base = srcs[s] + ((size_t)ph * Wh + pw) * C;
+          int rc = make_act_map(&maps.a[4 + ph * 2 + pw], base, C, L.Win, L.B, L.Hin, (uint64_t)2 * C * 2,
+                                (uint64_t)Hh * Wh * C * 2, (uint64_t)2 * Wh * C * 2, p.CB, slab_w, SBt, slab_h);
+          if (rc) return rc;
+        }
+    } else if (L.mode == CONV_3X3_S2) {
       for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
           const bf16* base = srcs[s] + ((size_t)ph * L.Win + pw) * C;
@@ -1240,8 +1290,13 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
     }
   }
   {
-    int rc = make_weight_map(&maps.w, L.wpacked, p.CB, (size_t)nwt * p.N, p.cta2 ? p.NT / 2 : p.NT);
+    const size_t rows_a = L.mode == CONV_UPSC ? (size_t)p.ncb0 * p.N : (size_t)nwt * p.N;
+    int rc = make_weight_map(&maps.w, L.wpacked, p.CB, rows_a, p.cta2 ? p.NT / 2 : p.NT);
     if (rc) return rc;
+    if (L.mode == CONV_UPSC) {
+      rc = make_weight_map(&maps.w2, L.wpacked + rows_a * p.CB, p.CB, (size_t)p.ncb1 * L.Cout, L.Cout);
+      if (rc) return rc;
+    }
   }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;

@@ -7,6 +7,11 @@ enum ConvMode {
   CONV_1X1 = 1,     // 1x1 (plain GEMM over pixels)
   CONV_3X3_S2 = 2,  // 3x3, stride 2, pad 1 (GuidedResUnet / SNRnet "pool"; parity-split tensor maps)
   CONVT_2X2 = 3,    // ConvTranspose2d 2x2 stride 2 (GEMM with N = 4*Cout, scatter epilogue)
+  // Fused decoder hand-over of GuidedResUnet / SNRnet: ConvTranspose2d(2x2, s2)(src0) followed by the 1x1 shortcut conv on
+  // cat[up, src1].  The up-sampling folds into the shortcut's weights (W'[a,b] = Wsc[:, :C] * Wt[:, :, a, b]^T), so the layer is
+  // one GEMM per output parity (a,b): [src0 | src1 at parity (a,b)] x [W'[a,b] ; Wsc[:, C:]] and the up-sampled tensor is
+  // never written.  src0: (B, Hin, Win, Cin0) low resolution, src1: (B, 2 Hin, 2 Win, Cin1 = Cout) skip.
+  CONV_UPSC = 4,
 };
 enum ConvAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_SILU = 2 };
 
@@ -17,7 +22,8 @@ struct ConvLayer {
   const bf16* src0;
   const bf16* src1;
   int Cout;                 // real output channels
-  const bf16* wpacked;      // [cbg][tap][N][CB] bf16, N = Cout (x4 for CONVT_2X2: n = (a*2+b)*Cout + co)
+  const bf16* wpacked;      // [cbg][tap][N][CB] bf16, N = Cout (x4 for CONVT_2X2: n = (a*2+b)*Cout + co);
+                            // CONV_UPSC: [cb0][4*Cout][CB] (folded up-sampling part) then [cb1][Cout][CB] (skip part)
   const float* bias;        // [Cout]
   const float* scale;       // [B][Cout] or null: v = v*scale + shift   (FiLM / SNR gates)
   const float* shift;       // [B][Cout] or null

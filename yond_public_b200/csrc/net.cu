@@ -15,6 +15,7 @@ namespace {
 struct LayerW {
   int mode = 0, Cin0 = 0, Cin1 = 0, Cout = 0;
   std::string wkey, bkey;
+  std::string wkey2, bkey2;  // CONV_UPSC: the 1x1 shortcut conv folded behind the transposed conv (wkey / bkey)
   bf16* w = nullptr;
   float* bias = nullptr;
 };
@@ -142,6 +143,14 @@ void describe(yond_net* n) {
       add_convT_keys(n, "upv" + l, 2 * c, c);
       add_layer(n, "upv" + l, CONVT_2X2, 2 * c, 0, c);
       block("conv" + l, 2 * c, c);
+      if (c <= 64) {  // up-sampling + 1x1 shortcut on cat[up, skip] as ONE layer (weights resident in shared memory)
+        add_layer(n, "conv" + l + ".upsc", CONV_UPSC, 2 * c, c, c);
+        LayerW& F = n->conv["conv" + l + ".upsc"];
+        F.wkey = "upv" + l + ".weight";
+        F.bkey = "upv" + l + ".bias";
+        F.wkey2 = "conv" + l + ".short_cut.0.weight";
+        F.bkey2 = "conv" + l + ".short_cut.0.bias";
+      }
     }
     add_conv_keys(n, "conv10", cout, nf, 1);
   }
@@ -184,6 +193,37 @@ std::vector<bf16> pack_weights(const LayerW& L, const std::vector<float>& w) {
   return out;
 }
 
+// CONV_UPSC: fold ConvTranspose2d(2x2, s2) into the 1x1 shortcut that follows it on cat[up, skip].
+//   Wt (Cl, C, 2, 2), bt (C);  Wsc (C, 2C, 1, 1), bsc (C)
+//   part A [cb][n = (a*2+b)*C + co][CB] = sum_m Wsc[co][m] * Wt[cl][m][a][b]      (float64 accumulation, one bf16 rounding)
+//   part B [cb][co][CB]                 = Wsc[co][C + cs]
+//   bias'[co] = bsc[co] + sum_m Wsc[co][m] * bt[m]
+std::vector<bf16> pack_upsc(const LayerW& L, const std::vector<float>& wt, const std::vector<float>& bt, const std::vector<float>& wsc,
+                            const std::vector<float>& bsc, std::vector<float>* bias_out) {
+  const int C = L.Cout, Cl = L.Cin0, CB = conv_tc_channel_block(L.Cin0, L.Cin1);
+  std::vector<bf16> out((size_t)Cl * 4 * C + (size_t)C * C);
+  for (int cb = 0; cb < Cl / CB; ++cb)
+    for (int q = 0; q < 4; ++q)
+      for (int co = 0; co < C; ++co)
+        for (int j = 0; j < CB; ++j) {
+          const int cl = cb * CB + j;
+          double acc = 0.0;
+          for (int m = 0; m < C; ++m) acc += (double)wsc[(size_t)co * 2 * C + m] * (double)wt[(((size_t)cl * C + m) * 2 + (q >> 1)) * 2 + (q & 1)];
+          out[(((size_t)cb * 4 * C) + (size_t)q * C + co) * CB + j] = __float2bfloat16_rn((float)acc);
+        }
+  const size_t offB = (size_t)Cl * 4 * C;
+  for (int cb = 0; cb < C / CB; ++cb)
+    for (int co = 0; co < C; ++co)
+      for (int j = 0; j < CB; ++j) out[offB + ((size_t)cb * C + co) * CB + j] = __float2bfloat16_rn(wsc[(size_t)co * 2 * C + C + cb * CB + j]);
+  bias_out->resize(C);
+  for (int co = 0; co < C; ++co) {
+    double acc = bsc[co];
+    for (int m = 0; m < C; ++m) acc += (double)wsc[(size_t)co * 2 * C + m] * (double)bt[m];
+    (*bias_out)[co] = (float)acc;
+  }
+  return out;
+}
+
 int upload_f32(yond_net* n, const std::string& key) {
   const std::vector<float>& h = n->host[key];
   float* d = nullptr;
@@ -207,6 +247,19 @@ int finalize(yond_net* n) {
   }
   for (auto& kv : n->conv) {
     LayerW& L = kv.second;
+    if (L.mode == CONV_UPSC) {
+      std::vector<float> fb;
+      std::vector<bf16> packed = pack_upsc(L, n->host[L.wkey], n->host[L.bkey], n->host[L.wkey2], n->host[L.bkey2], &fb);
+      YOND_CUDA_CHECK(cudaMalloc(&L.w, packed.size() * sizeof(bf16)));
+      YOND_CUDA_CHECK(cudaMemcpy(L.w, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+      const std::string fk = kv.first + ".bias(folded)";
+      n->host[fk] = fb;
+      int rc = upload_f32(n, fk);
+      n->host.erase(fk);
+      if (rc) return rc;
+      L.bias = n->f32[fk];
+      continue;
+    }
     std::vector<bf16> packed = pack_weights(L, n->host[L.wkey]);
     YOND_CUDA_CHECK(cudaMalloc(&L.w, packed.size() * sizeof(bf16)));
     YOND_CUDA_CHECK(cudaMemcpy(L.w, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice));
@@ -239,6 +292,8 @@ double layer_flops(const LayerW& L, int B, int Hin, int Win) {
     case CONV_3X3_S1: return 2.0 * B * Hin * Win * 9.0 * cin * L.Cout;
     case CONV_3X3_S2: return 2.0 * B * (Hin / 2) * (Win / 2) * 9.0 * cin * L.Cout;
     case CONV_1X1: return 2.0 * B * Hin * Win * cin * L.Cout;
+    case CONV_UPSC:  // the algorithmic work of the two reference layers it replaces (transposed conv + 1x1 on 2 Cout channels)
+      return 2.0 * B * Hin * Win * L.Cin0 * 4.0 * L.Cout + 2.0 * B * (2.0 * Hin) * (2.0 * Win) * 2.0 * L.Cout * L.Cout;
     default: return 2.0 * B * Hin * Win * cin * 4.0 * L.Cout;  // CONVT_2X2
   }
 }
@@ -310,6 +365,8 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
   // Sub-batch of the full-resolution levels.  Measured on B200 (bench.py, 1280 blocks): splitting costs more in
   // launch tails than L2 residency returns (43.7 ms/step unsplit vs 49-60 ms at 16-48 blocks), so the default is the
   // whole batch; YOND_SUB_BATCH=n re-enables the split for experiments.
+  static const int env_fuse = getenv("YOND_FUSE_UPSC") ? atoi(getenv("YOND_FUSE_UPSC")) : 1;
+  const bool fuse_up = env_fuse && !n->conv_impl;  // the CUDA-core cross-check path keeps the two reference layers
   static const int env_sub = getenv("YOND_SUB_BATCH") ? atoi(getenv("YOND_SUB_BATCH")) : 0;
   int SBn = env_sub > 0 ? env_sub : B;
   if (SBn < 1) SBn = 1;
@@ -479,11 +536,19 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
     bf16* u9 = buf(SBn, 0, C0); bf16* c9 = buf(SBn, 0, C0);
     for (int b0 = 0; b0 < B; b0 += SBn) {
       const int nb = B - b0 < SBn ? B - b0 : SBn;
-      R.conv("upv8", nb, H2, W2, c7 + (size_t)b0 * px(2) * C2, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u8, nullptr);
-      R.conv("conv8.short_cut.0", nb, H1, W1, u8, skip1 + (size_t)b0 * px(1) * C1, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x1, x1s);
+      if (fuse_up && n->conv.count("conv8.upsc")) {
+        R.conv("conv8.upsc", nb, H2, W2, c7 + (size_t)b0 * px(2) * C2, skip1 + (size_t)b0 * px(1) * C1, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x1, x1s);
+      } else {
+        R.conv("upv8", nb, H2, W2, c7 + (size_t)b0 * px(2) * C2, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u8, nullptr);
+        R.conv("conv8.short_cut.0", nb, H1, W1, u8, skip1 + (size_t)b0 * px(1) * C1, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x1, x1s);
+      }
       block(8, 1, b0, nb, x1, x1s, z1, c8);
-      R.conv("upv9", nb, H1, W1, c8, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u9, nullptr);
-      R.conv("conv9.short_cut.0", nb, H, W, u9, skip0 + (size_t)b0 * px(0) * C0, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x0, x0s);
+      if (fuse_up && n->conv.count("conv9.upsc")) {
+        R.conv("conv9.upsc", nb, H1, W1, c8, skip0 + (size_t)b0 * px(0) * C0, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x0, x0s);
+      } else {
+        R.conv("upv9", nb, H1, W1, c8, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u9, nullptr);
+        R.conv("conv9.short_cut.0", nb, H, W, u9, skip0 + (size_t)b0 * px(0) * C0, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x0, x0s);
+      }
       block(9, 0, b0, nb, x0, x0s, z0, c9);
       RUN(tail_conv_launch(c9, n->tail_w, n->f32["conv10.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->res, nb, H, W,
                            nf, y + (size_t)b0 * px(0) * 4, s));

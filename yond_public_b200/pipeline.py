@@ -406,8 +406,9 @@ class YOND_SIDD:
         estimator (three small synchronisations per group) of one lane are covered by the other lane's kernels.
         lanes = 1: one host thread; the H2D copy of the next group and the D2H copy of the previous one run on their own
         streams while the current group computes (double-buffered device staging, event-ordered)."""
-        if lanes > 1 and host_in.shape[0] > group:
+        if lanes > 1 and (not isinstance(group, int) or host_in.shape[0] > group):
             return self._iter_denoise_host_lanes(host_in, host_out, p, group, lanes)
+        assert isinstance(group, int), "a list of group sizes needs lanes > 1"
         assert host_in.is_pinned() and host_out.is_pinned(), "pinned host buffers required for asynchronous copies"
         nimg = host_in.shape[0]
         dev = self.device
@@ -462,7 +463,13 @@ class YOND_SIDD:
         assert host_in.is_pinned() and host_out.is_pinned(), "pinned host buffers required for asynchronous copies"
         nimg = host_in.shape[0]
         dev = self.device
-        key = (tuple(host_in.shape[1:]), tuple(host_out.shape[1:]), group, lanes)
+        if isinstance(group, int):
+            sizes = [min(group, nimg - a) for a in range(0, nimg, group)]
+        else:  # explicit group sizes, e.g. a small first group so that compute starts early
+            sizes = [int(g) for g in group]
+            assert sum(sizes) == nimg and min(sizes) > 0, "group sizes must add up to the number of images"
+        gmax = max(sizes)
+        key = (tuple(host_in.shape[1:]), tuple(host_out.shape[1:]), gmax, lanes)
         if getattr(self, "_lanes_key", None) != key:
             sd = self.net.state_dict()
             self._lanes = []
@@ -470,10 +477,11 @@ class YOND_SIDD:
                 drv = self if i == 0 else YOND_SIDD(self.arch, self.pipe, state_dict=sd, biaslut=self.biaslut, device=dev,
                                                      chunk=self.engine.chunk)
                 self._lanes.append(dict(drv=drv, stream=torch.cuda.Stream(dev),
-                                        din=torch.empty((group,) + tuple(host_in.shape[1:]), device=dev),
-                                        dout=torch.empty((group,) + tuple(host_out.shape[1:]), device=dev)))
+                                        din=torch.empty((gmax,) + tuple(host_in.shape[1:]), device=dev),
+                                        dout=torch.empty((gmax,) + tuple(host_out.shape[1:]), device=dev)))
             self._lanes_key = key
-        groups = [(a, min(a + group, nimg)) for a in range(0, nimg, group)]
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        groups = [(int(starts[i]), int(starts[i + 1])) for i in range(len(sizes))]
         results = [None] * len(groups)
         errors = []
         start = torch.cuda.Event()
