@@ -12,11 +12,6 @@ namespace {
 
 constexpr int kMaxK = 31;
 
-struct D4 {
-  double x, y, z, w;
-};
-__device__ __forceinline__ void d4_add(D4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
-__device__ __forceinline__ void d4_sub(D4& a, const float4& v) { a.x -= v.x; a.y -= v.y; a.z -= v.z; a.w -= v.w; }
 __device__ __forceinline__ float4 sq4(const float4& v) {
   return make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w));
 }
@@ -31,12 +26,16 @@ __device__ __forceinline__ float4 sq4(const float4& v) {
 // fewer instructions than scanning the column sums where they live).  All sums are float64 sums of float32 values,
 // so the result equals cv2.blur's float64 accumulation rounded to float32 up to the (far below float32) float64
 // rounding of the summation order.  S is double-buffered by row parity: two __syncthreads per row.
-enum { OP_MEAN = 0, OP_MEAN_STD = 1, OP_STD = 2 };
+// OP_MEAN_VAR: out0 = mean, out1 = std^2 (SelfNLF's var).  OP_COLLAB: out0 = mean, out1 = std (lap), out2 = aux^2 - std^2
+// with aux = the std map of the other frame (CollabNLF's var).  Squares / difference in float32 with explicit rounding,
+// like the reference's elementwise float32 expressions.
+enum { OP_MEAN = 0, OP_MEAN_STD = 1, OP_STD = 2, OP_MEAN_VAR = 3, OP_COLLAB = 4 };
 constexpr int kBoxThreads = 256;
 template <bool kSq, int kCols>  // kCols = 256, or 160 when the whole row plus both halos fits (SIDD blocks: 128 + 28)
 __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(const float4* __restrict__ x, float4* __restrict__ out0,
                                                                 float4* __restrict__ out1, int h, int w, int k, int op,
-                                                                int rows_per_strip) {
+                                                                int rows_per_strip, const float4* __restrict__ aux,
+                                                                float4* __restrict__ out2) {
   constexpr int NQ = kSq ? 8 : 4;
   constexpr int CH = kCols / 32;           // columns per scan chunk (8 or 5)
   constexpr int PITCH = kCols + 32 + 1;    // padded: column c sits at c + c / CH, so chunk reads are bank-conflict free
@@ -121,6 +120,14 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(const float4* __
         if (op == OP_MEAN_STD) {
           out0[o] = m;
           out1[o] = st;
+        } else if (op == OP_MEAN_VAR) {
+          out0[o] = m;
+          out1[o] = sq4(st);
+        } else if (op == OP_COLLAB) {
+          out0[o] = m;
+          out1[o] = st;
+          const float4 a = __ldg(aux + o), a2 = sq4(a), s2 = sq4(st);
+          out2[o] = make_float4(__fsub_rn(a2.x, s2.x), __fsub_rn(a2.y, s2.y), __fsub_rn(a2.z, s2.z), __fsub_rn(a2.w, s2.w));
         } else {
           out0[o] = st;
         }
@@ -131,19 +138,6 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(const float4* __
       accum(vout, -1.0);
     }
     // the other S buffer is written next; this one is rewritten two rows later, after the next row's barriers
-  }
-}
-
-// var = std^2 (self)  |  var = std_lr^2 - std_hr^2 (collab), elementwise in float32 like the reference
-__global__ void var_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ var, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float s = a[i];
-    float v = __fmul_rn(s, s);  // no FMA contraction: the reference rounds each square to float32 first
-    if (b) {
-      const float t = b[i];
-      v = __fsub_rn(v, __fmul_rn(t, t));
-    }
-    var[i] = v;
   }
 }
 
@@ -448,7 +442,7 @@ inline int stream_grid(size_t n) {
 }
 
 int box_pass(const float* x, float* out0, float* out1, int B, int h, int w, int k, int square_input, bool with_sq, int op,
-             void* work, cudaStream_t s) {
+             void* work, cudaStream_t s, const float* aux = nullptr, float* out2 = nullptr) {
   (void)work;
   (void)square_input;
   const bool narrow = w + 2 * (k / 2) <= 160;
@@ -460,12 +454,14 @@ int box_pass(const float* x, float* out0, float* out1, int B, int h, int w, int 
   const float4* x4 = reinterpret_cast<const float4*>(x);
   float4* o0 = reinterpret_cast<float4*>(out0);
   float4* o1 = reinterpret_cast<float4*>(out1);
+  const float4* ax = reinterpret_cast<const float4*>(aux);
+  float4* o2 = reinterpret_cast<float4*>(out2);
   if (with_sq) {
-    if (narrow) box_fused_kernel<true, 160><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, op, rows_per_strip);
-    else box_fused_kernel<true, 256><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, op, rows_per_strip);
+    if (narrow) box_fused_kernel<true, 160><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, op, rows_per_strip, ax, o2);
+    else box_fused_kernel<true, 256><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, op, rows_per_strip, ax, o2);
   } else {
-    if (narrow) box_fused_kernel<false, 160><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, OP_MEAN, rows_per_strip);
-    else box_fused_kernel<false, 256><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, OP_MEAN, rows_per_strip);
+    if (narrow) box_fused_kernel<false, 160><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, OP_MEAN, rows_per_strip, ax, o2);
+    else box_fused_kernel<false, 256><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, OP_MEAN, rows_per_strip, ax, o2);
   }
   YOND_LAUNCH_CHECK();
   return YOND_OK;
@@ -503,10 +499,8 @@ int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float
   float* tmpB = tmpA + n;
   int rc;
   if (mode == 0) {
-    // mean = blur_k(x), std -> tmpA ; var = std^2
-    if ((rc = box_pass(x, mean, tmpA, B, h, w, k, 0, true, OP_MEAN_STD, work, s))) return rc;
-    var_kernel<<<stream_grid(n), 256, 0, s>>>(tmpA, nullptr, var, n);
-    YOND_LAUNCH_CHECK();
+    // mean = blur_k(x), var = std_k(x)^2 in one pass
+    if ((rc = box_pass(x, mean, var, B, h, w, k, 0, true, OP_MEAN_VAR, work, s))) return rc;
     // lap = std_k(blur_k2(x)), k2 = k//3*2+1 (YOND_SIDD.py:70)
     const int k2 = k / 3 * 2 + 1;
     if ((rc = box_pass(x, tmpB, nullptr, B, h, w, k2, 0, false, OP_MEAN, work, s))) return rc;
@@ -514,9 +508,7 @@ int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float
   } else {
     // std_k(lr) -> tmpA ; mean = blur_k(hr), lap = std_k(hr) ; var = std_lr^2 - std_hr^2
     if ((rc = box_pass(x, tmpA, nullptr, B, h, w, k, 0, true, OP_STD, work, s))) return rc;
-    if ((rc = box_pass(y, mean, lap, B, h, w, k, 0, true, OP_MEAN_STD, work, s))) return rc;
-    var_kernel<<<stream_grid(n), 256, 0, s>>>(tmpA, lap, var, n);
-    YOND_LAUNCH_CHECK();
+    if ((rc = box_pass(y, mean, lap, B, h, w, k, 0, true, OP_COLLAB, work, s, tmpA, var))) return rc;
   }
   return YOND_OK;
 }
