@@ -4,18 +4,23 @@
 // archs/modules.py:117-125,163-233 (library kernels in the reference) with one persistent,
 // warp-specialised kernel:
 //
-//   warp 0    TMA producer — activations: halo-extended NHWC slabs (cp.async.bulk.tensor.4d; out-of-bounds
-//                            zero-fill is the conv's zero padding); weights: per-tap K-major tiles (2d)
-//   warp 1    MMA issuer   — one elected thread issues tcgen05.mma (M=128 pixels, N<=128 channels, K=16),
-//                            accumulating taps x channel blocks into TMEM; tcgen05.commit frees the stages
-//   warps 2-9 epilogue     — tcgen05.ld the accumulators (double-buffered in TMEM so the next tile's MMAs
-//                            overlap), bias / FiLM / activation / residual, bf16 NHWC stores
+//   warp 0     TMA producer — activations: halo-extended NHWC slabs (cp.async.bulk.tensor.4d; out-of-bounds
+//                             zero-fill is the conv's zero padding); weights: per-tap K-major tiles (2d), resident in
+//                             shared memory for narrow layers, streamed through a ring otherwise
+//   warp 1     MMA issuer   — one elected thread issues tcgen05.mma (M=128 pixels — 256 over a CTA pair —, N<=256
+//                             channels, K=16) as straight-line code, accumulating taps x channel blocks into TMEM;
+//                             tcgen05.commit frees the stages
+//   warps 2-17 epilogue     — tcgen05.ld the accumulators (double-buffered in TMEM so the next tile's MMAs overlap),
+//                             bias / FiLM / activation / residual, 256-bit bf16 NHWC stores
 //
 // GEMM view: M = output pixels, N = Cout, K = taps*Cin.  A 3x3 stride-1 conv loads ONE halo slab per channel
 // block — (rows+2) x (8+2) pixels, 128 B (or 64 B) per pixel, hardware-swizzled by TMA — and reaches all nine
 // taps by moving the UMMA descriptor's start address by whole pixels (the swizzle XOR is a function of the
 // absolute shared-memory address, so any pixel-aligned start reads consistently).  T sub-tiles of 128 pixels
-// (stacked rows, or T images) share every weight tile, which cuts weight traffic from L2 by T.
+// (stacked rows, or T images) share every weight tile, which cuts weight traffic from L2 by T.  Two builds:
+// conv_tc_kernel<false> (one CTA per SM) and conv_tc_kernel<true> (cluster of 2, cta_group::2: each CTA holds its own
+// pixels and half of every weight tile).  Modes: 3x3 s1, 3x3 s2, 1x1 (on up to two concatenated sources), ConvT 2x2,
+// and the fused ConvT 2x2 + 1x1-on-concat hand-over of the decoder (CONV_UPSC).  See DESIGN.md section 4.
 #include "conv_tc.cuh"
 
 #include <cstdlib>
@@ -123,13 +128,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-// Copies a kernel parameter into a register the compiler cannot rematerialise from the constant bank: inside the MMA
-// issue loop every re-load of a parameter (LDCU) sits on the critical path of the next tcgen05.mma.
-__device__ __forceinline__ uint32_t pin(uint32_t v) {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
-  return r;
-}
 // One lane of a converged warp (elect.sync); returns 1 on the elected lane.
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred = 0;
@@ -170,36 +168,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// Same MMA with the two shared-memory descriptors given as (low, high) 32-bit halves and packed inside the asm
-// block: the running low words are then plain 32-bit uniform adds (no 64-bit carry chains between MMAs).
-__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                               uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// A operand in TMEM (lanes = rows, 8 columns per K=16 step), B from shared memory.
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -253,18 +221,6 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -274,26 +230,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
-template <int NC>
-__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&v)[NC]);
-template <>
-__device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
-template <>
-__device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major operand, 64B / 128B swizzle (rows of CB bf16; `sbo` = byte distance
-// between consecutive 8-row groups of the M/N dimension).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t row_bytes, uint32_t sbo) {
-  const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;  // SWIZZLE_128B : SWIZZLE_64B
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
-  d |= 1ull << 16;                             // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)((sbo & 0x3FFFFu) >> 4) << 32;  // stride byte offset
-  d |= 1ull << 46;                             // descriptor version (Blackwell)
-  d |= layout << 61;
-  return d;
-}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
