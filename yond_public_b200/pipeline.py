@@ -194,8 +194,8 @@ class YondEngine:
 
         A tile is its core plus a halo that is CUT at the frame border: the network zero-pads every feature map at the
         true border, so nothing outside the frame may be fed to it (zeros at the input would become non-zero features
-        after the first bias).  Tiles therefore differ in shape and are forwarded one at a time (a 768x768 tile is as
-        much work as 36 SIDD blocks)."""
+        after the first bias).  Tiles therefore differ in shape (corner / edge / interior); tiles of equal shape are
+        forwarded together as one batch (a 768x768 tile is as much work as 36 SIDD blocks)."""
         _, hp, wp, _ = z.shape
         halo = self.HALO
         grid = self.tile_grid(hp, wp, core)
@@ -203,16 +203,27 @@ class YondEngine:
         if y is None:
             y = torch.zeros_like(z)
         st = stream_ptr()
+        groups = {}
         for ti in tiles:
             y0, x0, ch, cw = grid[ti]
             ty0, tx0 = max(0, y0 - halo), max(0, x0 - halo)
             ty1, tx1 = min(hp, y0 + ch + halo), min(wp, x0 + cw + halo)
-            th, tw = ty1 - ty0, tx1 - tx0
-            zt = self._buf("tile_in", (1, th, tw, 4), torch.float32, z.device)
-            yt = self._buf("tile_out", (1, th, tw, 4), torch.float32, z.device)
-            check(self.lib.yond_tile_extract(ptr(z[0]), ptr(zt[0]), hp, wp, ty0, tx0, th, tw, st))
-            self.net.forward_nhwc(zt, ub, t, out=yt)
-            check(self.lib.yond_tile_insert(ptr(yt[0]), ptr(y[0]), hp, wp, ty0, tx0, th, tw, y0 - ty0, x0 - tx0, ch, cw, st))
+            groups.setdefault((ty1 - ty0, tx1 - tx0), []).append((y0, x0, ch, cw, ty0, tx0))
+        max_px = 640 * 128 * 128  # same activation budget as a 640-block chunk
+        for (th, tw), members in groups.items():
+            per = max(1, max_px // (th * tw))
+            for g0 in range(0, len(members), per):
+                part = members[g0:g0 + per]
+                n = len(part)
+                zt = self._buf("tile_in", (n, th, tw, 4), torch.float32, z.device)
+                yt = self._buf("tile_out", (n, th, tw, 4), torch.float32, z.device)
+                for i, (y0, x0, ch, cw, ty0, tx0) in enumerate(part):
+                    check(self.lib.yond_tile_extract(ptr(z[0]), ptr(zt[i]), hp, wp, ty0, tx0, th, tw, st))
+                ubn = ub.reshape(1).expand(n).contiguous()
+                tn = None if t is None else t.reshape(1).expand(n).contiguous()
+                self.net.forward_nhwc(zt, ubn, tn, out=yt)
+                for i, (y0, x0, ch, cw, ty0, tx0) in enumerate(part):
+                    check(self.lib.yond_tile_insert(ptr(yt[i]), ptr(y[0]), hp, wp, ty0, tx0, th, tw, y0 - ty0, x0 - tx0, ch, cw, st))
         return y
 
     def vst_denoise_tiled(self, frame, gain, sigma, scale, bias_corr="pre", vst_type="exact", clip01=True, core=512,
