@@ -469,9 +469,17 @@ class YOND_SIDD:
         torch.cuda.synchronize(dev)
         return {"regs": regs, "rounds": np.concatenate(rounds)}
 
+    def iter_denoise_lanes(self, blocks, p, group=20, lanes=2):
+        """iter_denoise_batch for DEVICE-resident blocks (nimg,nblk,H,W), with the images dealt to `lanes` host threads
+        (own stream + driver clone each) in groups: the estimator's read-backs of one lane are covered by the other
+        lane's kernels.  Returns {'raw_dns': per-group final mosaics, 'regs', 'rounds'}."""
+        assert blocks.is_cuda
+        return self._iter_denoise_host_lanes(blocks, None, p, group, max(1, lanes))
+
     def _iter_denoise_host_lanes(self, host_in, host_out, p, group, lanes):
         import threading
-        assert host_in.is_pinned() and host_out.is_pinned(), "pinned host buffers required for asynchronous copies"
+        on_device = host_in.is_cuda  # device-resident input: no staging, outputs are returned per group
+        assert on_device or (host_in.is_pinned() and host_out.is_pinned()), "pinned host buffers required for asynchronous copies"
         nimg = host_in.shape[0]
         dev = self.device
         if isinstance(group, int):
@@ -480,16 +488,19 @@ class YOND_SIDD:
             sizes = [int(g) for g in group]
             assert sum(sizes) == nimg and min(sizes) > 0, "group sizes must add up to the number of images"
         gmax = max(sizes)
-        key = (tuple(host_in.shape[1:]), tuple(host_out.shape[1:]), gmax, lanes)
+        out_shape = (host_in.shape[2], host_in.shape[1] * host_in.shape[3]) if on_device else tuple(host_out.shape[1:])
+        key = (tuple(host_in.shape[1:]), out_shape, gmax if not on_device else 0, lanes)
         if getattr(self, "_lanes_key", None) != key:
             sd = self.net.state_dict()
             self._lanes = []
             for i in range(lanes):
                 drv = self if i == 0 else YOND_SIDD(self.arch, self.pipe, state_dict=sd, biaslut=self.biaslut, device=dev,
                                                      chunk=self.engine.chunk)
-                self._lanes.append(dict(drv=drv, stream=torch.cuda.Stream(dev),
-                                        din=torch.empty((gmax,) + tuple(host_in.shape[1:]), device=dev),
-                                        dout=torch.empty((gmax,) + tuple(host_out.shape[1:]), device=dev)))
+                lane = dict(drv=drv, stream=torch.cuda.Stream(dev))
+                if not on_device:
+                    lane["din"] = torch.empty((gmax,) + tuple(host_in.shape[1:]), device=dev)
+                    lane["dout"] = torch.empty((gmax,) + out_shape, device=dev)
+                self._lanes.append(lane)
             self._lanes_key = key
         starts = np.concatenate([[0], np.cumsum(sizes)])
         groups = [(int(starts[i]), int(starts[i + 1])) for i in range(len(sizes))]
@@ -509,6 +520,10 @@ class YOND_SIDD:
                     lane["stream"].wait_event(start)
                     for g in range(li, len(groups), lanes):
                         a, b = groups[g]
+                        if on_device:
+                            res = lane["drv"].iter_denoise_batch(host_in[a:b], dict(p))
+                            results[g] = (res["regs"], res["rounds"], res["raw_dns"][-1])
+                            continue
                         if g > 0:
                             h2d_issued[g - 1].wait()
                             lane["stream"].wait_event(h2d_done[g - 1])
@@ -533,8 +548,12 @@ class YOND_SIDD:
             t.join()
         if errors:
             raise errors[0]
-        torch.cuda.current_stream(dev).wait_stream(self._lanes[0]["stream"])
-        return {"regs": [r[0] for r in results], "rounds": np.concatenate([r[1] for r in results])}
+        for lane in self._lanes:
+            torch.cuda.current_stream(dev).wait_stream(lane["stream"])
+        out = {"regs": [r[0] for r in results], "rounds": np.concatenate([r[1] for r in results])}
+        if on_device:
+            out["raw_dns"] = [r[2] for r in results]
+        return out
 
     def iter_denoise_device(self, blocks, p, lr_full=None):
         """Device-resident IterDenoise.  `blocks`: (nblk,H,W) CUDA f32 (SIDD layout) or (H,W) frame.
