@@ -168,7 +168,7 @@ def _conv_cases():
     return G
 
 
-@pytest.mark.parametrize("idx", range(20))
+@pytest.mark.parametrize("idx", range(22))
 def test_conv_layer_tcgen05(Y, idx):
     G = _conv_cases()
     mode, B, H, W, c0, c1, co, act, res, sc, dual = G.CONV_CASES[idx]

@@ -106,6 +106,8 @@ CONV_CASES = [
     (0, 1, 40, 24, 128, 0, 128, 0, True, False, False),    # ragged super-tiles along H
     (0, 3, 16, 16, 256, 0, 256, 1, False, False, False),   # odd batch with T=2 along the batch, two n tiles
     (0, 1, 96, 126, 32, 32, 32, 2, False, True, False),    # full-frame-like ragged width, concat, T=4
+    (0, 1, 16, 24, 128, 0, 128, 1, False, False, False),   # CTA pair with an odd number of M tiles (the peer's last tile is empty)
+    (0, 5, 8, 8, 512, 0, 512, 2, True, True, False),       # CTA pair, two n tiles, NB=2 image pairs, odd batch, full epilogue
 ]
 
 
