@@ -3,7 +3,7 @@
 //   reference: utils/isp_algos.py:234-242 (stdfilt via cv2.blur), :345-365 (polyfit);
 //              YOND_SIDD.py:22-49 (get_threshold 'score3'), :62-115 (SelfNLF / CollabNLF).
 // cv2.blur on float32 = normalised box, BORDER_REFLECT_101, float64 running sums, result rounded to float32;
-// the kernels below keep float64 sums (vertical pass -> float64 scratch -> horizontal pass) to match it.
+// the box kernel below keeps float64 sums (vertical sliding window in registers, horizontal prefix in shared memory).
 #include <mutex>
 
 #include "common.cuh"
