@@ -43,17 +43,17 @@ DEV_LANES = int(os.environ.get("YOND_DEV_LANES", "1"))  # >1: device-resident st
 
 def synth_images(n_images, seed=2024):
     """(n_images, 32, 256, 256) float32 noisy blocks + the (K, sigma) drawn per image (yond_datasets.py:664-682,720)."""
-    from oracle import yond_oracle as O
+    from yond_public_b200 import synth
     rng = np.random.default_rng(seed)
     out = np.empty((n_images, N_BLOCKS, BLK, BLK), np.float32)
     params = []
     for i in range(n_images):
         # K >= 0.6 DN/e-: below that the blind estimate of sigma/K leaves the BiasLUT's range (>= 10 e-) on smooth
         # synthetic content and both arms would spend their time in the host-side fallback-table generator (A6)
-        K, S = O.sample_noise_params(rng, logk_min=-0.5)
+        K, S = synth.sample_noise_params(rng, logk_min=-0.5)
         params.append((K, S))
         for b in range(N_BLOCKS):
-            out[i, b] = O.synth_noisy(rng, O.synth_clean_smooth(rng, BLK, BLK), K, S, clip=True)
+            out[i, b] = synth.noisy(rng, synth.clean_smooth(rng, BLK, BLK), K, S, clip=True)
     return out, params
 
 
@@ -122,7 +122,8 @@ def run_reference(args):
         return  # rank 0 alone runs the CPU arm
     from oracle import yond_oracle as O
     lut = O.BiasLUT(os.path.join(ROOT, "yond_public_b200", "data", "bias_lut_2d_f32.npz"))
-    sd = O.init_state_dict(ARCH, seed=0)
+    from yond_public_b200 import synth
+    sd = synth.random_init_state_dict(ARCH, seed=0)
     n_img = 2
     imgs, _ = synth_images(n_img)
     for w in range(args.warmup):
@@ -155,7 +156,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import yond_public_b200 as Y
-    from oracle import yond_oracle as O
+    from yond_public_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,7 +172,7 @@ def run_b200(args):
     host_in = torch.from_numpy(imgs_np).pin_memory()
     host_out = torch.empty((N_IMAGES, BLK, N_BLOCKS * BLK), dtype=torch.float32).pin_memory()
     dev_in = host_in.to(dev)
-    sd = O.init_state_dict(ARCH, seed=0)
+    sd = synth.random_init_state_dict(ARCH, seed=0)  # the reference's random init (no checkpoint reachable offline)
     drv = Y.YOND_SIDD(ARCH, PIPE, state_dict=sd, device=dev)
     net = drv.net
     gather_buf = None
@@ -279,6 +280,7 @@ def run_b200(args):
         pass
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import yond_oracle as O  # the CPU-baseline leg is the only place the GPU arm touches oracle/
         lut = O.BiasLUT(drv.biaslut.bias_lut)
         t0 = time.perf_counter()
         reps = 0

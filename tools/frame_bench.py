@@ -11,15 +11,15 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 import yond_public_b200 as Y  # noqa: E402
-from oracle import yond_oracle as O  # noqa: E402
+from yond_public_b200 import synth  # noqa: E402
 
 H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3024, 4032)
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 rng = np.random.default_rng(3)
-noisy = O.synth_noisy(rng, O.synth_clean_smooth(rng, H, W), 3.0, 5.0)
+noisy = synth.noisy(rng, synth.clean_smooth(rng, H, W), 3.0, 5.0)
 pipe = dict(bench.PIPE, full_dn=True, iter="once")
 for name, arch in (("GuidedResUnet", bench.ARCH), ("UNetSeeInDark", {"name": "UNetSeeInDark", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True})):
-    drv = Y.YOND_SIDD(arch, pipe, state_dict=O.init_state_dict(arch, seed=0))
+    drv = Y.YOND_SIDD(arch, pipe, state_dict=synth.random_init_state_dict(arch, seed=0))
     x = torch.from_numpy(noisy).cuda()
     p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
 

@@ -9,7 +9,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import yond_public_b200 as Y  # noqa: E402
-from oracle import yond_oracle as O  # noqa: E402
+from yond_public_b200 import synth  # noqa: E402
 from yond_public_b200 import parallel  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -18,10 +18,10 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 arch = {"name": "GuidedResUnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
 net = Y.build_net(arch, dev)
-net.load_state_dict(O.init_state_dict(arch, seed=5))
+net.load_state_dict(synth.random_init_state_dict(arch, seed=5))
 eng = Y.YondEngine(net, arch, Y.BiasLUT())
 rng = np.random.default_rng(7)  # same frame on every rank
-frame = torch.from_numpy(O.synth_noisy(rng, O.synth_clean_smooth(rng, 3024, 4032), 3.0, 5.0)).to(dev)
+frame = torch.from_numpy(synth.noisy(rng, synth.clean_smooth(rng, 3024, 4032), 3.0, 5.0)).to(dev)
 out = parallel.denoise_frame_tile_sharded(eng, frame, 3.1, 5.2, 959.0, core=512)
 if rank == 0:
     ref = eng.vst_denoise_tiled(frame, 3.1, 5.2, 959.0, core=512)

@@ -11,7 +11,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 import yond_public_b200 as Y  # noqa: E402
-from oracle import yond_oracle as O  # noqa: E402
+from yond_public_b200 import synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--net-only", type=int, default=0, help="profile only the network forward on this many 128x128 packed blocks")
@@ -20,7 +20,7 @@ ap.add_argument("--step", type=int, default=0, help="profile one batched pipelin
 ap.add_argument("--frame", default=None, help="HxW packed frame for --net-only, e.g. 1536x2016")
 args = ap.parse_args()
 arch = bench.ARCH if args.arch == "gru" else {"name": "UNetSeeInDark", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
-sd = O.init_state_dict(arch, seed=0)
+sd = synth.random_init_state_dict(arch, seed=0)
 drv = Y.YOND_SIDD(arch, bench.PIPE, state_dict=sd)
 if args.net_only:
     B = args.net_only
