@@ -38,6 +38,15 @@ uint64_t yond_launch_count(void);
 int yond_pack(const float* bayer, float* rggb, int B, int H, int W, void* stream);
 int yond_unpack(const float* rggb, float* bayer, int B, int h, int w, void* stream);
 
+/* ---- RAW ingest — data_process/process.py:40-64 (pack_raw_bayer) ----
+ * uint16 sensor mosaic -> four float32 planes in the order R, G1, B, G2 given by the 2x2 `raw_pattern`
+ * (pos4[c] = 2*row + col of colour c inside the CFA cell), out = (v - black[c]) / (white - black[c]) in float32 with
+ * IEEE subtraction / division like NumPy, optionally clipped to [0,1].  `pos4` and `black4` are HOST arrays.
+ * layout 0: (B,4,H/2,W/2) planes like the reference; layout 1: (B,H/2,W/2,4) interleaved (what yond_vst_fwd-style
+ * kernels and the estimator consume).  Reads 2 B/px instead of the 4 B/px of a float32 mosaic. */
+int yond_pack_raw(const uint16_t* raw, float* out, int B, int H, int W, const int* pos4, const float* black4, float white,
+                  int clip, int layout, void* stream);
+
 /* ---- A3/A4 elementwise, for the function-level surface — utils/isp_algos.py:5-14, :17-33 ---- */
 int yond_vst(const float* x, float* z, size_t n, double sigma, double gain, void* stream);
 int yond_inverse_vst(const float* z, float* x, size_t n, double sigma, double gain, int exact, void* stream);

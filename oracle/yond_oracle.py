@@ -44,6 +44,26 @@ def rggb2bayer(rggb):
 
 
 # --------------------------------------------------------------------------------------------------
+# 8(f)-1  RAW ingest                                              data_process/process.py:40-64
+# --------------------------------------------------------------------------------------------------
+def pack_raw_bayer(raw_image, raw_pattern, black_level_per_channel, wp=1023, clip=True):
+    """pack_raw_bayer on plain arrays (the reference takes a rawpy object: `.raw_image_visible`, `.raw_pattern`,
+    `.black_level_per_channel`).  uint16 mosaic -> (4, H/2, W/2) float32 planes in R, G1, B, G2 order (:43-57),
+    `(out - black) / (wp - black)` in float32 (:59-61), clipped to [0,1] when `clip` (:62)."""
+    im = np.asarray(raw_image).astype(np.float32)
+    pat = np.asarray(raw_pattern)
+    H, W = im.shape
+    planes = []
+    for colour in range(4):  # 0 R, 1 G1, 2 B, 3 G2
+        r, c = np.where(pat == colour)
+        planes.append(im[r[0]:H:2, c[0]:W:2])
+    out = np.stack(planes, axis=0).astype(np.float32)
+    black = np.array(black_level_per_channel)[:, None, None].astype(np.float32)
+    out = (out - black) / (wp - black)
+    return np.clip(out, 0.0, 1.0) if clip else out
+
+
+# --------------------------------------------------------------------------------------------------
 # A3 / A4  generalized Anscombe VST and its algebraic / exact-unbiased inverse   utils/isp_algos.py:5-33
 # --------------------------------------------------------------------------------------------------
 def VST(x, sigma, mu=0, gain=1.0):

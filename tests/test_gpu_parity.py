@@ -176,6 +176,36 @@ def test_conv_layer_tcgen05(Y, idx):
     assert G.run_conv_case(mode, 1, B, H, W, c0, c1, co, act, res, sc, dual).startswith("OK"), "CUDA-core cross-check"
 
 
+# ------------------------------------------------------------------ 8(f)-1 RAW ingest
+def test_pack_raw_bayer_bit_exact(Y, golden):
+    """yond_pack_raw == the reference's pack_raw_bayer (golden) and == the oracle on a 24 MP 14-bit frame, bit for bit; both
+    output layouts; the rawpy-object calling convention of the reference."""
+    import types
+    g = golden("pack_raw")
+    for i in range(int(g["n"])):
+        raw = types.SimpleNamespace(raw_image_visible=g[f"img{i}"], raw_pattern=g[f"pattern{i}"], black_level_per_channel=g[f"black{i}"].tolist())
+        out = Y.pack_raw_bayer(raw, wp=int(g[f"wp{i}"]), clip=bool(g[f"clip{i}"]))
+        assert out.dtype == np.float32 and np.array_equal(out, g[f"out{i}"]), i
+        hwc = Y.pack_raw_bayer(g[f"img{i}"], wp=int(g[f"wp{i}"]), clip=bool(g[f"clip{i}"]), raw_pattern=g[f"pattern{i}"],
+                               black_level_per_channel=g[f"black{i}"].tolist(), interleaved=True)
+        assert np.array_equal(hwc, g[f"out{i}"].transpose(1, 2, 0)), i
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 2 ** 14, size=(2, 4000, 6000), dtype=np.uint16)  # two 24 MP Sony-like frames (config C4 size)
+    pat, black = [[0, 1], [3, 2]], [512, 511, 513, 512]
+    dev = torch.from_numpy(img.view(np.int16)).cuda()
+    out = Y.pack_raw_bayer(dev, wp=16383, clip=False, raw_pattern=pat, black_level_per_channel=black)
+    assert out.shape == (2, 4, 2000, 3000)
+    ref = O.pack_raw_bayer(img[1], pat, black, wp=16383, clip=False)
+    assert np.array_equal(out[1].cpu().numpy(), ref)
+    small = rng.integers(0, 1024, size=(10, 14), dtype=np.uint16)  # W % 4 == 2: the one-cell-per-thread kernel
+    for inter in (False, True):
+        got = Y.pack_raw_bayer(small, wp=1023, clip=True, raw_pattern=[[2, 3], [1, 0]], black_level_per_channel=[64, 63, 65, 64], interleaved=inter)
+        ref = O.pack_raw_bayer(small, [[2, 3], [1, 0]], [64, 63, 65, 64], wp=1023, clip=True)
+        assert np.array_equal(got, ref.transpose(1, 2, 0) if inter else ref)
+    with pytest.raises(Y._lib.YondError):
+        Y.pack_raw_bayer(img[0, :, :5999].copy(), raw_pattern=pat, black_level_per_channel=black)  # odd width
+
+
 # ------------------------------------------------------------------ A14-A17, A20 networks
 @pytest.mark.parametrize("key", ["unet", "gru", "snr"])
 def test_network_golden_and_statedict(Y, golden, key):

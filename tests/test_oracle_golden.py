@@ -165,3 +165,13 @@ def test_iterdenoise_two_rounds(golden, lut_table, key):
     np.testing.assert_allclose(np.array([np.asarray(r) for r in res["regs"]]), g["regs"], rtol=1e-9)
     np.testing.assert_allclose(res["raw_dns"][0][::8, ::8], g["dn0_sub"], rtol=0, atol=3e-6)
     np.testing.assert_allclose(res["raw_dns"][1][::8, ::8], g["dn1_sub"], rtol=0, atol=3e-6)
+
+
+def test_pack_raw_bayer_golden(golden):
+    """the oracle's pack_raw_bayer == the reference's (data_process/process.py:40-64), bit for bit, on four CFA
+    patterns, 10/12/14-bit ranges, per-channel black levels, clip on and off."""
+    g = golden("pack_raw")
+    for i in range(int(g["n"])):
+        out = O.pack_raw_bayer(g[f"img{i}"], g[f"pattern{i}"], g[f"black{i}"].tolist(), wp=int(g[f"wp{i}"]), clip=bool(g[f"clip{i}"]))
+        assert out.dtype == np.float32
+        assert np.array_equal(out, g[f"out{i}"]), i

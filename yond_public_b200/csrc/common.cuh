@@ -61,6 +61,11 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint2 ldg_stream_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ float2 ldg_stream_f2(const float2* p) {
   float2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));

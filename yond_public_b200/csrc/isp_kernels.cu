@@ -50,6 +50,61 @@ __global__ void unpack_kernel(const float* __restrict__ rggb, float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ 8(f)-1 RAW ingest (process.py:40-64)
+// One thread = one CFA cell: two 32-bit loads (2 x uint16 each), four IEEE float32 (v - black) / (white - black), one
+// 128-bit store (interleaved layout) or four plane stores.  2 B/px in, 4 B/px out.
+struct RawParams {
+  int pos[4];       // position (2*row + col) of R, G1, B, G2 inside the cell
+  float black[4];
+  float denom[4];   // fl32(white) - black[c], rounded like NumPy's float32 subtraction
+};
+__device__ __forceinline__ void raw_cell(uint32_t a, uint32_t d, const RawParams& q, int clip, float (&v)[4]) {
+  const float c0 = (float)(a & 0xffffu), c1 = (float)(a >> 16), c2 = (float)(d & 0xffffu), c3 = (float)(d >> 16);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int p = q.pos[c];
+    const float cell = p == 0 ? c0 : (p == 1 ? c1 : (p == 2 ? c2 : c3));  // selects: no dynamically indexed local array
+    float t = __fdiv_rn(__fsub_rn(cell, q.black[c]), q.denom[c]);
+    if (clip) t = fminf(fmaxf(t, 0.f), 1.f);
+    v[c] = t;
+  }
+}
+// kCells = CFA cells per thread along the row: 2 (64-bit loads; W % 4 == 0 and 8-byte aligned rows) or 1.
+template <int kCells>
+__global__ void pack_raw_kernel(const uint16_t* __restrict__ raw, float* __restrict__ out, int B, int H, int W, RawParams q,
+                                int clip, int layout) {
+  const int h = H >> 1, w = W >> 1, wq = w / kCells;
+  const size_t total = (size_t)B * h * wq;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % wq) * kCells;
+    const int i = (int)((idx / wq) % h);
+    const int b = (int)(idx / ((size_t)wq * h));
+    const uint16_t* r0 = raw + ((size_t)b * H + 2 * i) * W + 2 * j;
+    uint32_t a[kCells], d[kCells];
+    if (kCells == 2) {
+      const uint2 ua = ldg_stream_u2(reinterpret_cast<const uint2*>(r0)), ud = ldg_stream_u2(reinterpret_cast<const uint2*>(r0 + W));
+      a[0] = ua.x; a[kCells - 1] = ua.y; d[0] = ud.x; d[kCells - 1] = ud.y;
+    } else {
+      a[0] = __ldg(reinterpret_cast<const uint32_t*>(r0));
+      d[0] = __ldg(reinterpret_cast<const uint32_t*>(r0 + W));
+    }
+    const size_t plane = (size_t)h * w, cellidx = ((size_t)b * h + i) * w + j, pbase = (size_t)b * 4 * plane + (size_t)i * w + j;
+    float v[kCells][4];
+#pragma unroll
+    for (int k = 0; k < kCells; ++k) raw_cell(a[k], d[k], q, clip, v[k]);
+    if (layout == 1) {
+#pragma unroll
+      for (int k = 0; k < kCells; ++k) reinterpret_cast<float4*>(out)[cellidx + k] = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+    } else if (kCells == 2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) *reinterpret_cast<float2*>(out + pbase + c * plane) = make_float2(v[0][c], v[kCells - 1][c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) out[pbase + c * plane] = v[0][c];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ A3 / A4 / A5 device functions
 struct VstConst {
   float K, c0, two_over_K, lower, inv_range, range, scale, inv_scale, sig2e, sigma;
@@ -263,6 +318,30 @@ int yond_pack(const float* bayer, float* rggb, int B, int H, int W, void* stream
   const bool vec = (W % 4 == 0) && ((uintptr_t)bayer % 16 == 0) && ((uintptr_t)rggb % 16 == 0);
   if (vec) pack_kernel<<<grid_for((size_t)B * (H / 2) * (W / 4)), kBlock, 0, s>>>(bayer, rggb, B, H, W);
   else pack_kernel_scalar<<<grid_for((size_t)B * (H / 2) * (W / 2)), kBlock, 0, s>>>(bayer, rggb, B, H, W);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_pack_raw(const uint16_t* raw, float* out, int B, int H, int W, const int* pos4, const float* black4, float white,
+                  int clip, int layout, void* stream) {
+  YOND_REQUIRE(raw && out && pos4 && black4, "yond_pack_raw: null argument");
+  YOND_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "yond_pack_raw: H,W must be even (got %d,%d)", H, W);
+  YOND_REQUIRE((uintptr_t)raw % 4 == 0 && (uintptr_t)out % 16 == 0, "yond_pack_raw: raw must be 4-byte and out 16-byte aligned");
+  YOND_REQUIRE(layout == 0 || layout == 1, "yond_pack_raw: layout 0 (planes) or 1 (interleaved)");
+  RawParams q;
+  int seen = 0;
+  for (int c = 0; c < 4; ++c) {
+    YOND_REQUIRE(pos4[c] >= 0 && pos4[c] < 4, "yond_pack_raw: CFA position out of range");
+    seen |= 1 << pos4[c];
+    q.pos[c] = pos4[c];
+    q.black[c] = black4[c];
+    q.denom[c] = white - black4[c];  // float32 subtraction, like `white_point - black_level` on a float32 array
+  }
+  YOND_REQUIRE(seen == 15, "yond_pack_raw: raw_pattern must place R, G1, B, G2 on four distinct cell positions");
+  if (W % 4 == 0 && (uintptr_t)raw % 8 == 0)
+    pack_raw_kernel<2><<<grid_for((size_t)B * (H / 2) * (W / 4)), kBlock, 0, (cudaStream_t)stream>>>(raw, out, B, H, W, q, clip, layout);
+  else
+    pack_raw_kernel<1><<<grid_for((size_t)B * (H / 2) * (W / 2)), kBlock, 0, (cudaStream_t)stream>>>(raw, out, B, H, W, q, clip, layout);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

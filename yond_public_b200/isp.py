@@ -65,6 +65,38 @@ def rggb2bayer(rggb):
 
 
 bayer2rggbs = bayer2rggb
+
+
+# ------------------------------------------------------------------ 8(f)-1  data_process/process.py:40-64
+def pack_raw_bayer(raw, wp=1023, clip=True, raw_pattern=None, black_level_per_channel=None, interleaved=False):
+    """RAW ingest.  `raw`: a rawpy-like object (`.raw_image_visible`, `.raw_pattern`, `.black_level_per_channel`) exactly
+    as the reference takes it, or a uint16 mosaic (H,W) / batch (B,H,W) (NumPy or CUDA tensor) with `raw_pattern` and
+    `black_level_per_channel` given.  Returns (4,H/2,W/2) float32 planes in R, G1, B, G2 order like the reference
+    ((B,4,h,w) for a batch); `interleaved=True` returns (h,w,4), the layout the rest of the path consumes."""
+    if raw_pattern is None:
+        img, raw_pattern, black_level_per_channel = raw.raw_image_visible, raw.raw_pattern, raw.black_level_per_channel
+    else:
+        img = raw
+    dev = _dev()  # raises without CUDA: there is no CPU path
+    np_in = not torch.is_tensor(img)
+    if np_in:
+        a = np.ascontiguousarray(np.asarray(img))
+        assert a.dtype == np.uint16, "the sensor mosaic must be uint16"
+        x = torch.from_numpy(a.view(np.int16)).to(dev)  # same bits; torch's uint16 support is partial
+    else:
+        assert img.dtype in (torch.uint16, torch.int16), "the sensor mosaic must be a 16-bit integer tensor"
+        x = img.to(dev).contiguous()
+    batched = x.dim() == 3
+    xb = x if batched else x[None]
+    B, H, W = xb.shape
+    pat = np.asarray(raw_pattern)
+    pos = (C.c_int * 4)(*[int(2 * np.where(pat == c)[0][0] + np.where(pat == c)[1][0]) for c in range(4)])
+    black = (C.c_float * 4)(*[float(np.float32(b)) for b in black_level_per_channel])
+    h, w = H // 2, W // 2
+    out = torch.empty((B, h, w, 4) if interleaved else (B, 4, h, w), device=dev, dtype=torch.float32)
+    check(_lib.load().yond_pack_raw(ptr(xb), ptr(out), B, H, W, pos, black, float(np.float32(wp)), int(bool(clip)), int(bool(interleaved)),
+                                    stream_ptr()))
+    return _back(out if batched else out[0], np_in)
 rggb2bayers = rggb2bayer
 
 
