@@ -47,6 +47,11 @@ int yond_unpack(const float* rggb, float* bayer, int B, int h, int w, void* stre
 int yond_pack_raw(const uint16_t* raw, float* out, int B, int H, int W, const int* pos4, const float* black4, float white,
                   int clip, int layout, void* stream);
 
+/* CFA canonicalisation — utils/sidd_utils.py:198-213 (rot_bayer = np.rot90 by k quarter turns, counter-clockwise, over the
+ * last two axes; the driver rotates every SIDD frame to the RGGB phase before denoising and back afterwards,
+ * YOND_SIDD.py:403,463).  in: (B,H,W) float32, out: (B,W,H) for odd k, (B,H,W) for even k.  Pure data movement. */
+int yond_rot90(const float* in, float* out, int B, int H, int W, int k, void* stream);
+
 /* ---- A3/A4 elementwise, for the function-level surface — utils/isp_algos.py:5-14, :17-33 ---- */
 int yond_vst(const float* x, float* z, size_t n, double sigma, double gain, void* stream);
 int yond_inverse_vst(const float* z, float* x, size_t n, double sigma, double gain, int exact, void* stream);

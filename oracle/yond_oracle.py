@@ -43,6 +43,16 @@ def rggb2bayer(rggb):
     return rggb.reshape(H, W, 2, 2).transpose(0, 2, 1, 3).reshape(H * 2, W * 2)
 
 
+def rot_bayer(image, bayer_pattern, rev=False):
+    """utils/sidd_utils.py:198-213: rotate the frame by k quarter turns (np.rot90 over the last two axes) so that the CFA phase
+    becomes the canonical one; `rev` undoes it.  k: [[1,2],[2,3]] 0, [[2,1],[3,2]] 3, [[2,3],[1,2]] 1, [[3,2],[2,1]] 2."""
+    table = {((1, 2), (2, 3)): 0, ((2, 1), (3, 2)): 3, ((2, 3), (1, 2)): 1, ((3, 2), (2, 1)): 2}
+    k = table[tuple(tuple(int(v) for v in row) for row in bayer_pattern)]
+    if rev:
+        k = (4 - k) % 4
+    return np.rot90(image, k=k, axes=(-2, -1))
+
+
 # --------------------------------------------------------------------------------------------------
 # 8(f)-1  RAW ingest                                              data_process/process.py:40-64
 # --------------------------------------------------------------------------------------------------

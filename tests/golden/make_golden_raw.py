@@ -1,5 +1,5 @@
 """Golden vectors for SURVEY 8(f)-1 (RAW ingest): runs the UNMODIFIED reference `pack_raw_bayer`
-(/root/reference/data_process/process.py:40-64) on stand-in rawpy objects and stores inputs + outputs in
+(/root/reference/data_process/process.py:40-64) on stand-in rawpy objects, and `rot_bayer` (utils/sidd_utils.py:198-213), and stores inputs + outputs in
 tests/golden/pack_raw.npz.
 
     python tests/golden/make_golden_raw.py        # needs /root/reference
@@ -35,6 +35,15 @@ for i, (name, bits, wp, black, clip) in enumerate(specs):
     assert out.dtype == np.float32 and out.shape == (4, H // 2, W // 2)
     cases.update({f"img{i}": img, f"pattern{i}": np.array(patterns[name], dtype=np.int32), f"black{i}": np.array(black, dtype=np.int32),
                   f"wp{i}": np.int32(wp), f"clip{i}": np.int32(clip), f"out{i}": out})
+# rot_bayer (utils/sidd_utils.py:198-213) through the reference: every pattern, forward and reverse, 2-D and batched
+S = importlib.import_module("utils.sidd_utils")
+rot_in = rng.random((2, 18, 26)).astype(np.float32)
+cases["rot_in"] = rot_in
+for pi, pat in enumerate([[[1, 2], [2, 3]], [[2, 1], [3, 2]], [[2, 3], [1, 2]], [[3, 2], [2, 1]]]):
+    cases[f"rot_pat{pi}"] = np.array(pat, dtype=np.int32)
+    for rev in (0, 1):
+        cases[f"rot_out{pi}_{rev}"] = np.ascontiguousarray(S.rot_bayer(rot_in, pat, rev=bool(rev)))
+        cases[f"rot2d_out{pi}_{rev}"] = np.ascontiguousarray(S.rot_bayer(rot_in[0], pat, rev=bool(rev)))
 cases["n"] = np.int32(len(specs))
 np.savez_compressed(os.path.join(HERE, "pack_raw.npz"), **cases)
 print("wrote pack_raw.npz:", len(specs), "cases")

@@ -206,6 +206,24 @@ def test_pack_raw_bayer_bit_exact(Y, golden):
         Y.pack_raw_bayer(img[0, :, :5999].copy(), raw_pattern=pat, black_level_per_channel=black)  # odd width
 
 
+def test_rot_bayer_bit_exact(Y, golden):
+    """yond_rot90 == the reference's rot_bayer (goldens) for every pattern / direction, 2-D and batched; == np.rot90 on a
+    12 MP frame with ragged tiles; rot_bayer(rot_bayer(x), rev=True) == x."""
+    g = golden("pack_raw")
+    for pi in range(4):
+        pat = g[f"rot_pat{pi}"].tolist()
+        for rev in (0, 1):
+            assert np.array_equal(Y.rot_bayer(g["rot_in"], pat, rev=bool(rev)), g[f"rot_out{pi}_{rev}"]), (pi, rev)
+            assert np.array_equal(Y.rot_bayer(g["rot_in"][0], pat, rev=bool(rev)), g[f"rot2d_out{pi}_{rev}"]), (pi, rev)
+    x = torch.rand((3024, 4032), device="cuda")
+    for pat, k in (([[2, 3], [1, 2]], 1), ([[3, 2], [2, 1]], 2), ([[2, 1], [3, 2]], 3)):
+        y = Y.rot_bayer(x, pat)
+        assert torch.equal(y, torch.rot90(x, k, dims=(0, 1)))
+        assert torch.equal(Y.rot_bayer(y, pat, rev=True), x)
+    with pytest.raises(ValueError):
+        Y.rot_bayer(x, [[0, 1], [1, 2]])
+
+
 # ------------------------------------------------------------------ A14-A17, A20 networks
 @pytest.mark.parametrize("key", ["unet", "gru", "snr"])
 def test_network_golden_and_statedict(Y, golden, key):

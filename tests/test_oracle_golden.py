@@ -175,3 +175,12 @@ def test_pack_raw_bayer_golden(golden):
         out = O.pack_raw_bayer(g[f"img{i}"], g[f"pattern{i}"], g[f"black{i}"].tolist(), wp=int(g[f"wp{i}"]), clip=bool(g[f"clip{i}"]))
         assert out.dtype == np.float32
         assert np.array_equal(out, g[f"out{i}"]), i
+
+
+def test_rot_bayer_golden(golden):
+    """The oracle's rot_bayer == the reference's (utils/sidd_utils.py:198-213) for every CFA pattern, forward and reverse."""
+    g = golden("pack_raw")
+    for pi in range(4):
+        for rev in (0, 1):
+            assert np.array_equal(O.rot_bayer(g["rot_in"], g[f"rot_pat{pi}"].tolist(), rev=bool(rev)), g[f"rot_out{pi}_{rev}"])
+            assert np.array_equal(O.rot_bayer(g["rot_in"][0], g[f"rot_pat{pi}"].tolist(), rev=bool(rev)), g[f"rot2d_out{pi}_{rev}"])

@@ -8,10 +8,10 @@ All per-pixel work runs in hand-written CUDA kernels behind the C-ABI of include
 from . import _lib  # noqa: F401
 from .archs import GuidedResUnet, SNRnet, UNetSeeInDark, initialize_weights, load_weights  # noqa: F401
 from .isp import (VST, BiasLUT, bayer2rggb, bayer2rggbs, blur, get_bias_table, get_p2d, inverse_VST,  # noqa: F401
-                  pack_raw_bayer, rggb2bayer, rggb2bayers, stdfilt)
+                  pack_raw_bayer, rggb2bayer, rggb2bayers, rot_bayer, stdfilt)
 from .nlf import CollabNLF, SelfNLF, SimpleNLF  # noqa: F401
 from .pipeline import YOND_SIDD, YondEngine, build_net  # noqa: F401
 
 __all__ = ["UNetSeeInDark", "GuidedResUnet", "SNRnet", "initialize_weights", "load_weights", "bayer2rggb", "rggb2bayer",
            "bayer2rggbs", "rggb2bayers", "VST", "inverse_VST", "BiasLUT", "stdfilt", "blur", "get_p2d", "get_bias_table",
-           "pack_raw_bayer", "SimpleNLF", "SelfNLF", "CollabNLF", "YOND_SIDD", "YondEngine", "build_net"]
+           "pack_raw_bayer", "rot_bayer", "SimpleNLF", "SelfNLF", "CollabNLF", "YOND_SIDD", "YondEngine", "build_net"]

@@ -30,6 +30,7 @@ SIGNATURES = {
     "yond_launch_count": (_U64, []),
     "yond_pack": (_I, [_P, _P, _I, _I, _I, _P]),
     "yond_unpack": (_I, [_P, _P, _I, _I, _I, _P]),
+    "yond_rot90": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "yond_pack_raw": (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_float, _I, _I, _P]),
     "yond_vst": (_I, [_P, _P, _SZ, _D, _D, _P]),
     "yond_inverse_vst": (_I, [_P, _P, _SZ, _D, _D, _I, _P]),

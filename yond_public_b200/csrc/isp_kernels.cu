@@ -105,6 +105,39 @@ __global__ void pack_raw_kernel(const uint16_t* __restrict__ raw, float* __restr
   }
 }
 
+// ------------------------------------------------------------------ rot_bayer (sidd_utils.py:198-213): np.rot90
+// Quarter turns go through a 32x32 shared-memory tile so that both the global read and the global write are row-contiguous:
+//   k = 1: out[i][j] = in[j][W-1-i]      tile[r][c] = in[j0 + r][W-1-i0-31 + c],   out(i0+a, j0+b) = tile[b][31-a]
+//   k = 3: out[i][j] = in[H-1-j][i]      tile[r][c] = in[H-1-j0-31 + r][i0 + c],   out(i0+a, j0+b) = tile[31-b][a]
+// block (32, 8); out is (W, H) per image.
+__global__ void rot90_odd_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int k) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* src = in + (size_t)b * H * W;
+  float* dst = out + (size_t)b * H * W;
+  const int Ho = W, Wo = H;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int rb = k == 1 ? j0 : H - 1 - j0 - 31;
+  const int cb = k == 1 ? W - 1 - i0 - 31 : i0;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int rr = rb + r, cc = cb + (int)threadIdx.x;
+    tile[r][threadIdx.x] = (rr >= 0 && rr < H && cc >= 0 && cc < W) ? src[(size_t)rr * W + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int a = threadIdx.y; a < 32; a += 8) {
+    const int i = i0 + a, j = j0 + (int)threadIdx.x;
+    if (i < Ho && j < Wo) dst[(size_t)i * Wo + j] = k == 1 ? tile[threadIdx.x][31 - a] : tile[31 - threadIdx.x][a];
+  }
+}
+// k = 2: out[i][j] = in[H-1-i][W-1-j]; k = 0: copy
+__global__ void rot90_even_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int k) {
+  const size_t per = (size_t)H * W, total = (size_t)B * per;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = idx / per, e = idx - b * per;
+    out[idx] = k == 2 ? in[b * per + (per - 1 - e)] : in[idx];  // reversing both axes = reversing the flattened image
+  }
+}
+
 // ------------------------------------------------------------------ A3 / A4 / A5 device functions
 struct VstConst {
   float K, c0, two_over_K, lower, inv_range, range, scale, inv_scale, sig2e, sigma;
@@ -318,6 +351,17 @@ int yond_pack(const float* bayer, float* rggb, int B, int H, int W, void* stream
   const bool vec = (W % 4 == 0) && ((uintptr_t)bayer % 16 == 0) && ((uintptr_t)rggb % 16 == 0);
   if (vec) pack_kernel<<<grid_for((size_t)B * (H / 2) * (W / 4)), kBlock, 0, s>>>(bayer, rggb, B, H, W);
   else pack_kernel_scalar<<<grid_for((size_t)B * (H / 2) * (W / 2)), kBlock, 0, s>>>(bayer, rggb, B, H, W);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_rot90(const float* in, float* out, int B, int H, int W, int k, void* stream) {
+  YOND_REQUIRE(in && out && in != out && B > 0 && H > 0 && W > 0, "yond_rot90: bad arguments (out of place only)");
+  YOND_REQUIRE(B <= 65535, "yond_rot90: at most 65535 images per call");
+  k = ((k % 4) + 4) % 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (k & 1) rot90_odd_kernel<<<dim3((H + 31) / 32, (W + 31) / 32, B), dim3(32, 8), 0, s>>>(in, out, H, W, k);
+  else rot90_even_kernel<<<grid_for((size_t)B * H * W), kBlock, 0, s>>>(in, out, B, H, W, k);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

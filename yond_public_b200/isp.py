@@ -67,6 +67,27 @@ def rggb2bayer(rggb):
 bayer2rggbs = bayer2rggb
 
 
+_ROT_K = {((1, 2), (2, 3)): 0, ((2, 1), (3, 2)): 3, ((2, 3), (1, 2)): 1, ((3, 2), (2, 1)): 2}
+
+
+def rot_bayer(image, bayer_pattern, rev=False):
+    """utils/sidd_utils.py:198-213: quarter-turn rotation that brings the CFA to its canonical phase (np.rot90 over the last
+    two axes; `rev=True` undoes it).  (H,W) or (B,H,W) float32, NumPy or CUDA tensor."""
+    key = tuple(tuple(int(v) for v in row) for row in bayer_pattern)
+    if key not in _ROT_K:
+        raise ValueError(f"unknown Bayer pattern {bayer_pattern}")
+    k = _ROT_K[key]
+    if rev:
+        k = (4 - k) % 4
+    x, np_in = to_dev(image)
+    batched = x.dim() == 3
+    xb = x if batched else x[None]
+    B, H, W = xb.shape
+    out = torch.empty((B, W, H) if k % 2 else (B, H, W), device=x.device, dtype=torch.float32)
+    check(_lib.load().yond_rot90(ptr(xb), ptr(out), B, H, W, k, stream_ptr()))
+    return _back(out if batched else out[0], np_in)
+
+
 # ------------------------------------------------------------------ 8(f)-1  data_process/process.py:40-64
 def pack_raw_bayer(raw, wp=1023, clip=True, raw_pattern=None, black_level_per_channel=None, interleaved=False):
     """RAW ingest.  `raw`: a rawpy-like object (`.raw_image_visible`, `.raw_pattern`, `.black_level_per_channel`) exactly
