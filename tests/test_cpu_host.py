@@ -78,6 +78,25 @@ def test_no_cpu_fallback(Y):
     if not torch.cuda.is_available():
         with pytest.raises(Y._lib.YondError):
             Y.bayer2rggb(np.zeros((4, 4), np.float32))
+        with pytest.raises(Y._lib.YondError):
+            Y.pack_raw_bayer(np.zeros((4, 4), np.uint16), raw_pattern=[[0, 1], [3, 2]], black_level_per_channel=[0, 0, 0, 0])
+        with pytest.raises(Y._lib.YondError):
+            Y.rot_bayer(np.zeros((4, 4), np.float32), [[2, 3], [1, 2]])
+
+
+def test_synth_module_matches_reference_recipes(Y):
+    """bench.py's inputs come from the product-side synth module: its random init is the reference's `initialize_weights`
+    under the seed (== the oracle's, which is pinned against the reference), and its generators are deterministic."""
+    from yond_public_b200 import synth
+    from oracle import yond_oracle as O
+    arch = {"name": "GuidedResUnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
+    a, b = synth.random_init_state_dict(arch, seed=3), O.init_state_dict(arch, seed=3)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    r1, r2 = np.random.default_rng(9), np.random.default_rng(9)
+    K1, S1 = synth.sample_noise_params(r1, logk_min=-0.5)
+    K2, S2 = O.sample_noise_params(r2, logk_min=-0.5)
+    assert (K1, S1) == (K2, S2)
+    assert np.array_equal(synth.noisy(r1, synth.clean_smooth(r1, 32, 32), K1, S1), O.synth_noisy(r2, O.synth_clean_smooth(r2, 32, 32), K2, S2))
 
 
 def test_unknown_arch_and_key_rejected(Y):
