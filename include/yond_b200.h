@@ -65,6 +65,9 @@ int yond_lut_row(const float* lut2d, int nx, int nsg, double sg_pos, float* row,
 int yond_lut_apply(const float* x, float* bias, size_t n, const float* row, const float* xnodes, int nx,
                    double gain, double sigma, void* stream);
 
+/* interp1d(nodes, vals)(clip(max(x,0), <= nodes[-1])): how the reference applies a get_bias table (YOND_SIDD.py:257). */
+int yond_table_apply(const float* x, float* bias, size_t n, const float* vals, const float* nodes, int n_nodes, void* stream);
+
 /* Per-frame parameters of the fused VST stages (one entry per frame of a batch). */
 typedef struct {
   float gain;      /* K   (DN)                                   YOND_SIDD.py:356 */
@@ -89,6 +92,13 @@ int yond_vst_fwd(const float* bayer, float* z, float* ub, int B, int H, int W, i
  * de-normalise -> inverse VST -> unpack -> /scale -> [clip 0..1] -> Bayer (B,H,W) f32. */
 int yond_vst_inv(const float* y, float* bayer, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
                  const yond_vst_params* params_dev, int clip01, void* stream);
+/* Back half with output placement and round selection: frames frame0 .. frame0+B-1 of a batch whose whole output is
+ * `out`.  frames_per_row = 1: (N,H,W); n > 1: frame f is block f % n of mosaic f / n, (N/n, H, n*W) — the reference's
+ * np.concatenate(blocks, axis=-1) (YOND_SIDD.py:408).  seg_ok_dev (optional, per image of frames_per_seg frames): where 0
+ * (round-2 beta1 < 0, :445-447) the frame is copied from `fallback` (round-1 output, same layout) instead. */
+int yond_vst_inv_place(const float* y, float* out, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
+                       const yond_vst_params* params_dev, int clip01, int frames_per_row, int frame0,
+                       const int32_t* seg_ok_dev, int frames_per_seg, const float* fallback, void* stream);
 /* Simple_Denoiser's front/back (YOND_SIDD.py:238-248): pack -> reflect pad -> clamp, and clamp -> crop -> unpack. */
 int yond_pack_pad(const float* bayer, float* z, float* ub, int B, int H, int W, int pad_l, int pad_r, int pad_t,
                   int pad_b, void* stream);
@@ -124,6 +134,52 @@ int yond_score3_bins(const float* lap, const float* mean, size_t seg_len, int ns
  * sums_dev[s][6..11] = same over {lap < th, 1e-4 < mean < 0.8} (polyfit's non-saturated subset), float64. */
 int yond_masked_sums(const float* lap, const float* mean, const float* var, size_t seg_len, int nseg,
                      const double* ths_dev, double* sums_dev, void* stream);
+
+/* ---- the estimator without host round trips (same reference lines as above, arithmetic in float64 on the device) ----
+ * yond_nlf_maps_bayer: the maps straight from the Bayer frames (no pack pass).  Inputs are `nimg` images of `nblk`
+ *   blocks of (H,W) each, in the blocks layout (nimg,nblk,H,W) (`*_mosaic` = 0, the SIDD dataset layout) or the mosaic
+ *   layout (nimg,H,nblk*W) (`*_mosaic` = 1, np.concatenate(blocks, -1) of YOND_SIDD.py:315/:408).  split_blocks = 0: an
+ *   image's blocks form one mosaic for the box filters (SelfNLF on the mosaic, :315,:341; plain frames are nblk = 1);
+ *   split_blocks = 1: every block is its own image (SIDD_256, :65,:91-93).  Maps come out packed, (B,h,w,4) with
+ *   B = nimg*nblk / w = W/2 (split) or B = nimg / w = nblk*W/2.  `seg_max` (optional, nimg floats): max(x, 0) per image
+ *   of the first input — the bound of the fallback bias table (:393, isp_algos.py:101).  `work`: yond_nlf_work_bytes(B,h,w,4).
+ * yond_nlf_fit: percentiles -> score3 threshold -> masked sums (with the empty-mask fallbacks of :77-84) -> line fit,
+ *   per segment, all on the device: regs_dev (nseg,2) float64 = (beta1, beta2).  `quants_host`: the nq <= 24 ascending
+ *   percentiles of get_threshold (np.linspace(step,100,100//step)).  detail_dev (optional, (nseg, 52) float64):
+ *   th, index, percent, redo flag, ths[24], npeaks[24].  `work`: yond_nlf_fit_work_bytes(nseg), 256-byte aligned. */
+int yond_nlf_maps_bayer(const float* x, int x_mosaic, const float* y, int y_mosaic, float* var, float* mean, float* lap,
+                        int nimg, int nblk, int H, int W, int split_blocks, int k, int mode, float* seg_max, void* work,
+                        void* stream);
+size_t yond_nlf_fit_work_bytes(int nseg);
+int yond_nlf_fit(const float* var, const float* mean, const float* lap, size_t seg_len, int nseg, const double* quants_host,
+                 int nq, double* regs_dev, double* detail_dev, void* work, void* stream);
+
+/* ---- the VST parameter chain on the device — YOND_SIDD.py:356 (round 1) / :438-447 (round 2 guards), :252-269,
+ * :284-285 (bias source, VST(0), VST(scale), t = nsr*1.03), utils/isp_algos.py:179-231 (sigma row of the BiasLUT),
+ * :49-140 (get_bias: the numeric Poisson (*) Gaussian fallback table — SURVEY 8(f)-2, generated on the device).
+ * yond_vst_params_fill: regs_dev (nseg,2) -> per-frame yond_vst_params (nseg*frames_per_seg), t_dev (same count), and per
+ *   image one bias row + its node positions in rows / xnodes (nseg, row_stride).  round 1: sigma = sqrt(max(beta2,0));
+ *   round 2: beta2 < 0 -> beta1^2 and ok_dev[s] = (beta1 >= 0) (images with ok = 0 get `prev_params`, their output is
+ *   discarded by yond_vst_inv_place).  bias_mode: 0 = None, 1 = 'pre' (bias applied, t*1.03), 2 = 'post' (no bias is
+ *   applied, like the reference).  lut2d (nx,nsg) f32 + sg_lut_dev (nsg) f64 + x_lut_dev (nx) f32: the BiasLUT, or NULL:
+ *   then — and for sigma/K beyond the table — the numeric table up to bound = seg_max[s]*bound_scale (float32 product).
+ *   regs_out (optional, (nseg,4) f64): beta1, beta2 (after the guard), gain, sigma.  `work`: yond_chain_work_bytes(nseg).
+ * yond_bias_table: get_bias(bound, sigma, gain) nodes / values (float32, `cap` entries available) for one parameter
+ *   set; n_nodes_dev receives the node count (= yond_bias_table_nodes(bound), a host-side helper). */
+size_t yond_chain_work_bytes(int nseg);
+int yond_bias_table_nodes(float bound);
+int yond_vst_params_fill(const double* regs_dev, const float* seg_max_dev, int nseg, int frames_per_seg, double scale_est,
+                         double scale, double bound_scale, int round, int bias_mode, int exact_inverse, const float* lut2d,
+                         const double* sg_lut_dev, const float* x_lut_dev, int nx, int nsg,
+                         const yond_vst_params* prev_params, yond_vst_params* params_dev, float* t_dev, float* rows,
+                         float* xnodes, int row_stride, double* regs_out, int32_t* ok_dev, void* work, void* stream);
+int yond_bias_table(double gain, double sigma, float bound, float* nodes_dev, float* vals_dev, int cap,
+                    int32_t* n_nodes_dev, void* work, void* stream);
+/* get_bias_points(lams, K, sigGs, pho_min, close_form=True) (isp_algos.py:142-160): the bias at explicit float64 points
+ * (BiasLUT.get_lut's small-input fallback, :204-212, and — with K = 1, pho_min = 100 on the x-grid — one column of the
+ * offline bias_lut_2d.npy builder).  float64 in / out. */
+int yond_bias_points(const double* lams_dev, int n, double gain, double sigma, int pho_min, double* bias_dev, void* work,
+                     void* stream);
 
 /* ---- A14-A17, A20: denoiser networks — archs/Unet.py:4-104 (UNetSeeInDark), :380-470 (GuidedResUnet),
  * :288-378 (SNRnet); blocks archs/modules.py:117-125,163-233.  Plugin descriptor = the yml `arch:` block. */

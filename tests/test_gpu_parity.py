@@ -430,3 +430,146 @@ def test_full_frame_identity_roundtrip(Y):
     out = drv.VST_Denoiser(x, None, None, None, denoiser="net", p=p)
     assert out.shape == x.shape
     assert float((out - x).abs().max()) < 2e-5
+
+
+# ------------------------------------------------------------------ device-resident estimator tail and parameter chain
+def _host_tail(est, var, mean, lap, nseg):
+    th, pct, info = est.threshold_score3(lap, mean, step=5, nseg=nseg)
+    reg, th2 = est.masked_fit(var, mean, lap, th, nseg=nseg)
+    return np.atleast_2d(reg), np.atleast_1d(th2), np.atleast_1d(pct), {k: np.atleast_2d(v) for k, v in info.items()}
+
+
+@pytest.mark.parametrize("case", ["noise", "ties", "flat"])
+def test_device_estimator_tail_equals_host_path(Y, case):
+    """yond_nlf_fit (percentile lerp, score3 argmin, empty-mask fallbacks, line fit — all on the device) against the
+    host-scalar path of the same maps: thresholds and bin counts identical, (beta1, beta2) to 1e-10."""
+    from yond_public_b200.nlf import NlfEstimator
+    from yond_public_b200._lib import check, ptr, stream_ptr
+    import ctypes as C
+    rng = np.random.default_rng(17)
+    nseg, n = 3, 64 * 96 * 4
+    lap = (rng.random((nseg, n)).astype(np.float32) ** 2) * 0.05
+    mean = rng.random((nseg, n)).astype(np.float32)
+    var = (0.01 * mean + 1e-4 + 1e-3 * rng.standard_normal((nseg, n))).astype(np.float32)
+    if case == "ties":
+        lap = np.round(lap * 200).astype(np.float32) / 200  # many equal values, also at the percentile boundaries
+    if case == "flat":
+        lap[1] = 0.25          # constant: th = min, the strict mask is empty and the 25th percentile equals th -> unmasked fit
+        lap[2, : n // 2] = 0.0  # th25 == th == 0 as well
+    est = NlfEstimator()
+    tv, tm, tl = (torch.from_numpy(a).cuda() for a in (var, mean, lap))
+    reg_h, th_h, pct_h, info = _host_tail(est, tv, tm, tl, nseg)
+    lib = Y._lib.load()
+    quants = np.ascontiguousarray(np.linspace(5, 100, 20), np.float64)
+    regs = torch.empty((nseg, 2), device="cuda", dtype=torch.float64)
+    detail = torch.empty((nseg, est.DETAIL), device="cuda", dtype=torch.float64)
+    work = torch.empty(lib.yond_nlf_fit_work_bytes(nseg) + 256, device="cuda", dtype=torch.uint8)
+    off = (-work.data_ptr()) % 256
+    check(lib.yond_nlf_fit(ptr(tv), ptr(tm), ptr(tl), n, nseg, quants.ctypes.data_as(C.POINTER(C.c_double)), 20, ptr(regs), ptr(detail),
+                           ptr(work[off:]), stream_ptr()))
+    d = detail.cpu().numpy()
+    assert np.array_equal(d[:, 4:24], info["ths"])
+    assert np.array_equal(d[:, 28:48], info["npeaks"])
+    assert np.array_equal(d[:, 2], pct_h)
+    assert np.array_equal(d[:, 0], th_h)
+    np.testing.assert_allclose(regs.cpu().numpy(), reg_h, rtol=1e-10)
+    for s in range(nseg):  # and the host path itself against NumPy / the oracle's fit
+        ths = np.percentile(lap[s], quants, method="linear")
+        assert np.array_equal(d[s, 4:24], ths)
+
+
+@pytest.mark.parametrize("img_max,sig,K", [(700.0, 6.0, 4.0), (40.0, 0.9, 0.4), (961.0, 31.0, 2.9), (30.2, 0.8, 0.31), (333.0, 0.0, 1.0),
+                                           (959.0, 120.0, 9.7), (420.5, 55.0, 27.0), (2400.0, 11.0, 1.4)])
+def test_fallback_bias_table_device_generator(Y, img_max, sig, K):
+    """SURVEY 8(f)-2: get_bias's numeric Poisson (*) Gaussian table generated on the device == the oracle (SciPy) to 1e-7;
+    node positions identical (float32 dtype flow of the reference)."""
+    nodes, vals = Y.get_bias_table(np.float32(img_max), sig, K)
+    lams, bias = O.get_bias_table(np.float32(img_max), np.float64(sig), np.float64(K))
+    assert np.array_equal(nodes, lams)
+    np.testing.assert_allclose(vals, bias, rtol=0, atol=1e-7)
+    dn, dv = Y.get_bias_table(np.float32(img_max), sig, K, device=True)
+    assert np.array_equal(dn.cpu().numpy(), lams.astype(np.float32)) and np.array_equal(dv.cpu().numpy(), vals)
+
+
+def test_bias_points_and_lut_fallback(Y, lut_table):
+    """get_bias_points on the device (pho_min = 100: one column slice of the offline LUT builder) and BiasLUT.get_lut's
+    out-of-range semantics (isp_algos.py:204-212: sigma/K >= 10 falls back to get_bias / get_bias_points)."""
+    x_lut, _ = Y.isp.lut_grids()
+    pts = x_lut[[0, 5, 130, 400, 900, 1300, 1500, 1900]]
+    got = Y.isp.get_bias_points(pts, 1.0, 2.35, pho_min=100)
+    ref = O.get_bias_points(pts.copy(), 1.0, 2.35, pho_min=100, close_form=True)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
+    lut = Y.BiasLUT()
+    K, s = 0.5, 7.0  # sigma/K = 14 e-: beyond the table
+    x = np.linspace(0, 900, 2000).astype(np.float32)
+    ref = O.get_bias(x, np.float64(s), np.float64(K), close_form=True)(x)
+    np.testing.assert_allclose(lut.get_lut(x, K, s), ref, rtol=0, atol=2e-6)
+    xs = np.linspace(0, 200, 50).astype(np.float32)  # <= 1000 points: exact per point
+    ref = O.get_bias_points(xs.astype(np.float64), np.float64(K), np.float64(s), pho_min=100, close_form=True)
+    np.testing.assert_allclose(lut.get_lut(xs, K, s), ref, rtol=0, atol=2e-6)
+
+
+def test_chain_params_equal_host_make_params(Y):
+    """yond_vst_params_fill (device) fills the same per-frame parameters, guidance values and bias rows as the host-side
+    make_params does for given (gain, sigma): bitwise for the LUT case, table values to 1e-7 for the fallback case."""
+    lut = Y.BiasLUT()
+    net = Y.build_net(ARCHS["gru"])
+    for biaslut in (lut, None):
+        eng = Y.YondEngine(net, ARCHS["gru"], biaslut)
+        regs = np.array([[5e-3, 4e-5], [2.1e-2, -3e-6], [8e-4, 9e-5]], np.float64)  # third: sigma/K = 12.4 -> fallback
+        seg_max = torch.tensor([0.93, 1.0, 0.4], device="cuda")
+        ch = eng.chain_params(torch.from_numpy(regs).cuda(), seg_max, 3, 2, 959, 959.0, 959, 1, "pre", "exact")
+        gains, sigmas = regs[:, 0] * 959, np.sqrt(np.maximum(regs[:, 1], 0)) * 959
+        fmax = lambda: np.repeat(seg_max.cpu().numpy() * np.float32(959), 2)
+        params, rows, xnodes, stride, t = eng.make_params(np.repeat(gains, 2), np.repeat(sigmas, 2), 959.0, "pre", "exact", fmax, "cuda")
+        rec_dt = np.dtype([("gain", "<f4"), ("sigma", "<f4"), ("scale", "<f4"), ("lower", "<f4"), ("upper", "<f4"), ("lut_row", "<i4"),
+                           ("table_n", "<i4"), ("exact", "<i4")])
+        a, b = ch["params"].cpu().numpy().view(rec_dt), params.cpu().numpy().view(rec_dt)
+        for f in ("gain", "sigma", "scale", "lower", "upper", "table_n", "exact"):
+            assert np.array_equal(a[f], b[f]), f
+        assert np.array_equal(ch["t"].cpu().numpy(), t.cpu().numpy())
+        r4 = ch["regs4"].cpu().numpy()
+        assert np.array_equal(r4[:, 2], gains) and np.array_equal(r4[:, 3], sigmas)
+        for fr in range(6):
+            n = int(a["table_n"][fr]) or 1921
+            ra, rb = ch["rows"][a["lut_row"][fr], :n].cpu().numpy(), rows[b["lut_row"][fr], :n].cpu().numpy()
+            np.testing.assert_allclose(ra, rb, rtol=0, atol=0 if a["table_n"][fr] == 0 else 1e-7)
+            assert np.array_equal(ch["xnodes"][a["lut_row"][fr], :n].cpu().numpy(), xnodes[b["lut_row"][fr], :n].cpu().numpy())
+    # round-2 guards: beta2 < 0 -> beta1^2, beta1 < 0 -> not ok
+    eng = Y.YondEngine(net, ARCHS["gru"], lut)
+    regs2 = torch.tensor([[4e-3, -1e-6], [-2e-3, 1e-5]], device="cuda", dtype=torch.float64)
+    ch1 = eng.chain_params(torch.tensor([[4e-3, 1e-5], [3e-3, 2e-5]], device="cuda", dtype=torch.float64), None, 2, 1, 959, 959.0, 959, 1, "pre", "exact")
+    ch2 = eng.chain_params(regs2, None, 2, 1, 959, 959.0, 959, 2, "pre", "exact", prev=ch1)
+    r4 = ch2["regs4"].cpu().numpy()
+    assert r4[0, 1] == 4e-3 ** 2 and r4[0, 3] == np.sqrt(4e-3 ** 2) * 959
+    assert ch2["ok"].cpu().tolist() == [1, 0]
+
+
+def test_bias_corr_post_matches_oracle(Y, lut_table):
+    """bias_corr='post' computes a bias and never applies it (YOND_SIDD.py:261,294-295), sigma_corr = 1.00, algebraic inverse."""
+    rng = np.random.default_rng(41)
+    noisy = O.synth_noisy(rng, O.synth_clean(rng, 96, 128), 5.0, 7.0)
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "scale": 959.0, "gain": np.float64(5.2), "sigma": np.float64(6.8)}
+    sd = O.init_state_dict(ARCHS["gru"], seed=5)
+    drv = Y.YOND_SIDD(ARCHS["gru"], dict(PIPE, bias_corr="post"), state_dict=sd)
+    out = drv.VST_Denoiser(noisy, None, "post", None, denoiser="net", p=dict(p))
+    ref = O.VST_Denoiser(ARCHS["gru"], sd, noisy, dict(p), "post", O.BiasLUT(lut_table))
+    assert float(np.abs(out - ref).max()) < TOL_ABS
+    pre = O.VST_Denoiser(ARCHS["gru"], sd, noisy, dict(p), "pre", O.BiasLUT(lut_table))
+    assert float(np.abs(pre - ref).max()) > 10 * float(np.abs(out - ref).max())  # the two modes really differ
+
+
+def test_iterdenoise_no_lut_and_out_of_range_on_device(Y, lut_table):
+    """The blind pipeline without a LUT file (reference default: biaslut None -> get_bias tables) and with a LUT but a frame
+    whose sigma/K leaves it: both run without host round trips (device table generator) and match the oracle."""
+    rng = np.random.default_rng(23)
+    sd = O.init_state_dict(ARCHS["unet"], seed=5)
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+    blocks = np.stack([O.synth_noisy(rng, O.synth_clean_smooth(rng, 128, 128), 0.25, 3.4) for _ in range(32)])  # sigma/K ~ 13.6
+    for biaslut, oref in ((None, None), ("default", O.BiasLUT(lut_table))):
+        drv = Y.YOND_SIDD(ARCHS["unet"], PIPE, state_dict=sd, biaslut=biaslut)
+        res = drv.IterDenoise({"lr": blocks, "name": "x"}, {"p": dict(p), "img_id": 0})
+        ref = O.IterDenoise(ARCHS["unet"], sd, blocks, dict(p), PIPE, biaslut=oref)
+        np.testing.assert_allclose(np.asarray(res["regs"][0]), np.asarray(ref["regs"][0]), rtol=TOL_EST)
+        assert len(res["raw_dns"]) == len(ref["raw_dns"])
+        assert float(np.abs(res["raw_dns"][0] - ref["raw_dns"][0]).max()) < TOL_ABS

@@ -36,6 +36,7 @@ SIGNATURES = {
     "yond_inverse_vst": (_I, [_P, _P, _SZ, _D, _D, _I, _P]),
     "yond_lut_row": (_I, [_P, _I, _I, _D, _P, _P]),
     "yond_lut_apply": (_I, [_P, _P, _SZ, _P, _P, _I, _D, _D, _P]),
+    "yond_table_apply": (_I, [_P, _P, _SZ, _P, _P, _I, _P]),
     "yond_vst_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "yond_vst_inv": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "yond_pack_pad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -47,6 +48,15 @@ SIGNATURES = {
     "yond_order_stats": (_I, [_P, _SZ, _I, _P, _I, _P, _P, _P]),
     "yond_score3_bins": (_I, [_P, _P, _SZ, _I, _P, _I, _P, _P, _P]),
     "yond_masked_sums": (_I, [_P, _P, _P, _SZ, _I, _P, _P, _P]),
+    "yond_nlf_maps_bayer": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "yond_nlf_fit_work_bytes": (_SZ, [_I]),
+    "yond_nlf_fit": (_I, [_P, _P, _P, _SZ, _I, C.POINTER(_D), _I, _P, _P, _P, _P]),
+    "yond_chain_work_bytes": (_SZ, [_I]),
+    "yond_bias_table_nodes": (_I, [C.c_float]),
+    "yond_vst_params_fill": (_I, [_P, _P, _I, _I, _D, _D, _D, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "yond_bias_table": (_I, [_D, _D, C.c_float, _P, _P, _I, _P, _P, _P]),
+    "yond_bias_points": (_I, [_P, _I, _D, _D, _I, _P, _P, _P]),
+    "yond_vst_inv_place": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _P, _P]),
     "yond_net_create": (_I, [_I, _I, _I, _I, _I, _I, C.POINTER(_P)]),
     "yond_net_destroy": (None, [_P]),
     "yond_net_set_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),

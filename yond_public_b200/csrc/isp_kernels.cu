@@ -1,6 +1,8 @@
 // Elementwise / LUT kernels of the YOND path: Bayer pack/unpack, generalized-Anscombe VST with LUT bias
 // correction, normalisation, reflect padding, inverse VST.  All HBM-bound: one pass, 64/128-bit accesses.
 //   reference: utils/isp_ops.py:57-63, utils/isp_algos.py:5-33,162-231, YOND_SIDD.py:238-299.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -245,22 +247,102 @@ __device__ __forceinline__ void block_max_to(float v, float* dst) {
 
 // ------------------------------------------------------------------ A18 front: fused pack+bias+VST+normalise+clamp+pad
 // grid = (blocks per frame, B); every block stays inside one frame so the per-frame constants are uniform.
+// The frame's bias row is staged in shared memory as one 16-byte record per interval {x_l, y_l, slope, x_r}: a lookup is
+// an index guess (analytic on the BiasLUT's lin+log grid and on get_bias's three uniform pieces, binary search for
+// anything else), one LDS.128, a fix-up that almost never iterates, and one FMA.  The float32 slope form differs from the
+// reference's y_l (1 - w) + y_r w by one rounding of a value that is itself ~0.1 (BiasLUT goldens: <= 2e-6 allowed, ~1e-8 seen).
+constexpr int kFwdPix = 16;  // packed pixels per thread: amortises the table staging (1921 records per block)
+struct TabInfo {
+  int n;            // nodes
+  int kind;         // 0: none, 1: BiasLUT grid (electrons), 2: get_bias pieces (DN), 3: generic ascending nodes
+  float last;       // last node
+  float ext;        // LUT: last + (last - prev): beyond it the closed form applies (isp_algos.py:228-230)
+  int n1, n2;       // get_bias pieces: first index of piece 2 / piece 3
+  float v1, v2;     // their first node values
+  float is0, is1, is2;  // inverse steps of the pieces
+};
+__device__ __forceinline__ float tab_lookup(float xq, const float4* __restrict__ tab, const TabInfo& ti) {
+  int g;
+  if (ti.kind == 1) {
+    g = xq < 0.0625f ? (int)(xq * 2048.f) : 128 + (int)(128.f * (__log2f(xq) + 4.f));
+  } else if (ti.kind == 2) {
+    g = xq < ti.v1 ? (int)(xq * ti.is0) : (xq < ti.v2 ? ti.n1 + (int)((xq - ti.v1) * ti.is1) : ti.n2 + (int)((xq - ti.v2) * ti.is2));
+  } else {
+    int lo = 0, hi = ti.n - 1;  // last interval whose left node is < xq
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tab[mid].x < xq) lo = mid; else hi = mid;
+    }
+    g = lo;
+  }
+  g = max(0, min(g, ti.n - 2));
+  float4 e = tab[g];
+  while (xq > e.w && g < ti.n - 2) e = tab[++g];
+  while (xq < e.x && g > 0) e = tab[--g];
+  return fmaf(fmaxf(xq - e.x, 0.f), e.z, e.y);
+}
 template <bool kVst>
 __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict__ bayer, float* __restrict__ z,
                                                          float* __restrict__ ub, int H, int W, int pl, int pt, int hp, int wp,
                                                          const yond_vst_params* __restrict__ params,
                                                          const float* __restrict__ rows, const float* __restrict__ xnodes,
                                                          int row_stride) {
+  extern __shared__ float4 tab[];
+  __shared__ TabInfo ti;
   const int b = blockIdx.y;
   const int h = H >> 1, w = W >> 1;
   VstConst c{};
-  if (kVst) c = load_const(params[b]);
+  if (kVst) {
+    c = load_const(params[b]);
+    if (c.lut_row >= 0) {
+      const float* row = rows + (size_t)c.lut_row * row_stride;
+      const float* nodes = xnodes + (size_t)c.lut_row * row_stride;
+      const int n = c.table_n > 0 ? c.table_n : 1921;
+      for (int i = threadIdx.x; i < n - 1; i += kBlock) {
+        const float xl = __ldg(nodes + i), xr = __ldg(nodes + i + 1), yl = __ldg(row + i), yr = __ldg(row + i + 1);
+        tab[i] = make_float4(xl, yl, xr > xl ? (yr - yl) / (xr - xl) : 0.f, xr);
+      }
+      if (threadIdx.x == 0) {
+        TabInfo t{};
+        t.n = n;
+        t.last = __ldg(nodes + n - 1);
+        t.ext = t.last + (t.last - __ldg(nodes + n - 2));
+        if (c.table_n == 0) {
+          t.kind = 1;
+        } else {
+          // get_bias node layout (isp_algos.py:101-108): [0,50] step 0.1 | [50,500] step 1 | [500,ub] step ~10, or a single
+          // piece below 50 — recognised from the node values, anything else takes the binary search
+          t.kind = 3;
+          const float n0 = __ldg(nodes);
+          if (n0 == 0.f && t.last < 50.f && n >= 3) {
+            t.kind = 2; t.n1 = t.n2 = n; t.v1 = t.v2 = 3.0e38f; t.is0 = (float)(n - 1) / t.last;
+          } else if (n0 == 0.f && n >= 504 && __ldg(nodes + 500) == 50.f && __ldg(nodes + 501) == 50.f) {
+            t.kind = 2; t.n1 = 501; t.v1 = 50.f; t.is0 = 10.f;
+            if (t.last < 500.f || n < 955) {
+              t.n2 = n; t.v2 = 3.0e38f; t.is1 = (float)(n - 502) / (t.last - 50.f);
+            } else if (__ldg(nodes + 951) == 500.f && __ldg(nodes + 952) == 500.f) {
+              t.n2 = 952; t.v2 = 500.f; t.is1 = 1.f; t.is2 = (float)(n - 953) / (t.last - 500.f);
+            } else {
+              t.kind = 3;
+            }
+          }
+        }
+        ti = t;
+      }
+    }
+  }
+  __syncthreads();
+  const float invK = kVst ? 1.0f / c.K : 0.f;
   const float* frame = bayer + (size_t)b * H * W;
   float4* zo = reinterpret_cast<float4*>(z) + (size_t)b * hp * wp;
   const int npix = hp * wp;
   float vmax = 0.f;
-  for (int idx = blockIdx.x * kBlock + threadIdx.x; idx < npix; idx += gridDim.x * kBlock) {
-    const int j = idx % wp, i = idx / wp;
+  const int base = blockIdx.x * (kBlock * kFwdPix) + threadIdx.x;
+#pragma unroll 4
+  for (int it = 0; it < kFwdPix; ++it) {
+    const int idx = base + it * kBlock;
+    if (idx >= npix) break;
+    const int i = idx / wp, j = idx - i * wp;
     const int si = reflect101(i - pt, h), sj = reflect101(j - pl, w);
     const float* r0 = frame + (size_t)(2 * si) * W + 2 * sj;
     const float2 a = ldg_stream_f2(reinterpret_cast<const float2*>(r0));
@@ -270,7 +352,17 @@ __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float x = v[k] * c.scale;
-        const float zz = vst_f(x, c) - bias_eval(x, c, rows, xnodes, row_stride);
+        float bias = 0.f;
+        if (c.lut_row >= 0) {
+          const float xb = fmaxf(x, 0.f);
+          if (c.table_n > 0) {
+            bias = tab_lookup(fminf(xb, ti.last), tab, ti);
+          } else {
+            const float xe = xb * invK;
+            bias = xe >= ti.ext ? close_form_bias_f(xb, c) : tab_lookup(xe, tab, ti);
+          }
+        }
+        const float zz = vst_f(x, c) - bias;
         v[k] = (zz - c.lower) * c.inv_range;
       }
     }
@@ -285,19 +377,43 @@ __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------ A18 back: clamp+crop+denorm+inverse+unpack(+clip)
+// Output placement: frames_per_row = 1 writes (B,H,W); n > 1 writes frame b as block b % n of the mosaic b / n — the
+// reference's np.concatenate(blocks, axis=-1) layout (YOND_SIDD.py:408) — so no permute pass follows.
+// Round selection: with `seg_ok`, frames of an image whose round-2 estimate failed the beta1 >= 0 guard (:445-447) copy
+// `fallback` (the round-1 result, same layout as the output) instead of the network output.
+struct InvPlace {
+  int frames_per_row;
+  const int32_t* seg_ok;
+  int frames_per_seg;
+  const float* fallback;
+};
 template <bool kVst>
 __global__ void __launch_bounds__(kBlock) vst_inv_kernel(const float* __restrict__ y, float* __restrict__ bayer, int H, int W,
                                                          int pl, int pt, int hp, int wp,
-                                                         const yond_vst_params* __restrict__ params, int clip01) {
+                                                         const yond_vst_params* __restrict__ params, int clip01, InvPlace place) {
   const int b = blockIdx.y;
   const int h = H >> 1, w = W >> 1;
   VstConst c{};
   if (kVst) c = load_const(params[b]);
   const float4* yi = reinterpret_cast<const float4*>(y) + (size_t)b * hp * wp;
-  float* frame = bayer + (size_t)b * H * W;
+  const int fpr = place.frames_per_row;
+  const size_t pitch = (size_t)fpr * W;
+  const size_t origin = (size_t)(b / fpr) * H * pitch + (size_t)(b % fpr) * W;
+  float* frame = bayer + origin;
+  const bool keep = place.seg_ok == nullptr || place.seg_ok[b / place.frames_per_seg] != 0;
+  const float* fb = place.fallback ? place.fallback + origin : nullptr;
   const int npix = h * w;
   for (int idx = blockIdx.x * kBlock + threadIdx.x; idx < npix; idx += gridDim.x * kBlock) {
     const int j = idx % w, i = idx / w;
+    float* r0 = frame + (size_t)(2 * i) * pitch + 2 * j;
+    if (!keep) {
+      if (fb) {
+        const float* f0 = fb + (size_t)(2 * i) * pitch + 2 * j;
+        *reinterpret_cast<float2*>(r0) = ldg_stream_f2(reinterpret_cast<const float2*>(f0));
+        *reinterpret_cast<float2*>(r0 + pitch) = ldg_stream_f2(reinterpret_cast<const float2*>(f0 + pitch));
+      }
+      continue;
+    }
     const float4 q = ldg_stream_f4(yi + (size_t)(i + pt) * wp + (j + pl));
     float v[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -309,9 +425,8 @@ __global__ void __launch_bounds__(kBlock) vst_inv_kernel(const float* __restrict
       }
       v[k] = t;
     }
-    float* r0 = frame + (size_t)(2 * i) * W + 2 * j;
     *reinterpret_cast<float2*>(r0) = make_float2(v[0], v[1]);
-    *reinterpret_cast<float2*>(r0 + W) = make_float2(v[2], v[3]);
+    *reinterpret_cast<float2*>(r0 + pitch) = make_float2(v[2], v[3]);
   }
 }
 
@@ -439,6 +554,17 @@ int yond_lut_apply(const float* x, float* bias, size_t n, const float* row, cons
   return YOND_OK;
 }
 
+int yond_table_apply(const float* x, float* bias, size_t n, const float* vals, const float* nodes, int n_nodes, void* stream) {
+  YOND_REQUIRE(x && bias && vals && nodes && n_nodes >= 2, "yond_table_apply: bad arguments");
+  VstConst c{};
+  c.K = 1.f;
+  c.lut_row = 0;
+  c.table_n = n_nodes;
+  lut_apply_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, bias, n, vals, nodes, n_nodes, c);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
 static int launch_fwd(bool vst, const float* bayer, float* z, float* ub, int B, int H, int W, int pl, int pr, int pt, int pb,
                       const yond_vst_params* params, const float* rows, const float* xnodes, int row_stride, void* stream) {
   YOND_REQUIRE(B > 0 && H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0, "vst_fwd: H,W must be even");
@@ -448,12 +574,21 @@ static int launch_fwd(bool vst, const float* bayer, float* z, float* ub, int B, 
   const int hp = h + pt + pb, wp = w + pl + pr;
   cudaStream_t s = (cudaStream_t)stream;
   YOND_CUDA_CHECK(cudaMemsetAsync(ub, 0, sizeof(float) * B, s));
-  int gx = ceil_div(hp * wp, kBlock * 4);
-  if (gx < 1) gx = 1;
-  if (gx > 65535) gx = 65535;
+  YOND_REQUIRE(B <= 65535, "vst_fwd: at most 65535 frames per call");
+  const int gx = ceil_div(hp * wp, kBlock * kFwdPix);
   dim3 grid(gx, B);
-  if (vst) vst_fwd_kernel<true><<<grid, kBlock, 0, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, params, rows, xnodes, row_stride);
-  else vst_fwd_kernel<false><<<grid, kBlock, 0, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, nullptr, nullptr, nullptr, 0);
+  if (vst) {
+    const int tab_n = rows ? (row_stride > 1921 ? row_stride : 1921) : 0;
+    const size_t smem = (size_t)tab_n * sizeof(float4);
+    YOND_REQUIRE(smem <= 200 * 1024, "vst_fwd: bias tables of more than %d nodes are not supported (row_stride %d)", 200 * 1024 / 16, row_stride);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(vst_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (attr_err != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(vst_fwd_kernel) failed: %s", cudaGetErrorString(attr_err));
+    vst_fwd_kernel<true><<<grid, kBlock, smem, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, params, rows, xnodes, row_stride);
+  } else {
+    vst_fwd_kernel<false><<<grid, kBlock, 0, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, nullptr, nullptr, nullptr, 0);
+  }
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
@@ -469,27 +604,41 @@ int yond_pack_pad(const float* bayer, float* z, float* ub, int B, int H, int W, 
 }
 
 static int launch_inv(bool vst, const float* y, float* bayer, int B, int H, int W, int pl, int pr, int pt, int pb,
-                      const yond_vst_params* params, int clip01, void* stream) {
+                      const yond_vst_params* params, int clip01, const InvPlace& place, void* stream) {
   YOND_REQUIRE(B > 0 && H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0, "vst_inv: H,W must be even");
+  YOND_REQUIRE(B <= 65535, "vst_inv: at most 65535 frames per call");
   const int h = H / 2, w = W / 2, hp = h + pt + pb, wp = w + pl + pr;
   int gx = ceil_div(h * w, kBlock * 4);
   if (gx < 1) gx = 1;
   if (gx > 65535) gx = 65535;
   dim3 grid(gx, B);
   cudaStream_t s = (cudaStream_t)stream;
-  if (vst) vst_inv_kernel<true><<<grid, kBlock, 0, s>>>(y, bayer, H, W, pl, pt, hp, wp, params, clip01);
-  else vst_inv_kernel<false><<<grid, kBlock, 0, s>>>(y, bayer, H, W, pl, pt, hp, wp, nullptr, 0);
+  if (vst) vst_inv_kernel<true><<<grid, kBlock, 0, s>>>(y, bayer, H, W, pl, pt, hp, wp, params, clip01, place);
+  else vst_inv_kernel<false><<<grid, kBlock, 0, s>>>(y, bayer, H, W, pl, pt, hp, wp, nullptr, 0, place);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
 int yond_vst_inv(const float* y, float* bayer, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
                  const yond_vst_params* params_dev, int clip01, void* stream) {
   YOND_REQUIRE(params_dev != nullptr, "yond_vst_inv: params required");
-  return launch_inv(true, y, bayer, B, H, W, pad_l, pad_r, pad_t, pad_b, params_dev, clip01, stream);
+  return launch_inv(true, y, bayer, B, H, W, pad_l, pad_r, pad_t, pad_b, params_dev, clip01, InvPlace{1, nullptr, 1, nullptr}, stream);
+}
+int yond_vst_inv_place(const float* y, float* out, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
+                       const yond_vst_params* params_dev, int clip01, int frames_per_row, int frame0, const int32_t* seg_ok_dev,
+                       int frames_per_seg, const float* fallback, void* stream) {
+  YOND_REQUIRE(params_dev != nullptr, "yond_vst_inv_place: params required");
+  YOND_REQUIRE(frames_per_row >= 1 && frame0 >= 0 && frame0 % frames_per_row == 0 && B % frames_per_row == 0,
+               "yond_vst_inv_place: a call covers whole mosaics (B and frame0 multiples of frames_per_row)");
+  YOND_REQUIRE(!seg_ok_dev || (frames_per_seg >= 1 && frame0 % frames_per_seg == 0), "yond_vst_inv_place: frame0 must start an image");
+  // `out` / `fallback` / `seg_ok_dev` are the buffers of the WHOLE batch; this call covers frames frame0 .. frame0 + B - 1
+  const size_t off = (size_t)frame0 * H * W;
+  InvPlace place{frames_per_row, seg_ok_dev ? seg_ok_dev + frame0 / frames_per_seg : nullptr, frames_per_seg < 1 ? 1 : frames_per_seg,
+                 fallback ? fallback + off : nullptr};
+  return launch_inv(true, y, out + off, B, H, W, pad_l, pad_r, pad_t, pad_b, params_dev, clip01, place, stream);
 }
 int yond_crop_unpack(const float* y, float* bayer, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
                      void* stream) {
-  return launch_inv(false, y, bayer, B, H, W, pad_l, pad_r, pad_t, pad_b, nullptr, 0, stream);
+  return launch_inv(false, y, bayer, B, H, W, pad_l, pad_r, pad_t, pad_b, nullptr, 0, InvPlace{1, nullptr, 1, nullptr}, stream);
 }
 
 }  // extern "C"

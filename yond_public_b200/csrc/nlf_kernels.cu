@@ -31,8 +31,22 @@ __device__ __forceinline__ float4 sq4(const float4& v) {
 // like the reference's elementwise float32 expressions.
 enum { OP_MEAN = 0, OP_MEAN_STD = 1, OP_STD = 2, OP_MEAN_VAR = 3, OP_COLLAB = 4 };
 constexpr int kBoxThreads = 256;
-template <bool kSq, int kCols>  // kCols = 256, or 160 when the whole row plus both halos fits (SIDD blocks: 128 + 28)
-__global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(const float4* __restrict__ x, float4* __restrict__ out0,
+// Where the k x k window reads its pixels from.  kBayer = false: packed frames (B,h,w,4) float32.  kBayer = true: the Bayer
+// mosaic itself (two 64-bit loads per packed pixel, rows 2i and 2i+1) — the estimator then needs no pack pass at all — with
+// optional SIDD geometry: packed column c of image b lives in block c / blk_w of that image (blocks laid side by side,
+// YOND_SIDD.py:315), `blk_stride` floats apart.
+struct BoxSrc {
+  const float* base;
+  long long img_stride;  // floats between images
+  long long blk_stride;  // floats between the blocks of an image (Bayer mode)
+  int blk_w;             // packed pixels per block row (Bayer mode; = w for plain frames)
+  int row_len;           // floats per source row: Bayer W of a block, or 4*w
+  float* seg_max;        // optional: per-image maximum of max(x, 0) (atomicMax on the float bits), image = b / imgs_per_seg
+  int imgs_per_seg;
+  int mosaic_blocks;     // > 0: box-filter image b is block b % n of mosaic b / n (mosaic layout, blocks as separate images)
+};
+template <bool kSq, int kCols, bool kBayer>  // kCols = 256, or 160 when the whole row plus both halos fits (SIDD blocks: 128 + 28)
+__global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, float4* __restrict__ out0,
                                                                 float4* __restrict__ out1, int h, int w, int k, int op,
                                                                 int rows_per_strip, const float4* __restrict__ aux,
                                                                 float4* __restrict__ out2) {
@@ -49,7 +63,17 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(const float4* __
   const int col_src = reflect101(col_out, w);               // BORDER_REFLECT_101
   const int i0 = blockIdx.y * rows_per_strip;
   const int i1 = min(h, i0 + rows_per_strip);
-  const float4* xb = x + (size_t)b * h * w;
+  const float* colbase;
+  if (kBayer) {
+    const int blk = col_src / src.blk_w;
+    colbase = src.base + (size_t)b * src.img_stride + (size_t)blk * src.blk_stride + 2 * (col_src - blk * src.blk_w);
+    if (src.mosaic_blocks > 0)
+      colbase += (size_t)(b / src.mosaic_blocks) * (2 * h) * src.row_len + (size_t)(b % src.mosaic_blocks) * src.blk_stride;
+  } else {
+    colbase = src.base + (size_t)b * src.img_stride + 4 * (size_t)col_src;
+  }
+  const size_t row_pitch = kBayer ? 2 * (size_t)src.row_len : (size_t)src.row_len;
+  float vmax = 0.f;
   double s[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) s[q] = 0.0;
@@ -60,7 +84,18 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(const float4* __
       s[4] += sign * q2.x; s[5] += sign * q2.y; s[6] += sign * q2.z; s[7] += sign * q2.w;
     }
   };
-  auto load = [&](int i) { return __ldg(xb + (size_t)reflect101(i, h) * w + col_src); };
+  auto load = [&](int i) {
+    const float* p = colbase + (size_t)reflect101(i, h) * row_pitch;
+    float4 v;
+    if (kBayer) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(p)), d = __ldg(reinterpret_cast<const float2*>(p + src.row_len));
+      v = make_float4(a.x, a.y, d.x, d.y);
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(p));
+    }
+    if (src.seg_max) vmax = fmaxf(vmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    return v;
+  };
   if (colthread)
     for (int i = i0 - r; i <= i0 + r; ++i) accum(load(i), 1.0);
   const double inv = 1.0 / ((double)k * (double)k);
@@ -139,6 +174,10 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(const float4* __
     }
     // the other S buffer is written next; this one is rewritten two rows later, after the next row's barriers
   }
+  if (src.seg_max) {  // values are >= 0: integer order of the bits == float order
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<int*>(src.seg_max + b / src.imgs_per_seg), __float_as_int(vmax));
+  }
 }
 
 // ------------------------------------------------------------------ exact order statistics (radix select)
@@ -162,7 +201,23 @@ struct SelectWork {
   int q_slot1[kMaxRanks], q_slot2[kMaxRanks];
   uint32_t q_prefix[kMaxRanks];
   int nslot1, nslot2;
+  int nq_live;  // number of queries (q_* entries in use)
 };
+
+// Streaming loops keep kUnroll 128-bit loads in flight per thread (the kernels are latency-bound otherwise: one float4 per
+// thread and a dependent shared-memory atomic leave ~16 KB in flight per SM against the ~40 KB Little's law asks for).
+constexpr int kUnroll = 4;
+#define YOND_STREAM4(d4, n4, ...)                                                                         \
+  {                                                                                                        \
+    const size_t stride_ = (size_t)gridDim.x * blockDim.x;                                                 \
+    size_t i_ = blockIdx.x * (size_t)blockDim.x + threadIdx.x;                                             \
+    for (; i_ + (kUnroll - 1) * stride_ < (n4); i_ += kUnroll * stride_) {                                 \
+      float4 v_[kUnroll];                                                                                  \
+      _Pragma("unroll") for (int u_ = 0; u_ < kUnroll; ++u_) v_[u_] = ldg_stream_f4((d4) + i_ + u_ * stride_); \
+      _Pragma("unroll") for (int u_ = 0; u_ < kUnroll; ++u_) { const float4 v = v_[u_]; __VA_ARGS__ }             \
+    }                                                                                                      \
+    for (; i_ < (n4); i_ += stride_) { const float4 v = ldg_stream_f4((d4) + i_); __VA_ARGS__ }                   \
+  }
 
 __global__ void __launch_bounds__(256) hist0_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
   d += (size_t)blockIdx.y * n;  // one segment (image) per blockIdx.y
@@ -171,13 +226,12 @@ __global__ void __launch_bounds__(256) hist0_kernel(const float* __restrict__ d,
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
   __syncthreads();
   const float4* d4 = reinterpret_cast<const float4*>(d);  // segments hold 4-channel pixels: n % 4 == 0, 16-byte aligned
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = ldg_stream_f4(d4 + i);
+  YOND_STREAM4(d4, n / 4, {
     atomicAdd(&h[f2key(v.x) >> 21], 1u);
     atomicAdd(&h[f2key(v.y) >> 21], 1u);
     atomicAdd(&h[f2key(v.z) >> 21], 1u);
     atomicAdd(&h[f2key(v.w) >> 21], 1u);
-  }
+  })
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += blockDim.x)
     if (h[i]) atomicAdd(&wk->hist0[i], (unsigned long long)h[i]);
@@ -240,27 +294,28 @@ __global__ void __launch_bounds__(1024) select0_kernel(SelectWork* wk, const uns
 constexpr int kHist1Slots = 16;
 constexpr int kHist1Threads = 1024;
 __global__ void __launch_bounds__(kHist1Threads) hist1_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
-  extern __shared__ unsigned int hs[];  // [kHist1Slots][2048]
+  extern __shared__ unsigned int hs[];  // [kHist1Slots][2048] counters, then the 2048-entry prefix -> slot table (int8)
+  signed char* s1tab = reinterpret_cast<signed char*>(hs + kHist1Slots * 2048);
   d += (size_t)blockIdx.y * n;
   wk += blockIdx.y;
   const int nsh = min(wk->nslot1, kHist1Slots);
   for (int i = threadIdx.x; i < nsh * 2048; i += blockDim.x) hs[i] = 0u;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s1tab[i] = (signed char)wk->slot1_of_prefix[i];  // slots < kMaxRanks = 64
   __syncthreads();
   const float4* d4 = reinterpret_cast<const float4*>(d);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = ldg_stream_f4(d4 + i);
+  YOND_STREAM4(d4, n / 4, {
     const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
+_Pragma("unroll")
     for (int j = 0; j < 4; ++j) {
       const uint32_t k = f2key(e[j]);
-      const int s = __ldg(&wk->slot1_of_prefix[k >> 21]);
+      const int s = s1tab[k >> 21];
       if (s >= 0) {
         const uint32_t mid = (k >> 10) & 2047u;
         if (s < kHist1Slots) atomicAdd(&hs[s * 2048 + mid], 1u);
         else atomicAdd(&wk->hist1[s][mid], 1ull);
       }
     }
-  }
+  })
   __syncthreads();
   for (int i = threadIdx.x; i < nsh * 2048; i += blockDim.x)
     if (hs[i]) atomicAdd(&wk->hist1[i >> 11][i & 2047], (unsigned long long)hs[i]);
@@ -289,24 +344,40 @@ __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nrank
       wk->q_slot2[q] = wk->slot2_of[s1][bin];
     }
     wk->nslot2 = ns;
+    wk->nq_live = nranks;
   }
 }
+// Third radix level.  Only elements whose upper 22 bits equal one of the <= 64 queried prefixes count (~0.2 % of the
+// data): the membership test runs against shared memory (prefix -> slot table + one 2048-bit map per slot), the hits
+// take the global slot2 lookup and a global atomic.
 __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
+  __shared__ signed char s1tab[2048];
+  __shared__ unsigned int bm[kMaxRanks * 64];
   d += (size_t)blockIdx.y * n;
   wk += blockIdx.y;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s1tab[i] = (signed char)wk->slot1_of_prefix[i];
+  for (int i = threadIdx.x; i < kMaxRanks * 64; i += blockDim.x) bm[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x < kMaxRanks && wk->q_slot2[threadIdx.x] >= 0 && (int)threadIdx.x < wk->nq_live) {
+    const uint32_t pre = wk->q_prefix[threadIdx.x];  // (top 11 bits << 11) | middle 11 bits
+    const uint32_t mid = pre & 2047u;
+    atomicOr(&bm[wk->q_slot1[threadIdx.x] * 64 + (mid >> 5)], 1u << (mid & 31u));
+  }
+  __syncthreads();
   const float4* d4 = reinterpret_cast<const float4*>(d);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = ldg_stream_f4(d4 + i);
+  YOND_STREAM4(d4, n / 4, {
     const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
+_Pragma("unroll")
     for (int j = 0; j < 4; ++j) {
       const uint32_t k = f2key(e[j]);
-      const int s1 = wk->slot1_of_prefix[k >> 21];
+      const int s1 = s1tab[k >> 21];
       if (s1 < 0) continue;
-      const int s2 = wk->slot2_of[s1][(k >> 10) & 2047u];
+      const uint32_t mid = (k >> 10) & 2047u;
+      if (!((bm[s1 * 64 + (mid >> 5)] >> (mid & 31u)) & 1u)) continue;
+      const int s2 = wk->slot2_of[s1][mid];
       if (s2 >= 0) atomicAdd(&wk->hist2[s2][k & 1023u], 1ull);
     }
-  }
+  })
 }
 __global__ void __launch_bounds__(1024) select2_kernel(SelectWork* wk, int nranks, float* __restrict__ out) {
   wk += blockIdx.x;
@@ -343,8 +414,7 @@ __global__ void __launch_bounds__(256) score3_kernel(const float* __restrict__ l
   __syncthreads();
   const float4* l4 = reinterpret_cast<const float4*>(lap);
   const float4* m4 = reinterpret_cast<const float4*>(mean);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 lv = ldg_stream_f4(l4 + i), mv = ldg_stream_f4(m4 + i);
+  auto visit = [&](const float4& lv, const float4& mv) {
     const float le[4] = {lv.x, lv.y, lv.z, lv.w}, me[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -361,6 +431,17 @@ __global__ void __launch_bounds__(256) score3_kernel(const float* __restrict__ l
         if (smin[bin] > j) atomicMin(&smin[bin], j);
       }
     }
+  };
+  {
+    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {  // two pixel quads (64 B) in flight per thread
+      const float4 l0 = ldg_stream_f4(l4 + i), m0 = ldg_stream_f4(m4 + i);
+      const float4 l1 = ldg_stream_f4(l4 + i + stride), m1 = ldg_stream_f4(m4 + i + stride);
+      visit(l0, m0);
+      visit(l1, m1);
+    }
+    for (; i < n4; i += stride) visit(ldg_stream_f4(l4 + i), ldg_stream_f4(m4 + i));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 1001; i += blockDim.x)
@@ -393,7 +474,9 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 // ------------------------------------------------------------------ masked regression sums
 __global__ void __launch_bounds__(256) masked_sums_kernel(const float* __restrict__ lap, const float* __restrict__ mean,
                                                           const float* __restrict__ var, size_t n,
-                                                          const double* __restrict__ ths, double* __restrict__ sums) {
+                                                          const double* __restrict__ ths, double* __restrict__ sums,
+                                                          const int* __restrict__ active) {
+  if (active && !active[blockIdx.y]) return;  // second pass of the device-side estimator: only the segments that redo
   lap += (size_t)blockIdx.y * n;
   mean += (size_t)blockIdx.y * n;
   var += (size_t)blockIdx.y * n;
@@ -435,35 +518,166 @@ __global__ void __launch_bounds__(256) masked_sums_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------ device-resident estimator tail
+// Everything the reference does on a few dozen scalars per image after the maps (YOND_SIDD.py:22-49 np.percentile lerp,
+// score, argmin; :77-84 empty-mask fallback; utils/isp_algos.py:345-365 polyfit) as tiny float64 kernels, so that the
+// estimate never leaves the GPU.  Arithmetic follows NumPy operation by operation (explicit round-to-nearest mul / add /
+// div: no FMA contraction), so thresholds are the same doubles the host path (nlf.py) computes.
+constexpr int kMaxQ = 24;
+struct QuantList {
+  int nq;
+  double q[kMaxQ];
+};
+// np.percentile(method='linear'): virtual index (n-1)*q/100, bracketing order statistics, gamma (numpy _quantile).
+// ranks: [lo_0..lo_nq | hi_0..hi_nq] with entry nq = the 25th percentile of the empty-mask fallback (:82).
+__global__ void ranks_kernel(QuantList ql, unsigned long long n, unsigned long long* __restrict__ ranks, double* __restrict__ gamma) {
+  const int i = threadIdx.x;
+  if (i > ql.nq) return;
+  const double q = i < ql.nq ? ql.q[i] : 25.0;
+  const double vi = __dmul_rn((double)(n - 1), __ddiv_rn(q, 100.0));
+  const double lo = floor(vi);
+  unsigned long long l = (unsigned long long)lo, h = l + 1;
+  if (h > n - 1) h = n - 1;
+  ranks[i] = l;
+  ranks[ql.nq + 1 + i] = h;
+  gamma[i] = __dsub_rn(vi, lo);
+}
+// numpy _lerp: float32 difference, float64 interpolation, the b - diff*(1-t) form for t >= 0.5
+__device__ __forceinline__ double np_lerp(float a, float b, double t) {
+  const double diff = (double)__fsub_rn(b, a);
+  if (t >= 0.5) return __dsub_rn((double)b, __dmul_rn(diff, __dsub_rn(1.0, t)));
+  return __dadd_rn((double)a, __dmul_rn(diff, t));
+}
+__global__ void pct_kernel(const float* __restrict__ stats, const double* __restrict__ gamma, int nq, double* __restrict__ ths,
+                           double* __restrict__ th25) {
+  const int s = blockIdx.x, i = threadIdx.x;
+  if (i > nq) return;
+  const float* st = stats + (size_t)s * (2 * (nq + 1));
+  const double v = np_lerp(st[i], st[nq + 1 + i], gamma[i]);
+  if (i < nq) ths[(size_t)s * nq + i] = v;
+  else th25[s] = v;
+}
+// score = ths / (quants * npeaks); i = argmin(score[1:]) + 1 (np.argmin: first minimum, a NaN wins)  — YOND_SIDD.py:45-48
+__global__ void pick_kernel(QuantList ql, const double* __restrict__ ths, const int* __restrict__ npeaks, double* __restrict__ th,
+                            int* __restrict__ idx_out, int nseg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  int best = 1;
+  double bs = 0.0;
+  for (int i = 1; i < ql.nq; ++i) {
+    const double sc = __ddiv_rn(ths[(size_t)s * ql.nq + i], __dmul_rn(ql.q[i], (double)npeaks[(size_t)s * ql.nq + i]));
+    if (i == 1 || sc < bs || (sc != sc && bs == bs)) {
+      best = i;
+      bs = sc;
+    }
+    if (bs != bs) break;
+  }
+  if (ql.nq == 1) best = 0;
+  th[s] = ths[(size_t)s * ql.nq + best];
+  idx_out[s] = best;
+}
+// Empty mask (YOND_SIDD.py:77-84): redo with the 25th percentile when it differs from th; when it does not, the
+// reference keeps the unmasked maps (fit over every pixel: threshold +inf).
+__global__ void backup_kernel(const double* __restrict__ sums, const double* __restrict__ th, const double* __restrict__ th25,
+                              double* __restrict__ th2, int* __restrict__ redo, double* __restrict__ sums2, int nseg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const bool empty = sums[(size_t)s * 12] == 0.0;
+  redo[s] = empty ? 1 : 0;
+  th2[s] = !empty ? th[s] : (th[s] != th25[s] ? th25[s] : __longlong_as_double(0x7ff0000000000000LL));
+  for (int i = 0; i < 12; ++i) sums2[(size_t)s * 12 + i] = 0.0;
+}
+// polyfit (isp_algos.py:348-364): the 1e-4 < x < 0.8 subset when it holds more than 1 % of the points, then the least
+// squares line through the normal equations in float64.
+__global__ void solve_kernel(const double* __restrict__ sums, const double* __restrict__ sums2, const int* __restrict__ redo,
+                             const double* __restrict__ th2, const int* __restrict__ idx, const double* __restrict__ ths,
+                             const int* __restrict__ npeaks, QuantList ql, double* __restrict__ regs, double* __restrict__ detail,
+                             int nseg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const double* a = (redo[s] ? sums2 : sums) + (size_t)s * 12;
+  const double* u = a[6] > 0.01 * a[0] ? a + 6 : a;
+  const double N = u[0], Sx = u[1], Sy = u[2], Sxx = u[3], Sxy = u[4];
+  const double det = N * Sxx - Sx * Sx;
+  const double b1 = (N * Sxy - Sx * Sy) / det;
+  regs[2 * s] = b1;
+  regs[2 * s + 1] = (Sy - b1 * Sx) / N;
+  if (detail) {
+    double* d = detail + (size_t)s * (4 + 2 * kMaxQ);
+    d[0] = th2[s];
+    d[1] = (double)idx[s];
+    d[2] = ql.q[idx[s]];
+    d[3] = (double)redo[s];
+    for (int i = 0; i < ql.nq; ++i) {
+      d[4 + i] = ths[(size_t)s * ql.nq + i];
+      d[4 + kMaxQ + i] = (double)npeaks[(size_t)s * ql.nq + i];
+    }
+  }
+}
+
 inline int stream_grid(size_t n) {
   size_t g = (n + 256 * 16 - 1) / (256 * 16);
   const size_t cap = (size_t)yond_num_sms() * 8;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-int box_pass(const float* x, float* out0, float* out1, int B, int h, int w, int k, int square_input, bool with_sq, int op,
-             void* work, cudaStream_t s, const float* aux = nullptr, float* out2 = nullptr) {
-  (void)work;
-  (void)square_input;
+BoxSrc packed_src(const float* x, int h, int w) {
+  BoxSrc s{};
+  s.base = x;
+  s.img_stride = (long long)h * w * 4;
+  s.blk_w = w;
+  s.row_len = 4 * w;
+  s.imgs_per_seg = 1;
+  return s;
+}
+
+int box_pass(const BoxSrc& src, bool bayer, float* out0, float* out1, int B, int h, int w, int k, bool with_sq, int op,
+             cudaStream_t s, const float* aux = nullptr, float* out2 = nullptr) {
   const bool narrow = w + 2 * (k / 2) <= 160;
   static const int env_rows = getenv("YOND_BOX_ROWS") ? atoi(getenv("YOND_BOX_ROWS")) : 0;
   const int rows_per_strip = env_rows > 0 ? env_rows : 64;
   const int cols = narrow ? 160 : 256;
   const int outc = cols - 2 * (k / 2);
   dim3 g(ceil_div(w, outc), ceil_div(h, rows_per_strip), B);
-  const float4* x4 = reinterpret_cast<const float4*>(x);
   float4* o0 = reinterpret_cast<float4*>(out0);
   float4* o1 = reinterpret_cast<float4*>(out1);
   const float4* ax = reinterpret_cast<const float4*>(aux);
   float4* o2 = reinterpret_cast<float4*>(out2);
+  const int opx = with_sq ? op : OP_MEAN;
+#define YOND_BOX(SQ, COLS, BAYER) box_fused_kernel<SQ, COLS, BAYER><<<g, kBoxThreads, 0, s>>>(src, o0, o1, h, w, k, opx, rows_per_strip, ax, o2)
   if (with_sq) {
-    if (narrow) box_fused_kernel<true, 160><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, op, rows_per_strip, ax, o2);
-    else box_fused_kernel<true, 256><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, op, rows_per_strip, ax, o2);
+    if (narrow) { if (bayer) YOND_BOX(true, 160, true); else YOND_BOX(true, 160, false); }
+    else { if (bayer) YOND_BOX(true, 256, true); else YOND_BOX(true, 256, false); }
   } else {
-    if (narrow) box_fused_kernel<false, 160><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, OP_MEAN, rows_per_strip, ax, o2);
-    else box_fused_kernel<false, 256><<<g, kBoxThreads, 0, s>>>(x4, o0, o1, h, w, k, OP_MEAN, rows_per_strip, ax, o2);
+    if (narrow) { if (bayer) YOND_BOX(false, 160, true); else YOND_BOX(false, 160, false); }
+    else { if (bayer) YOND_BOX(false, 256, true); else YOND_BOX(false, 256, false); }
   }
+#undef YOND_BOX
   YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+// Maps of SelfNLF / CollabNLF from either source kind
+int nlf_maps_impl(const BoxSrc& x, const BoxSrc* y, bool bayer, float* var, float* mean, float* lap, int B, int h, int w, int k, int mode,
+                  void* work, cudaStream_t s) {
+  const size_t n = (size_t)B * h * w * 4;
+  float* tmpA = reinterpret_cast<float*>(work);
+  float* tmpB = tmpA + n;
+  int rc;
+  BoxSrc x_nomax = x;
+  x_nomax.seg_max = nullptr;
+  if (mode == 0) {
+    // mean = blur_k(x), var = std_k(x)^2 in one pass
+    if ((rc = box_pass(x, bayer, mean, var, B, h, w, k, true, OP_MEAN_VAR, s))) return rc;
+    // lap = std_k(blur_k2(x)), k2 = k//3*2+1 (YOND_SIDD.py:70)
+    const int k2 = k / 3 * 2 + 1;
+    if ((rc = box_pass(x_nomax, bayer, tmpB, nullptr, B, h, w, k2, false, OP_MEAN, s))) return rc;
+    if ((rc = box_pass(packed_src(tmpB, h, w), false, lap, nullptr, B, h, w, k, true, OP_STD, s))) return rc;
+  } else {
+    // std_k(lr) -> tmpA ; mean = blur_k(hr), lap = std_k(hr) ; var = std_lr^2 - std_hr^2
+    if ((rc = box_pass(x, bayer, tmpA, nullptr, B, h, w, k, true, OP_STD, s))) return rc;
+    if ((rc = box_pass(*y, bayer, mean, lap, B, h, w, k, true, OP_COLLAB, s, tmpA, var))) return rc;
+  }
   return YOND_OK;
 }
 
@@ -479,11 +693,12 @@ size_t yond_nlf_work_bytes(int B, int h, int w, int C) {
 }
 
 int yond_box_blur(const float* x, float* out, int B, int h, int w, int C, int k, int square_input, void* work, void* stream) {
+  (void)work;
   YOND_REQUIRE(C == 4, "yond_box_blur: packed 4-channel frames only (pass SIDD block stacks as a batch)");
   YOND_REQUIRE(k % 2 == 1 && k >= 1 && k <= kMaxK, "yond_box_blur: odd k <= %d required (got %d)", kMaxK, k);
   YOND_REQUIRE(h > k / 2 && w > k / 2, "yond_box_blur: frame smaller than the filter radius");
   YOND_REQUIRE(square_input == 0, "yond_box_blur: square_input is not supported");
-  return box_pass(x, out, nullptr, B, h, w, k, 0, false, OP_MEAN, work, (cudaStream_t)stream);
+  return box_pass(packed_src(x, h, w), false, out, nullptr, B, h, w, k, false, OP_MEAN, (cudaStream_t)stream);
 }
 
 int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float* lap, int B, int h, int w, int C, int k,
@@ -492,25 +707,50 @@ int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float
   YOND_REQUIRE(k % 2 == 1 && k >= 3 && k <= kMaxK, "yond_nlf_maps: odd k <= %d required (got %d)", kMaxK, k);
   YOND_REQUIRE(h > k / 2 && w > k / 2, "yond_nlf_maps: frame smaller than the filter radius");
   YOND_REQUIRE(mode == 0 || (mode == 1 && y != nullptr), "yond_nlf_maps: collab mode needs the second input");
+  const BoxSrc xs = packed_src(x, h, w), ys = packed_src(y, h, w);
+  return nlf_maps_impl(xs, &ys, false, var, mean, lap, B, h, w, k, mode, work, (cudaStream_t)stream);
+}
+
+int yond_nlf_maps_bayer(const float* x, int x_mosaic, const float* y, int y_mosaic, float* var, float* mean, float* lap, int nimg,
+                        int nblk, int H, int W, int split_blocks, int k, int mode, float* seg_max, void* work, void* stream) {
+  YOND_REQUIRE(x && var && mean && lap && work, "yond_nlf_maps_bayer: null argument");
+  YOND_REQUIRE(nimg > 0 && nblk > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "yond_nlf_maps_bayer: H,W must be even");
+  YOND_REQUIRE(k % 2 == 1 && k >= 3 && k <= kMaxK, "yond_nlf_maps_bayer: odd k <= %d required (got %d)", kMaxK, k);
+  YOND_REQUIRE(mode == 0 || (mode == 1 && y != nullptr), "yond_nlf_maps_bayer: collab mode needs the second input");
+  YOND_REQUIRE((uintptr_t)x % 8 == 0 && (!y || (uintptr_t)y % 8 == 0), "yond_nlf_maps_bayer: 8-byte aligned frames required");
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t npix = (size_t)B * h * w, n = npix * 4;
-  uint8_t* wb = reinterpret_cast<uint8_t*>(work);
-  float* tmpA = reinterpret_cast<float*>(wb);
-  float* tmpB = tmpA + n;
-  int rc;
-  if (mode == 0) {
-    // mean = blur_k(x), var = std_k(x)^2 in one pass
-    if ((rc = box_pass(x, mean, var, B, h, w, k, 0, true, OP_MEAN_VAR, work, s))) return rc;
-    // lap = std_k(blur_k2(x)), k2 = k//3*2+1 (YOND_SIDD.py:70)
-    const int k2 = k / 3 * 2 + 1;
-    if ((rc = box_pass(x, tmpB, nullptr, B, h, w, k2, 0, false, OP_MEAN, work, s))) return rc;
-    if ((rc = box_pass(tmpB, lap, nullptr, B, h, w, k, 0, true, OP_STD, work, s))) return rc;
-  } else {
-    // std_k(lr) -> tmpA ; mean = blur_k(hr), lap = std_k(hr) ; var = std_lr^2 - std_hr^2
-    if ((rc = box_pass(x, tmpA, nullptr, B, h, w, k, 0, true, OP_STD, work, s))) return rc;
-    if ((rc = box_pass(y, mean, lap, B, h, w, k, 0, true, OP_COLLAB, work, s, tmpA, var))) return rc;
-  }
-  return YOND_OK;
+  // split_blocks = 1: every block is its own image for the box filters (SIDD_256, YOND_SIDD.py:65,91-93);
+  // split_blocks = 0: the nblk blocks of an image form one mosaic (:315), h x (nblk*w) packed pixels.
+  const int h = H / 2, wb = W / 2;
+  const int B = split_blocks ? nimg * nblk : nimg;
+  const int w = split_blocks ? wb : nblk * wb;
+  YOND_REQUIRE(h > k / 2 && w > k / 2, "yond_nlf_maps_bayer: frame smaller than the filter radius");
+  YOND_REQUIRE(B <= 65535, "yond_nlf_maps_bayer: at most 65535 images per call");
+  // layouts of the Bayer inputs: blocks (nimg, nblk, H, W) — the SIDD dataset layout — or mosaic (nimg, H, nblk*W) — what
+  // the back half writes (yond_vst_inv_place).  With split_blocks the box-filter image index runs over blocks, and a
+  // block's origin in a mosaic is not a multiple of the image stride: it is folded into per-image / per-block strides.
+  auto describe = [&](const float* base, int mosaic) {
+    BoxSrc d{};
+    d.base = base;
+    d.blk_w = wb;
+    d.imgs_per_seg = split_blocks ? nblk : 1;
+    if (!mosaic) {
+      d.row_len = W;
+      d.blk_stride = (long long)H * W;
+      d.img_stride = split_blocks ? (long long)H * W : (long long)nblk * H * W;
+    } else {
+      d.row_len = nblk * W;
+      d.blk_stride = W;
+      d.img_stride = split_blocks ? 0 : (long long)nblk * H * W;  // split_blocks: see box kernel (image b = mosaic b / nblk, block b % nblk)
+      d.mosaic_blocks = split_blocks ? nblk : 0;
+    }
+    return d;
+  };
+  BoxSrc xs = describe(x, x_mosaic);
+  xs.seg_max = seg_max;
+  if (seg_max) YOND_CUDA_CHECK(cudaMemsetAsync(seg_max, 0, sizeof(float) * nimg, s));
+  BoxSrc ys = describe(y, y_mosaic);
+  return nlf_maps_impl(xs, &ys, true, var, mean, lap, B, h, w, k, mode, work, s);
 }
 
 size_t yond_select_work_bytes(int nseg) { return (size_t)(nseg < 1 ? 1 : nseg) * sizeof(SelectWork) + 256; }
@@ -533,7 +773,7 @@ int yond_order_stats(const float* data, size_t seg_len, int nseg, const uint64_t
   {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    const size_t smem = (size_t)kHist1Slots * 2048 * sizeof(unsigned int);
+    const size_t smem = (size_t)kHist1Slots * 2048 * sizeof(unsigned int) + 2048;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(hist1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     if (attr_err != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(hist1_kernel) failed: %s", cudaGetErrorString(attr_err));
     int bx = yond_num_sms() / nseg;  // one 128 KB block per SM
@@ -578,7 +818,87 @@ int yond_masked_sums(const float* lap, const float* mean, const float* var, size
   YOND_CUDA_CHECK(cudaMemsetAsync(sums_dev, 0, (size_t)nseg * 12 * sizeof(double), s));
   dim3 g(stream_grid(seg_len), nseg);
   if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
-  masked_sums_kernel<<<g, 256, 0, s>>>(lap, mean, var, seg_len, ths_dev, sums_dev);
+  masked_sums_kernel<<<g, 256, 0, s>>>(lap, mean, var, seg_len, ths_dev, sums_dev, nullptr);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+
+// Scratch of yond_nlf_fit: the radix-select tables + a few hundred bytes of scalars per segment.
+}  // extern "C"
+namespace {
+struct FitWork {
+  SelectWork* sel;
+  unsigned long long* ranks;
+  double *gamma, *ths, *th25, *th, *th2, *sums, *sums2;
+  float* stats;
+  int *npeaks, *minj, *idx, *redo;
+  size_t bytes;
+};
+FitWork carve_fit(void* base, int nseg) {
+  FitWork w{};
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    off = align_up(off, 256);
+    void* r = p ? p + off : nullptr;
+    off += nbytes;
+    return r;
+  };
+  w.sel = (SelectWork*)take((size_t)nseg * sizeof(SelectWork));
+  w.ranks = (unsigned long long*)take(kMaxRanks * 8);
+  w.gamma = (double*)take(kMaxQ * 2 * 8);
+  w.ths = (double*)take((size_t)nseg * kMaxQ * 8);
+  w.th25 = (double*)take((size_t)nseg * 8);
+  w.th = (double*)take((size_t)nseg * 8);
+  w.th2 = (double*)take((size_t)nseg * 8);
+  w.sums = (double*)take((size_t)nseg * 12 * 8);
+  w.sums2 = (double*)take((size_t)nseg * 12 * 8);
+  w.stats = (float*)take((size_t)nseg * kMaxRanks * 4);
+  w.npeaks = (int*)take((size_t)nseg * kMaxQ * 4);
+  w.minj = (int*)take((size_t)nseg * 1001 * 4);
+  w.idx = (int*)take((size_t)nseg * 4);
+  w.redo = (int*)take((size_t)nseg * 4);
+  w.bytes = align_up(off, 256);
+  return w;
+}
+}  // namespace
+extern "C" {
+
+size_t yond_nlf_fit_work_bytes(int nseg) { return carve_fit(nullptr, nseg < 1 ? 1 : nseg).bytes + 256; }
+
+int yond_nlf_fit(const float* var, const float* mean, const float* lap, size_t seg_len, int nseg, const double* quants_host,
+                 int nq, double* regs_dev, double* detail_dev, void* work, void* stream) {
+  YOND_REQUIRE(var && mean && lap && regs_dev && work && quants_host, "yond_nlf_fit: null argument");
+  YOND_REQUIRE(nq >= 1 && nq <= kMaxQ && 2 * (nq + 1) <= kMaxRanks, "yond_nlf_fit: 1..%d quantiles (got %d)", kMaxQ, nq);
+  YOND_REQUIRE(seg_len > 0 && nseg > 0 && nseg <= 65535, "yond_nlf_fit: bad segment geometry");
+  YOND_REQUIRE((uintptr_t)work % 256 == 0, "yond_nlf_fit: work must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const FitWork w = carve_fit(work, nseg);
+  QuantList ql{};
+  ql.nq = nq;
+  for (int i = 0; i < nq; ++i) ql.q[i] = quants_host[i];
+  for (int i = 1; i < nq; ++i) YOND_REQUIRE(ql.q[i] > ql.q[i - 1], "yond_nlf_fit: quantiles must ascend");
+  const int nranks = 2 * (nq + 1);
+  ranks_kernel<<<1, 32, 0, s>>>(ql, (unsigned long long)seg_len, w.ranks, w.gamma);
+  YOND_LAUNCH_CHECK();
+  int rc = yond_order_stats(lap, seg_len, nseg, reinterpret_cast<const uint64_t*>(w.ranks), nranks, w.stats, w.sel, stream);
+  if (rc) return rc;
+  pct_kernel<<<nseg, 32, 0, s>>>(w.stats, w.gamma, nq, w.ths, w.th25);
+  YOND_LAUNCH_CHECK();
+  if ((rc = yond_score3_bins(lap, mean, seg_len, nseg, w.ths, nq, w.npeaks, w.minj, stream))) return rc;
+  pick_kernel<<<ceil_div(nseg, 64), 64, 0, s>>>(ql, w.ths, w.npeaks, w.th, w.idx, nseg);
+  YOND_LAUNCH_CHECK();
+  if ((rc = yond_masked_sums(lap, mean, var, seg_len, nseg, w.th, w.sums, stream))) return rc;
+  backup_kernel<<<ceil_div(nseg, 64), 64, 0, s>>>(w.sums, w.th, w.th25, w.th2, w.redo, w.sums2, nseg);
+  YOND_LAUNCH_CHECK();
+  {  // second pass: only the segments whose mask came out empty do any work
+    dim3 g(stream_grid(seg_len), nseg);
+    if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
+    masked_sums_kernel<<<g, 256, 0, s>>>(lap, mean, var, seg_len, w.th2, w.sums2, w.redo);
+    YOND_LAUNCH_CHECK();
+  }
+  solve_kernel<<<ceil_div(nseg, 64), 64, 0, s>>>(w.sums, w.sums2, w.redo, w.th2, w.idx, w.ths, w.npeaks, ql, regs_dev, detail_dev, nseg);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

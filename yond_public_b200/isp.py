@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 import torch
@@ -163,24 +164,44 @@ def sigma_pos(sg_lut, sg):
 
 class BiasLUT:
     """Bilinear lookup of the VST bias table, on device.  `lut_path`: .npy (the authors' file layout,
-    (1921,1101) [x,sigma]) or the .npz stand-in shipped in yond_public_b200/data (key 'bias_lut')."""
+    (1921,1101) [x,sigma]) or the .npz stand-in shipped in yond_public_b200/data (key 'bias_lut').
 
-    def __init__(self, lut_path="checkpoints/bias_lut_2d.npy"):
+    The reference enables the LUT only when checkpoints/bias_lut_2d.npy exists (YOND_SIDD.py:171); the authors' file is
+    not distributed, so `BiasLUT()` without that file loads the stand-in — a float32 regeneration with the reference's own
+    get_bias_points(x_lut, 1, sg, pho_min=100, close_form=True) (tests/golden/make_bias_lut.py) — and says so in
+    `self.source`.  Pass `standin=False` to get the reference behaviour (FileNotFoundError -> the driver runs LUT-less)."""
+
+    def __init__(self, lut_path="checkpoints/bias_lut_2d.npy", standin=True):
+        self.source = lut_path
         if not os.path.exists(lut_path) and lut_path == "checkpoints/bias_lut_2d.npy":
+            if not standin:
+                raise FileNotFoundError(lut_path)
             lut_path = DEFAULT_LUT
+            self.source = f"stand-in table {DEFAULT_LUT} (checkpoints/bias_lut_2d.npy not found)"
         arr = np.load(lut_path)
         table = arr["bias_lut"] if hasattr(arr, "files") else arr
         self.x_lut, self.sg_lut = lut_grids()
         assert table.shape == (len(self.x_lut), len(self.sg_lut)), f"bias LUT must be (1921,1101), got {table.shape}"
         self.bias_lut = np.ascontiguousarray(table, dtype=np.float32)
-        self._dev_table = None
-        self._dev_nodes = None
+        self._dev = None
+        self._lock = threading.Lock()
+
+    def device_arrays(self):
+        """(table (1921,1101) f32, x nodes (1921) f32, sigma nodes (1101) f64) on the current device; uploaded once, under a
+        lock and synchronised, so concurrent host lanes never see a partially uploaded table."""
+        if self._dev is None:
+            with self._lock:
+                if self._dev is None:
+                    dev = _dev()
+                    arrs = (torch.from_numpy(self.bias_lut).to(dev), torch.from_numpy(self.x_lut.astype(np.float32)).to(dev),
+                            torch.from_numpy(np.ascontiguousarray(self.sg_lut, np.float64)).to(dev))
+                    torch.cuda.synchronize(dev)
+                    self._dev = arrs
+        return self._dev
 
     def device_table(self):
-        if self._dev_table is None:
-            self._dev_table = torch.from_numpy(self.bias_lut).to(_dev())
-            self._dev_nodes = torch.from_numpy(self.x_lut.astype(np.float32)).to(_dev())
-        return self._dev_table, self._dev_nodes
+        t, x, _ = self.device_arrays()
+        return t, x
 
     def in_range(self, K, sigGs):
         return sigma_pos(self.sg_lut, sigGs / K) <= len(self.sg_lut) - 1
@@ -197,7 +218,17 @@ class BiasLUT:
     def get_lut(self, x, K=1, sigGs=2, func=False):
         assert not func, "func=True (scipy interp1d object) is host-only in the reference; not part of the device path"
         if not self.in_range(K, sigGs):
-            raise _lib.YondError("sigma/K outside the BiasLUT range (>= 10 e-): use the fallback table (get_bias)")
+            # sigma/K beyond the table: the reference falls back to get_bias (more than 1000 points: the interpolated
+            # table up to x.max()) or get_bias_points (exact per point, pho_min = 100) — isp_algos.py:204-212
+            t, np_in = to_dev(x)
+            if t.numel() > 1000:
+                nodes, vals = get_bias_table(float(t.max()), sigGs, K, device=True)
+                out = torch.empty_like(t)
+                n = nodes.numel()
+                # piecewise-linear evaluation on the device: the table as a one-row fallback table of the fused front end
+                check(_lib.load().yond_table_apply(ptr(t), ptr(out), t.numel(), ptr(vals), ptr(nodes), n, stream_ptr()))
+                return _back(out, np_in)
+            return _back(get_bias_points(t.reshape(-1).double(), K, sigGs, pho_min=100).reshape(t.shape).float(), np_in)
         t, np_in = to_dev(x)
         row = self.sigma_row(K, sigGs)
         _, nodes = self.device_table()
@@ -258,47 +289,50 @@ def get_p2d(shape, base=16):
     return (diffX // 2, diffX - diffX // 2, diffY // 2, diffY - diffY // 2)
 
 
-# ------------------------------------------------------------------ A6  fallback bias table (host-side generator)
-def get_bias_table(img_max, sigGs, K, pho_min=1, close_form=True):
-    """Node positions / values of the reference's fallback table `get_bias` (isp_algos.py:98-140): numeric
-    Poisson (*) Gaussian expectation on a piecewise grid, Foi's closed form above 50*sqrt(K).  The table
-    (a few hundred nodes) is host arithmetic (SciPy), exactly like the reference; its per-pixel application
-    (`interp1d`) runs on the device inside yond_vst_fwd.  Device generation is a SURVEY §8(f) 'next' row."""
-    from scipy.signal import convolve
-    from scipy.stats import norm, poisson
-    # dtype flow of the reference call sites (YOND_SIDD.py:256,395,452): the bound is a float32 scalar, K and sigma float64
-    img_max, sigGs, K = np.float32(img_max), np.float64(sigGs), np.float64(K)
+# ------------------------------------------------------------------ A6  fallback bias table (device generator)
+def bias_table_nodes(img_max):
+    """Node positions of get_bias (isp_algos.py:101-108) in the reference's own dtype flow: `ub` is a float32 scalar, so
+    the pieces ending in `ub` are float32 linspaces.  Host index math only (the values come from the device)."""
+    img_max = np.float32(img_max)
     lb, ub = 0, np.ceil(img_max) + 1
     if ub < 50:
-        lams = np.linspace(lb, ub, int((ub - lb) / 0.1) + 2)
-    elif ub < 500:
-        lams = np.concatenate((np.linspace(lb, 50, int((50 - lb) / 0.1) + 1), np.linspace(50, ub, int(ub - 50) + 2)))
-    else:
-        lams = np.concatenate((np.linspace(lb, 50, int((50 - lb) / 0.1) + 1), np.linspace(50, 500, 451),
-                               np.linspace(500, ub, int(ub - 500) // 10 + 2)))
-    bias = np.zeros(len(lams), np.float32)
-    pho = int(np.maximum(int(K ** 0.5), pho_min))
-    sg = sigGs / K
-    if close_form:
-        th = 50 * K if K < 1 else 50 * K ** 0.5
-        hi = lams > th
-        y = lams[hi] / K
-        yh = y + 3 / 8 + sg ** 2
-        bias[hi] = 2 * yh ** 0.5 * (-1 / 8 * (y + sg ** 2) / yh ** 2 + 1 / 16 * y / yh ** 3
-                                    - 5 / 128 * (y + 3 * (y + sg ** 2) ** 2) / yh ** 4)
-    else:
-        th = lams.max() + 1
+        return np.linspace(lb, ub, int((ub - lb) / 0.1) + 2)
+    if ub < 500:
+        return np.concatenate((np.linspace(lb, 50, int((50 - lb) / 0.1) + 1), np.linspace(50, ub, int(ub - 50) + 2)))
+    return np.concatenate((np.linspace(lb, 50, int((50 - lb) / 0.1) + 1), np.linspace(50, 500, 451),
+                           np.linspace(500, ub, int(ub - 500) // 10 + 2)))
 
-    def vst(v):
-        return 2 / K * np.maximum(K * v + (3 / 8) * K ** 2 + sigGs ** 2, 0) ** 0.5
-    for i, lam in enumerate(lams[lams <= th]):
-        r = int(lam * (1 / K) * 2 + sigGs * 2 + lam + 10)
-        xs = np.linspace(-r, r, 2 * pho * r + 1)
-        if sigGs > 0:
-            pdf = convolve(poisson.pmf(xs, lam / K), norm.pdf(xs, loc=0, scale=sg), mode="same")
-        else:
-            pdf = poisson.pmf(xs, lam / K)
-        pdf[pdf < 0] = 0
-        pdf = pdf / (pdf.sum() / pho)
-        bias[i] = np.sum(pdf * vst(K * xs) / pho) - vst(lam)
-    return lams, bias
+
+def get_bias_table(img_max, sigGs, K, pho_min=1, close_form=True, device=False):
+    """Node positions / values of the reference's fallback table `get_bias` (isp_algos.py:98-140): numeric
+    Poisson (*) Gaussian expectation on a piecewise grid, Foi's closed form above 50*sqrt(K) — generated ON THE DEVICE
+    (yond_bias_table).  Returns (nodes float64, values float32) NumPy arrays like `interp1d(...).x/.y`, or
+    with device=True the (nodes, values) float32 CUDA tensors the kernels consume."""
+    assert pho_min == 1 and close_form, "the YOND path calls get_bias with its defaults (pho_min=1, close_form=True)"
+    lib = _lib.load()
+    dev = _dev()
+    bound = float(np.float32(img_max))
+    n = int(lib.yond_bias_table_nodes(bound))
+    nodes = torch.empty(n, device=dev, dtype=torch.float32)
+    vals = torch.empty(n, device=dev, dtype=torch.float32)
+    work = torch.empty(int(lib.yond_chain_work_bytes(1)), device=dev, dtype=torch.uint8)
+    check(lib.yond_bias_table(float(K), float(sigGs), bound, ptr(nodes), ptr(vals), n, None, ptr(work), stream_ptr()))
+    if device:
+        return nodes, vals
+    lams = bias_table_nodes(img_max)
+    assert len(lams) == n
+    return lams, vals.cpu().numpy()
+
+
+def get_bias_points(lams, K, sigGs, pho_min=100, close_form=True):
+    """get_bias_points (isp_algos.py:142-160) on the device: the bias at explicit points (ascending, like the reference
+    assumes), float64.  NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor out."""
+    assert close_form, "only close_form=True is used on the YOND path"
+    lib = _lib.load()
+    dev = _dev()
+    np_in = not torch.is_tensor(lams)
+    t = (torch.from_numpy(np.ascontiguousarray(lams, np.float64)) if np_in else lams).to(device=dev, dtype=torch.float64).contiguous()
+    out = torch.empty_like(t)
+    work = torch.empty(int(lib.yond_chain_work_bytes(1)), device=dev, dtype=torch.uint8)
+    check(lib.yond_bias_points(ptr(t), t.numel(), float(K), float(sigGs), int(pho_min), ptr(out), ptr(work), stream_ptr()))
+    return out.cpu().numpy() if np_in else out

@@ -7,6 +7,7 @@ and the 2x2 least-squares solve.
 """
 from __future__ import annotations
 
+import ctypes as C
 import threading
 
 import numpy as np
@@ -106,13 +107,13 @@ class NlfEstimator:
             return sums_dev.cpu().numpy()
         s = sums(th)
         empty = s[:, 0] == 0
-        if empty.any():  # "no flat area": fall back to the 25th percentile (:79-84)
+        if empty.any():  # "no flat area": fall back to the 25th percentile (:79-84) ...
             th_backup = np.atleast_1d(self.percentiles(lap, [25.0], nseg)).reshape(nseg)
             redo = empty & (th != th_backup)
-            if redo.any():
-                th[redo] = th_backup[redo]
-                s2 = sums(th)
-                s[redo] = s2[redo]
+            th[redo] = th_backup[redo]
+            th[empty & ~redo] = np.inf  # ... and when that IS the threshold, the reference keeps the unmasked maps
+            s2 = sums(th)
+            s[empty] = s2[empty]
         regs = np.zeros((nseg, 2), np.float64)
         for i in range(nseg):
             # polyfit keeps 1e-4 < x < 0.8 when that is > 1 % of the points (:348-350)
@@ -124,6 +125,46 @@ class NlfEstimator:
         if nseg == 1:
             return regs[0], th[0]
         return regs, th
+
+    # -- device-resident estimate (no host read-back) ----------------------------------------------
+    DETAIL = 4 + 2 * 24
+
+    def estimate_dev(self, x, y=None, k=29, split_blocks=False, x_mosaic=False, y_mosaic=False, nblk=None, seg_max=None,
+                     details=False, step=5):
+        """SelfNLF (y None) / CollabNLF straight from Bayer frames, everything on the device.
+
+        x: blocks layout (nimg, nblk, H, W) or, with x_mosaic, mosaic layout (nimg, H, nblk*W) (`nblk` then required; plain
+        frames are nblk = 1 in either layout).  split_blocks: every block is its own image for the box filters (SIDD_256).
+        seg_max (optional, (nimg,) f32 CUDA): receives max(x, 0) per image.  Returns regs (nimg, 2) float64 on the
+        device [, detail (nimg, DETAIL)]; nothing is read back."""
+        lib = self.lib
+        if x_mosaic:
+            nimg, H, Wm = x.shape
+            nb = int(nblk or 1)
+            W = Wm // nb
+        else:
+            nimg, nb, H, W = x.shape
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        dev = x.device
+        h, wb = H // 2, W // 2
+        B, w = (nimg * nb, wb) if split_blocks else (nimg, nb * wb)
+        n_el = B * h * w * 4
+        maps = self._buf("maps3", 3 * n_el * 4, dev).view(torch.float32)
+        var, mean, lap = maps[:n_el], maps[n_el:2 * n_el], maps[2 * n_el:3 * n_el]
+        work = self._buf("maps", lib.yond_nlf_work_bytes(B, h, w, 4), dev)
+        mode = 0 if y is None else 1
+        if y is not None:
+            assert y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and y.numel() == x.numel()
+        check(lib.yond_nlf_maps_bayer(ptr(x), int(bool(x_mosaic)), ptr(y), int(bool(y_mosaic)), ptr(var), ptr(mean), ptr(lap), nimg, nb,
+                                      H, W, int(bool(split_blocks)), int(k), mode, ptr(seg_max), ptr(work), stream_ptr()))
+        quants = np.ascontiguousarray(np.linspace(step, 100, 100 // step, endpoint=True), np.float64)
+        regs = torch.empty((nimg, 2), device=dev, dtype=torch.float64)
+        detail = torch.empty((nimg, self.DETAIL), device=dev, dtype=torch.float64) if details else None
+        fwork = self._buf("fit", lib.yond_nlf_fit_work_bytes(nimg) + 256, dev)
+        off = (-fwork.data_ptr()) % 256
+        check(lib.yond_nlf_fit(ptr(var), ptr(mean), ptr(lap), n_el // nimg, nimg, quants.ctypes.data_as(C.POINTER(C.c_double)),
+                               len(quants), ptr(regs), ptr(detail), ptr(fwork[off:]), stream_ptr()))
+        return (regs, detail) if details else regs
 
     # -- SelfNLF / CollabNLF ----------------------------------------------------------------------
     def estimate(self, lr_rggb, hr_rggb=None, k=29, details=False, nseg=1, timings=None):
@@ -185,12 +226,20 @@ def CollabNLF(lr_rggb, hr_rggb, k=29, kwargs=None):
 
 
 def SimpleNLF(lr_raw, hr_raw=None, k=29, setting=None):
-    """YOND_SIDD.py:117-124 — pack + dispatch.  Returns array-like (beta1, beta2), float64."""
+    """YOND_SIDD.py:117-124 — pack + dispatch.  Returns array-like (beta1, beta2), float64.  Bayer frames (H,W) in (NumPy or
+    CUDA); the maps are computed straight from the mosaic and the whole estimate runs on the device (one 16-byte read-back)."""
     setting = setting or {"mode": "self"}
     sidd = bool(setting.get("SIDD_256", False))
-    lr = _rggb_batch(lr_raw, sidd)
-    if setting["mode"] == "self":
-        return _estimator().estimate(lr, None, k)
+    if setting["mode"] not in ("self", "collab"):
+        raise NotImplementedError(setting["mode"])
+    lr, _ = to_dev(lr_raw)
+    hr = None
     if setting["mode"] == "collab":
-        return _estimator().estimate(lr, _rggb_batch(hr_raw, sidd), k)
-    raise NotImplementedError(setting["mode"])
+        hr, _ = to_dev(hr_raw)
+        assert hr.shape == lr.shape
+    assert lr.dim() == 2
+    if sidd:
+        assert lr.shape[1] % 64 == 0, "SIDD_256 splits the mosaic into 32 blocks along W (YOND_SIDD.py:65,91-93)"
+    regs = _estimator().estimate_dev(lr[None], None if hr is None else hr[None], k, split_blocks=sidd, x_mosaic=True, y_mosaic=True,
+                                     nblk=32 if sidd else 1)
+    return regs[0].cpu().numpy()

@@ -59,33 +59,31 @@ class YondEngine:
 
     # ------------------------------------------------------------------------------------------
     def make_params(self, gains, sigmas, scale, bias_corr, vst_type, frame_max, device, fixed_table=None):
-        """Per-frame yond_vst_params + the bias rows they index.
+        """Per-frame yond_vst_params + the bias rows they index, for CALLER-GIVEN (gain, sigma) — the function-level
+        VST_Denoiser surface.  (The blind pipeline fills the same structures on the device: `chain_params`.)
 
-        Bias source per frame, like the reference (YOND_SIDD.py:252-259, utils/isp_algos.py:196-231): the BiasLUT row
-        for this sigma/K when a LUT is loaded and sigma/K is inside its range, otherwise the fallback `get_bias`
-        table built on the host up to this frame's maximum (`frame_max`: callable returning per-frame max in DN)."""
+        Bias source per frame, like the reference (YOND_SIDD.py:252-262, utils/isp_algos.py:196-231): only
+        bias_corr == 'pre' applies a bias ('post' computes one and never uses it, :261 / :294-295); the BiasLUT row for this
+        sigma/K when a LUT is loaded and sigma/K is inside its range, otherwise the fallback `get_bias` table up to this
+        frame's maximum (`frame_max`: callable returning per-frame max in DN), generated on the device."""
         gains = np.asarray(gains, np.float64)
         sigmas = np.asarray(sigmas, np.float64)
         B = len(gains)
         exact = 1 if (bias_corr is None and vst_type == "exact") else 0
-        rows_np, nodes_np, table_n, key_row = [], [], [], {}
         row_of = np.full(B, -1, np.int32)
-        lut_rows = []  # (row index, K, sigma) filled on device
-        if bias_corr is not None:
+        table_n_of = np.zeros(B, np.int32)
+        jobs = []  # (row index, kind, payload)
+        if bias_corr == "pre":
             # frames come in runs sharing (K, sigma) (the 32 blocks of an image): resolve each distinct pair once
             pairs, inverse = np.unique(np.stack([gains, sigmas], 1), axis=0, return_inverse=True)
             inverse = np.asarray(inverse).reshape(-1)
-            fmax = None
+            fmax, key_row = None, {}
             for u, (k, s) in enumerate(pairs):
                 k, s = float(k), float(s)
                 idx = np.nonzero(inverse == u)[0]
                 if self.biaslut is not None and self.biaslut.in_range(k, s):
-                    key_row[("lut", k, s)] = len(rows_np)
-                    lut_rows.append((len(rows_np), k, s))
-                    row_of[idx] = len(rows_np)
-                    rows_np.append(None)
-                    nodes_np.append(self.biaslut.x_lut.astype(np.float32))
-                    table_n.append(0)
+                    row_of[idx] = len(jobs)
+                    jobs.append(("lut", k, s))
                     continue
                 for b in idx:
                     if fixed_table is not None:
@@ -93,28 +91,40 @@ class YondEngine:
                     else:
                         if fmax is None:
                             fmax = frame_max()
-                        ub = np.float32(fmax[b])
-                        key = ("tab", k, s, float(np.ceil(ub)))
+                        key = ("tab", k, s, float(np.ceil(np.float32(fmax[b]))))
                     if key not in key_row:
-                        nodes, vals = fixed_table if fixed_table is not None else self.table_fn(ub, s, k)
-                        key_row[key] = len(rows_np)
-                        rows_np.append(np.asarray(vals, np.float32))
-                        nodes_np.append(np.asarray(nodes, np.float32))
-                        table_n.append(len(nodes))
+                        key_row[key] = len(jobs)
+                        jobs.append(("fixed", fixed_table) if fixed_table is not None else ("tab", k, s, np.float32(fmax[b])))
                     row_of[b] = key_row[key]
         rows = xnodes = None
         stride = 1921
-        if rows_np:
-            stride = max(1921, max(len(n) for n in nodes_np))
-            r = np.zeros((len(rows_np), stride), np.float32)
-            xn = np.zeros((len(rows_np), stride), np.float32)
-            for i, (vals, nodes) in enumerate(zip(rows_np, nodes_np)):
-                xn[i, :len(nodes)] = nodes
-                if vals is not None:
-                    r[i, :len(vals)] = vals
-            rows, xnodes = torch.from_numpy(r).to(device), torch.from_numpy(xn).to(device)
-            for i, k, s in lut_rows:
-                self.biaslut.sigma_row(k, s, out=rows[i, :1921])
+        if jobs:
+            lib = self.lib
+            sizes = []
+            for j in jobs:
+                if j[0] == "lut":
+                    sizes.append(1921)
+                elif j[0] == "fixed":
+                    sizes.append(len(j[1][0]))
+                else:
+                    sizes.append(int(lib.yond_bias_table_nodes(float(j[3]))))
+            stride = max(1921, max(sizes))
+            rows = torch.zeros((len(jobs), stride), device=device, dtype=torch.float32)
+            xnodes = torch.zeros((len(jobs), stride), device=device, dtype=torch.float32)
+            work = self._buf("chain1", (int(lib.yond_chain_work_bytes(1)),), torch.uint8, device)
+            for i, j in enumerate(jobs):
+                if j[0] == "lut":
+                    self.biaslut.sigma_row(j[1], j[2], out=rows[i, :1921])
+                    xnodes[i, :1921] = self.biaslut.device_table()[1]
+                elif j[0] == "fixed":
+                    nodes, vals = j[1]
+                    xnodes[i, :len(nodes)] = torch.from_numpy(np.asarray(nodes, np.float32)).to(device)
+                    rows[i, :len(vals)] = torch.from_numpy(np.asarray(vals, np.float32)).to(device)
+                else:
+                    check(lib.yond_bias_table(j[1], j[2], float(j[3]), ptr(xnodes[i]), ptr(rows[i]), stride, None, ptr(work), stream_ptr()))
+            sz = np.asarray(sizes, np.int32)
+            is_tab = np.asarray([j[0] != "lut" for j in jobs])
+            table_n_of = np.where(row_of >= 0, np.where(is_tab, sz, 0)[np.maximum(row_of, 0)], 0).astype(np.int32)
         # VST(0) / VST(scale) / nsr in float64 on the host (YOND_SIDD.py:264-268), vectorised over the batch
         c0 = (3 / 8) * gains ** 2 + sigmas ** 2
         lower = 2 / gains * np.sqrt(np.maximum(c0, 0))
@@ -124,21 +134,70 @@ class YondEngine:
         assert rec.dtype.itemsize == C.sizeof(VstParams)
         rec["gain"], rec["sigma"], rec["scale"], rec["lower"], rec["upper"] = gains, sigmas, scale, lower, upper
         rec["lut_row"] = row_of
-        tn = np.asarray(table_n + [0], np.int32)
-        rec["table_n"] = np.where(row_of >= 0, tn[np.maximum(row_of, 0)], 0)
+        rec["table_n"] = table_n_of
         rec["exact"] = exact
         t = (1 / (upper - lower) * (SIGMA_CORR_PRE if bias_corr == "pre" else 1.0)).astype(np.float32)  # :268, :284-285
         raw = torch.from_numpy(rec.view(np.uint8).copy()).to(device)
         return raw, rows, xnodes, stride, torch.from_numpy(t).to(device)
 
-    def table_fn(self, ub, sigma, gain):
-        """Fallback table generator; memoised because SIDD blocks of one image mostly share (max, K, sigma)."""
-        key = (float(ub), float(sigma), float(gain))
-        if key not in self._tables:
-            if len(self._tables) > 256:
-                self._tables.clear()
-            self._tables[key] = isp.get_bias_table(ub, sigma, gain)
-        return self._tables[key]
+    # ------------------------------------------------------------------------------------------
+    # The same structures filled ON THE DEVICE from the estimator's (beta1, beta2): no host read-back between the
+    # estimate and the denoiser (YOND_SIDD.py:356, :438-447, :252-269, :284-285).
+    BIAS_MODES = {None: 0, "pre": 1, "post": 2}
+    max_value = 1.0  # upper bound of the (normalised) input data assumed when sizing fallback bias tables; raise for noclip data
+
+    def chain_params(self, regs, seg_max, nseg, fps, scale_est, scale, bound_scale, rnd, bias_corr, vst_type, prev=None):
+        """regs: (nseg,2) float64 CUDA.  Returns a dict of device buffers: params (bytes), t, rows, xnodes, stride,
+        regs4 (nseg,4: beta1, beta2 after the guards, gain, sigma), ok (nseg int32)."""
+        if bias_corr not in self.BIAS_MODES:
+            raise NotImplementedError(f"bias_corr={bias_corr!r}")
+        lib, dev = self.lib, regs.device
+        mode = self.BIAS_MODES[bias_corr]
+        exact = 1 if (bias_corr is None and vst_type == "exact") else 0
+        lut = self.biaslut.device_arrays() if (self.biaslut is not None and mode == 1) else None
+        stride = 1921
+        rows = xnodes = None
+        if mode == 1:
+            cap = int(lib.yond_bias_table_nodes(float(np.float32(self.max_value) * np.float32(bound_scale))))
+            stride = max(1921, cap) if lut is not None else max(cap, 8)
+            rows = torch.empty((nseg, stride), device=dev, dtype=torch.float32)
+            xnodes = torch.empty((nseg, stride), device=dev, dtype=torch.float32)
+        psz = C.sizeof(VstParams)
+        out = dict(params=torch.empty(nseg * fps * psz, device=dev, dtype=torch.uint8),
+                   t=torch.empty(nseg * fps, device=dev, dtype=torch.float32), rows=rows, xnodes=xnodes, stride=stride,
+                   regs4=torch.empty((nseg, 4), device=dev, dtype=torch.float64), ok=torch.empty(nseg, device=dev, dtype=torch.int32))
+        work = self._buf("chain", (int(lib.yond_chain_work_bytes(nseg)),), torch.uint8, dev)
+        check(lib.yond_vst_params_fill(ptr(regs), ptr(seg_max), nseg, fps, float(scale_est), float(scale), float(bound_scale), int(rnd), mode,
+                                       exact, ptr(lut[0]) if lut else None, ptr(lut[2]) if lut else None, ptr(lut[1]) if lut else None,
+                                       1921, 1101, ptr(prev["params"]) if prev is not None else None, ptr(out["params"]), ptr(out["t"]),
+                                       ptr(rows), ptr(xnodes), stride, ptr(out["regs4"]), ptr(out["ok"]), ptr(work), stream_ptr()))
+        return out
+
+    def vst_denoise_dev(self, frames, chain, out, frames_per_row=1, fps=1, select=False, fallback=None, clip01=True):
+        """VST_Denoiser for frames (B,H,W) with device-filled parameters; writes `out` (plain (B,H,W) or the mosaic layout
+        (B/n, H, n*W) for frames_per_row = n).  select: frames of images with chain['ok'] == 0 copy `fallback` instead."""
+        B, H, W = frames.shape
+        dev = frames.device
+        h, w = H // 2, W // 2
+        pl, pr, pt, pb = isp.get_p2d((B, 4, h, w), base=32)
+        hp, wp = h + pt + pb, w + pl + pr
+        unit = int(np.lcm(frames_per_row, fps))
+        cb = max(unit, self.default_chunk(B, hp, wp) // unit * unit)
+        z = self._buf("z", (cb, hp, wp, 4), torch.float32, dev)
+        y = self._buf("y", (cb, hp, wp, 4), torch.float32, dev)
+        ub = self._buf("ub", (cb,), torch.float32, dev)
+        psz = C.sizeof(VstParams)
+        st = stream_ptr()
+        params, t = chain["params"], chain["t"]
+        for b0 in range(0, B, cb):
+            n = min(cb, B - b0)
+            pch = params[b0 * psz:]
+            check(self.lib.yond_vst_fwd(ptr(frames[b0:b0 + n]), ptr(z[:n]), ptr(ub[:n]), n, H, W, pl, pr, pt, pb, ptr(pch),
+                                        ptr(chain["rows"]), ptr(chain["xnodes"]), chain["stride"], st))
+            self.net.forward_nhwc(z[:n], ub[:n], t[b0:b0 + n] if self.guided else None, out=y[:n])
+            check(self.lib.yond_vst_inv_place(ptr(y[:n]), ptr(out), n, H, W, pl, pr, pt, pb, ptr(pch), int(clip01), frames_per_row, b0,
+                                              ptr(chain["ok"]) if select else None, fps, ptr(fallback) if select else None, st))
+        return out
 
     # ------------------------------------------------------------------------------------------
     def vst_denoise(self, bayer, gains, sigmas, scale, bias_corr="pre", vst_type="exact", clip01=True, table_bound=None, fixed_table=None, out=None):
@@ -337,18 +396,25 @@ class YOND_SIDD:
         results["hr_raw"] = (np.concatenate(list(hr), axis=-1) if isinstance(hr, np.ndarray) and hr.ndim == 3 else hr)
         return results
 
-    def iter_denoise_batch(self, blocks, p, log=None, timings=None):
-        """IterDenoise for a BATCH of SIDD-shaped images at once: blocks (nimg, nblk, H, W) CUDA f32.  Same per-image
-        algorithm and guards as iter_denoise_device / the reference (YOND_SIDD.py:301-483), but every device stage
-        runs once for all images, so the host reads back three small arrays per estimate instead of per image.
-        Returns {'raw_dns': [round-1 (nimg,H,nblk*W), final (nimg,H,nblk*W)], 'regs': [(nimg,2) per round],
-        'rounds': (nimg,) number of denoise rounds each image completed}."""
+    # -- the blind two-round pipeline, device-resident and free of host synchronisation -----------------------------
+    def iter_denoise_dev(self, x, p, lr_full=None, timings=None):
+        """IterDenoise (YOND_SIDD.py:301-483, `simple` estimator) for a batch of images: x (nimg, nblk, H, W) CUDA f32 —
+        SIDD images of nblk blocks, or full frames with nblk = 1.  Every stage runs once for the whole batch; the noise
+        estimate, the reference's guards, the VST constants, the bias rows and the round-2 selection all stay on the device,
+        so nothing is read back until the caller asks for the numbers.
+
+        Returns device tensors: dn1 / final (nimg, H, nblk*W) (the reference's mosaic layout), regs1 / regs2 (nimg, 4) float64
+        = (beta1, beta2 after the guards, gain, sigma) per round (regs2 None without round 2), ok (nimg,) int32 = the round-2
+        result was kept (beta1 >= 0, :445-447)."""
         pipe = self.pipe
-        assert pipe["full_est"] and "simple" in pipe["est_type"] and not pipe["full_dn"], "batched path = the SIDD configuration"
-        nimg, nblk, H, W = blocks.shape
+        assert pipe["full_est"] and "simple" in pipe["est_type"]
+        nimg, nblk, H, W = x.shape
+        dev = x.device
+        eng = self.engine
         scale_est = p["wp"] - p["bl"]
         scale = p.get("scale", scale_est)
         k, bias_corr, vst_type = pipe["k"], pipe["bias_corr"], pipe.get("vst_type", "exact")
+        full_dn = bool(pipe["full_dn"])
         est = nlf._estimator()
 
         def mark(name):  # optional stage timing (synchronising; for profiling only)
@@ -359,53 +425,73 @@ class YOND_SIDD:
                 timings[name] = timings.get(name, 0.0) + (now - timings.get("_t", now))
                 timings["_t"] = now
         mark("start")
-        mosaic = blocks.permute(0, 2, 1, 3).reshape(nimg, H, nblk * W).contiguous()  # :315, per image
-        reg1 = np.atleast_2d(est.estimate(isp.bayer2rggb(mosaic), None, k, nseg=nimg))  # :338-341 (mode 'self')
+        if full_dn and nblk > 1:  # one network pass over the whole mosaic (:387-389): make it a frame
+            x = x.permute(0, 2, 1, 3).reshape(nimg, 1, H, nblk * W).contiguous()
+            mos_blocks, W, nblk = nblk, nblk * W, 1
+        else:
+            mos_blocks = nblk
+        need_max = bias_corr == "pre"
+        seg_max = torch.empty(nimg, device=dev, dtype=torch.float32) if need_max else None
+        # ---- round 1: self-calibration on the mosaic (:315, :338-341) or on the full-resolution frame when given
+        if lr_full is None:
+            regs = est.estimate_dev(x, None, k, split_blocks=False, seg_max=seg_max)
+        else:
+            assert nimg == 1
+            regs = est.estimate_dev(lr_full.reshape(1, 1, *lr_full.shape[-2:]), None, k)
+            if need_max:
+                seg_max = x.amax().clamp_min(0).reshape(1)
         mark("estimate_self")
-        gains = reg1[:, 0] * scale_est
-        sigmas = np.sqrt(np.maximum(reg1[:, 1], 0)) * scale_est  # :356
-        flat = blocks.reshape(nimg * nblk, H, W)
-
-        def denoise(g, s, sel=None):
-            src = flat if sel is None else blocks[sel].reshape(-1, H, W)
-            bound = None
-            gg, ss = np.repeat(g, nblk), np.repeat(s, nblk)
-            if bias_corr is not None and self.biaslut is None:
-                # one fallback table per image up to the image max (:393-395); expressed per frame for the engine
-                imax = (blocks if sel is None else blocks[sel]).amax(dim=(1, 2, 3)).cpu().numpy().astype(np.float32)
-                bound = np.repeat(imax * np.float32(scale_est), nblk)
-            dn = self.engine.vst_denoise(src, gg, ss, scale, bias_corr=bias_corr, vst_type=vst_type, clip01=True,
-                                         table_bound=bound)
-            n = dn.shape[0] // nblk
-            return dn.reshape(n, nblk, H, W).permute(0, 2, 1, 3).reshape(n, H, nblk * W).contiguous(), dn  # :408 (+ block layout)
-
-        dn1, dn1_blocks = denoise(gains, sigmas)
+        # the bound of a fallback bias table: full_dn round 1 = the frame's max in DN of p['scale'] (:256); everything else
+        # lr_raw.max()*(wp-bl) (:393, :449)
+        ch1 = eng.chain_params(regs, seg_max, nimg, nblk, scale_est, scale, scale if full_dn else scale_est, 1, bias_corr, vst_type)
+        frames = x.reshape(nimg * nblk, H, W)
+        dn1 = torch.empty((nimg, H, nblk * W), device=dev, dtype=torch.float32)
+        eng.vst_denoise_dev(frames, ch1, dn1, frames_per_row=nblk, fps=nblk)
         mark("denoise_round1")
-        regs, rounds = [reg1], np.ones(nimg, np.int64)
-        final = dn1
+        res = {"dn1": dn1, "final": dn1, "regs1": ch1["regs4"], "regs2": None, "ok": None, "lr": x, "nblk": nblk}
         if pipe.get("iter") == "iter" and pipe["max_iter"] >= 1:
             assert pipe["max_iter"] == 1, "the shipped configurations use max_iter = 1"
-            sidd = bool(pipe.get("sidd_256", nblk == 32))
-            if sidd:  # blocks become separate images of the box filters (:91-93); segments stay per image
-                lr_b = isp.bayer2rggb(flat)
-                dn_b = isp.bayer2rggb(dn1_blocks)  # the denoised blocks as they left the network (no mosaic round trip)
+            sidd = bool(pipe.get("sidd_256", mos_blocks == 32))
+            if sidd and nblk == 1 and mos_blocks > 1:  # mosaic frame: blocks are split out of the mosaic layout
+                regs2 = est.estimate_dev(x.reshape(nimg, H, W), dn1, k, split_blocks=True, x_mosaic=True, y_mosaic=True, nblk=mos_blocks)
             else:
-                lr_b, dn_b = isp.bayer2rggb(mosaic), isp.bayer2rggb(dn1)
-            reg2 = np.atleast_2d(est.estimate(lr_b, dn_b, k, nseg=nimg)).copy()  # :431 (mode 'collab')
+                regs2 = est.estimate_dev(x, dn1, k, split_blocks=sidd, y_mosaic=True)  # :431 (mode 'collab')
             mark("estimate_collab")
-            neg_b = reg2[:, 1] < 0
-            reg2[neg_b, 1] = reg2[neg_b, 0] ** 2  # :438-440
-            ok = reg2[:, 0] >= 0  # :445-447: beta1 < 0 keeps the round-1 result
+            ch2 = eng.chain_params(regs2, seg_max, nimg, nblk, scale_est, scale, scale_est, 2, bias_corr, vst_type, prev=ch1)
+            final = torch.empty_like(dn1)
+            eng.vst_denoise_dev(frames, ch2, final, frames_per_row=nblk, fps=nblk, select=True, fallback=dn1)
+            mark("denoise_round2")
+            res.update(final=final, regs2=ch2["regs4"], ok=ch2["ok"])
+        return res
+
+    @staticmethod
+    def read_summary(res):
+        """One read-back of the numbers of a finished batch: regs per round as (nimg,2) float64 arrays (rows of images whose
+        round 2 was abandoned are NaN in round 2 — the reference does not append them, :445-447), rounds per image."""
+        r1 = res["regs1"].cpu().numpy()
+        nimg = r1.shape[0]
+        regs = [r1[:, :2].copy()]
+        rounds = np.ones(nimg, np.int64)
+        gains = [r1[:, 2:].copy()]
+        if res["regs2"] is not None:
+            r2 = res["regs2"].cpu().numpy()
+            ok = res["ok"].cpu().numpy().astype(bool)
+            reg2 = r2[:, :2].copy()
+            reg2[~ok] = np.nan
             regs.append(reg2)
-            if ok.any():
-                sel = torch.from_numpy(np.nonzero(ok)[0]).to(blocks.device)
-                g2, s2 = reg2[ok, 0] * scale_est, np.sqrt(reg2[ok, 1]) * scale_est  # :442
-                dn2, _ = denoise(g2, s2, sel if not ok.all() else None)
-                final = dn1.clone()
-                final[sel] = dn2
-                rounds[ok] = 2
-                mark("denoise_round2")
-        return {"raw_dns": [dn1, final], "regs": regs, "rounds": rounds, "lr_raw": mosaic}
+            gains.append(r2[:, 2:].copy())
+            rounds[ok] = 2
+        return regs, rounds, gains
+
+    def iter_denoise_batch(self, blocks, p, log=None, timings=None):
+        """IterDenoise for a BATCH of SIDD-shaped images (or full frames, nblk = 1) at once: blocks (nimg, nblk, H, W) CUDA
+        f32.  Same per-image algorithm and guards as the reference (YOND_SIDD.py:301-483); every device stage runs once for
+        all images and the host reads back ONE small array at the end.
+        Returns {'raw_dns': [round-1 (nimg,H,nblk*W), final (nimg,H,nblk*W)], 'regs': [(nimg,2) per round; NaN rows in round
+        2 where the beta1 < 0 guard kept the round-1 result], 'rounds': (nimg,) number of denoise rounds each image completed}."""
+        res = self.iter_denoise_dev(blocks, p, timings=timings)
+        regs, rounds, _ = self.read_summary(res)
+        return {"raw_dns": [res["dn1"], res["final"]], "regs": regs, "rounds": rounds, "lr_raw": None, "dev": res}
 
     def iter_denoise_host(self, host_in, host_out, p, group=8, lanes=2):
         """End-to-end batched IterDenoise on HOST buffers: host_in (nimg,nblk,H,W) f32 pinned -> host_out
@@ -560,57 +646,30 @@ class YOND_SIDD:
         Returns CUDA tensors in the reference's mosaic layout: (H, nblk*W)."""
         pipe = self.pipe
         p = p  # updated in place like the reference (p['gain'], p['sigma'])
-        scale_est = p["wp"] - p["bl"]
-        scale = p.get("scale", scale_est)
-        full_dn = bool(pipe["full_dn"])
         single = blocks.dim() == 2
         blk = blocks[None] if single else blocks
         nblk, H, W = blk.shape
-        mosaic = blk[0] if nblk == 1 else blk.permute(1, 0, 2).reshape(H, nblk * W).contiguous()  # :315
-        k = pipe["k"]
-        sidd_256 = bool(pipe.get("sidd_256", nblk == 32))
-        bias_corr = pipe["bias_corr"]
-        vst_type = pipe.get("vst_type", "exact")
-        regs = []
+        mosaic = lambda: (blk[0] if nblk == 1 else blk.permute(1, 0, 2).reshape(H, nblk * W).contiguous())  # :315
         if not pipe["full_est"]:
             # :367-378 — no estimator configured: plain network pass per block, returned as-is (not clipped)
             dn = self.engine.simple_denoise(blk)
             dn = dn[0] if nblk == 1 else dn.permute(1, 0, 2).reshape(H, nblk * W)
-            return {"raw_dns": [dn], "regs": (0, 0), "lr_raw": mosaic}
+            return {"raw_dns": [dn], "regs": (0, 0), "lr_raw": mosaic()}
         if "simple" not in pipe["est_type"]:
             raise NotImplementedError(f"est_type '{pipe['est_type']}' needs external estimate files / networks (YOND_SIDD.py:316-353)")
-        # ---- round 1: self-calibration (:338-341, :356)
-        raw4est = mosaic if lr_full is None else lr_full
-        reg = nlf.SimpleNLF(raw4est, k=k, setting={"mode": "self"})
-        regs.append(reg)
-        p["gain"], p["sigma"] = reg[0] * scale_est, np.sqrt(max(reg[1], 0)) * scale_est
-        self._log(f"Self Est: K={p['gain']:.4f}, b={p['sigma']:.4f} (beta1={reg[0]:.3e}, beta2={reg[1]:.3e})")
-
-        def denoise():
-            src = mosaic[None] if full_dn else blk
-            bound = None
-            if bias_corr is not None and self.biaslut is None and not full_dn:
-                # one fallback table per image, up to the image max (:393-395 / :450-452), shared by its blocks
-                bound = np.float32(float(blk.max())) * np.float32(scale_est)
-            n = src.shape[0]
-            dn = self.engine.vst_denoise(src, [p["gain"]] * n, [p["sigma"]] * n, scale, bias_corr=bias_corr,
-                                         vst_type=vst_type, clip01=True, table_bound=bound)  # .clip(0,1): :389 / :406
-            return dn[0] if (full_dn or nblk == 1) else dn.permute(1, 0, 2).reshape(H, nblk * W).contiguous()  # :408
-
-        raw_dn = denoise()
-        raw_dns = [raw_dn]
-        # ---- round 2: iterative calibration (:419-472)
-        if pipe.get("iter") == "iter":
-            for _ in range(1, pipe["max_iter"] + 1):
-                reg = nlf.SimpleNLF(mosaic, raw_dn, k=k, setting={"mode": "collab", "SIDD_256": sidd_256})  # :431
-                if reg[1] < 0:  # :438-440
-                    self._log(f"Warning!!! b={reg[1]:.4f} is backup to {reg[0] ** 2:.4f}")
-                    reg = (reg[0], reg[0] ** 2)
-                p["gain"], p["sigma"] = reg[0] * scale_est, np.sqrt(reg[1]) * scale_est  # :442
-                if reg[0] < 0:  # :445-447
-                    self._log("Warning!!! Wrong noise level! Backup to iter_0 result.")
-                    break
-                raw_dn = denoise()
-                raw_dns.append(raw_dn)
-                regs.append(reg)
-        return {"raw_dns": raw_dns, "regs": regs, "lr_raw": mosaic}
+        res = self.iter_denoise_dev(blk[None].contiguous(), p, lr_full=lr_full)
+        regs, rounds, gs = self.read_summary(res)
+        reg = regs[0][0]
+        self._log(f"Self Est: K={gs[0][0, 0]:.4f}, b={gs[0][0, 1]:.4f} (beta1={reg[0]:.3e}, beta2={reg[1]:.3e})")
+        p["gain"], p["sigma"] = gs[0][0, 0], gs[0][0, 1]  # :356
+        raw_dns, out_regs = [res["dn1"][0]], [reg]
+        if res["regs2"] is not None:
+            r2 = res["regs2"].cpu().numpy()[0]
+            p["gain"], p["sigma"] = r2[2], r2[3]  # :442 — set before the guard, like the reference
+            self._log(f"Iter 1 Est: K={r2[2]:.4f}, sigma={r2[3]:.4f} (beta1={r2[0]:.3e}, beta2={r2[1]:.3e})")
+            if rounds[0] == 2:
+                raw_dns.append(res["final"][0])
+                out_regs.append(regs[1][0])
+            else:
+                self._log("Warning!!! Wrong noise level! Backup to iter_0 result.")  # :445-447
+        return {"raw_dns": raw_dns, "regs": out_regs, "lr_raw": mosaic()}
