@@ -4,12 +4,17 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
 
-Workload (BASELINE.json configs[1]): 40 synthetic SIDD-shaped images = 1280 noisy 256x256 Bayer blocks
-(Poisson-Gaussian, 10-bit: wp 1023, bl 64), GuidedResUnet (GRU_5to50_norm_mix arch block) random-init,
-`SIDD_simple+full_pre_grumix` pipeline: per image self-calibration estimate -> VST -> denoise 32 blocks -> inverse ->
-collab estimate (round 2; with random-init weights the reference's beta1<0 guard then keeps the round-1 result, in both arms).
-A step = one pass over all 1280 blocks.  `value`: inputs resident in HBM.  `e2e`: the reference-facing
-`YOND_SIDD.IterDenoise` call with pinned HOST buffers, H2D + D2H inside the timed region.
+Headline workload (north_star target, BASELINE.json configs[4]/[2]): synthetic 12 MP Bayer frames (4032x3024, 10-bit:
+wp 1023, bl 64, Poisson-Gaussian noise), 8 frames per GPU per step, image-parallel across the GPUs; GuidedResUnet
+(GRU_5to50_norm_mix arch block), the reference's full-frame pipeline (runfiles/YOND/{ANY,DND,ELD,LRID}_simple+full_pre_grumix.yml:
+full_est, full_dn, bias_corr 'pre', iter, max_iter 1): per frame self-calibration estimate -> bias LUT -> VST -> network ->
+inverse VST -> collab estimate -> second round.  Both rounds execute for every frame (`round2_denoise_images`).
+A step = one pass over the GPU's 8 frames (97.5 MP).  `value`: inputs resident in HBM.  `e2e`: the same step from pinned
+HOST buffers to pinned host buffers, H2D + D2H inside the timed region.
+Secondary keys: `secondary` (BASELINE configs[1]: 1280 SIDD-shaped 256x256 blocks, the reference's shipped SIDD pipeline),
+`e2e_dropin` (per-image `IterDenoise(np arrays)` through the reference's own call signature), `frame_sharded` (ONE 12 MP /
+24 MP frame with the network stage band-sharded across the ranks: configs[2] / [3]), `roofline_hbm` (every HBM-bound kernel
+timed live with CUDA events against its algorithmic bytes).
 """
 import argparse
 import json
@@ -27,18 +32,20 @@ sys.path.insert(0, ROOT)
 ARCH = {"name": "GuidedResUnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
 PIPE = {"data_type": "SIDD", "full_est": True, "est_type": "simple+full", "k": 29, "full_dn": False, "vst_type": "exact",
         "bias_corr": "pre", "iter": "iter", "max_iter": 1, "clip": False}
+PIPE_FRAME = dict(PIPE, data_type="ANY", full_dn=True)
 P0 = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+P_C4 = {"wp": 16383, "bl": 512, "ratio": 100, "gain": 1, "sigma": 0, "scale": (16383 - 512) / 100}
 N_IMAGES, N_BLOCKS, BLK = 40, 32, 256
+FRAME_H, FRAME_W, N_FRAMES = 3024, 4032, 8
 METRIC = "raw_MP_per_s_end_to_end_YOND_denoise"
-WORKLOAD = ("configs[1]: 1280 synthetic 256x256 Bayer blocks (40 images x 32), GuidedResUnet (GRU_5to50_norm_mix) random-init, "
-            "SIDD_simple+full_pre pipeline: self estimate + VST denoise + collab estimate per image")
-
-
-E2E_GROUP = os.environ.get("YOND_E2E_GROUP", "8")
-E2E_GROUP = int(E2E_GROUP) if "," not in E2E_GROUP else [int(v) for v in E2E_GROUP.split(",")]
-E2E_LANES = int(os.environ.get("YOND_E2E_LANES", "5"))
-DEV_GROUP = int(os.environ.get("YOND_DEV_GROUP", "20"))
-DEV_LANES = int(os.environ.get("YOND_DEV_LANES", "1"))  # >1: device-resident step dealt to host lanes (measured: no gain, 24.0 vs 23.2 ms)
+WORKLOAD = ("configs[4]/[2]: synthetic 12 MP Bayer frames (4032x3024, 10-bit), 8 per GPU per step, image-parallel; GuidedResUnet "
+            "(GRU_5to50_norm_mix), full-frame pipeline *_simple+full_pre_grumix (full_est, full_dn, bias_corr pre, iter): "
+            "self estimate + VST denoise + collab estimate + second VST denoise per frame; weights = mild smoother + 0.25 x the "
+            "reference's random init (no checkpoint offline; passes the reference's round-2 guard so both rounds run)")
+WORKLOAD_C2 = ("configs[1]: 1280 synthetic 256x256 Bayer blocks (40 images x 32), GuidedResUnet, SIDD_simple+full_pre_grumix "
+               "pipeline (per-image estimate on the mosaic, 32 block-wise VST denoises, SIDD_256 collab estimate, second round)")
+E2E_GROUP_FRAMES = int(os.environ.get("YOND_E2E_GROUP_FRAMES", "2"))
+E2E_GROUP_IMAGES = int(os.environ.get("YOND_E2E_GROUP", "8"))
 
 
 def synth_images(n_images, seed=2024):
@@ -48,13 +55,29 @@ def synth_images(n_images, seed=2024):
     out = np.empty((n_images, N_BLOCKS, BLK, BLK), np.float32)
     params = []
     for i in range(n_images):
-        # K >= 0.6 DN/e-: below that the blind estimate of sigma/K leaves the BiasLUT's range (>= 10 e-) on smooth
-        # synthetic content and both arms would spend their time in the host-side fallback-table generator (A6)
+        # K >= 0.6 DN/e-: keeps most blind estimates of sigma/K inside the BiasLUT (< 10 e-); the ones that leave it take
+        # the numeric fallback table, which is generated on the device
         K, S = synth.sample_noise_params(rng, logk_min=-0.5)
         params.append((K, S))
         for b in range(N_BLOCKS):
             out[i, b] = synth.noisy(rng, synth.clean_smooth(rng, BLK, BLK), K, S, clip=True)
     return out, params
+
+
+def synth_frame(rng, H, W, p):
+    """One noisy frame in the dataset's normalisation.  10-bit (P0): clipped, K / sigma drawn like the reference's synthesis.
+    14-bit low light (P_C4): (raw - bl) * ratio / (wp - bl), unclipped (yond_datasets.py:1053-1056), Sony-like K = 2.2, sigma = 3.1 DN."""
+    from yond_public_b200 import synth
+    clean = synth.clean_smooth(rng, H, W)
+    if p["ratio"] == 1:
+        K, S = synth.sample_noise_params(rng, logk_min=-0.5)
+        return synth.noisy(rng, clean, K, S, scale=float(p["wp"] - p["bl"]), clip=True)
+    return synth.noisy(rng, clean, 2.2 * p["ratio"], 3.1 * p["ratio"], scale=float(p["wp"] - p["bl"]), clip=False)
+
+
+def synth_frames(n, seed, H=FRAME_H, W=FRAME_W):
+    rng = np.random.default_rng(seed)
+    return np.stack([synth_frame(rng, H, W, P0) for _ in range(n)])
 
 
 class ClockSampler:
@@ -109,54 +132,84 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_step(blocks_img, sd, lut):
-    """One image (32 blocks) through the oracle's IterDenoise on the host cores."""
+# CPU legs: the ONLY places bench.py touches oracle/ (the reference is Python and cannot travel to the GPU box: the
+# oracle port is the reference algorithm, pinned against goldens generated by the reference itself)
+CPU_SAMPLE = (1512, 2016)  # a quarter-area crop of a 12 MP frame per step: bounds the CPU arm to a few minutes
+
+
+def cpu_reference_step(frame, sd, lut):
     from oracle import yond_oracle as O
-    return O.IterDenoise(ARCH, sd, blocks_img, dict(P0), PIPE, biaslut=lut)
+    return O.IterDenoise(ARCH, sd, frame, dict(P0), PIPE_FRAME, biaslut=lut, sidd_256=False)
+
+
+def cpu_threads():
+    """All host cores, also under torchrun (which exports OMP_NUM_THREADS=1)."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
 def run_reference(args):
-    import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
+    cores = cpu_threads()
     from oracle import yond_oracle as O
-    lut = O.BiasLUT(os.path.join(ROOT, "yond_public_b200", "data", "bias_lut_2d_f32.npz"))
     from yond_public_b200 import synth
-    sd = synth.random_init_state_dict(ARCH, seed=0)
-    n_img = 2
-    imgs, _ = synth_images(n_img)
+    lut = O.BiasLUT(os.path.join(ROOT, "yond_public_b200", "data", "bias_lut_2d_f32.npz"))
+    sd = synth.bench_state_dict(ARCH, seed=0)
+    frames = synth_frames(2, seed=2024, H=CPU_SAMPLE[0], W=CPU_SAMPLE[1])
+    rounds = []
     for w in range(args.warmup):
-        cpu_reference_step(imgs[w % n_img], sd, lut)
+        cpu_reference_step(frames[w % 2], sd, lut)
     t0 = time.perf_counter()
     for s in range(args.steps):
-        cpu_reference_step(imgs[s % n_img], sd, lut)
+        rounds.append(len(cpu_reference_step(frames[s % 2], sd, lut)["raw_dns"]))
     dt = time.perf_counter() - t0
-    mp = args.steps * N_BLOCKS * BLK * BLK / 1e6
+    mp = args.steps * CPU_SAMPLE[0] * CPU_SAMPLE[1] / 1e6
     val = mp / dt
     try:
         import cv2
         cvt = cv2.getNumThreads()
     except Exception:
         cvt = None
-    sample = f"1 image (32 blocks of 256x256 = 2.1 MP) per step, {args.steps} steps; oracle port of YOND_SIDD.IterDenoise, fp32"
+    sample = (f"one {CPU_SAMPLE[1]}x{CPU_SAMPLE[0]} frame (quarter-area crop of the 12 MP frame, {CPU_SAMPLE[0] * CPU_SAMPLE[1] / 1e6:.2f} MP) per step, "
+              f"{args.steps} steps; oracle port of YOND_SIDD.IterDenoise (full_dn, two rounds), fp32, {cores} torch threads")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+            "config": {"workload": WORKLOAD, "sample": sample, "round2_denoise_images": int(sum(r == 2 for r in rounds)), "steps_run": len(rounds)},
+            "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample,
                              "os_cpu_count": os.cpu_count(), "cv2_threads": cvt},
             "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------
+# algorithmic bytes per Bayer pixel of the HBM-bound stages (SURVEY 8d) are stated where the stages are launched
+# (YondProfScope in csrc/): the live profiler returns bytes and milliseconds per stage
+def hbm_table(prof, peak_gbs):
+    rows = []
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        if v["ms"] <= 0 or v["bytes"] <= 0:
+            continue
+        gbs = v["bytes"] / (v["ms"] / 1e3) / 1e9
+        rows.append({"kernel": name, "launch_groups": int(v["scopes"]), "algorithmic_bytes": float(v["bytes"]), "ms": float(v["ms"]),
+                     "achieved_gbs": gbs, "frac": gbs / peak_gbs})
+    return rows
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
     import yond_public_b200 as Y
-    from yond_public_b200 import synth
+    from yond_public_b200 import parallel, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -165,59 +218,19 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    # weak scaling: every rank denoises its own 40 images (image-parallel, no data-path collective);
-    # the final gather of the denoised frames to rank 0 is part of the step when N > 1.
-    imgs_np, _ = synth_images(N_IMAGES, seed=2024 + rank)
-    host_in = torch.from_numpy(imgs_np).pin_memory()
-    host_out = torch.empty((N_IMAGES, BLK, N_BLOCKS * BLK), dtype=torch.float32).pin_memory()
-    dev_in = host_in.to(dev)
-    sd = synth.random_init_state_dict(ARCH, seed=0)  # the reference's random init (no checkpoint reachable offline)
-    drv = Y.YOND_SIDD(ARCH, PIPE, state_dict=sd, device=dev)
-    net = drv.net
-    gather_buf = None
-    if world > 1 and rank == 0:
-        gather_buf = [torch.empty((N_IMAGES, BLK, N_BLOCKS * BLK), dtype=torch.float32, device=dev) for _ in range(world)]
-    dev_out = torch.empty((N_IMAGES, BLK, N_BLOCKS * BLK), dtype=torch.float32, device=dev)
-
-    pending = []  # outstanding gathers: (work handle, tensor kept alive)
-
-    def gather_async(final):
-        # the final gather of step i runs on NCCL's stream while step i+1 computes; at most two are in flight and all of
-        # them are waited for before the timed region ends (`drain`)
-        pending.append((dist.gather(final, gather_buf, dst=0, async_op=True), final))
-        if len(pending) > 2:
-            pending.pop(0)[0].wait()
-
-    def drain():
-        while pending:
-            pending.pop(0)[0].wait()
-
-    def step_single():  # one host thread, one stream: every stage once for all 40 images
-        res = drv.iter_denoise_batch(dev_in, dict(P0))
-        if world > 1:
-            gather_async(res["raw_dns"][-1])
-        return res
-
-    def step_device():
-        if DEV_LANES <= 1:
-            return step_single()
-        # same work dealt to DEV_LANES host threads / streams in groups of DEV_GROUP images (640 blocks = one network
-        # chunk): the estimator's host read-backs of one lane are covered by the other lane's kernels
-        res = drv.iter_denoise_lanes(dev_in, dict(P0), group=DEV_GROUP, lanes=DEV_LANES)
-        if world > 1:
-            gather_async(torch.cat(res["raw_dns"]))
-        return res
-
-    def step_e2e():
-        # host buffers in, host buffers out: H2D of the step's inputs and D2H of the denoised frames are inside the
-        # timed region (on side streams, overlapped with compute group by group)
-        return drv.iter_denoise_host(host_in, host_out, dict(P0), group=E2E_GROUP, lanes=E2E_LANES)
+    peaks, peak_src = measured_peaks()
+    sd = synth.bench_state_dict(ARCH, seed=0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    pending = []  # outstanding gathers: (work handle, tensor kept alive)
+
+    def drain():
+        while pending:
+            pending.pop(0)[0].wait()
 
     def timed(fn, steps):
         barrier()
@@ -235,76 +248,175 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
-    rounds = None
+    def make_gather(shape):
+        buf = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+        def gather_async(final):
+            # the final gather of step i runs on NCCL's stream while step i+1 computes; at most two are in flight and all of
+            # them are waited for before the timed region ends (`drain`)
+            pending.append((dist.gather(final, buf, dst=0, async_op=True), final))
+            if len(pending) > 2:
+                pending.pop(0)[0].wait()
+        return gather_async
+
+    # =========================================== headline: 12 MP frames, image-parallel (weak scaling: 8 frames per rank)
+    frames_np = synth_frames(N_FRAMES, seed=2024 + rank)
+    host_in = torch.from_numpy(frames_np.reshape(N_FRAMES, 1, FRAME_H, FRAME_W)).pin_memory()
+    host_out = torch.empty((N_FRAMES, FRAME_H, FRAME_W), dtype=torch.float32).pin_memory()
+    dev_in = host_in.to(dev)
+    drv = Y.YOND_SIDD(ARCH, PIPE_FRAME, state_dict=sd, device=dev)
+    net = drv.net
+    gather_frames = make_gather((N_FRAMES, FRAME_H, FRAME_W))
+    last = {}
+
+    def step_frames():  # one host thread, one stream: every stage once for all 8 frames; one small read-back at the end
+        res = drv.iter_denoise_batch(dev_in, dict(P0))
+        last["rounds"] = res["rounds"]
+        if world > 1:
+            gather_frames(res["raw_dns"][-1])
+
+    def step_frames_e2e():
+        r = drv.iter_denoise_host(host_in, host_out, dict(P0), group=E2E_GROUP_FRAMES)
+        last["rounds_e2e"] = r["rounds"]
+
     for _ in range(args.warmup):
-        rounds = step_device()["rounds"]
+        step_frames()
     drain()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    if DEV_LANES <= 1:  # the timed region itself is profiled: CUDA events around every conv launch on the launching stream
-        net.set_profile(True)
-        net.read_profile(reset=True)
+    net.set_profile(True)  # the timed region itself is profiled: CUDA events around every conv launch / every HBM stage
+    net.read_profile(reset=True)
+    Y._lib.prof_enable(True)
+    Y._lib.prof_read(reset=True)
     l0 = Y._lib.launch_count()
-    ms = timed(step_device, args.steps)
+    ms = timed(step_frames, args.steps)
     launches = Y._lib.launch_count() - l0
-    ms_single = ms
-    if DEV_LANES > 1:
-        # kernel-time accounting on ONE stream (with several lanes the events around a conv launch would also span the
-        # other lanes' kernels)
-        net.set_profile(True)
-        net.read_profile(reset=True)
-        ms_single = timed(step_single, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     prof = net.read_profile(reset=True)
+    hbm_prof = Y._lib.prof_read(reset=True)
     net.set_profile(False)
-
+    Y._lib.prof_enable(False)
     for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-
-    mp_step = N_IMAGES * N_BLOCKS * BLK * BLK / 1e6
+        step_frames_e2e()
+    ms_e2e = timed(step_frames_e2e, args.steps)
+    mp_step = N_FRAMES * FRAME_H * FRAME_W / 1e6
     value = world * mp_step * args.steps / (ms / 1e3)
     e2e = world * mp_step * args.steps / (ms_e2e / 1e3)
-    peaks, peak_src = measured_peaks()
-    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-    ach_tf = prof["conv_flops"] / (prof["conv_ms"] / 1e3) / 1e12 if prof["conv_ms"] > 0 else 0.0
 
+    # drop-in call: per-frame IterDenoise(np arrays) -> np arrays through the reference's signature (pageable NumPy in / out)
+    def dropin(drv_, arrays, p):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for a in arrays:
+            out = drv_.IterDenoise({"lr": a, "name": "bench"}, {"p": dict(p), "img_id": 0})
+            assert isinstance(out["raw_dns"][-1], np.ndarray)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+    dropin(drv, [frames_np[0]], P0)
+    dt_drop = dropin(drv, list(frames_np[:4]), P0)
+    dropin_frames = 4 * FRAME_H * FRAME_W / 1e6 / dt_drop
+
+    # =========================================== one frame across the ranks (configs[2] / [3]): network stage band-sharded
+    frame_sharded = {}
+    for name, (H, W), p in (("C3_12MP_10bit", (FRAME_H, FRAME_W), P0), ("C4_24MP_14bit_ratio100_noclip", (4000, 6000), P_C4)):
+        rng = np.random.default_rng(99)  # the same frame on every rank
+        fr = torch.from_numpy(synth_frame(rng, H, W, p)).to(dev)
+        drv.engine.max_value = 1.0 if p["ratio"] == 1 else 4.0
+        step = lambda: parallel.denoise_frame_sharded(drv, fr, dict(p))  # noqa: E731
+        for _ in range(2):
+            step()
+        k = max(3, min(args.steps, 10))
+        ms_f = timed(step, k) / k
+        res = step()
+        _, rnds, _ = drv.read_summary(res)
+        frame_sharded[name] = {"ms_per_frame": ms_f, "MP_per_s": H * W / 1e6 / (ms_f / 1e3), "ranks": world, "rounds": int(rnds[0]),
+                               "scaling": "strong (one frame, N ranks)"}
+        del fr
+    drv.engine.max_value = 1.0
+    del dev_in
+    torch.cuda.empty_cache()
+
+    # =========================================== secondary: configs[1], 1280 SIDD-shaped blocks
+    imgs_np, _ = synth_images(N_IMAGES, seed=2024 + rank)
+    host_in2 = torch.from_numpy(imgs_np).pin_memory()
+    host_out2 = torch.empty((N_IMAGES, BLK, N_BLOCKS * BLK), dtype=torch.float32).pin_memory()
+    dev_in2 = host_in2.to(dev)
+    drv2 = Y.YOND_SIDD(ARCH, PIPE, state_dict=sd, device=dev)
+    gather_blocks = make_gather((N_IMAGES, BLK, N_BLOCKS * BLK))
+
+    def step_blocks():
+        res = drv2.iter_denoise_batch(dev_in2, dict(P0))
+        last["rounds2"] = res["rounds"]
+        if world > 1:
+            gather_blocks(res["raw_dns"][-1])
+
+    def step_blocks_e2e():
+        drv2.iter_denoise_host(host_in2, host_out2, dict(P0), group=E2E_GROUP_IMAGES)
+
+    for _ in range(args.warmup):
+        step_blocks()
+    drain()
+    ms2 = timed(step_blocks, args.steps)
+    for _ in range(min(args.warmup, 2)):
+        step_blocks_e2e()
+    ms2_e2e = timed(step_blocks_e2e, args.steps)
+    mp2 = N_IMAGES * N_BLOCKS * BLK * BLK / 1e6
+    dropin(drv2, [imgs_np[0]], P0)
+    dt_drop2 = dropin(drv2, list(imgs_np[:8]), P0)
+    secondary = {"workload": WORKLOAD_C2, "value": world * mp2 * args.steps / (ms2 / 1e3), "unit": "MP/s", "ms_per_step": ms2 / args.steps,
+                 "e2e": {"value": world * mp2 * args.steps / (ms2_e2e / 1e3), "unit": "MP/s", "ms_per_step": ms2_e2e / args.steps,
+                         "h2d_bytes_per_step": int(host_in2.numel() * 4), "d2h_bytes_per_step": int(host_out2.numel() * 4)},
+                 "e2e_dropin": {"value": 8 * N_BLOCKS * BLK * BLK / 1e6 / dt_drop2, "unit": "MP/s (one rank)",
+                                "api": "YOND_SIDD.IterDenoise({'lr': np (32,256,256)}, {'p': p}) -> np, one image per call, 8 calls"},
+                 "round2_denoise_images": int((last["rounds2"] == 2).sum()), "images_per_gpu": N_IMAGES}
+
+    # =========================================== roofline + CPU baseline
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    ach_tf = prof["conv_flops"] / (prof["conv_ms"] / 1e3) / 1e12 if prof["conv_ms"] > 0 else 0.0
     traffic, traffic_note = None, None
-    try:  # ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the conv launches of one 640-block chunk
-        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_per_launch"]
-        traffic_note = "profiles/r01_conv_traffic.json: mean DRAM bytes per conv_tc_kernel launch (ncu, cold cache, one 640-block chunk = half a step)"
-    except Exception:
-        pass
+    for name in ("r02_conv_traffic_frames.json", "r01_conv_traffic.json"):
+        try:  # ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the conv launches of one forward
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_note = f"profiles/{name}: mean DRAM bytes per conv_tc_kernel launch (ncu, cold cache): {tj.get('note', 'one network forward')}"
+            break
+        except Exception:
+            pass
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = cpu_threads()
         from oracle import yond_oracle as O  # the CPU-baseline leg is the only place the GPU arm touches oracle/
         lut = O.BiasLUT(drv.biaslut.bias_lut)
+        crop = frames_np[0][:CPU_SAMPLE[0], :CPU_SAMPLE[1]]
         t0 = time.perf_counter()
         reps = 0
-        while reps < 2 or (time.perf_counter() - t0 < 10 and reps < 8):
-            cpu_reference_step(imgs_np[reps % N_IMAGES], sd, lut)
+        while reps < 2 or (time.perf_counter() - t0 < 10 and reps < 6):
+            cpu_reference_step(np.ascontiguousarray(crop), sd, lut)
             reps += 1
         dt = time.perf_counter() - t0
-        cpu_base = {"value": reps * N_BLOCKS * BLK * BLK / 1e6 / dt, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port",
-                    "sample": f"{reps} images (32 blocks of 256x256 each) through the oracle port of IterDenoise, fp32, {dt:.1f} s",
+        cpu_base = {"value": reps * CPU_SAMPLE[0] * CPU_SAMPLE[1] / 1e6 / dt, "unit": "MP/s", "cores": cores, "kind": "port",
+                    "sample": f"{reps} x one {CPU_SAMPLE[1]}x{CPU_SAMPLE[0]} crop of a bench frame through the oracle port of IterDenoise (full_dn, two rounds), fp32, {dt:.1f} s",
                     "os_cpu_count": os.cpu_count()}
 
     if rank == 0:
+        steps = args.steps
         line = {
-            "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "round2_denoise_images": int((rounds == 2).sum()) if rounds is not None else None,
-                       "images_per_gpu": N_IMAGES, "blocks_per_image": N_BLOCKS, "block": [BLK, BLK],
-                       "l2_policy": "inputs (335 MB per step) and activations exceed the 126 MB L2; no explicit flush",
-                       "device_lanes": f"{DEV_LANES} host threads / streams x groups of {DEV_GROUP} images" if DEV_LANES > 1 else "one host thread, one stream",
+            "config": {"workload": WORKLOAD, "round2_denoise_images": int((last["rounds"] == 2).sum()), "frames_per_gpu": N_FRAMES,
+                       "frame": [FRAME_H, FRAME_W], "whole_frame_forward": "each frame is forwarded whole after reflect-padding to x32 (the reference's semantics; 180 GB of HBM hold it); halo tiling is used where a frame is sharded (frame_sharded) and is parity-tested against the whole-frame forward",
+                       "l2_policy": "inputs (390 MB per step) and activations exceed the 126 MB L2; no explicit flush",
+                       "device_lanes": "one host thread, one stream, no host synchronisation between pack and the final inverse VST",
                        "parallelism": f"image-parallel x{world}, NCCL gather of the denoised frames to rank 0 every step (asynchronous: overlaps the next step, drained inside the timed region)" if world > 1 else "single GPU"},
             "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4),
-                    "ms_per_step": ms_e2e / args.steps, "api": f"YOND_SIDD.iter_denoise_host: pinned host buffers in/out, groups of {E2E_GROUP} images dealt to {E2E_LANES} host threads (own stream + driver clone each); H2D copies chained in group order; copies and estimator read-backs of one lane overlap the other lanes' kernels"},
+                    "ms_per_step": ms_e2e / steps,
+                    "api": f"YOND_SIDD.iter_denoise_host: pinned host buffers in/out, groups of {E2E_GROUP_FRAMES} frames; H2D of group g+1 and D2H of group g-1 on their own streams while group g computes; one host thread"},
+            "e2e_dropin": {"value": dropin_frames, "unit": "MP/s (one rank)",
+                           "api": "YOND_SIDD.IterDenoise({'lr': np (3024,4032)}, {'p': p}) -> np arrays, one frame per call, 4 calls (pageable NumPy in and out, like the reference's eval loop)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
@@ -312,11 +424,16 @@ def run_b200(args):
                          "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv stack)",
                          "flops_per_launch": prof["conv_flops"] / max(prof["launches"], 1),
                          "ms_per_launch": prof["conv_ms"] / max(prof["launches"], 1),
-                         "share_of_step": (prof["conv_ms"] / args.steps) / (ms_single / args.steps), "single_stream_ms_per_step": ms_single / args.steps,
-                         "measured_in": "the timed region (CUDA events around every conv launch on the launching stream)" if DEV_LANES <= 1 else "a single-stream pass of the same step",
+                         "share_of_step": (prof["conv_ms"] / steps) / (ms / steps),
+                         "measured_in": "the timed region (CUDA events around every conv launch on the launching stream)",
                          "peak_source": peak_src + " bf16_tflops_sustained",
-                         "conv_ms_per_step": prof["conv_ms"] / args.steps, "conv_launches": prof["launches"],
-                         "algorithmic_flops_per_step": prof["conv_flops"] / args.steps},
+                         "conv_ms_per_step": prof["conv_ms"] / steps, "conv_launches": prof["launches"],
+                         "algorithmic_flops_per_step": prof["conv_flops"] / steps},
+            "roofline_hbm": {"peak_gbs": peak_hbm, "peak_source": peak_src + " hbm_gbs", "bound": "hbm",
+                             "measured_in": "the timed region (CUDA events around every stage on the launching stream); bytes = algorithmic bytes per Bayer pixel (SURVEY 8d) x pixels",
+                             "kernels": hbm_table(hbm_prof, peak_hbm)},
+            "frame_sharded": frame_sharded,
+            "secondary": secondary,
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(line), flush=True)

@@ -34,6 +34,12 @@ int yond_version(void);
 /* Number of kernels launched by this library since process start (bench.py's `gpu_launches`). */
 uint64_t yond_launch_count(void);
 
+/* Live stage profiler (bench.py's per-kernel roofline): while enabled, every library stage is bracketed by CUDA events on
+ * its launching stream and booked with its algorithmic bytes / FLOPs.  yond_prof_read writes a JSON object
+ * {"stage": {"scopes": n, "ms": t, "bytes": b, "flops": f}, ...} (it waits for the recorded events). */
+int yond_prof_enable(int on);
+int yond_prof_read(char* buf, size_t cap, int reset);
+
 /* ---- A1/A2: Bayer pack / unpack — utils/isp_ops.py:57-63 (bayer2rggb, rggb2bayer), batched :65-71 ---- */
 int yond_pack(const float* bayer, float* rggb, int B, int H, int W, void* stream);
 int yond_unpack(const float* rggb, float* bayer, int B, int h, int w, void* stream);

@@ -598,7 +598,7 @@ def Simple_Denoiser(arch, sd, lr_raw, bf16=False):  # YOND_SIDD.py:238-248
 # --------------------------------------------------------------------------------------------------
 # A19  IterDenoise — two-round orchestration with the reference's guards   YOND_SIDD.py:301-483
 # --------------------------------------------------------------------------------------------------
-def IterDenoise(arch, sd, lr_blocks, p, pipe, biaslut=None, lr_full=None, bf16=False):
+def IterDenoise(arch, sd, lr_blocks, p, pipe, biaslut=None, lr_full=None, bf16=False, sidd_256=True):
     """`lr_blocks`: (nblk,H,W) Bayer blocks (SIDD layout) — or a single (H,W) frame when pipe['full_dn'].
     Follows the 'simple' estimator branch (:338-341), bias_corr / denoise loops (:384-408) and round 2
     (:419-472).  Returns {'raw_dns': [...], 'regs': [...]} like the reference."""
@@ -634,7 +634,8 @@ def IterDenoise(arch, sd, lr_blocks, p, pipe, biaslut=None, lr_full=None, bf16=F
     raw_dns = [raw_dn.copy()]
     if pipe.get("iter") == "iter":
         for _ in range(1, pipe["max_iter"] + 1):
-            reg = SimpleNLF(mosaic, raw_dn, k=k, setting={"mode": "collab", "SIDD_256": True})  # :431
+            # :431 hard-codes SIDD_256 = True; `sidd_256=False` is the plain-frame variant (widths not divisible by 64)
+            reg = SimpleNLF(mosaic, raw_dn, k=k, setting={"mode": "collab", "SIDD_256": bool(sidd_256)})
             if reg[1] < 0:  # :438-440
                 reg = (reg[0], reg[0] ** 2)
             p["gain"], p["sigma"] = reg[0] * scale, np.sqrt(reg[1]) * scale  # :442

@@ -97,6 +97,11 @@ def test_synth_module_matches_reference_recipes(Y):
     K2, S2 = O.sample_noise_params(r2, logk_min=-0.5)
     assert (K1, S1) == (K2, S2)
     assert np.array_equal(synth.noisy(r1, synth.clean_smooth(r1, 32, 32), K1, S1), O.synth_noisy(r2, O.synth_clean_smooth(r2, 32, 32), K2, S2))
+    for a_ in (arch, {"name": "UNetSeeInDark", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}):
+        s1, s2 = synth.smoother_state_dict(a_), O.smoother_state_dict(a_)
+        assert list(s1) == list(s2) and all(torch.equal(s1[k], s2[k]) for k in s1)
+    bw = synth.bench_state_dict(arch, seed=0)
+    assert all(float(v.abs().max()) > 0 for v in bw.values())  # dense: no tensor is left at zero
 
 
 def test_unknown_arch_and_key_rejected(Y):
@@ -169,17 +174,20 @@ def _gloo_worker(rank, world, port, q):
     units = torch.arange(7 * 6, dtype=torch.float32).reshape(7, 2, 3)  # 7 units: ragged shares (4 + 3)
     out = run_sharded(units, lambda u: u * 2 + 1, dst=0)
     ok = bool(torch.equal(out, units * 2 + 1)) if rank == 0 else out is None
-    # tile-sharded frame: disjoint supports assembled by a SUM reduction
-    from yond_public_b200.parallel import gather_disjoint, shard_range
-    from yond_public_b200.pipeline import YondEngine
-    grid = YondEngine.tile_grid(96, 160, 64)  # 2 x 3 tiles, ragged last column
-    full = torch.arange(96 * 160 * 4, dtype=torch.float32).reshape(1, 96, 160, 4) + 1
-    part = torch.zeros_like(full)
-    a, b = shard_range(len(grid), rank, world)
-    for (y0, x0, ch, cw) in grid[a:b]:
-        part[:, y0:y0 + ch, x0:x0 + cw] = full[:, y0:y0 + ch, x0:x0 + cw]
-    got = gather_disjoint(part, dst=0)
-    ok = ok and (bool(torch.equal(got, full)) if rank == 0 else got is None)
+    # band-sharded frame: each rank "forwards" its row band (+ halo, cut at the border) and one all-gather assembles the
+    # frame; the stand-in network is a 3x3 row-local box sum, so a missing or misplaced halo row would show
+    from yond_public_b200.parallel import BandShardedForward, band_range
+    for hp in (96, 80):  # 80: ragged last band (48 + 32)
+        full = (torch.arange(hp * 20 * 4, dtype=torch.float32).reshape(1, hp, 20, 4) % 97) * 0.25
+
+        def fake_net(z, ub, t, out=None):
+            p_ = torch.nn.functional.pad(z.permute(0, 3, 1, 2), (0, 0, 1, 1))  # zero rows outside the slice, like the conv padding
+            return (p_[:, :, :-2] + p_[:, :, 1:-1] + p_[:, :, 2:]).permute(0, 2, 3, 1).contiguous()
+        fwd = BandShardedForward(fake_net, halo=16)
+        got = fwd(full, None, None)
+        ok = ok and bool(torch.equal(got, fake_net(full, None, None)))
+        r0, r1, band = band_range(hp, rank, world)
+        ok = ok and band % 16 == 0 and 0 <= r0 <= r1 <= hp
     q.put(ok)
     dist.destroy_process_group()
 

@@ -573,3 +573,51 @@ def test_iterdenoise_no_lut_and_out_of_range_on_device(Y, lut_table):
         np.testing.assert_allclose(np.asarray(res["regs"][0]), np.asarray(ref["regs"][0]), rtol=TOL_EST)
         assert len(res["raw_dns"]) == len(ref["raw_dns"])
         assert float(np.abs(res["raw_dns"][0] - ref["raw_dns"][0]).max()) < TOL_ABS
+
+
+# ------------------------------------------------------------------ BASELINE configs[3]: 14-bit, noclip, low-light gain
+PIPE_C4 = dict(PIPE, full_dn=True)
+
+
+@pytest.mark.parametrize("ratio,wname", [(1, "smooth"), (100, "smooth"), (100, "mix")])
+def test_c4_frame_golden(Y, golden, ratio, wname):
+    """Whole-frame (`full_dn`) two-round IterDenoise with scale = (16383-512)/ratio != wp-bl, unclipped input, against goldens
+    produced by the unmodified reference (tests/golden/make_golden_c4.py); SIDD_256 = True like the shipped driver."""
+    from test_oracle_golden import c4_frame, c4_weights
+    g = golden("c4_frame")
+    H, W = int(g["H"]), int(g["W"])
+    noisy = c4_frame(ratio, H, W)
+    p = {"wp": 16383, "bl": 512, "ratio": ratio, "gain": 1, "sigma": 0, "scale": (16383 - 512) / ratio}
+    drv = Y.YOND_SIDD(ARCHS["gru"], dict(PIPE_C4, sidd_256=True), state_dict=c4_weights(wname))
+    drv.engine.max_value = 4.0  # unclipped data: room in the fallback bias tables
+    res = drv.IterDenoise({"lr": noisy, "name": "x"}, {"p": dict(p), "img_id": 0})
+    tag = f"r{ratio}_{wname}"
+    assert len(res["raw_dns"]) == 2
+    regs = g[f"{tag}_regs"]
+    np.testing.assert_allclose(np.asarray(res["regs"][0]), regs[0], rtol=TOL_EST)
+    np.testing.assert_allclose(np.asarray(res["regs"][1]), regs[1], rtol=5e-3)  # a function of OUR round-1 output (bf16 conv stack)
+    for i in range(2):
+        assert float(np.abs(res["raw_dns"][i][::4, ::8] - g[f"{tag}_dn{i}_sub"]).max()) < TOL_ABS, (tag, i)
+
+
+def test_c4_full_size_frame_vs_oracle(Y, lut_table):
+    """6000 x 4000 (24 MP), 14-bit, ratio 100, unclipped: estimate + VST + network + inverse, two rounds, vs the oracle's
+    fp32 path (round 2 with the plain-frame collab estimate: 3000 packed columns are not divisible by 32)."""
+    from test_oracle_golden import c4_weights
+    rng = np.random.default_rng(77)
+    H, W, ratio = 4000, 6000, 100
+    clean = O.synth_clean_smooth(rng, H, W)
+    noisy = O.synth_noisy(rng, clean, 2.2 * ratio, 3.1 * ratio, scale=16383.0 - 512.0, clip=False)
+    p = {"wp": 16383, "bl": 512, "ratio": ratio, "gain": 1, "sigma": 0, "scale": (16383 - 512) / ratio}
+    sd = c4_weights("mix")
+    drv = Y.YOND_SIDD(ARCHS["gru"], PIPE_C4, state_dict=sd)
+    drv.engine.max_value = 4.0
+    res = drv.IterDenoise({"lr": noisy, "name": "x"}, {"p": dict(p), "img_id": 0})
+    ref = O.IterDenoise(ARCHS["gru"], sd, noisy, dict(p), PIPE_C4, biaslut=O.BiasLUT(lut_table), sidd_256=False)
+    assert len(res["raw_dns"]) == len(ref["raw_dns"]) == 2
+    np.testing.assert_allclose(np.asarray(res["regs"][0]), np.asarray(ref["regs"][0]), rtol=TOL_EST)
+    np.testing.assert_allclose(np.asarray(res["regs"][1]), np.asarray(ref["regs"][1]), rtol=5e-3)
+    for i in range(2):
+        assert res["raw_dns"][i].shape == (H, W)
+        assert float(np.abs(res["raw_dns"][i] - ref["raw_dns"][i]).max()) < TOL_ABS, i
+    assert abs(psnr(res["raw_dns"][1], clean) - psnr(ref["raw_dns"][1], clean)) < TOL_PSNR

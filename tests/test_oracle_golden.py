@@ -184,3 +184,37 @@ def test_rot_bayer_golden(golden):
         for rev in (0, 1):
             assert np.array_equal(O.rot_bayer(g["rot_in"], g[f"rot_pat{pi}"].tolist(), rev=bool(rev)), g[f"rot_out{pi}_{rev}"])
             assert np.array_equal(O.rot_bayer(g["rot_in"][0], g[f"rot_pat{pi}"].tolist(), rev=bool(rev)), g[f"rot2d_out{pi}_{rev}"])
+
+
+# ---- BASELINE configs[3]: 14-bit frame, noclip, low-light gain, whole-frame denoise (full_dn), two rounds ----
+ARCH_GRU = ARCHS["gru"]
+PIPE_C4 = {"k": 29, "full_dn": True, "vst_type": "exact", "bias_corr": "pre", "iter": "iter", "max_iter": 1}
+
+
+def c4_frame(ratio, H, W):
+    """The frame make_golden_c4.py fed to the reference, regenerated from its seed."""
+    rng = np.random.default_rng(4000 + ratio)
+    clean = O.synth_clean_smooth(rng, H, W)
+    return O.synth_noisy(rng, clean, 2.2 * ratio, 3.1 * ratio, scale=16383.0 - 512.0, clip=False)
+
+
+def c4_weights(name):
+    sm = O.smoother_state_dict(ARCH_GRU)
+    if name == "smooth":
+        return sm
+    rnd = O.init_state_dict(ARCH_GRU, seed=0)
+    return {k: sm[k] + 0.25 * rnd[k] for k in rnd}
+
+
+@pytest.mark.parametrize("ratio,wname", [(1, "smooth"), (100, "smooth"), (100, "mix")])
+def test_iterdenoise_c4_frame(golden, lut_table, ratio, wname):
+    g = golden("c4_frame")
+    H, W = int(g["H"]), int(g["W"])
+    noisy = c4_frame(ratio, H, W)
+    p = {"wp": 16383, "bl": 512, "ratio": ratio, "gain": 1, "sigma": 0, "scale": (16383 - 512) / ratio}
+    res = O.IterDenoise(ARCH_GRU, c4_weights(wname), noisy, p, PIPE_C4, biaslut=O.BiasLUT(lut_table))
+    tag = f"r{ratio}_{wname}"
+    assert len(res["raw_dns"]) == int(g[f"{tag}_nrounds"]) == 2
+    np.testing.assert_allclose(np.array([np.asarray(r, np.float64) for r in res["regs"]]), g[f"{tag}_regs"], rtol=1e-6)
+    for i, dn in enumerate(res["raw_dns"]):
+        assert float(np.abs(dn[::4, ::8] - g[f"{tag}_dn{i}_sub"]).max()) < 3e-6

@@ -28,6 +28,8 @@ SIGNATURES = {
     "yond_last_error": (C.c_char_p, []),
     "yond_version": (_I, []),
     "yond_launch_count": (_U64, []),
+    "yond_prof_enable": (_I, [_I]),
+    "yond_prof_read": (_I, [C.c_char_p, _SZ, _I]),
     "yond_pack": (_I, [_P, _P, _I, _I, _I, _P]),
     "yond_unpack": (_I, [_P, _P, _I, _I, _I, _P]),
     "yond_rot90": (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -112,6 +114,18 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prof_enable(on=True):
+    check(load().yond_prof_enable(int(bool(on))))
+
+
+def prof_read(reset=True):
+    """{stage: {scopes, ms, bytes, flops}} accumulated by the library's live stage profiler."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(load().yond_prof_read(buf, len(buf), int(bool(reset))))
+    return json.loads(buf.value.decode())
 
 
 def launch_count():

@@ -36,6 +36,17 @@ void yond_count_launch(int n = 1);
     if (!(cond)) return yond_set_error(YOND_ERR_INVALID, __VA_ARGS__);                               \
   } while (0)
 
+// Library-wide stage profiler (bench.py's live per-kernel roofline): while enabled (yond_prof_enable), a scope brackets
+// the launches issued during its lifetime with CUDA events on the launching stream and books them under `name` together
+// with the ALGORITHMIC bytes / FLOPs the caller states for them.  Disabled: one relaxed atomic load.
+struct YondProfScope {
+  int slot;
+  cudaStream_t stream;
+  void* end_event;
+  YondProfScope(const char* name, cudaStream_t s, double bytes, double flops = 0.0);
+  ~YondProfScope();
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

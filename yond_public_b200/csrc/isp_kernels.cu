@@ -164,7 +164,11 @@ __device__ __forceinline__ VstConst load_const(const yond_vst_params& q) {
   return c;
 }
 __device__ __forceinline__ float vst_f(float x, const VstConst& c) {
-  return c.two_over_K * sqrtf(fmaxf(fmaf(c.K, x, c.c0), 0.f));
+  // sqrt.approx: 1 ulp (2^-23 relative) instead of correctly rounded — far below the 2e-3 output budget, a third of the
+  // instructions of the IEEE sequence; the function-level VST (vst_elem_kernel) keeps sqrtf
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(fmaf(c.K, x, c.c0), 0.f)));
+  return c.two_over_K * r;
 }
 // Foi's closed-form bias (utils/isp_algos.py:84-96), used beyond the table like the reference does (:228-230).
 __device__ __forceinline__ float close_form_bias_f(float x, const VstConst& c) {
@@ -337,14 +341,13 @@ __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict
   float4* zo = reinterpret_cast<float4*>(z) + (size_t)b * hp * wp;
   const int npix = hp * wp;
   float vmax = 0.f;
-  const int base = blockIdx.x * (kBlock * kFwdPix) + threadIdx.x;
-#pragma unroll 4
-  for (int it = 0; it < kFwdPix; ++it) {
-    const int idx = base + it * kBlock;
-    if (idx >= npix) break;
-    const int i = idx / wp, j = idx - i * wp;
-    const int si = reflect101(i - pt, h), sj = reflect101(j - pl, w);
-    const float* r0 = frame + (size_t)(2 * si) * W + 2 * sj;
+  int idx = blockIdx.x * (kBlock * kFwdPix) + threadIdx.x;
+  int i = idx / wp, j = idx - i * wp;
+  // the padding is smaller than the frame (checked by the launcher): one reflection per side
+  auto refl = [](int t, int n) { t = t < 0 ? -t : t; return t >= n ? 2 * (n - 1) - t : t; };
+#pragma unroll 1
+  for (int it = 0; it < kFwdPix && idx < npix; ++it) {
+    const float* r0 = frame + (size_t)(2 * refl(i - pt, h)) * W + 2 * refl(j - pl, w);
     const float2 a = ldg_stream_f2(reinterpret_cast<const float2*>(r0));
     const float2 d = ldg_stream_f2(reinterpret_cast<const float2*>(r0 + W));
     float v[4] = {a.x, a.y, d.x, d.y};
@@ -372,6 +375,12 @@ __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict
       vmax = fmaxf(vmax, v[k]);
     }
     zo[idx] = make_float4(v[0], v[1], v[2], v[3]);
+    idx += kBlock;
+    j += kBlock;
+    while (j >= wp) {
+      j -= wp;
+      ++i;
+    }
   }
   block_max_to(vmax, ub + b);
 }
@@ -464,6 +473,7 @@ int yond_pack(const float* bayer, float* rggb, int B, int H, int W, void* stream
   YOND_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "yond_pack: H,W must be even (got %d,%d)", H, W);
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (W % 4 == 0) && ((uintptr_t)bayer % 16 == 0) && ((uintptr_t)rggb % 16 == 0);
+  YondProfScope prof("pack", s, 8.0 * (double)B * H * W);
   if (vec) pack_kernel<<<grid_for((size_t)B * (H / 2) * (W / 4)), kBlock, 0, s>>>(bayer, rggb, B, H, W);
   else pack_kernel_scalar<<<grid_for((size_t)B * (H / 2) * (W / 2)), kBlock, 0, s>>>(bayer, rggb, B, H, W);
   YOND_LAUNCH_CHECK();
@@ -497,6 +507,7 @@ int yond_pack_raw(const uint16_t* raw, float* out, int B, int H, int W, const in
     q.denom[c] = white - black4[c];  // float32 subtraction, like `white_point - black_level` on a float32 array
   }
   YOND_REQUIRE(seen == 15, "yond_pack_raw: raw_pattern must place R, G1, B, G2 on four distinct cell positions");
+  YondProfScope prof("pack_raw", (cudaStream_t)stream, 6.0 * (double)B * H * W);
   if (W % 4 == 0 && (uintptr_t)raw % 8 == 0)
     pack_raw_kernel<2><<<grid_for((size_t)B * (H / 2) * (W / 4)), kBlock, 0, (cudaStream_t)stream>>>(raw, out, B, H, W, q, clip, layout);
   else
@@ -585,6 +596,7 @@ static int launch_fwd(bool vst, const float* bayer, float* z, float* ub, int B, 
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] { attr_err = cudaFuncSetAttribute(vst_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (attr_err != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(vst_fwd_kernel) failed: %s", cudaGetErrorString(attr_err));
+    YondProfScope prof("vst_fwd", s, 8.0 * (double)B * H * W);  // 4 R (Bayer f32) + 4 W (z f32) per Bayer pixel
     vst_fwd_kernel<true><<<grid, kBlock, smem, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, params, rows, xnodes, row_stride);
   } else {
     vst_fwd_kernel<false><<<grid, kBlock, 0, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, nullptr, nullptr, nullptr, 0);
@@ -613,6 +625,7 @@ static int launch_inv(bool vst, const float* y, float* bayer, int B, int H, int 
   if (gx > 65535) gx = 65535;
   dim3 grid(gx, B);
   cudaStream_t s = (cudaStream_t)stream;
+  YondProfScope prof(vst ? "vst_inv" : "crop_unpack", s, 8.0 * (double)B * H * W);
   if (vst) vst_inv_kernel<true><<<grid, kBlock, 0, s>>>(y, bayer, H, W, pl, pt, hp, wp, params, clip01, place);
   else vst_inv_kernel<false><<<grid, kBlock, 0, s>>>(y, bayer, H, W, pl, pt, hp, wp, nullptr, 0, place);
   YOND_LAUNCH_CHECK();

@@ -415,6 +415,8 @@ inline int cap_grid(size_t blocks) {
 int head_conv_launch(const float* z, const float* ub, const float* w, const float* bias, int B, int H, int W, int nf,
                      float slope, bf16* out0, bf16* out1, cudaStream_t s) {
   const size_t npix = (size_t)B * H * W;
+  // per packed pixel: 16 B read (f32 x 4) + nf bf16 written once or twice (x and SiLU(x))
+  YondProfScope prof("head_conv (4->nf, 3x3)", s, (double)npix * (16.0 + 2.0 * nf * (out1 ? 2 : 1)), 2.0 * 36.0 * nf * (double)npix);
   if (nf == 32) {
     const size_t tiles = (size_t)B * ((H + kHeadTH - 1) / kHeadTH) * ((W + kHeadTW - 1) / kHeadTW);
     const size_t resident = (size_t)yond_num_sms() * 2;  // persistent: two blocks per SM walk the tiles
@@ -430,6 +432,7 @@ int head_conv_launch(const float* z, const float* ub, const float* w, const floa
 int tail_conv_launch(const bf16* act, const float* w, const float* bias, const float* z, const float* ub, int res, int B,
                      int H, int W, int nf, float* y, cudaStream_t s) {
   const size_t npix = (size_t)B * H * W;
+  YondProfScope prof("tail_conv (nf->4, 1x1, +x, *ub)", s, (double)npix * (2.0 * nf + 16.0 + 16.0), 2.0 * 4.0 * nf * (double)npix);
   tail_conv_kernel<<<cap_grid((npix + 255) / 256), 256, (size_t)(nf * 4 + 4) * sizeof(float), s>>>(
       act, w, bias, z, ub, res, npix, (size_t)H * W, nf, y);
   YOND_LAUNCH_CHECK();

@@ -45,9 +45,18 @@ struct BoxSrc {
   int imgs_per_seg;
   int mosaic_blocks;     // > 0: box-filter image b is block b % n of mosaic b / n (mosaic layout, blocks as separate images)
 };
-template <bool kSq, int kCols, bool kBayer>  // kCols = 256, or 160 when the whole row plus both halos fits (SIDD blocks: 128 + 28)
+// BORDER_REFLECT_101 for an index at most one image away from the valid range (the filter radius is smaller than the image)
+__device__ __forceinline__ int reflect_once(int i, int n) {
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * (n - 1) - i : i;
+}
+// kNarrow: images no wider than half a block (SIDD blocks: 128 packed pixels) — a block then holds 256 / w WHOLE images side
+// by side, every thread is a real column (no halo threads), and the reflected border columns are taken from the same
+// prefix array: sum over [c-r, c+r] with reflection = P[min(c+r, w-1)] - P[c-r-1] + (P[r-c] - P[0]) on the left edge and
+// + (P[w-2] - P[2(w-1)-(c+r)-1]) on the right edge.
+template <bool kSq, int kCols, bool kBayer, bool kNarrow>  // kCols = 256, or 160 when a whole row plus both halos fits
 __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, float4* __restrict__ out0,
-                                                                float4* __restrict__ out1, int h, int w, int k, int op,
+                                                                float4* __restrict__ out1, int B, int h, int w, int k, int op,
                                                                 int rows_per_strip, const float4* __restrict__ aux,
                                                                 float4* __restrict__ out2) {
   constexpr int NQ = kSq ? 8 : 4;
@@ -57,10 +66,22 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
   const int r = k / 2;
   const int outc = kCols - 2 * r;
   const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
-  const bool colthread = c < kCols;
-  const int b = blockIdx.z;
-  const int col_out = blockIdx.x * outc + (c - r);          // image column this thread's window is centred on
-  const int col_src = reflect101(col_out, w);               // BORDER_REFLECT_101
+  int b, col_out, col_src, img0 = 0;
+  bool colthread, writer;
+  if (kNarrow) {
+    const int ipb = kCols / w, il = c / w;  // images per block, this thread's image inside the block
+    b = blockIdx.z * ipb + il;
+    col_out = col_src = c - il * w;
+    img0 = il * w;                           // first column of this image in the block's prefix array
+    colthread = writer = il < ipb && b < B;
+    if (!colthread) b = B - 1;
+  } else {
+    b = blockIdx.z;
+    col_out = blockIdx.x * outc + (c - r);          // image column this thread's window is centred on
+    col_src = reflect101(col_out, w);               // BORDER_REFLECT_101
+    colthread = c < kCols;
+    writer = (c >= r) && (c < r + outc) && (col_out < w);
+  }
   const int i0 = blockIdx.y * rows_per_strip;
   const int i1 = min(h, i0 + rows_per_strip);
   const float* colbase;
@@ -72,7 +93,7 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
   } else {
     colbase = src.base + (size_t)b * src.img_stride + 4 * (size_t)col_src;
   }
-  const size_t row_pitch = kBayer ? 2 * (size_t)src.row_len : (size_t)src.row_len;
+  const uint32_t row_pitch = kBayer ? 2u * (uint32_t)src.row_len : (uint32_t)src.row_len;  // an image stays below 2^32 floats
   float vmax = 0.f;
   double s[NQ];
 #pragma unroll
@@ -85,7 +106,7 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
     }
   };
   auto load = [&](int i) {
-    const float* p = colbase + (size_t)reflect101(i, h) * row_pitch;
+    const float* p = colbase + (uint32_t)reflect_once(i, h) * row_pitch;
     float4 v;
     if (kBayer) {
       const float2 a = __ldg(reinterpret_cast<const float2*>(p)), d = __ldg(reinterpret_cast<const float2*>(p + src.row_len));
@@ -102,15 +123,29 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
   // stdfilt (isp_algos.py:236-241): float32 square of the blurred image, float32 difference, sqrt; explicit
   // round-to-nearest mul/sub: an FMA contraction would skip the float32 rounding of mean^2 the reference has
   auto sd = [](float e2, float e1) { return sqrtf(fmaxf(__fsub_rn(e2, __fmul_rn(e1, e1)), 0.f)); };
-  const bool writer = (c >= r) && (c < r + outc) && (col_out < w);
-  const int my_idx = c + c / CH;
-  const int hi_idx = (c + r) + (c + r) / CH;
-  const int lo_col = c - r - 1;
-  const int lo_idx = lo_col >= 0 ? lo_col + lo_col / CH : 0;
+  auto pidx = [](int col) { return col + col / CH; };  // position of block column `col` in the padded prefix row
+  const int my_idx = pidx(c);
+  // window = P[hi] - P[lo] (+ P[e1] - P[e0] for the reflected part of a border column in the narrow layout); index -1 = "0"
+  int hi_idx, lo_idx, e1_idx = -1, e0_idx = -1;
+  if (kNarrow) {
+    const int hc = min(col_out + r, w - 1), lc = col_out - r - 1;
+    hi_idx = pidx(img0 + hc);
+    lo_idx = lc >= 0 ? pidx(img0 + lc) : (img0 > 0 ? pidx(img0 - 1) : -1);
+    if (col_out - r < 0) {                 // columns -1 .. col-r reflect onto 1 .. r-col
+      e1_idx = pidx(img0 + (r - col_out));
+      e0_idx = pidx(img0);
+    } else if (col_out + r > w - 1) {      // columns w .. col+r reflect onto w-2 .. 2(w-1)-(col+r)
+      e1_idx = pidx(img0 + w - 2);
+      e0_idx = pidx(img0 + 2 * (w - 1) - (col_out + r) - 1);
+    }
+  } else {
+    hi_idx = pidx(c + r);
+    lo_idx = c - r - 1 >= 0 ? pidx(c - r - 1) : -1;
+  }
+  // rows i+1 (entering / leaving the window) are in flight while row i is scanned
+  float4 vin = make_float4(0.f, 0.f, 0.f, 0.f), vout = vin;
   for (int i = i0; i < i1; ++i) {
     double(*Sb)[PITCH] = S[i & 1];
-    // next row's two pixels: in flight while this row is scanned
-    float4 vin = make_float4(0.f, 0.f, 0.f, 0.f), vout = vin;
     const bool more = colthread && (i + 1 < i1);
     if (more) {
       vin = load(i + 1 + r);
@@ -144,7 +179,10 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
     if (writer) {
       double a[NQ];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) a[q] = Sb[q][hi_idx] - (lo_col >= 0 ? Sb[q][lo_idx] : 0.0);
+      for (int q = 0; q < NQ; ++q) {
+        a[q] = Sb[q][hi_idx] - (lo_idx >= 0 ? Sb[q][lo_idx] : 0.0);
+        if (kNarrow && e1_idx >= 0) a[q] += Sb[q][e1_idx] - Sb[q][e0_idx];
+      }
       const size_t o = ((size_t)b * h + i) * w + col_out;
       const float4 m = make_float4((float)(a[0] * inv), (float)(a[1] * inv), (float)(a[2] * inv), (float)(a[3] * inv));
       if (!kSq || op == OP_MEAN) {
@@ -175,12 +213,19 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
     // the other S buffer is written next; this one is rewritten two rows later, after the next row's barriers
   }
   if (src.seg_max) {  // values are >= 0: integer order of the bits == float order
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<int*>(src.seg_max + b / src.imgs_per_seg), __float_as_int(vmax));
+    if (!colthread) vmax = 0.f;
+    if (kNarrow) {    // a warp may straddle two images
+      if (vmax > 0.f) atomicMax(reinterpret_cast<int*>(src.seg_max + b / src.imgs_per_seg), __float_as_int(vmax));
+    } else {
+      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<int*>(src.seg_max + b / src.imgs_per_seg), __float_as_int(vmax));
+    }
   }
 }
 
 // ------------------------------------------------------------------ exact order statistics (radix select)
+// Three counting passes over the data (11 + 11 + 10 key bits), each followed by a one-block-per-segment "select" kernel
+// that turns the histogram into the bucket of every queried rank (block prefix sum + binary search).
 __device__ __forceinline__ uint32_t f2key(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -191,91 +236,143 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 }
 
 constexpr int kMaxRanks = 64;
+constexpr int kBins = 1001;  // get_threshold: int(clip(mean,0,1)*1000) -> 1001 bins (YOND_SIDD.py:26,38-41)
 struct SelectWork {
-  unsigned long long hist0[2048];
-  unsigned long long hist1[kMaxRanks][2048];
-  unsigned long long hist2[kMaxRanks][1024];
-  int slot1_of_prefix[2048];             // top-11-bit prefix -> slot (or -1)
-  int slot2_of[kMaxRanks][2048];         // (slot1, middle 11 bits) -> slot2 (or -1)
-  unsigned long long rank_in[kMaxRanks];  // residual rank of each query inside its current bucket
+  unsigned int hist0[2048];
+  unsigned int hist1[kMaxRanks][2048];
+  unsigned int hist2[kMaxRanks][1024];
+  unsigned int rank_in[kMaxRanks];          // residual rank of each query inside its current bucket
+  int slot1_of_prefix[2048];                // top-11-bit prefix -> slot (or -1)
   int q_slot1[kMaxRanks], q_slot2[kMaxRanks];
   uint32_t q_prefix[kMaxRanks];
-  int nslot1, nslot2;
-  int nq_live;  // number of queries (q_* entries in use)
+  int nslot1, nslot2, nq_live;
+  int level;  // 1 after select0 (q_prefix = 11 bits), 2 after select1 (22 bits)
 };
 
-// Streaming loops keep kUnroll 128-bit loads in flight per thread (the kernels are latency-bound otherwise: one float4 per
-// thread and a dependent shared-memory atomic leave ~16 KB in flight per SM against the ~40 KB Little's law asks for).
+// Streaming loops keep kUnroll 128-bit loads in flight per thread (one float4 per thread and a dependent shared-memory
+// atomic leave ~16 KB in flight per SM against the ~40 KB Little's law asks for).
 constexpr int kUnroll = 4;
-#define YOND_STREAM4(d4, n4, ...)                                                                         \
-  {                                                                                                        \
-    const size_t stride_ = (size_t)gridDim.x * blockDim.x;                                                 \
-    size_t i_ = blockIdx.x * (size_t)blockDim.x + threadIdx.x;                                             \
-    for (; i_ + (kUnroll - 1) * stride_ < (n4); i_ += kUnroll * stride_) {                                 \
-      float4 v_[kUnroll];                                                                                  \
-      _Pragma("unroll") for (int u_ = 0; u_ < kUnroll; ++u_) v_[u_] = ldg_stream_f4((d4) + i_ + u_ * stride_); \
-      _Pragma("unroll") for (int u_ = 0; u_ < kUnroll; ++u_) { const float4 v = v_[u_]; __VA_ARGS__ }             \
-    }                                                                                                      \
-    for (; i_ < (n4); i_ += stride_) { const float4 v = ldg_stream_f4((d4) + i_); __VA_ARGS__ }                   \
+template <typename F>
+__device__ __forceinline__ void stream_f4(const float4* __restrict__ d4, size_t n4, F&& body) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u] = ldg_stream_f4(d4 + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      body(v[u].x); body(v[u].y); body(v[u].z); body(v[u].w);
+    }
   }
+  for (; i < n4; i += stride) {
+    const float4 v = ldg_stream_f4(d4 + i);
+    body(v.x); body(v.y); body(v.z); body(v.w);
+  }
+}
 
-__global__ void __launch_bounds__(256) hist0_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
+// First level, optionally fused with the score3 bin pass (get_threshold 'score3', YOND_SIDD.py:34-43): npeaks[i] counts
+// the `mean` bins that hold a pixel with lap <= ths[i], i.e. the bins whose SMALLEST lap is <= ths[i] — so the pass only
+// needs the per-bin minimum of lap and does not depend on the thresholds: it rides along with the first histogram.
+template <bool kBinMin>
+__global__ void __launch_bounds__(256) hist0_kernel(const float* __restrict__ d, const float* __restrict__ mean, size_t n,
+                                                    SelectWork* wk, unsigned int* __restrict__ binmin) {
   d += (size_t)blockIdx.y * n;  // one segment (image) per blockIdx.y
-  wk += blockIdx.y;
+  if (wk) wk += blockIdx.y;
+  if (kBinMin) binmin += (size_t)blockIdx.y * 1024;  // smallest lap key per `mean` bin, ~0u = bin empty
   __shared__ unsigned int h[2048];
+  __shared__ unsigned int smin[kBinMin ? 1024 : 1];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
+  if (kBinMin)
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) smin[i] = ~0u;
   __syncthreads();
   const float4* d4 = reinterpret_cast<const float4*>(d);  // segments hold 4-channel pixels: n % 4 == 0, 16-byte aligned
-  YOND_STREAM4(d4, n / 4, {
-    atomicAdd(&h[f2key(v.x) >> 21], 1u);
-    atomicAdd(&h[f2key(v.y) >> 21], 1u);
-    atomicAdd(&h[f2key(v.z) >> 21], 1u);
-    atomicAdd(&h[f2key(v.w) >> 21], 1u);
-  })
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
-    if (h[i]) atomicAdd(&wk->hist0[i], (unsigned long long)h[i]);
-}
-// Warp-cooperative search of the bin holding rank r in a histogram: returns the bin, *before = #elements below it.
-__device__ __forceinline__ int warp_find_bin(const unsigned long long* __restrict__ hist, int nbins, unsigned long long r,
-                                             unsigned long long* before) {
-  const int lane = threadIdx.x & 31;
-  unsigned long long running = 0;
-  for (int base = 0; base < nbins; base += 32) {
-    const unsigned long long h = hist[base + lane];
-    unsigned long long incl = h;
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+  if (!kBinMin) {
+    stream_f4(d4, n / 4, [&](float e) { atomicAdd(&h[f2key(e) >> 21], 1u); });
+  } else {
+    const float4* m4 = reinterpret_cast<const float4*>(mean + (size_t)blockIdx.y * n);
+    auto one = [&](float l, float m) {
+      const uint32_t k = f2key(l);
+      if (wk) atomicAdd(&h[k >> 21], 1u);
+      const int bin = (int)__fmul_rn(fminf(fmaxf(m, 0.f), 1.f), 1000.f);
+      if (smin[bin] > k) atomicMin(&smin[bin], k);
+    };
+    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {  // two pixel quads of each map (64 B) in flight per thread
+      const float4 l0 = ldg_stream_f4(d4 + i), m0 = ldg_stream_f4(m4 + i);
+      const float4 l1 = ldg_stream_f4(d4 + i + stride), m1 = ldg_stream_f4(m4 + i + stride);
+      one(l0.x, m0.x); one(l0.y, m0.y); one(l0.z, m0.z); one(l0.w, m0.w);
+      one(l1.x, m1.x); one(l1.y, m1.y); one(l1.z, m1.z); one(l1.w, m1.w);
     }
-    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
-    if (r < running + total) {
-      const unsigned int m = __ballot_sync(0xffffffffu, running + incl > r);
-      const int l = __ffs(m) - 1;
-      const unsigned long long excl = __shfl_sync(0xffffffffu, incl - h, l);
-      *before = running + excl;
-      return base + l;
+    for (; i < n4; i += stride) {
+      const float4 l0 = ldg_stream_f4(d4 + i), m0 = ldg_stream_f4(m4 + i);
+      one(l0.x, m0.x); one(l0.y, m0.y); one(l0.z, m0.z); one(l0.w, m0.w);
     }
-    running += total;
   }
-  *before = running - hist[nbins - 1];
-  return nbins - 1;
+  __syncthreads();
+  if (wk)
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+      if (h[i]) atomicAdd(&wk->hist0[i], h[i]);
+  if (kBinMin)
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x)
+      if (smin[i] < binmin[i]) atomicMin(&binmin[i], smin[i]);  // plain read first: most blocks have nothing new
 }
 
-// One block of 32 warps; warp w resolves queries w, w+32.  Thread 0 then assigns slots (deduplicated buckets).
+// Block-wide inclusive prefix sum of a 2048-entry (or shorter) histogram into shared memory; blockDim.x = 1024, each
+// thread owns two consecutive entries.
+__device__ __forceinline__ void block_prefix(const unsigned int* __restrict__ hist, int nbins, unsigned int* __restrict__ pre,
+                                             unsigned int* __restrict__ wsum) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned int a = 2 * t < nbins ? hist[2 * t] : 0u, b = 2 * t + 1 < nbins ? hist[2 * t + 1] : 0u;
+  unsigned int incl = a + b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned int w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  const unsigned int off = warp ? wsum[warp - 1] : 0u;
+  if (2 * t < nbins) pre[2 * t] = off + incl - b;
+  if (2 * t + 1 < nbins) pre[2 * t + 1] = off + incl;
+  __syncthreads();
+}
+// smallest bin with pre[bin] > r (pre inclusive, ascending); *before = elements below that bin
+__device__ __forceinline__ int find_bin(const unsigned int* __restrict__ pre, int nbins, unsigned int r, unsigned int* before) {
+  int lo = 0, hi = nbins - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (pre[mid] > r) hi = mid; else lo = mid + 1;
+  }
+  *before = lo ? pre[lo - 1] : 0u;
+  return lo;
+}
+
 __global__ void __launch_bounds__(1024) select0_kernel(SelectWork* wk, const unsigned long long* __restrict__ ranks, int nranks) {
   wk += blockIdx.x;
+  __shared__ unsigned int pre[2048];
+  __shared__ unsigned int wsum[32];
   __shared__ int s_bin[kMaxRanks];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) wk->slot1_of_prefix[i] = -1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int q = warp; q < nranks; q += 32) {
-    unsigned long long before;
-    const int bin = warp_find_bin(wk->hist0, 2048, ranks[q], &before);
-    if (lane == 0) {
-      s_bin[q] = bin;
-      wk->q_prefix[q] = (uint32_t)bin;
-      wk->rank_in[q] = ranks[q] - before;
-    }
+  block_prefix(wk->hist0, 2048, pre, wsum);
+  if ((int)threadIdx.x < nranks) {
+    const int q = threadIdx.x;
+    unsigned int before;
+    const int bin = find_bin(pre, 2048, (unsigned int)ranks[q], &before);
+    s_bin[q] = bin;
+    wk->q_prefix[q] = (uint32_t)bin;
+    wk->rank_in[q] = (unsigned int)ranks[q] - before;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -286,13 +383,23 @@ __global__ void __launch_bounds__(1024) select0_kernel(SelectWork* wk, const uns
       wk->q_slot1[q] = wk->slot1_of_prefix[bin];
     }
     wk->nslot1 = ns;
+    wk->nq_live = nranks;
+    wk->level = 1;
   }
 }
 // Second radix level.  The queried ranks (percentiles 5..95) sit in a handful of top-11-bit buckets that together
 // hold most of the data, so nearly every element increments a counter: the counters of the first kHist1Slots buckets
-// are privatised in shared memory (32-bit, flushed once per block), later buckets fall back to global atomics.
+// (slots are handed out in rank order, so these are the dense ones) are privatised in shared memory and flushed once per
+// block; later buckets fall back to global atomics.  The pass is bound by the shared-memory atomic rate (one per element).
 constexpr int kHist1Slots = 16;
 constexpr int kHist1Threads = 1024;
+__device__ __forceinline__ void load_slot_table(const SelectWork* wk, signed char* s1tab) {
+  // prefix -> slot table from the query list (a handful of entries), not from the 2048-entry global table
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<unsigned int*>(s1tab)[i] = 0xffffffffu;
+  __syncthreads();
+  const int nq = wk->nq_live;
+  if ((int)threadIdx.x < nq) s1tab[wk->q_prefix[threadIdx.x] >> ((wk->level - 1) * 11)] = (signed char)wk->q_slot1[threadIdx.x];
+}
 __global__ void __launch_bounds__(kHist1Threads) hist1_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
   extern __shared__ unsigned int hs[];  // [kHist1Slots][2048] counters, then the 2048-entry prefix -> slot table (int8)
   signed char* s1tab = reinterpret_cast<signed char*>(hs + kHist1Slots * 2048);
@@ -300,161 +407,185 @@ __global__ void __launch_bounds__(kHist1Threads) hist1_kernel(const float* __res
   wk += blockIdx.y;
   const int nsh = min(wk->nslot1, kHist1Slots);
   for (int i = threadIdx.x; i < nsh * 2048; i += blockDim.x) hs[i] = 0u;
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s1tab[i] = (signed char)wk->slot1_of_prefix[i];  // slots < kMaxRanks = 64
+  load_slot_table(wk, s1tab);
   __syncthreads();
-  const float4* d4 = reinterpret_cast<const float4*>(d);
-  YOND_STREAM4(d4, n / 4, {
-    const float e[4] = {v.x, v.y, v.z, v.w};
-_Pragma("unroll")
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t k = f2key(e[j]);
-      const int s = s1tab[k >> 21];
-      if (s >= 0) {
-        const uint32_t mid = (k >> 10) & 2047u;
-        if (s < kHist1Slots) atomicAdd(&hs[s * 2048 + mid], 1u);
-        else atomicAdd(&wk->hist1[s][mid], 1ull);
-      }
+  stream_f4(reinterpret_cast<const float4*>(d), n / 4, [&](float e) {
+    const uint32_t k = f2key(e);
+    const int s = s1tab[k >> 21];
+    if (s >= 0) {
+      const uint32_t mid = (k >> 10) & 2047u;
+      if (s < kHist1Slots) atomicAdd(&hs[s * 2048 + mid], 1u);
+      else atomicAdd(&wk->hist1[s][mid], 1u);
     }
-  })
+  });
   __syncthreads();
   for (int i = threadIdx.x; i < nsh * 2048; i += blockDim.x)
-    if (hs[i]) atomicAdd(&wk->hist1[i >> 11][i & 2047], (unsigned long long)hs[i]);
+    if (hs[i]) atomicAdd(&wk->hist1[i >> 11][i & 2047], hs[i]);
 }
+// select1 / select2: one WARP per distinct bucket — lane-local sums of the bucket's histogram (64 / 32 entries per lane), a
+// warp scan of the lane totals, then the lane that holds a query's rank walks its own entries.
 __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nranks) {
   wk += blockIdx.x;
-  __shared__ int s_bin[kMaxRanks];
-  for (int i = threadIdx.x; i < kMaxRanks * 2048; i += blockDim.x) (&wk->slot2_of[0][0])[i] = -1;
+  __shared__ int s_bin[kMaxRanks], s_s1[kMaxRanks], s_s2[kMaxRanks];
+  __shared__ unsigned int s_rank[kMaxRanks];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int q = warp; q < nranks; q += 32) {
-    unsigned long long before;
-    const int bin = warp_find_bin(wk->hist1[wk->q_slot1[q]], 2048, wk->rank_in[q], &before);
-    __syncwarp();
-    if (lane == 0) {
-      s_bin[q] = bin;
-      wk->q_prefix[q] = (wk->q_prefix[q] << 11) | (uint32_t)bin;
-      wk->rank_in[q] -= before;
-    }
+  if ((int)threadIdx.x < nranks) {
+    s_s1[threadIdx.x] = wk->q_slot1[threadIdx.x];
+    s_rank[threadIdx.x] = wk->rank_in[threadIdx.x];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  const int ns1 = wk->nslot1;
+  extern __shared__ unsigned int stage[];  // [16 warps][2048 + 32]: entry e of a bucket sits at e + e / 64 (conflict-free lane rows)
+  for (int s0 = 0; s0 < ns1; s0 += 16) {
+    const int s1 = s0 + warp;
+    if (warp < 16 && s1 < ns1) {
+      const unsigned int* hist = wk->hist1[s1];
+      unsigned int* st = stage + warp * (2048 + 32);
+#pragma unroll 8
+      for (int j = 0; j < 64; ++j) st[j * 32 + lane + ((j * 32 + lane) >> 6)] = hist[j * 32 + lane];  // coalesced
+      __syncwarp();
+      const unsigned int* mine = st + lane * 65;
+      unsigned int tot = 0;
+#pragma unroll 8
+      for (int j = 0; j < 64; ++j) tot += mine[j];
+      unsigned int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const unsigned int lane_excl = incl - tot;
+      for (int q = 0; q < nranks; ++q) {
+        if (s_s1[q] != s1) continue;  // uniform across the warp
+        const unsigned int r = s_rank[q];
+        const unsigned int m = __ballot_sync(0xffffffffu, lane_excl <= r);
+        const int owner = 31 - __clz(m);
+        if (lane == owner) {
+          unsigned int run = lane_excl;
+          int j = 0;
+          for (; j < 63; ++j) {
+            const unsigned int v = mine[j];
+            if (run + v > r) break;
+            run += v;
+          }
+          const int bin = lane * 64 + j;
+          s_bin[q] = bin;
+          wk->q_prefix[q] = (wk->q_prefix[q] << 11) | (uint32_t)bin;
+          wk->rank_in[q] = r - run;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // queries sharing (bucket, bin) share a third-level histogram
     int ns = 0;
     for (int q = 0; q < nranks; ++q) {
-      const int s1 = wk->q_slot1[q], bin = s_bin[q];
-      if (wk->slot2_of[s1][bin] < 0) wk->slot2_of[s1][bin] = ns++;
-      wk->q_slot2[q] = wk->slot2_of[s1][bin];
+      int found = -1;
+      for (int p = 0; p < q && found < 0; ++p)
+        if (s_s1[p] == s_s1[q] && s_bin[p] == s_bin[q]) found = s_s2[p];
+      s_s2[q] = found >= 0 ? found : ns++;
+      wk->q_slot2[q] = s_s2[q];
     }
     wk->nslot2 = ns;
-    wk->nq_live = nranks;
+    wk->level = 2;
   }
 }
 // Third radix level.  Only elements whose upper 22 bits equal one of the <= 64 queried prefixes count (~0.2 % of the
-// data): the membership test runs against shared memory (prefix -> slot table + one 2048-bit map per slot), the hits
-// take the global slot2 lookup and a global atomic.
+// data): the membership test runs against shared memory (prefix -> slot table + one 2048-bit map per first-level slot),
+// a hit looks its slot up in the query list and takes a global atomic.
 __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
   __shared__ signed char s1tab[2048];
   __shared__ unsigned int bm[kMaxRanks * 64];
+  __shared__ uint32_t qpre[kMaxRanks];
+  __shared__ int qs2[kMaxRanks];
+  __shared__ int nq;
   d += (size_t)blockIdx.y * n;
   wk += blockIdx.y;
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s1tab[i] = (signed char)wk->slot1_of_prefix[i];
-  for (int i = threadIdx.x; i < kMaxRanks * 64; i += blockDim.x) bm[i] = 0u;
+  const int ns1 = wk->nslot1;
+  for (int i = threadIdx.x; i < ns1 * 64; i += blockDim.x) bm[i] = 0u;
+  if (threadIdx.x == 0) nq = wk->nq_live;
+  load_slot_table(wk, s1tab);
   __syncthreads();
-  if (threadIdx.x < kMaxRanks && wk->q_slot2[threadIdx.x] >= 0 && (int)threadIdx.x < wk->nq_live) {
+  if ((int)threadIdx.x < nq) {
     const uint32_t pre = wk->q_prefix[threadIdx.x];  // (top 11 bits << 11) | middle 11 bits
     const uint32_t mid = pre & 2047u;
+    qpre[threadIdx.x] = pre;
+    qs2[threadIdx.x] = wk->q_slot2[threadIdx.x];
     atomicOr(&bm[wk->q_slot1[threadIdx.x] * 64 + (mid >> 5)], 1u << (mid & 31u));
   }
   __syncthreads();
-  const float4* d4 = reinterpret_cast<const float4*>(d);
-  YOND_STREAM4(d4, n / 4, {
-    const float e[4] = {v.x, v.y, v.z, v.w};
-_Pragma("unroll")
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t k = f2key(e[j]);
-      const int s1 = s1tab[k >> 21];
-      if (s1 < 0) continue;
-      const uint32_t mid = (k >> 10) & 2047u;
-      if (!((bm[s1 * 64 + (mid >> 5)] >> (mid & 31u)) & 1u)) continue;
-      const int s2 = wk->slot2_of[s1][mid];
-      if (s2 >= 0) atomicAdd(&wk->hist2[s2][k & 1023u], 1ull);
-    }
-  })
+  stream_f4(reinterpret_cast<const float4*>(d), n / 4, [&](float e) {
+    const uint32_t k = f2key(e);
+    const int s1 = s1tab[k >> 21];
+    if (s1 < 0) return;
+    const uint32_t mid = (k >> 10) & 2047u;
+    if (!((bm[s1 * 64 + (mid >> 5)] >> (mid & 31u)) & 1u)) return;
+    const uint32_t p22 = k >> 10;
+    for (int q = 0; q < nq; ++q)
+      if (qpre[q] == p22) {
+        atomicAdd(&wk->hist2[qs2[q]][k & 1023u], 1u);
+        break;
+      }
+  });
 }
 __global__ void __launch_bounds__(1024) select2_kernel(SelectWork* wk, int nranks, float* __restrict__ out) {
   wk += blockIdx.x;
   out += (size_t)blockIdx.x * nranks;
+  __shared__ int s_s2[kMaxRanks];
+  if ((int)threadIdx.x < nranks) s_s2[threadIdx.x] = wk->q_slot2[threadIdx.x];
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int q = warp; q < nranks; q += 32) {
-    unsigned long long before;
-    const int bin = warp_find_bin(wk->hist2[wk->q_slot2[q]], 1024, wk->rank_in[q], &before);
-    if (lane == 0) out[q] = key2f((wk->q_prefix[q] << 10) | (uint32_t)bin);
+  const int ns2 = wk->nslot2;
+  for (int s2 = warp; s2 < ns2; s2 += 32) {
+    const unsigned int* hist = wk->hist2[s2];
+    unsigned int tot = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) tot += hist[lane * 32 + j];
+    unsigned int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned int lane_excl = incl - tot;
+    for (int q = 0; q < nranks; ++q) {
+      if (s_s2[q] != s2) continue;
+      const unsigned int r = wk->rank_in[q];
+      const unsigned int m = __ballot_sync(0xffffffffu, lane_excl <= r);
+      const int owner = 31 - __clz(m);
+      if (lane == owner) {
+        unsigned int run = lane_excl;
+        int j = 0;
+        for (; j < 31; ++j) {
+          const unsigned int v = hist[lane * 32 + j];
+          if (run + v > r) break;
+          run += v;
+        }
+        out[q] = key2f((wk->q_prefix[q] << 10) | (uint32_t)(lane * 32 + j));
+      }
+      __syncwarp();
+    }
   }
 }
 
 // ------------------------------------------------------------------ score3 bin occupancy
-// minj[bin] = smallest threshold index i such that some pixel with lap <= ths[i] falls in `bin`
-__global__ void __launch_bounds__(256) score3_kernel(const float* __restrict__ lap, const float* __restrict__ mean, size_t n,
-                                                     const double* __restrict__ ths, int nth, int* __restrict__ minj) {
-  lap += (size_t)blockIdx.y * n;
-  mean += (size_t)blockIdx.y * n;
-  ths += (size_t)blockIdx.y * nth;
-  minj += (size_t)blockIdx.y * 1001;
-  __shared__ int smin[1001];
-  __shared__ float sthf[32];
-  for (int i = threadIdx.x; i < 1001; i += blockDim.x) smin[i] = 0x7fffffff;
-  if (threadIdx.x < 32) {
-    // lap is float32: (double)l <= t  <=>  l <= the largest float32 not above t, so the comparison runs in float32
-    float f = __int_as_float(0x7f800000);  // +inf pads the table
-    if ((int)threadIdx.x < nth) {
-      const double t = ths[threadIdx.x];
-      f = __double2float_rn(t);
-      if ((double)f > t) f = nextafterf(f, -__int_as_float(0x7f800000));
-    }
-    sthf[threadIdx.x] = f;
-  }
-  __syncthreads();
-  const float4* l4 = reinterpret_cast<const float4*>(lap);
-  const float4* m4 = reinterpret_cast<const float4*>(mean);
-  auto visit = [&](const float4& lv, const float4& mv) {
-    const float le[4] = {lv.x, lv.y, lv.z, lv.w}, me[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float l = le[e];
-      // ths ascending: j = number of thresholds that do not admit this pixel = index of the first that does
-      int j = 0;
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) {
-        const int m = j + step;
-        if (m <= nth && !(l <= sthf[m - 1])) j = m;
-      }
-      if (j < nth) {
-        const int bin = (int)__fmul_rn(fminf(fmaxf(me[e], 0.f), 1.f), 1000.f);
-        if (smin[bin] > j) atomicMin(&smin[bin], j);
-      }
-    }
-  };
-  {
-    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    for (; i + stride < n4; i += 2 * stride) {  // two pixel quads (64 B) in flight per thread
-      const float4 l0 = ldg_stream_f4(l4 + i), m0 = ldg_stream_f4(m4 + i);
-      const float4 l1 = ldg_stream_f4(l4 + i + stride), m1 = ldg_stream_f4(m4 + i + stride);
-      visit(l0, m0);
-      visit(l1, m1);
-    }
-    for (; i < n4; i += stride) visit(ldg_stream_f4(l4 + i), ldg_stream_f4(m4 + i));
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 1001; i += blockDim.x)
-    if (smin[i] != 0x7fffffff) atomicMin(&minj[i], smin[i]);
-}
-__global__ void score3_count_kernel(const int* __restrict__ minj, int nth, int* __restrict__ npeaks) {
-  minj += (size_t)blockIdx.x * 1001;
+// npeaks[s][i] = #bins whose smallest lap is <= ths[s][i]  ((double)lap <= th, like the reference's float32 <= float64)
+__global__ void score3_count_kernel(const unsigned int* __restrict__ binmin, const double* __restrict__ ths, int nth,
+                                    int* __restrict__ npeaks) {
+  binmin += (size_t)blockIdx.x * 1024;
+  ths += (size_t)blockIdx.x * nth;
   npeaks += (size_t)blockIdx.x * nth;
-  __shared__ int cnt[32];
-  if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+  __shared__ int cnt[33];
+  if (threadIdx.x < 33) cnt[threadIdx.x] = 0;
   __syncthreads();
-  for (int b = threadIdx.x; b < 1001; b += blockDim.x) {
-    const int j = minj[b];
+  for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
+    const unsigned int k = binmin[b];
+    if (k == ~0u) continue;
+    const double l = (double)key2f(k);
+    int j = 0;
+    while (j < nth && !(l <= ths[j])) ++j;  // ths ascending: index of the first threshold that admits the bin
     if (j < nth) atomicAdd(&cnt[j], 1);
   }
   __syncthreads();
@@ -465,10 +596,6 @@ __global__ void score3_count_kernel(const int* __restrict__ minj, int nth, int* 
       npeaks[i] = c;
     }
   }
-}
-__global__ void fill_int_kernel(int* p, int n, int v) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
 }
 
 // ------------------------------------------------------------------ masked regression sums
@@ -633,25 +760,40 @@ BoxSrc packed_src(const float* x, int h, int w) {
 
 int box_pass(const BoxSrc& src, bool bayer, float* out0, float* out1, int B, int h, int w, int k, bool with_sq, int op,
              cudaStream_t s, const float* aux = nullptr, float* out2 = nullptr) {
-  const bool narrow = w + 2 * (k / 2) <= 160;
   static const int env_rows = getenv("YOND_BOX_ROWS") ? atoi(getenv("YOND_BOX_ROWS")) : 0;
+  static const int env_narrow = getenv("YOND_BOX_NARROW") ? atoi(getenv("YOND_BOX_NARROW")) : 1;
+  const int r = k / 2;
+  // narrow images (SIDD blocks): 256 / w whole images per block, no halo threads; needs a single reflection (r < w - 1)
+  const bool multi = env_narrow && 2 * w <= 256 && w >= 2 * r + 2;
+  const bool narrow = !multi && w + 2 * r <= 160;
   const int rows_per_strip = env_rows > 0 ? env_rows : 64;
   const int cols = narrow ? 160 : 256;
-  const int outc = cols - 2 * (k / 2);
+  const int outc = cols - 2 * r;
   dim3 g(ceil_div(w, outc), ceil_div(h, rows_per_strip), B);
+  if (multi) g = dim3(1, ceil_div(h, rows_per_strip), ceil_div(B, 256 / w));
+  YOND_REQUIRE(g.z <= 65535, "box filter: at most 65535 images per call");
   float4* o0 = reinterpret_cast<float4*>(out0);
   float4* o1 = reinterpret_cast<float4*>(out1);
   const float4* ax = reinterpret_cast<const float4*>(aux);
   float4* o2 = reinterpret_cast<float4*>(out2);
   const int opx = with_sq ? op : OP_MEAN;
-#define YOND_BOX(SQ, COLS, BAYER) box_fused_kernel<SQ, COLS, BAYER><<<g, kBoxThreads, 0, s>>>(src, o0, o1, h, w, k, opx, rows_per_strip, ax, o2)
+#define YOND_BOX(SQ, COLS, BAYER, NARROW) \
+  box_fused_kernel<SQ, COLS, BAYER, NARROW><<<g, kBoxThreads, 0, s>>>(src, o0, o1, B, h, w, k, opx, rows_per_strip, ax, o2)
+#define YOND_BOX_B(SQ, COLS, NARROW)                        \
+  do {                                                      \
+    if (bayer) YOND_BOX(SQ, COLS, true, NARROW);            \
+    else YOND_BOX(SQ, COLS, false, NARROW);                 \
+  } while (0)
   if (with_sq) {
-    if (narrow) { if (bayer) YOND_BOX(true, 160, true); else YOND_BOX(true, 160, false); }
-    else { if (bayer) YOND_BOX(true, 256, true); else YOND_BOX(true, 256, false); }
+    if (multi) YOND_BOX_B(true, 256, true);
+    else if (narrow) YOND_BOX_B(true, 160, false);
+    else YOND_BOX_B(true, 256, false);
   } else {
-    if (narrow) { if (bayer) YOND_BOX(false, 160, true); else YOND_BOX(false, 160, false); }
-    else { if (bayer) YOND_BOX(false, 256, true); else YOND_BOX(false, 256, false); }
+    if (multi) YOND_BOX_B(false, 256, true);
+    else if (narrow) YOND_BOX_B(false, 160, false);
+    else YOND_BOX_B(false, 256, false);
   }
+#undef YOND_BOX_B
 #undef YOND_BOX
   YOND_LAUNCH_CHECK();
   return YOND_OK;
@@ -664,6 +806,8 @@ int nlf_maps_impl(const BoxSrc& x, const BoxSrc* y, bool bayer, float* var, floa
   float* tmpA = reinterpret_cast<float*>(work);
   float* tmpB = tmpA + n;
   int rc;
+  // algorithmic bytes per Bayer pixel: self 4 R + 12 W (lap, mean, var), collab 8 R + 12 W
+  YondProfScope prof(mode == 0 ? "nlf_maps_self (3 box_fused passes)" : "nlf_maps_collab (2 box_fused passes)", s, (mode == 0 ? 16.0 : 20.0) * (double)n);
   BoxSrc x_nomax = x;
   x_nomax.seg_max = nullptr;
   if (mode == 0) {
@@ -755,18 +899,25 @@ int yond_nlf_maps_bayer(const float* x, int x_mosaic, const float* y, int y_mosa
 
 size_t yond_select_work_bytes(int nseg) { return (size_t)(nseg < 1 ? 1 : nseg) * sizeof(SelectWork) + 256; }
 
-int yond_order_stats(const float* data, size_t seg_len, int nseg, const uint64_t* ranks_dev, int nranks, float* out_dev,
-                     void* work, void* stream) {
-  YOND_REQUIRE(nranks > 0 && nranks <= kMaxRanks, "yond_order_stats: 1..%d ranks (got %d)", kMaxRanks, nranks);
-  YOND_REQUIRE(seg_len > 0 && nseg > 0 && nseg <= 65535, "yond_order_stats: empty input");
-  YOND_REQUIRE(seg_len % 4 == 0 && (uintptr_t)data % 16 == 0, "yond_order_stats: segments must hold whole 4-channel pixels (16-byte aligned)");
-  cudaStream_t s = (cudaStream_t)stream;
+}  // extern "C"
+namespace {
+// data = lap; with `mean` + `binmin` the first counting pass also collects the per-bin minimum of lap (score3)
+int order_stats_impl(const float* data, const float* mean, unsigned int* binmin, size_t seg_len, int nseg, const uint64_t* ranks_dev,
+                     int nranks, float* out_dev, void* work, cudaStream_t s) {
   SelectWork* wk = reinterpret_cast<SelectWork*>(work);
   // one memset for all segments (the slot tables behind the histograms are rewritten by the select kernels anyway)
   YOND_CUDA_CHECK(cudaMemsetAsync(wk, 0, (size_t)nseg * sizeof(SelectWork), s));
   dim3 g(stream_grid(seg_len), nseg);
   if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
-  hist0_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
+  const double nel = (double)seg_len * nseg;
+  if (binmin) {
+    YOND_CUDA_CHECK(cudaMemsetAsync(binmin, 0xff, (size_t)nseg * 1024 * sizeof(unsigned int), s));
+    YondProfScope prof("hist0+score3_binmin", s, 8.0 * nel);
+    hist0_kernel<true><<<g, 256, 0, s>>>(data, mean, seg_len, wk, binmin);
+  } else {
+    YondProfScope prof("hist0", s, 4.0 * nel);
+    hist0_kernel<false><<<g, 256, 0, s>>>(data, nullptr, seg_len, wk, nullptr);
+  }
   YOND_LAUNCH_CHECK();
   select0_kernel<<<nseg, 1024, 0, s>>>(wk, reinterpret_cast<const unsigned long long*>(ranks_dev), nranks);
   YOND_LAUNCH_CHECK();
@@ -774,22 +925,40 @@ int yond_order_stats(const float* data, size_t seg_len, int nseg, const uint64_t
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     const size_t smem = (size_t)kHist1Slots * 2048 * sizeof(unsigned int) + 2048;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(hist1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    std::call_once(once, [&] {
+      attr_err = cudaFuncSetAttribute(hist1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(select1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (2048 + 32) * (int)sizeof(unsigned int));
+    });
     if (attr_err != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(hist1_kernel) failed: %s", cudaGetErrorString(attr_err));
-    int bx = yond_num_sms() / nseg;  // one 128 KB block per SM
+    int bx = yond_num_sms() / nseg;  // one 130 KB block per SM
     if (bx < 1) bx = 1;
     const size_t need = (seg_len / 4 + kHist1Threads - 1) / kHist1Threads;
     if ((size_t)bx > need) bx = (int)need;
+    YondProfScope prof("hist1", s, 4.0 * nel);
     hist1_kernel<<<dim3(bx, nseg), kHist1Threads, smem, s>>>(data, seg_len, wk);
     YOND_LAUNCH_CHECK();
   }
-  select1_kernel<<<nseg, 1024, 0, s>>>(wk, nranks);
+  select1_kernel<<<nseg, 1024, 16 * (2048 + 32) * sizeof(unsigned int), s>>>(wk, nranks);
   YOND_LAUNCH_CHECK();
-  hist2_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
+  {
+    YondProfScope prof("hist2", s, 4.0 * nel);
+    hist2_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
+  }
   YOND_LAUNCH_CHECK();
   select2_kernel<<<nseg, 1024, 0, s>>>(wk, nranks, out_dev);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
+}
+}  // namespace
+extern "C" {
+
+int yond_order_stats(const float* data, size_t seg_len, int nseg, const uint64_t* ranks_dev, int nranks, float* out_dev,
+                     void* work, void* stream) {
+  YOND_REQUIRE(nranks > 0 && nranks <= kMaxRanks, "yond_order_stats: 1..%d ranks (got %d)", kMaxRanks, nranks);
+  YOND_REQUIRE(seg_len > 0 && seg_len < 0xffffffffull && nseg > 0 && nseg <= 65535, "yond_order_stats: 1 .. 2^32-2 elements per segment");
+  YOND_REQUIRE(seg_len % 4 == 0 && (uintptr_t)data % 16 == 0, "yond_order_stats: segments must hold whole 4-channel pixels (16-byte aligned)");
+  return order_stats_impl(data, nullptr, nullptr, seg_len, nseg, ranks_dev, nranks, out_dev, work, (cudaStream_t)stream);
 }
 
 int yond_score3_bins(const float* lap, const float* mean, size_t seg_len, int nseg, const double* ths_dev, int nth,
@@ -798,14 +967,16 @@ int yond_score3_bins(const float* lap, const float* mean, size_t seg_len, int ns
   YOND_REQUIRE(nseg > 0 && nseg <= 65535, "yond_score3_bins: bad segment count");
   YOND_REQUIRE(seg_len % 4 == 0 && (uintptr_t)lap % 16 == 0 && (uintptr_t)mean % 16 == 0, "yond_score3_bins: 4-channel pixel segments required");
   cudaStream_t s = (cudaStream_t)stream;
-  int* minj = reinterpret_cast<int*>(work);
-  fill_int_kernel<<<ceil_div(1001 * nseg, 256), 256, 0, s>>>(minj, 1001 * nseg, 0x7fffffff);
-  YOND_LAUNCH_CHECK();
+  unsigned int* binmin = reinterpret_cast<unsigned int*>(work);
+  YOND_CUDA_CHECK(cudaMemsetAsync(binmin, 0xff, (size_t)nseg * 1024 * sizeof(unsigned int), s));
   dim3 g(stream_grid(seg_len), nseg);
   if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
-  score3_kernel<<<g, 256, 0, s>>>(lap, mean, seg_len, ths_dev, nth, minj);
+  {
+    YondProfScope prof("score3_binmin", s, 8.0 * (double)seg_len * nseg);
+    hist0_kernel<true><<<g, 256, 0, s>>>(lap, mean, seg_len, nullptr, binmin);
+  }
   YOND_LAUNCH_CHECK();
-  score3_count_kernel<<<nseg, 256, 0, s>>>(minj, nth, npeaks_dev);
+  score3_count_kernel<<<nseg, 256, 0, s>>>(binmin, ths_dev, nth, npeaks_dev);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
@@ -818,7 +989,10 @@ int yond_masked_sums(const float* lap, const float* mean, const float* var, size
   YOND_CUDA_CHECK(cudaMemsetAsync(sums_dev, 0, (size_t)nseg * 12 * sizeof(double), s));
   dim3 g(stream_grid(seg_len), nseg);
   if ((size_t)g.x * nseg > (size_t)yond_num_sms() * 16) g.x = (unsigned)((yond_num_sms() * 16 + nseg - 1) / nseg);
-  masked_sums_kernel<<<g, 256, 0, s>>>(lap, mean, var, seg_len, ths_dev, sums_dev, nullptr);
+  {
+    YondProfScope prof("masked_sums", s, 12.0 * (double)seg_len * nseg);
+    masked_sums_kernel<<<g, 256, 0, s>>>(lap, mean, var, seg_len, ths_dev, sums_dev, nullptr);
+  }
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
@@ -856,7 +1030,7 @@ FitWork carve_fit(void* base, int nseg) {
   w.sums2 = (double*)take((size_t)nseg * 12 * 8);
   w.stats = (float*)take((size_t)nseg * kMaxRanks * 4);
   w.npeaks = (int*)take((size_t)nseg * kMaxQ * 4);
-  w.minj = (int*)take((size_t)nseg * 1001 * 4);
+  w.minj = (int*)take((size_t)nseg * 1024 * 4);
   w.idx = (int*)take((size_t)nseg * 4);
   w.redo = (int*)take((size_t)nseg * 4);
   w.bytes = align_up(off, 256);
@@ -882,11 +1056,16 @@ int yond_nlf_fit(const float* var, const float* mean, const float* lap, size_t s
   const int nranks = 2 * (nq + 1);
   ranks_kernel<<<1, 32, 0, s>>>(ql, (unsigned long long)seg_len, w.ranks, w.gamma);
   YOND_LAUNCH_CHECK();
-  int rc = yond_order_stats(lap, seg_len, nseg, reinterpret_cast<const uint64_t*>(w.ranks), nranks, w.stats, w.sel, stream);
+  YOND_REQUIRE(seg_len < 0xffffffffull && seg_len % 4 == 0 && (uintptr_t)lap % 16 == 0 && (uintptr_t)mean % 16 == 0,
+               "yond_nlf_fit: segments must hold whole 4-channel pixels (16-byte aligned), fewer than 2^32 elements");
+  unsigned int* binmin = reinterpret_cast<unsigned int*>(w.minj);
+  // the first counting pass of the radix select also collects the per-bin minimum of lap (all score3 needs from the maps)
+  int rc = order_stats_impl(lap, mean, binmin, seg_len, nseg, reinterpret_cast<const uint64_t*>(w.ranks), nranks, w.stats, w.sel, s);
   if (rc) return rc;
   pct_kernel<<<nseg, 32, 0, s>>>(w.stats, w.gamma, nq, w.ths, w.th25);
   YOND_LAUNCH_CHECK();
-  if ((rc = yond_score3_bins(lap, mean, seg_len, nseg, w.ths, nq, w.npeaks, w.minj, stream))) return rc;
+  score3_count_kernel<<<nseg, 256, 0, s>>>(binmin, w.ths, nq, w.npeaks);
+  YOND_LAUNCH_CHECK();
   pick_kernel<<<ceil_div(nseg, 64), 64, 0, s>>>(ql, w.ths, w.npeaks, w.th, w.idx, nseg);
   YOND_LAUNCH_CHECK();
   if ((rc = yond_masked_sums(lap, mean, var, seg_len, nseg, w.th, w.sums, stream))) return rc;

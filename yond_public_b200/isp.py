@@ -26,12 +26,27 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_STAGE = threading.local()
+
+
+def _pinned_stage(nbytes):
+    """Grow-only pinned host buffer of this thread: NumPy inputs go host -> pinned -> device without a cudaHostAlloc per call."""
+    buf = getattr(_STAGE, "buf", None)
+    if buf is None or buf.numel() < nbytes:
+        buf = _STAGE.buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8).pin_memory()
+    return buf
+
+
 def to_dev(a, dtype=torch.float32):
     """numpy / tensor -> contiguous CUDA tensor; returns (tensor, was_numpy)."""
     dev = _dev()  # raises without CUDA: there is no CPU path
     if isinstance(a, np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32 if dtype == torch.float32 else None))
-        return t.pin_memory().to(dev, non_blocking=True), True
+        src = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32 if dtype == torch.float32 else None))
+        n = src.numel() * src.element_size()
+        stage = _pinned_stage(n)[:n].view(src.dtype).view(src.shape)
+        torch.cuda.current_stream(dev).synchronize()  # the previous upload out of this buffer has left it
+        stage.copy_(src)
+        return stage.to(dev, non_blocking=True), True
     if not torch.is_tensor(a):
         a = torch.as_tensor(np.asarray(a, dtype=np.float32))
         return a.to(dev), True

@@ -2,7 +2,8 @@
 
 Frames (and the halo tiles of one frame) are independent units: ranks take contiguous shares, run the whole path
 locally, and the only exchange is the FINAL GATHER of the denoised output (NCCL over NVLink on GPUs, gloo in the CPU
-tests).  There is no data-path collective.
+tests).  There is no data-path collective.  A SINGLE frame is split into row bands for the network stage
+(BandShardedForward): one all-gather of the network output per round.
 """
 from __future__ import annotations
 
@@ -50,36 +51,60 @@ def run_sharded(units: torch.Tensor, fn, dst: int = 0):
     return gather_units(fn(units[a:b]), units.shape[0], dst)
 
 
-def gather_disjoint(partial: torch.Tensor, dst: int = 0):
-    """Final gather for tile-sharded frames: every rank holds the full-size padded output with ITS tile cores filled
-    and zeros elsewhere; the supports are disjoint, so a SUM reduction onto `dst` assembles the frame exactly
-    (x + 0 is exact in floating point).  One collective of frame size (48.8 MB for a 12 MP frame)."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
-        return partial
-    dist.reduce(partial, dst=dst, op=dist.ReduceOp.SUM)
-    return partial if dist.get_rank() == dst else None
+def band_range(hp: int, rank: int, world: int, align: int = 16):
+    """Rows [r0, r1) of a padded frame of `hp` rows owned by `rank`: equal bands of a multiple of `align` rows (the network
+    has four stride-2 stages: tile origins on multiples of 16); trailing ranks may get a short or empty band.  Returns
+    (r0, r1, band) with band = the common band height."""
+    band = -(-hp // (world * align)) * align
+    r0 = min(hp, rank * band)
+    return r0, min(hp, r0 + band), band
 
 
-def denoise_frame_tile_sharded(engine, frame, gain, sigma, scale, bias_corr="pre", vst_type="exact", clip01=True,
-                               core=512, dst=0):
-    """One full-resolution frame across the ranks: every rank runs the cheap HBM-bound pre-stage (pack + bias + VST +
-    normalise + pad + global max) on the whole frame — replicated rather than exchanged — denoises its
-    share of the halo tiles, and the cores are gathered on `dst`, which applies the inverse VST."""
-    import numpy as np  # noqa: F401
-    from . import isp
-    from ._lib import check, ptr, stream_ptr
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    H, W = frame.shape
-    h, w = H // 2, W // 2
-    pl, pr, pt, pb = isp.get_p2d((1, 4, h, w), base=32)
-    ntiles = len(engine.tile_grid(h + pt + pb, w + pl + pr, core))
-    a, b = shard_range(ntiles, rank, world)
-    y, (params, p2d) = engine.vst_denoise_tiled(frame, gain, sigma, scale, bias_corr, vst_type, clip01, core=core,
-                                                 tiles=range(a, b), return_padded=True)
-    y = gather_disjoint(y, dst)
-    if y is None:
-        return None
-    out = torch.empty_like(frame)
-    check(engine.lib.yond_vst_inv(ptr(y), ptr(out), 1, H, W, *p2d, ptr(params), int(clip01), stream_ptr()))
-    return out
+class BandShardedForward:
+    """Network forward of ONE padded frame split across the ranks into row bands (tile-sharded single frame, BASELINE
+    configs[2]/[3]).  A rank forwards its band plus a halo of `halo` rows that is cut at the frame border — the halo covers
+    the receptive field (107 / 123 packed pixels), full-width bands need no left / right halo and the slice is a
+    contiguous view of the NHWC frame, so there is no tile copy at all — and the bands are exchanged with ONE all-gather
+    (NCCL over NVLink; gloo in the CPU test).  Everything else of the pipeline (estimate, VST, inverse) is cheap and HBM
+    bound and is replicated on every rank instead of exchanged, so every rank ends with the whole result."""
+
+    def __init__(self, forward, rank=None, world=None, halo=128, group=None):
+        self.forward = forward
+        live = dist.is_initialized()
+        self.rank = (dist.get_rank(group) if live else 0) if rank is None else rank
+        self.world = (dist.get_world_size(group) if live else 1) if world is None else world
+        self.halo, self.group = halo, group
+        self._buf = {}
+
+    def __call__(self, z, ub, t=None, out=None):
+        B, hp, wp, c = z.shape
+        assert B == 1, "band sharding splits one frame; batches of frames are image-parallel"
+        r0, r1, band = band_range(hp, self.rank, self.world)
+        key = (band, wp, c, z.device, z.dtype)
+        if key not in self._buf:
+            self._buf = {key: (torch.zeros((band, wp, c), device=z.device, dtype=z.dtype),
+                               torch.empty((self.world * band, wp, c), device=z.device, dtype=z.dtype))}
+        mine, full = self._buf[key]
+        if r1 > r0:
+            ty0, ty1 = max(0, r0 - self.halo), min(hp, r1 + self.halo)
+            yt = self.forward(z[:, ty0:ty1], ub, t)
+            mine[:r1 - r0].copy_(yt[0, r0 - ty0:r1 - ty0])
+        if self.world > 1:
+            dist.all_gather_into_tensor(full.view(-1), mine.view(-1), group=self.group)
+        else:
+            full = mine
+        y = torch.empty_like(z) if out is None else out
+        y[0].copy_(full[:hp])
+        return y
+
+
+def denoise_frame_sharded(drv, frame, p):
+    """IterDenoise of ONE full-resolution frame (H,W) with the network stage band-sharded across the ranks of the default
+    process group; returns the device result dict of YOND_SIDD.iter_denoise_dev on every rank."""
+    eng = drv.engine
+    prev = eng.forward
+    eng.forward = BandShardedForward(drv.net.forward_nhwc)
+    try:
+        return drv.iter_denoise_dev(frame.reshape(1, 1, *frame.shape[-2:]), p)
+    finally:
+        eng.forward = prev

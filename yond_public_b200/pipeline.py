@@ -39,8 +39,7 @@ class YondEngine:
         self.biaslut = biaslut
         self.chunk = chunk
         self._bufs = {}
-        self._tables = {}
-        self.tile_batch = 4
+        self.forward = None  # optional replacement of net.forward_nhwc (parallel.BandShardedForward: one frame across ranks)
 
     def _buf(self, name, shape, dtype, device):
         n = int(np.prod(shape))
@@ -53,9 +52,10 @@ class YondEngine:
     def default_chunk(self, B, hp, wp):
         if self.chunk:
             return min(B, int(self.chunk))
-        per = max(1, hp * wp * 800)  # ~bytes of activations per frame
+        per = max(1, hp * wp * 400)  # ~bytes of activations per frame (yond_net_workspace_bytes: ~335 B per packed pixel)
         cap = int(os.environ.get("YOND_CHUNK", "640"))
-        return int(max(1, min(B, (8 << 30) // per, cap)))
+        budget = int(os.environ.get("YOND_CHUNK_GIB", "16")) << 30  # of the 180 GB: a 12 MP frame needs ~1.1 GiB
+        return int(max(1, min(B, budget // per, cap)))
 
     # ------------------------------------------------------------------------------------------
     def make_params(self, gains, sigmas, scale, bias_corr, vst_type, frame_max, device, fixed_table=None):
@@ -194,7 +194,7 @@ class YondEngine:
             pch = params[b0 * psz:]
             check(self.lib.yond_vst_fwd(ptr(frames[b0:b0 + n]), ptr(z[:n]), ptr(ub[:n]), n, H, W, pl, pr, pt, pb, ptr(pch),
                                         ptr(chain["rows"]), ptr(chain["xnodes"]), chain["stride"], st))
-            self.net.forward_nhwc(z[:n], ub[:n], t[b0:b0 + n] if self.guided else None, out=y[:n])
+            (self.forward or self.net.forward_nhwc)(z[:n], ub[:n], t[b0:b0 + n] if self.guided else None, out=y[:n])
             check(self.lib.yond_vst_inv_place(ptr(y[:n]), ptr(out), n, H, W, pl, pr, pt, pb, ptr(pch), int(clip01), frames_per_row, b0,
                                               ptr(chain["ok"]) if select else None, fps, ptr(fallback) if select else None, st))
         return out
@@ -451,9 +451,14 @@ class YOND_SIDD:
         res = {"dn1": dn1, "final": dn1, "regs1": ch1["regs4"], "regs2": None, "ok": None, "lr": x, "nblk": nblk}
         if pipe.get("iter") == "iter" and pipe["max_iter"] >= 1:
             assert pipe["max_iter"] == 1, "the shipped configurations use max_iter = 1"
+            # The shipped driver hard-codes SIDD_256 = True (:431): the mosaic is cut into 32 strips along W that the box
+            # filters treat as separate images.  That is the SIDD layout; for plain frames (the drivers of the other
+            # datasets are not in the repository) the default here is one image, `sidd_256: True` in the pipeline dict
+            # restores the hard-coded behaviour (needs W % 64 == 0).
             sidd = bool(pipe.get("sidd_256", mos_blocks == 32))
-            if sidd and nblk == 1 and mos_blocks > 1:  # mosaic frame: blocks are split out of the mosaic layout
-                regs2 = est.estimate_dev(x.reshape(nimg, H, W), dn1, k, split_blocks=True, x_mosaic=True, y_mosaic=True, nblk=mos_blocks)
+            if sidd and nblk == 1:  # a frame (or a full_dn mosaic): the 32 strips are split out of the mosaic layout
+                assert W % 64 == 0, "SIDD_256 splits the packed frame into 32 strips along W (YOND_SIDD.py:91-93)"
+                regs2 = est.estimate_dev(x.reshape(nimg, H, W), dn1, k, split_blocks=True, x_mosaic=True, y_mosaic=True, nblk=32)
             else:
                 regs2 = est.estimate_dev(x, dn1, k, split_blocks=sidd, y_mosaic=True)  # :431 (mode 'collab')
             mark("estimate_collab")
@@ -493,19 +498,14 @@ class YOND_SIDD:
         regs, rounds, _ = self.read_summary(res)
         return {"raw_dns": [res["dn1"], res["final"]], "regs": regs, "rounds": rounds, "lr_raw": None, "dev": res}
 
-    def iter_denoise_host(self, host_in, host_out, p, group=8, lanes=2):
-        """End-to-end batched IterDenoise on HOST buffers: host_in (nimg,nblk,H,W) f32 pinned -> host_out
-        (nimg,H,nblk*W) f32 pinned (final round of every image).  Images are processed in groups.
+    def iter_denoise_host(self, host_in, host_out, p, group=8, lanes=1):
+        """End-to-end batched IterDenoise on HOST buffers: host_in (nimg,nblk,H,W) f32 pinned -> host_out (nimg,H,nblk*W) f32
+        pinned (final round of every image; full frames are nblk = 1).  Images are processed in groups of `group`.
 
-        lanes >= 2 (default): the groups are dealt to `lanes` host threads, each with its own CUDA stream, driver clone
-        (network handle + workspace) and staging buffers.  A lane's H2D copy, compute and D2H copy are ordered on its
-        stream; across lanes they overlap, and — what a single host thread cannot do — the read-backs of the noise
-        estimator (three small synchronisations per group) of one lane are covered by the other lane's kernels.
-        lanes = 1: one host thread; the H2D copy of the next group and the D2H copy of the previous one run on their own
-        streams while the current group computes (double-buffered device staging, event-ordered)."""
-        if lanes > 1 and (not isinstance(group, int) or host_in.shape[0] > group):
-            return self._iter_denoise_host_lanes(host_in, host_out, p, group, lanes)
-        assert isinstance(group, int), "a list of group sizes needs lanes > 1"
+        One host thread, three streams: the H2D copy of group g+1 and the D2H copy of group g-1 run on their own streams
+        while group g computes (double-buffered device staging, event-ordered).  Because the pipeline itself never waits
+        for the device (iter_denoise_dev), the host only enqueues; the per-image numbers are read back once, at the end.
+        `lanes` is accepted for compatibility and ignored (round 1 needed host threads to hide the estimator's read-backs)."""
         assert host_in.is_pinned() and host_out.is_pinned(), "pinned host buffers required for asynchronous copies"
         nimg = host_in.shape[0]
         dev = self.device
@@ -513,13 +513,16 @@ class YOND_SIDD:
         if not hasattr(self, "_io"):
             self._io = dict(s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), bufs={})
         s_in, s_out = self._io["s_in"], self._io["s_out"]
-        key = (tuple(host_in.shape[1:]), group)
+        sizes = [min(group, nimg - a) for a in range(0, nimg, group)] if isinstance(group, int) else [int(g) for g in group]
+        assert sum(sizes) == nimg and min(sizes) > 0, "group sizes must add up to the number of images"
+        gmax = max(sizes)
+        key = (tuple(host_in.shape[1:]), gmax)
         if key not in self._io["bufs"]:
-            self._io["bufs"] = {key: ([torch.empty((group,) + tuple(host_in.shape[1:]), device=dev) for _ in range(2)],
-                                      [torch.empty((group,) + tuple(host_out.shape[1:]), device=dev) for _ in range(2)])}
-        din, dout = self._io["bufs"][key]
-        groups = [(a, min(a + group, nimg)) for a in range(0, nimg, group)]
-        in_ready, comp_done, out_done = {}, {}, {}
+            self._io["bufs"] = {key: [torch.empty((gmax,) + tuple(host_in.shape[1:]), device=dev) for _ in range(2)]}
+        din = self._io["bufs"][key]
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        groups = [(int(starts[i]), int(starts[i + 1])) for i in range(len(sizes))]
+        in_ready, comp_done = {}, {}
 
         def stage_in(g):
             a, b = groups[g]
@@ -532,114 +535,25 @@ class YOND_SIDD:
                 in_ready[g] = torch.cuda.Event()
                 in_ready[g].record(s_in)
 
-        regs, rounds = [], []
+        results = []
         stage_in(0)
         for g, (a, b) in enumerate(groups):
             if g + 1 < len(groups):
                 stage_in(g + 1)
             cur.wait_event(in_ready[g])
-            if g >= 2:
-                cur.wait_event(out_done[g - 2])
-            res = self.iter_denoise_batch(din[g % 2][:b - a], dict(p))
-            dout[g % 2][:b - a].copy_(res["raw_dns"][-1])
+            res = self.iter_denoise_dev(din[g % 2][:b - a], dict(p))
             comp_done[g] = torch.cuda.Event()
             comp_done[g].record(cur)
             s_out.wait_event(comp_done[g])
             with torch.cuda.stream(s_out):
-                host_out[a:b].copy_(dout[g % 2][:b - a], non_blocking=True)
-                out_done[g] = torch.cuda.Event()
-                out_done[g].record(s_out)
-            regs.append(res["regs"])
-            rounds.append(res["rounds"])
+                host_out[a:b].copy_(res["final"], non_blocking=True)
+            res["final"].record_stream(s_out)
+            res.pop("lr", None)  # a view of the staging buffer, which is reused
+            results.append(res)
         cur.wait_stream(s_out)
         torch.cuda.synchronize(dev)
-        return {"regs": regs, "rounds": np.concatenate(rounds)}
-
-    def iter_denoise_lanes(self, blocks, p, group=20, lanes=2):
-        """iter_denoise_batch for DEVICE-resident blocks (nimg,nblk,H,W), with the images dealt to `lanes` host threads
-        (own stream + driver clone each) in groups: the estimator's read-backs of one lane are covered by the other
-        lane's kernels.  Returns {'raw_dns': per-group final mosaics, 'regs', 'rounds'}."""
-        assert blocks.is_cuda
-        return self._iter_denoise_host_lanes(blocks, None, p, group, max(1, lanes))
-
-    def _iter_denoise_host_lanes(self, host_in, host_out, p, group, lanes):
-        import threading
-        on_device = host_in.is_cuda  # device-resident input: no staging, outputs are returned per group
-        assert on_device or (host_in.is_pinned() and host_out.is_pinned()), "pinned host buffers required for asynchronous copies"
-        nimg = host_in.shape[0]
-        dev = self.device
-        if isinstance(group, int):
-            sizes = [min(group, nimg - a) for a in range(0, nimg, group)]
-        else:  # explicit group sizes, e.g. a small first group so that compute starts early
-            sizes = [int(g) for g in group]
-            assert sum(sizes) == nimg and min(sizes) > 0, "group sizes must add up to the number of images"
-        gmax = max(sizes)
-        out_shape = (host_in.shape[2], host_in.shape[1] * host_in.shape[3]) if on_device else tuple(host_out.shape[1:])
-        key = (tuple(host_in.shape[1:]), out_shape, gmax if not on_device else 0, lanes)
-        if getattr(self, "_lanes_key", None) != key:
-            sd = self.net.state_dict()
-            self._lanes = []
-            for i in range(lanes):
-                drv = self if i == 0 else YOND_SIDD(self.arch, self.pipe, state_dict=sd, biaslut=self.biaslut, device=dev,
-                                                     chunk=self.engine.chunk)
-                lane = dict(drv=drv, stream=torch.cuda.Stream(dev))
-                if not on_device:
-                    lane["din"] = torch.empty((gmax,) + tuple(host_in.shape[1:]), device=dev)
-                    lane["dout"] = torch.empty((gmax,) + out_shape, device=dev)
-                self._lanes.append(lane)
-            self._lanes_key = key
-        starts = np.concatenate([[0], np.cumsum(sizes)])
-        groups = [(int(starts[i]), int(starts[i + 1])) for i in range(len(sizes))]
-        results = [None] * len(groups)
-        errors = []
-        start = torch.cuda.Event()
-        start.record(torch.cuda.current_stream(dev))
-        # H2D copies are chained in group order (each waits for the previous group's copy): the first group then arrives
-        # at full PCIe rate and its lane starts computing while the later groups are still on the wire
-        h2d_done = [torch.cuda.Event() for _ in groups]
-        h2d_issued = [threading.Event() for _ in groups]
-
-        def work(li):
-            lane = self._lanes[li]
-            try:
-                with torch.cuda.device(dev), torch.cuda.stream(lane["stream"]):
-                    lane["stream"].wait_event(start)
-                    for g in range(li, len(groups), lanes):
-                        a, b = groups[g]
-                        if on_device:
-                            res = lane["drv"].iter_denoise_batch(host_in[a:b], dict(p))
-                            results[g] = (res["regs"], res["rounds"], res["raw_dns"][-1])
-                            continue
-                        if g > 0:
-                            h2d_issued[g - 1].wait()
-                            lane["stream"].wait_event(h2d_done[g - 1])
-                        lane["din"][:b - a].copy_(host_in[a:b], non_blocking=True)
-                        h2d_done[g].record(lane["stream"])
-                        h2d_issued[g].set()
-                        res = lane["drv"].iter_denoise_batch(lane["din"][:b - a], dict(p))
-                        lane["dout"][:b - a].copy_(res["raw_dns"][-1])
-                        host_out[a:b].copy_(lane["dout"][:b - a], non_blocking=True)
-                        results[g] = (res["regs"], res["rounds"])
-                    lane["stream"].synchronize()
-            except BaseException as e:  # surfaced on the calling thread
-                errors.append(e)
-                for ev in h2d_issued:  # never leave the other lanes waiting
-                    ev.set()
-
-        threads = [threading.Thread(target=work, args=(li,)) for li in range(1, lanes)]
-        for t in threads:
-            t.start()
-        work(0)
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        for lane in self._lanes:
-            torch.cuda.current_stream(dev).wait_stream(lane["stream"])
-        out = {"regs": [r[0] for r in results], "rounds": np.concatenate([r[1] for r in results])}
-        if on_device:
-            out["raw_dns"] = [r[2] for r in results]
-        return out
+        summaries = [self.read_summary(r) for r in results]
+        return {"regs": [s_[0] for s_ in summaries], "rounds": np.concatenate([s_[1] for s_ in summaries])}
 
     def iter_denoise_device(self, blocks, p, lr_full=None):
         """Device-resident IterDenoise.  `blocks`: (nblk,H,W) CUDA f32 (SIDD layout) or (H,W) frame.

@@ -52,3 +52,44 @@ def random_init_state_dict(arch, seed=0):
     net = getattr(archs, arch["name"])(arch)
     archs.initialize_weights(net)
     return {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+def smoother_state_dict(arch, alpha=1.0):
+    """Reference-layout weights that make either architecture a 3x3 mean filter, out = (1-alpha) x + alpha blur3(x), using
+    only the first conv -> skip -> last block -> 1x1 head (every other tensor zero)."""
+    import torch
+    sd = {k: torch.zeros_like(v) for k, v in random_init_state_dict(arch, seed=0).items()}
+    hp = torch.full((3, 3), 1.0 / 9.0)
+    hp[1, 1] -= 1.0
+    if arch["name"] == "UNetSeeInDark":
+        g = 1.0 / (1.0 + 0.2)
+        for c in range(4):
+            sd["conv1_1.weight"][c, c] = hp
+            sd["conv1_1.weight"][c + 4, c] = -hp
+        for name, off in (("conv1_2", 0), ("conv9_1", 32), ("conv9_2", 0)):
+            for c in range(4):
+                w = sd[name + ".weight"]
+                w[c, off + c, 1, 1], w[c, off + c + 4, 1, 1] = g, -g
+                w[c + 4, off + c, 1, 1], w[c + 4, off + c + 4, 1, 1] = -g, g
+        for c in range(4):
+            sd["conv10_1.weight"][c, c, 0, 0], sd["conv10_1.weight"][c, c + 4, 0, 0] = alpha * g, -alpha * g
+    else:
+        g = 1.0 / (1.0 + 0.01)
+        for c in range(4):
+            sd["conv_in.weight"][c, c] = hp
+            sd["conv_in.weight"][c + 4, c] = -hp
+        for c in range(32):
+            sd["conv9.short_cut.0.weight"][c, 32 + c, 0, 0] = 1.0
+        for c in range(4):
+            sd["conv10.weight"][c, c, 0, 0], sd["conv10.weight"][c, c + 4, 0, 0] = alpha * g, -alpha * g
+    return sd
+
+
+def bench_state_dict(arch, seed=0, eps=0.25):
+    """Weights for throughput runs: no checkpoint is reachable offline, and with the reference's plain random init the
+    round-2 estimate is degenerate (beta1 < 0), so the reference's guard (YOND_SIDD.py:445-447) would skip the second
+    network pass that the shipped pipeline runs.  A mild smoother plus `eps` x the reference's random init (every tensor
+    dense) behaves like a weak denoiser: the guard passes and both rounds execute, in the GPU arm and in the CPU arm alike.
+    FLOPs and memory traffic do not depend on the weight values."""
+    rnd, sm = random_init_state_dict(arch, seed=seed), smoother_state_dict(arch)
+    return {k: sm[k] + eps * rnd[k] for k in rnd}
