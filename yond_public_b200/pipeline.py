@@ -486,17 +486,31 @@ class YOND_SIDD:
         return res
 
     @staticmethod
+    def summary_async(res):
+        """Enqueues (on the current stream) the download of a batch's numbers into pinned host memory; read_summary then
+        needs no device synchronisation of its own beyond the event the caller waits for."""
+        host = {}
+        for k in ("regs1", "regs2", "ok"):
+            t = res.get(k)
+            if t is not None:
+                host[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                host[k].copy_(t, non_blocking=True)
+        res["host"] = host
+
+    @staticmethod
     def read_summary(res):
         """One read-back of the numbers of a finished batch: regs per round as (nimg,2) float64 arrays (rows of images whose
         round 2 was abandoned are NaN in round 2 — the reference does not append them, :445-447), rounds per image."""
-        r1 = res["regs1"].cpu().numpy()
+        host = res.get("host")
+        get = (lambda k: host[k].numpy()) if host is not None else (lambda k: res[k].cpu().numpy())
+        r1 = get("regs1")
         nimg = r1.shape[0]
         regs = [r1[:, :2].copy()]
         rounds = np.ones(nimg, np.int64)
         gains = [r1[:, 2:].copy()]
         if res["regs2"] is not None:
-            r2 = res["regs2"].cpu().numpy()
-            ok = res["ok"].cpu().numpy().astype(bool)
+            r2 = get("regs2")
+            ok = get("ok").astype(bool)
             reg2 = r2[:, :2].copy()
             reg2[~ok] = np.nan
             regs.append(reg2)
@@ -568,7 +582,10 @@ class YOND_SIDD:
             s_out.wait_event(done)
             with torch.cuda.stream(s_out):
                 host_out[a:b].copy_(res["final"], non_blocking=True)
-            res["final"].record_stream(s_out)
+                self.summary_async(res)
+            for k in ("final", "regs1", "regs2", "ok"):
+                if res.get(k) is not None:
+                    res[k].record_stream(s_out)
             res.pop("lr", None)  # a view of the staging buffer, which is reused
             results.append(res)
         out_done = torch.cuda.Event()
