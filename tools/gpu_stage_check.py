@@ -108,6 +108,9 @@ CONV_CASES = [
     (0, 1, 96, 126, 32, 32, 32, 2, False, True, False),    # full-frame-like ragged width, concat, T=4
     (0, 1, 16, 24, 128, 0, 128, 1, False, False, False),   # CTA pair with an odd number of M tiles (the peer's last tile is empty)
     (0, 5, 8, 8, 512, 0, 512, 2, True, True, False),       # CTA pair, two n tiles, NB=2 image pairs, odd batch, full epilogue
+    (0, 2, 24, 40, 32, 0, 32, 2, True, True, True),        # pixel-pair formulation (32 -> 32): FiLM + SiLU + residual + dual store
+    (0, 3, 96, 126, 32, 0, 32, 2, False, True, False),     # pixel pairs, ragged width (63 pairs), T=4, scale only
+    (0, 1, 16, 15, 32, 0, 32, 1, True, False, False),      # odd width: falls back to the N=32 path
 ]
 
 

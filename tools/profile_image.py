@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--net-only", type=int, default=0, help="profile only the network forward on this many 128x128 packed blocks")
 ap.add_argument("--arch", default="gru")
 ap.add_argument("--step", type=int, default=0, help="profile one batched pipeline step over this many images")
+ap.add_argument("--time", type=int, default=0, help="with --net-only: time this many forwards with CUDA events instead of profiling")
 ap.add_argument("--frame", default=None, help="HxW packed frame for --net-only, e.g. 1536x2016")
 args = ap.parse_args()
 arch = bench.ARCH if args.arch == "gru" else {"name": "UNetSeeInDark", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
@@ -31,6 +32,16 @@ if args.net_only:
     for _ in range(3):
         drv.net.forward_nhwc(z, ub, t if "guided" in arch else None)
     torch.cuda.synchronize()
+    if args.time:
+        drv.net.enable_profile(True) if hasattr(drv.net, "enable_profile") else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.time):
+            drv.net.forward_nhwc(z, ub, t if "guided" in arch else None)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"net forward {B} x {H}x{W}: {e0.elapsed_time(e1) / args.time:.3f} ms")
+        sys.exit(0)
     torch.cuda.cudart().cudaProfilerStart()
     drv.net.forward_nhwc(z, ub, t if "guided" in arch else None)
     torch.cuda.synchronize()

@@ -26,6 +26,14 @@
 #include <cstdlib>
 #include <mutex>
 
+// -DYOND_CONV_TIMING: cycle counters in the producer / issuer loops, printed with YOND_CONV_DBG=8 (six clock reads per tile in the
+// issuer otherwise cost ~5 % of a narrow layer)
+#ifdef YOND_CONV_TIMING
+#define YOND_TICK() YOND_TICK()
+#else
+#define YOND_TICK() 0LL
+#endif
+
 namespace {
 
 constexpr int kEpiWarps = 16;                 // four per TMEM lane quarter, splitting the column chunks
@@ -76,7 +84,13 @@ struct TcParams {
   FastDiv fd_tiles_n, fd_tiles_w, fd_tiles_h, fd_cout;
   int lg_nchunk;       // log2(NT / 16)
   uint32_t t_off;      // output element offset between consecutive sub-tiles
+  int epi_split;  // two accumulator stages: the epilogue warps form two groups of kEpiWarps/2 that take alternate tiles (group g owns
+                  // accumulator stage g), so one group's TMEM reads / MUFU burst / stores overlap the other group's and a tile's
+                  // epilogue may take up to two tile times of MMAs
   int epi_fixed;  // every visit of an epilogue warp covers the same 16 channels of the same image (see epilogue_loop)
+  int paired;      // pixel-pair formulation of a 32 -> 32 channel 3x3 conv (conv_tc.cuh): N = CB = 64 over (H, W/2)
+  int cvec;        // channels of the bias / scale / shift vectors (= Cout, or 32 in the paired formulation)
+  uint32_t cmask;  // paired: 31 (output column n = o*32 + co uses vector entry co), else all ones
   int dbg;    // bring-up switches (YOND_CONV_DBG): 1 = skip global stores, 2 = skip the epilogue math, 4 = skip residual loads
   const float* bias;
   const float* scale;
@@ -437,6 +451,35 @@ __device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t nt, uint32_t
   }
 }
 
+// K steps [K0, K1) of one tap (pixel-pair formulation: the other steps multiply all-zero weights)
+template <int K0, int K1, int TT>
+__device__ __forceinline__ void issue_tap_range(uint32_t d_tmem, uint32_t nt, uint32_t a_lo0, uint32_t sub_step, uint32_t b_lo0,
+                                                uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t accum) {
+  uint32_t al = a_lo0 + 2u * K0, dt = d_tmem;
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    uint32_t bl = b_lo0 + 2u * K0;
+#pragma unroll
+    for (int k = K0; k < K1; ++k) umma_step(dt, al, a_hi, bl, b_hi, idesc, k > K0 ? 1u : accum);
+    al += sub_step - 2u * (K1 - K0);
+    dt += nt;
+  }
+}
+// Nine taps of a pixel-pair slab (CB = 64: K steps 0,1 = first pixel of the pair, 2,3 = second): the left neighbour pair
+// contributes only its second pixel, the right neighbour pair only its first.
+template <int TT>
+__device__ __forceinline__ void issue_slab_paired(uint32_t d_tmem, uint32_t nt, uint32_t a_stage_lo, uint32_t tap_r16, uint32_t px16,
+                                                  uint32_t sub_step, uint32_t b_lo_first, uint32_t b_step16, uint32_t a_hi,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t first_accum) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const uint32_t a0 = a_stage_lo + (uint32_t)r * tap_r16, b0 = b_lo_first + (uint32_t)(r * 3) * b_step16;
+    issue_tap_range<2, 4, TT>(d_tmem, nt, a0, sub_step, b0, a_hi, b_hi, idesc, r ? 1u : first_accum);
+    issue_tap_range<0, 4, TT>(d_tmem, nt, a0 + px16, sub_step, b0 + b_step16, a_hi, b_hi, idesc, 1u);
+    issue_tap_range<0, 2, TT>(d_tmem, nt, a0 + 2u * px16, sub_step, b0 + 2u * b_step16, a_hi, b_hi, idesc, 1u);
+  }
+}
+
 // All nine taps of one halo slab as straight-line code (resident weights): the only run-time inputs are a handful of
 // uniform bases and strides, everything else is an immediate.
 template <int KS, int TT>
@@ -492,28 +535,39 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   // the MMA issuer that waits for "accumulator drained" lives in the pair's leader CTA
   const uint32_t acc_empty_remote = kPair ? mapa_shared(acc_empty, 0) : acc_empty;
   const int q = warp & 3;            // TMEM lane quarter this warp may access
-  const int part = (warp - 2) >> 2;  // kEpiWarps/4 warps share a quarter and split the column chunks
+  const int part4 = (warp - 2) >> 2; // kEpiWarps/4 warps share a quarter
+  const bool split = p.epi_split != 0;
+  const int grp = split ? (part4 & 1) : 0;         // tile parity (= accumulator stage) this warp serves
+  const int part = split ? (part4 >> 1) : part4;   // the warps of a group that share a quarter split the column chunks
+  const int nparts = split ? 2 : 4;
   const int row = q * 32 + lane;     // GEMM row inside a sub-tile
   const int w_i = row & (p.TW - 1);  // TW, NB are powers of two
   const int g_i = row / p.TW;        // (h, b) index inside the sub-tile, h-major
   const int dh = g_i / p.NB, db = g_i & (p.NB - 1);
-  const int nchunk_m1 = (1 << p.lg_nchunk) - 1, nvis = p.T << p.lg_nchunk;
-  const bool fixed = p.epi_fixed != 0 && !(kScale && kRes);  // both at once would not fit the register budget
+  const int nchunk = 1 << p.lg_nchunk, nchunk_m1 = nchunk - 1, nvis = p.T << p.lg_nchunk;
+  // `fixed`: a warp's visits cover the column chunks part, part + nparts, ... (mod nchunk): nsets = nchunk / nparts distinct
+  // 16-channel sets (1 or 2), visit j uses set j mod nsets
+  const int nsets = nchunk > nparts ? nchunk / nparts : 1;
+  const bool fixed = p.epi_fixed != 0 && nsets <= 2 && !(kScale && kRes);  // both at once would not fit the register budget
   const bool convt = p.mode == CONVT_2X2 || p.mode == CONV_UPSC;  // output pixel (2h+a, 2w+b), n = (a*2+b)*Cout + co
-  const int cfix = (part & nchunk_m1) * 16;
   const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
   const bool lrelu = p.act == ACT_LRELU;
   const float slope = p.slope;
-  // `fixed`: A[16] | Bc[16] of this warp's channels live in a 128-byte shared-memory row (registers are short: 18
-  // warps leave 96 per thread, and spilled values miss the ~28 KB of L1 that 227 KB of shared memory leaves)
-  const float bias_l = (fixed && lane < 16) ? __ldg(p.bias + cfix + lane) : 0.f;
-  if (fixed && lane < 16) {
-    sts_f32(ptab + 4 * lane, 1.f);
-    sts_f32(ptab + 64 + 4 * lane, bias_l);
+  // `fixed`: A[16] | Bc[16] of each of this warp's channel sets live in a 128-byte shared-memory row (registers are short: 18
+  // warps leave 96 per thread, and spilled values miss the ~28 KB of L1 that 227 KB of shared memory leaves); lanes 0-15 fill
+  // set 0, lanes 16-31 set 1
+  const int lset = lane >> 4;
+  const uint32_t cfix_v = (uint32_t)((((part + nparts * lset) & nchunk_m1) << 4) + (lane & 15)) & p.cmask;  // entry of the bias / scale / shift vectors
+  const bool pl = fixed && lset < nsets;  // this lane fills a parameter slot
+  const uint32_t pslot = ptab + 128 * lset + 4 * (lane & 15);
+  const float bias_l = pl ? __ldg(p.bias + cfix_v) : 0.f;
+  if (pl) {
+    sts_f32(pslot, 1.f);
+    sts_f32(pslot + 64, bias_l);
   }
   __syncwarp();
-  int as = 0, pacc = 0;
-  for (int u = sched.first; u < sched.n_units; u += sched.step) {
+  int as = grp, pacc = 0, b_prev = -1;
+  for (int u = sched.first + grp * sched.step; u < sched.n_units; u += (split ? 2 : 1) * sched.step) {
     const TileCoord tc = decode_tile(p, sched_tile(p, sched, u));
     const int w = tc.w0 + w_i, h0 = tc.h0 + dh;
     const int bb = tc.b0 + (p.t_along_h ? db : db * p.T);  // along the batch: sub-tile t = images t, t+T, ... of the tile
@@ -522,14 +576,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
     const uint32_t e0 = convt ? (((uint32_t)bb * (2 * p.H) + 2 * h0) * (uint32_t)(2 * p.W) + 2 * w) * (uint32_t)p.Cout
                               : (((uint32_t)bb * p.H + h0) * (uint32_t)p.W + w) * (uint32_t)p.Cout + tc.n0;
     // visits in groups of kV
-    for (int k0 = 0; part + 4 * k0 < nvis; k0 += kV) {
+    for (int k0 = 0; part + nparts * k0 < nvis; k0 += kV) {
       // ---- before the accumulator is ready: addresses, residual loads, per-tile parameters ----
       uint32_t off[kV];
       uint32_t vmask = 0;
       U8 rr[kV];
 #pragma unroll
       for (int k = 0; k < kV; ++k) {
-        const int ci = part + 4 * (k0 + k);
+        const int ci = part + nparts * (k0 + k);
         off[k] = 0;
         if (ci < nvis) {
           const int t = ci >> p.lg_nchunk, c = (ci & nchunk_m1) << 4;
@@ -550,21 +604,27 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
       }
       if (k0 == 0) {
         if (kScale && fixed) {
+          // the folded parameters change with the image only (NB == 1: one image per tile, uniform over the warp); every
+          // epilogue warp of every SM re-reading the same two cache lines per tile made this dependent global load the
+          // longest step of the epilogue (L2 hot line: ~2000 cycles per tile in the source-level profile)
           const int b = bb < p.B ? bb : p.B - 1;
-          if (lane < 16) {
-            const float sc = __ldg(p.scale + (size_t)b * p.Cout + cfix + lane);
-            const float sh = p.shift ? __ldg(p.shift + (size_t)b * p.Cout + cfix + lane) : 0.f;
-            sts_f32(ptab + 4 * lane, sc);
-            sts_f32(ptab + 64 + 4 * lane, fmaf(bias_l, sc, sh));
+          if (b != b_prev) {
+            b_prev = b;
+            if (pl) {
+              const float sc = __ldg(p.scale + (size_t)b * p.cvec + cfix_v);
+              const float sh = p.shift ? __ldg(p.shift + (size_t)b * p.cvec + cfix_v) : 0.f;
+              sts_f32(pslot, sc);
+              sts_f32(pslot + 64, fmaf(bias_l, sc, sh));
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         mbar_wait(acc_full + 8 * as, pacc);
         tc_fence_after();
       }
 #pragma unroll
       for (int k = 0; k < kV; ++k) {
-        const int ci = part + 4 * (k0 + k);
+        const int ci = part + nparts * (k0 + k);
         if (ci < nvis && !(p.dbg & 128)) {  // dbg 128: the epilogue does not touch TMEM
           const int t = ci >> p.lg_nchunk, c = (ci & nchunk_m1) << 4;
           uint32_t v[16];
@@ -573,11 +633,12 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
           if (!(p.dbg & 2) && ((vmask >> k) & 1u)) {
             float f[16];
             if (fixed) {
+              const uint32_t pt = ptab + 128u * (uint32_t)((k0 + k) & (nsets - 1));
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                const float4 bc = lds_f4(ptab + 64 + 16 * g);
+                const float4 bc = lds_f4(pt + 64 + 16 * g);
                 if (kScale) {
-                  const float4 a = lds_f4(ptab + 16 * g);
+                  const float4 a = lds_f4(pt + 16 * g);
                   f[g * 4 + 0] = fmaf(__uint_as_float(v[g * 4 + 0]), a.x, bc.x); f[g * 4 + 1] = fmaf(__uint_as_float(v[g * 4 + 1]), a.y, bc.y);
                   f[g * 4 + 2] = fmaf(__uint_as_float(v[g * 4 + 2]), a.z, bc.z); f[g * 4 + 3] = fmaf(__uint_as_float(v[g * 4 + 3]), a.w, bc.w);
                 } else {
@@ -587,7 +648,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
               }
             } else {
               const uint32_t n = (uint32_t)(tc.n0 + c);
-              const uint32_t co = convt ? n - fdiv(n, p.fd_cout) * p.Cout : n;
+              const uint32_t co = (convt ? n - fdiv(n, p.fd_cout) * p.Cout : n) & p.cmask;
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + co);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -598,8 +659,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
               if (kScale) {
                 int b = p.t_along_h ? bb : bb + t;
                 if (b > p.B - 1) b = p.B - 1;
-                const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + co);
-                const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.Cout + co) : nullptr;
+                const float4* s4 = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.cvec + co);
+                const float4* h4 = p.shift ? reinterpret_cast<const float4*>(p.shift + (size_t)b * p.cvec + co) : nullptr;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                   const float4 sc = __ldg(s4 + g), sh = h4 ? __ldg(h4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -649,7 +710,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
       if (kPair) mbar_arrive_cluster(acc_empty_remote + 8 * as);
       else mbar_arrive(acc_empty + 8 * as);
     }
-    if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
+    if (split) pacc ^= 1;  // this group's stage comes round every second tile
+    else if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
   }
 }
 
@@ -679,7 +741,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full + 8 * i, 1);
-      mbar_init(acc_empty + 8 * i, kPair ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogue warps report to the leader
+      // pair: both CTAs' epilogue warps report to the leader; split epilogue: one group of kEpiWarps/2 per stage
+      mbar_init(acc_empty + 8 * i, (kPair ? 2 * kEpiWarps : kEpiWarps) >> (p.epi_split ? 1 : 0));
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -721,7 +784,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     __syncwarp();
     int sa = 0, pa = 0, sb = 0, pb = 0;
-    long long t_wait = 0, t_begin = clock64();
+    long long t_wait = 0, t_begin = YOND_TICK();
     // CTA pair: "data landed" is counted on the LEADER's barriers (its MMA consumes both CTAs' stages); the leader
     // expects the bytes of both CTAs, the peer only issues its loads.  "Stage free" arrives on each CTA's own barrier
     // through the multicast commit.
@@ -732,9 +795,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const TileCoord tc = decode_tile(p, sched_tile(p, sched, u));
       for (int ai = 0; ai < n_ast; ++ai) {
         const AStage s = decode_astage(p, ai);
-        const long long tw0 = clock64();
+        const long long tw0 = YOND_TICK();
         mbar_wait(a_empty + 8 * sa, pa ^ 1);
-        t_wait += clock64() - tw0;
+        t_wait += YOND_TICK() - tw0;
         if (is_leader) {
           if (p.dbg & 16) {  // bring-up: no activation loads (MMA-rate experiment; results are garbage)
             mbar_arrive(a_full + 8 * sa);
@@ -768,7 +831,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
     }
     if ((p.dbg & 8) && blockIdx.x == 0 && is_leader)
-      printf("[conv dbg] producer: total %lld cyc, waiting for a free A stage %lld cyc\n", clock64() - t_begin, t_wait);
+      printf("[conv dbg] producer: total %lld cyc, waiting for a free A stage %lld cyc\n", YOND_TICK() - t_begin, t_wait);
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // The whole warp stays converged and ONE elected lane issues the tcgen05 instructions.  tcgen05.mma takes its
@@ -799,29 +862,33 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool leader = elect_one() != 0;
     if (p.wres) mbar_wait(uw_full, 0);
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-    long long t_acc = 0, t_a = 0, t_issue = 0, t_begin = clock64();
+    long long t_acc = 0, t_a = 0, t_issue = 0, t_begin = YOND_TICK();
     // CTA pair: only the leader CTA issues (its MMAs drive both SMs' tensor cores); the peer's warp 1 idles
     for (int u = (kPair && !pair_leader) ? sched.n_units : sched.first; u < sched.n_units; u += sched.step) {
-      long long tw0 = clock64();
+      long long tw0 = YOND_TICK();
       mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
-      t_acc += clock64() - tw0;
+      t_acc += YOND_TICK() - tw0;
       tc_fence_after();
       const uint32_t d_tmem = u_tmem + (uint32_t)(as * p.T) * nt;
       const uint32_t d_tmem_tile = d_tmem;
       for (int ai = 0; ai < n_ast; ++ai) {
         const AStage s = decode_astage(p, ai);
-        tw0 = clock64();
+        tw0 = YOND_TICK();
         mbar_wait(ua_full + 8 * sa, pa);
-        t_a += clock64() - tw0;
+        t_a += YOND_TICK() - tw0;
         tc_fence_after();
         const uint32_t a_stage_lo = (((u_smem_a + (uint32_t)sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
-        const long long ti0 = clock64();
+        const long long ti0 = YOND_TICK();
         if (leader && p.wres && p.slab && p.mode == CONV_3X3_S1 && !(p.dbg & 32)) {
           // resident weights, single slab: 9 taps x T sub-tiles x K steps as one straight-line burst
           const uint32_t b_first = (((u_smem_b + (uint32_t)s.widx0 * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
           const uint32_t b_step16 = p.b_stage_bytes >> 4;
           const uint32_t acc0 = ai ? 1u : 0u;
-          if (ksteps == 4) {
+          if (p.paired && !(p.dbg & 256)) {  // dbg 256: keep the all-zero K steps (cross-check of the skip)
+            if (p.T == 1) issue_slab_paired<1>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else if (p.T == 2) issue_slab_paired<2>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else issue_slab_paired<4>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+          } else if (ksteps == 4) {
             if (p.T == 1) issue_slab_resident<4, 1>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
             else if (p.T == 2) issue_slab_resident<4, 2>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
             else issue_slab_resident<4, 4>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
@@ -916,7 +983,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           umma_commit(ua_empty + 8 * sa);
         }
         __syncwarp();
-        t_issue += clock64() - ti0;
+        t_issue += YOND_TICK() - ti0;
         if (!p.wres) {  // advance the weight ring by this stage's taps, in converged code
           sb += s.ntaps;
           while (sb >= p.SB) { sb -= p.SB; pb ^= 1; }
@@ -932,11 +999,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     if ((p.dbg & 8) && blockIdx.x == 0 && leader)
       printf("[conv dbg] issuer: total %lld cyc; issue regions %lld; waiting: accumulator %lld, activations %lld; tiles %d, A stages/tile %d, SA %d SB %d T %d NT %d\n",
-             clock64() - t_begin, t_issue, t_acc, t_a, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
+             YOND_TICK() - t_begin, t_issue, t_acc, t_a, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
   } else {
     // ===================== epilogue (warps 2..2+kEpiWarps) =====================
     const bool silu = p.act == ACT_SILU;
-    const uint32_t ptab = smem_base + p.smem_epi_off + (uint32_t)(warp - 2) * 128u;
+    const uint32_t ptab = smem_base + p.smem_epi_off + (uint32_t)(warp - 2) * 256u;
 #define YOND_EPI(S, R, A, V) epilogue_loop<S, R, A, V, kPair>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles)
     const bool few = p.T * (p.NT / 16) <= 8;  // at most two visits per warp and tile: hold two residual rows, not four
     if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true, 2); else YOND_EPI(true, true, false, 2); }
@@ -1038,7 +1105,32 @@ size_t conv_tc_packed_elems(int mode, int Cin_total, int Cout) {
   return (size_t)taps * Cin_total * N;
 }
 
-int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
+void conv_tc_pack_paired(const float* w, bf16* out) {
+  for (int r = 0; r < 3; ++r)
+    for (int P = -1; P <= 1; ++P)
+      for (int o = 0; o < 2; ++o)
+        for (int co = 0; co < 32; ++co)
+          for (int i = 0; i < 2; ++i)
+            for (int ci = 0; ci < 32; ++ci) {
+              const int dx = 2 * P + i - o;
+              const float v = (dx >= -1 && dx <= 1) ? w[((size_t)co * 32 + ci) * 9 + r * 3 + (dx + 1)] : 0.f;
+              out[((size_t)(r * 3 + P + 1) * 64 + (o * 32 + co)) * 64 + (i * 32 + ci)] = __float2bfloat16_rn(v);
+            }
+}
+
+int conv_tc_launch(const ConvLayer& Lin, cudaStream_t stream) {
+  ConvLayer L = Lin;
+  static const int env_paired = env_int("YOND_CONV_PAIRED", 1);
+  // (layers with a residual input are bound by their 3 x 64 B per pixel of HBM traffic, not by the MMAs: measured 930 us plain
+  // vs 990-1030 us paired for 24.8 M pixels, so they keep the N = 32 form)
+  const bool paired = env_paired && L.wpaired && L.mode == CONV_3X3_S1 && L.Cin0 == 32 && L.Cin1 == 0 && L.Cout == 32 && L.Win % 2 == 0 &&
+                      (L.res == nullptr || env_paired > 1);
+  if (paired) {  // (B,H,W,32) is (B,H,W/2,64): same memory, pixel pairs as 64-channel pixels
+    L.Win /= 2;
+    L.Cin0 = 64;
+    L.Cout = 64;
+    L.wpacked = L.wpaired;
+  }
   YOND_REQUIRE(L.Cin0 % 32 == 0 && L.Cin1 % 32 == 0 && L.Cin0 > 0, "conv_tc: Cin must be a multiple of 32 (got %d,%d)",
                L.Cin0, L.Cin1);
   YOND_REQUIRE(L.Cout % 32 == 0, "conv_tc: Cout must be a multiple of 32 (got %d)", L.Cout);
@@ -1060,6 +1152,9 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
     p.W = L.Win;
   }
   p.Cout = L.Cout;
+  p.paired = paired ? 1 : 0;
+  p.cvec = paired ? 32 : L.Cout;
+  p.cmask = paired ? 31u : 0xffffffffu;
   const bool convt_like = L.mode == CONVT_2X2 || L.mode == CONV_UPSC;
   p.N = convt_like ? 4 * L.Cout : L.Cout;
   p.CB = conv_tc_channel_block(L.Cin0, L.Cin1);
@@ -1081,7 +1176,7 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.NB = rows / p.TH;
   const int ncb = p.ncb0 + p.ncb1;
   const int nwt = ((L.mode == CONV_3X3_S1 || L.mode == CONV_3X3_S2) ? 9 : 1) * ncb;
-  const size_t smem_budget = 227 * 1024 - 2048 - kEpiWarps * 128;  // dynamic smem minus alignment slack, barriers, parameter rows
+  const size_t smem_budget = 227 * 1024 - 2048 - kEpiWarps * 256;  // dynamic smem minus alignment slack, barriers, parameter rows
   p.b_stage_bytes = (uint32_t)p.NT * row_bytes;
   YOND_REQUIRE(p.b_stage_bytes % 1024 == 0, "conv_tc: weight stage not 1024-aligned");
   size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
@@ -1167,8 +1262,13 @@ int conv_tc_launch(const ConvLayer& L, cudaStream_t stream) {
   p.smem_b_off = (uint32_t)p.SA * p.a_stage_bytes;
   p.smem_bar_off = (uint32_t)align_up(p.smem_b_off + b_region, 1024);
   p.smem_epi_off = p.smem_bar_off + 512;
-  const size_t smem_bytes = p.smem_epi_off + kEpiWarps * 128 + 1024;  // barriers, parameter rows, alignment slack
+  const size_t smem_bytes = p.smem_epi_off + kEpiWarps * 256 + 1024;  // barriers, parameter rows, alignment slack
   p.acc_stages = 2 * p.T * p.NT <= 512 ? 2 : 1;
+  static const int env_split = env_int("YOND_CONV_EPI_SPLIT", 1);
+  // Measured inside a GuidedResUnet forward on 8 x 12 MP frames (ncu, profiles/r02_conv_layers_pairing.txt): the pixel-pair
+  // layers 890 -> 767 us; every other layer is within +-2 % or loses 4 % (64-channel FiLM layers, residual layers), and the wide
+  // layers (N tile >= 128: many visits per warp) lose up to 10 % in isolation — so only the paired layers split.
+  p.epi_split = (env_split && p.acc_stages == 2 && (p.paired || env_split > 1)) ? 1 : 0;
   p.tmem_cols = p.acc_stages * p.T * p.NT < 32 ? 32 : p.acc_stages * p.T * p.NT;
   if ((env_dbg & 64) && p.tmem_cols <= 256) p.tmem_cols = 512;
   YOND_REQUIRE(p.tmem_cols <= 512, "conv_tc: TMEM budget exceeded");

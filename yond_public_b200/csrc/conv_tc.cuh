@@ -24,6 +24,8 @@ struct ConvLayer {
   int Cout;                 // real output channels
   const bf16* wpacked;      // [cbg][tap][N][CB] bf16, N = Cout (x4 for CONVT_2X2: n = (a*2+b)*Cout + co);
                             // CONV_UPSC: [cb0][4*Cout][CB] (folded up-sampling part) then [cb1][Cout][CB] (skip part)
+  const bf16* wpaired;      // optional (3x3 s1, 32 -> 32 channels): the same weights packed for the pixel-pair formulation, see
+                            // conv_tc_pack_paired; conv_tc_launch uses it when the width is even
   const float* bias;        // [Cout]
   const float* scale;       // [B][Cout] or null: v = v*scale + shift   (FiLM / SNR gates)
   const float* shift;       // [B][Cout] or null
@@ -38,6 +40,14 @@ struct ConvLayer {
 int conv_tc_channel_block(int Cin0, int Cin1);
 // Packed weight size in elements for a layer.
 size_t conv_tc_packed_elems(int mode, int Cin_total, int Cout);
+// 3x3 stride-1 conv with 32 input and 32 output channels as a conv over PIXEL PAIRS: the NHWC tensor (B,H,W,32) is the
+// tensor (B,H,W/2,64) of pixel pairs, and out[2X+o] = sum_{r,P,i} W[r][2P+i-o] in[2(X+P)+i] is a 3x3 conv with 64 -> 64
+// "channels" whose weight is zero where |2P+i-o| > 1.  The MMA then runs with N = 64 (48 cycles per M=128,K=16 step instead of
+// 40 for N = 32, for twice the outputs) and the all-zero K steps (left pair: first pixel, right pair: second pixel) are skipped:
+// 24 MMAs per 256 pixels instead of 36 per 256.  Layout [tap = r*3 + (P+1)][n = o*32 + co][k = i*32 + ci], bf16.
+// w: torch layout (32, 32, 3, 3).
+void conv_tc_pack_paired(const float* w, bf16* out);
+constexpr size_t kConvPairedElems = 9 * 64 * 64;
 int conv_tc_launch(const ConvLayer& L, cudaStream_t stream);
 // CUDA-core direct convolution with identical semantics (debug cross-check; reads the same packed weights).
 int conv_ref_launch(const ConvLayer& L, cudaStream_t stream);

@@ -17,6 +17,7 @@ struct LayerW {
   std::string wkey, bkey;
   std::string wkey2, bkey2;  // CONV_UPSC: the 1x1 shortcut conv folded behind the transposed conv (wkey / bkey)
   bf16* w = nullptr;
+  bf16* wpaired = nullptr;  // 32 -> 32 channel 3x3 layers: pixel-pair pack (conv_tc_pack_paired)
   float* bias = nullptr;
 };
 
@@ -161,7 +162,8 @@ void free_device(yond_net* n) {
   n->f32.clear();
   for (auto& kv : n->conv) {
     if (kv.second.w) cudaFree(kv.second.w);
-    kv.second.w = nullptr;
+    if (kv.second.wpaired) cudaFree(kv.second.wpaired);
+    kv.second.w = kv.second.wpaired = nullptr;
     kv.second.bias = nullptr;
   }
   if (n->head_w) cudaFree(n->head_w);
@@ -263,6 +265,12 @@ int finalize(yond_net* n) {
     std::vector<bf16> packed = pack_weights(L, n->host[L.wkey]);
     YOND_CUDA_CHECK(cudaMalloc(&L.w, packed.size() * sizeof(bf16)));
     YOND_CUDA_CHECK(cudaMemcpy(L.w, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    if (L.mode == CONV_3X3_S1 && L.Cin0 == 32 && L.Cin1 == 0 && L.Cout == 32) {
+      std::vector<bf16> pp(kConvPairedElems);
+      conv_tc_pack_paired(n->host[L.wkey].data(), pp.data());
+      YOND_CUDA_CHECK(cudaMalloc(&L.wpaired, pp.size() * sizeof(bf16)));
+      YOND_CUDA_CHECK(cudaMemcpy(L.wpaired, pp.data(), pp.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    }
     L.bias = n->f32[L.bkey];
   }
   {  // head: (nf,4,3,3) -> [tap][ci][co];  tail: (4,nf,1,1) -> [ci][4]
@@ -322,6 +330,7 @@ struct Runner {
     c.src1 = src1;
     c.Cout = L.Cout;
     c.wpacked = L.w;
+    c.wpaired = L.wpaired;
     c.bias = L.bias;
     c.scale = scale;
     c.shift = shift;
@@ -697,7 +706,15 @@ int yond_conv2d(int mode, int impl, int B, int Hin, int Win, int Cin0, int Cin1,
   bf16* dw = nullptr;
   YOND_CUDA_CHECK(cudaMalloc(&dw, packed.size() * sizeof(bf16)));
   YOND_CUDA_CHECK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  bf16* dwp = nullptr;
+  if (mode == CONV_3X3_S1 && Cin0 == 32 && Cin1 == 0 && Cout == 32) {
+    std::vector<bf16> pp(kConvPairedElems);
+    conv_tc_pack_paired(weight_host, pp.data());
+    YOND_CUDA_CHECK(cudaMalloc(&dwp, pp.size() * sizeof(bf16)));
+    YOND_CUDA_CHECK(cudaMemcpy(dwp, pp.data(), pp.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  }
   ConvLayer c{};
+  c.wpaired = dwp;
   c.mode = mode; c.B = B; c.Hin = Hin; c.Win = Win; c.Cin0 = Cin0; c.Cin1 = Cin1;
   c.src0 = (const bf16*)src0; c.src1 = (const bf16*)src1; c.Cout = Cout; c.wpacked = dw; c.bias = bias;
   c.scale = scale; c.shift = shift; c.act = act; c.slope = slope; c.res = (const bf16*)res;
@@ -722,6 +739,7 @@ int yond_conv2d(int mode, int impl, int B, int Hin, int Win, int Cin0, int Cin1,
   }
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(dw);
+  if (dwp) cudaFree(dwp);
   if (rc) return rc;
   if (e != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "yond_conv2d: kernel failed: %s", cudaGetErrorString(e));
   return YOND_OK;

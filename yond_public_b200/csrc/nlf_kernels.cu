@@ -54,7 +54,11 @@ __device__ __forceinline__ int reflect_once(int i, int n) {
 // by side, every thread is a real column (no halo threads), and the reflected border columns are taken from the same
 // prefix array: sum over [c-r, c+r] with reflection = P[min(c+r, w-1)] - P[c-r-1] + (P[r-c] - P[0]) on the left edge and
 // + (P[w-2] - P[2(w-1)-(c+r)-1]) on the right edge.
-template <bool kSq, int kCols, bool kBayer, bool kNarrow>  // kCols = 256, or 160 when a whole row plus both halos fits
+// kRows: image rows per barrier round.  Every round a column thread pushes the window down kRows rows (all 2 kRows loads
+// of the round are issued up front), stores the kRows sets of column sums, the scan warps prefix kRows x NQ rows of the
+// staging array (two at a time, interleaved), the writers emit kRows image rows: three block barriers per kRows rows
+// instead of two per row, and kRows-fold more independent work between them.
+template <bool kSq, int kCols, bool kBayer, bool kNarrow, int kRows>  // kCols = 256, or 160 when a whole row plus both halos fits
 __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, float4* __restrict__ out0,
                                                                 float4* __restrict__ out1, int B, int h, int w, int k, int op,
                                                                 int rows_per_strip, const float4* __restrict__ aux,
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
   constexpr int NQ = kSq ? 8 : 4;
   constexpr int CH = kCols / 32;           // columns per scan chunk (8 or 5)
   constexpr int PITCH = kCols + 32 + 1;    // padded: column c sits at c + c / CH, so chunk reads are bank-conflict free
-  __shared__ double S[2][NQ][PITCH];
+  extern __shared__ double S[];  // [kRows][NQ][PITCH]
   const int r = k / 2;
   const int outc = kCols - 2 * r;
   const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
@@ -114,11 +118,22 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
     } else {
       v = __ldg(reinterpret_cast<const float4*>(p));
     }
-    if (src.seg_max) vmax = fmaxf(vmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
     return v;
   };
-  if (colthread)
-    for (int i = i0 - r; i <= i0 + r; ++i) accum(load(i), 1.0);
+  // every pixel of a column enters the window exactly once: the running maximum rides on the accumulate step (NOT on the
+  // load, which would make the load's first use immediate and expose its latency)
+  auto enter = [&](const float4& v) {
+    accum(v, 1.0);
+    if (src.seg_max) vmax = fmaxf(vmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  };
+  if (colthread) {  // initial window, loads batched four at a time
+    int i = i0 - r;
+    for (; i + 3 <= i0 + r; i += 4) {
+      const float4 v0 = load(i), v1 = load(i + 1), v2 = load(i + 2), v3 = load(i + 3);
+      enter(v0); enter(v1); enter(v2); enter(v3);
+    }
+    for (; i <= i0 + r; ++i) enter(load(i));
+  }
   const double inv = 1.0 / ((double)k * (double)k);
   // stdfilt (isp_algos.py:236-241): float32 square of the blurred image, float32 difference, sqrt; explicit
   // round-to-nearest mul/sub: an FMA contraction would skip the float32 rounding of mean^2 the reference has
@@ -142,75 +157,96 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
     hi_idx = pidx(c + r);
     lo_idx = c - r - 1 >= 0 ? pidx(c - r - 1) : -1;
   }
-  // rows i+1 (entering / leaving the window) are in flight while row i is scanned
-  float4 vin = make_float4(0.f, 0.f, 0.f, 0.f), vout = vin;
-  for (int i = i0; i < i1; ++i) {
-    double(*Sb)[PITCH] = S[i & 1];
-    const bool more = colthread && (i + 1 < i1);
-    if (more) {
-      vin = load(i + 1 + r);
-      vout = load(i - r);
-    }
-    if (colthread) {
+  auto Srow = [&](int j, int q) { return S + (size_t)(j * NQ + q) * PITCH; };
+  for (int i = i0; i < i1; i += kRows) {
+    const int nr = min(kRows, i1 - i);
+    // rows entering / leaving the window for the next kRows positions (the last pair prepares the next round)
+    float4 vin[kRows], vout[kRows];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) Sb[q][my_idx] = s[q];
+    for (int j = 0; j < kRows; ++j) {
+      if (colthread && i + j + 1 < i1) {
+        vin[j] = load(i + j + 1 + r);
+        vout[j] = load(i + j - r);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+      if (colthread && j < nr) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) Srow(j, q)[my_idx] = s[q];
+      }
+      if (colthread && i + j + 1 < i1) {
+        enter(vin[j]);
+        accum(vout[j], -1.0);
+      }
     }
     __syncthreads();
-    if (warp < NQ) {  // chunked inclusive scan of quantity `warp` over the block's columns
-      double* row = Sb[warp] + lane * (CH + 1);  // chunk `lane` starts at column lane*CH, i.e. index lane*CH + lane
-      double loc[CH];
-      double run = 0.0;
+    // chunked inclusive scans of the nr x NQ staging rows: task t = (row j, quantity q), two tasks per step per warp
+    for (int t0 = warp; t0 < nr * NQ; t0 += 2 * (kBoxThreads / 32)) {
+      const int t1 = t0 + kBoxThreads / 32;
+      const bool two = t1 < nr * NQ;
+      double* rowa = S + (size_t)t0 * PITCH + lane * (CH + 1);  // chunk `lane` starts at column lane*CH, i.e. index lane*CH + lane
+      double* rowb = S + (size_t)(two ? t1 : t0) * PITCH + lane * (CH + 1);
+      double la[CH], lb[CH];
+      double ra = 0.0, rb = 0.0;
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
-        run += row[j];
-        loc[j] = run;
+        ra += rowa[j];
+        rb += rowb[j];
+        la[j] = ra;
+        lb[j] = rb;
       }
-      double incl = run;
+      double ia = ra, ib = rb;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        const double ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
       }
-      const double excl = incl - run;
+      const double ea = ia - ra, eb = ib - rb;
 #pragma unroll
-      for (int j = 0; j < CH; ++j) row[j] = loc[j] + excl;
+      for (int j = 0; j < CH; ++j) rowa[j] = la[j] + ea;
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) rowb[j] = lb[j] + eb;
+      }
     }
     __syncthreads();
     if (writer) {
-      double a[NQ];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        a[q] = Sb[q][hi_idx] - (lo_idx >= 0 ? Sb[q][lo_idx] : 0.0);
-        if (kNarrow && e1_idx >= 0) a[q] += Sb[q][e1_idx] - Sb[q][e0_idx];
-      }
-      const size_t o = ((size_t)b * h + i) * w + col_out;
-      const float4 m = make_float4((float)(a[0] * inv), (float)(a[1] * inv), (float)(a[2] * inv), (float)(a[3] * inv));
-      if (!kSq || op == OP_MEAN) {
-        out0[o] = m;
-      } else {
-        const float4 m2 = make_float4((float)(a[4] * inv), (float)(a[5] * inv), (float)(a[6] * inv), (float)(a[7] * inv));
-        const float4 st = make_float4(sd(m2.x, m.x), sd(m2.y, m.y), sd(m2.z, m.z), sd(m2.w, m.w));
-        if (op == OP_MEAN_STD) {
+      for (int j = 0; j < kRows; ++j) {
+        if (j >= nr) break;
+        double a[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const double* Sq = Srow(j, q);
+          a[q] = Sq[hi_idx] - (lo_idx >= 0 ? Sq[lo_idx] : 0.0);
+          if (kNarrow && e1_idx >= 0) a[q] += Sq[e1_idx] - Sq[e0_idx];
+        }
+        const size_t o = ((size_t)b * h + (i + j)) * w + col_out;
+        const float4 m = make_float4((float)(a[0] * inv), (float)(a[1] * inv), (float)(a[2] * inv), (float)(a[3] * inv));
+        if (!kSq || op == OP_MEAN) {
           out0[o] = m;
-          out1[o] = st;
-        } else if (op == OP_MEAN_VAR) {
-          out0[o] = m;
-          out1[o] = sq4(st);
-        } else if (op == OP_COLLAB) {
-          out0[o] = m;
-          out1[o] = st;
-          const float4 a = __ldg(aux + o), a2 = sq4(a), s2 = sq4(st);
-          out2[o] = make_float4(__fsub_rn(a2.x, s2.x), __fsub_rn(a2.y, s2.y), __fsub_rn(a2.z, s2.z), __fsub_rn(a2.w, s2.w));
         } else {
-          out0[o] = st;
+          const float4 m2 = make_float4((float)(a[4] * inv), (float)(a[5] * inv), (float)(a[6] * inv), (float)(a[7] * inv));
+          const float4 st = make_float4(sd(m2.x, m.x), sd(m2.y, m.y), sd(m2.z, m.z), sd(m2.w, m.w));
+          if (op == OP_MEAN_STD) {
+            out0[o] = m;
+            out1[o] = st;
+          } else if (op == OP_MEAN_VAR) {
+            out0[o] = m;
+            out1[o] = sq4(st);
+          } else if (op == OP_COLLAB) {
+            out0[o] = m;
+            out1[o] = st;
+            const float4 ax = __ldg(aux + o), a2 = sq4(ax), s2 = sq4(st);
+            out2[o] = make_float4(__fsub_rn(a2.x, s2.x), __fsub_rn(a2.y, s2.y), __fsub_rn(a2.z, s2.z), __fsub_rn(a2.w, s2.w));
+          } else {
+            out0[o] = st;
+          }
         }
       }
     }
-    if (more) {
-      accum(vin, 1.0);
-      accum(vout, -1.0);
-    }
-    // the other S buffer is written next; this one is rewritten two rows later, after the next row's barriers
+    __syncthreads();  // the staging rows are rewritten by the next round
   }
   if (src.seg_max) {  // values are >= 0: integer order of the bits == float order
     if (!colthread) vmax = 0.f;
@@ -758,6 +794,20 @@ BoxSrc packed_src(const float* x, int h, int w) {
   return s;
 }
 
+template <bool SQ, int COLS, bool BAYER, bool NARROW, int R>
+int launch_box(dim3 g, cudaStream_t s, const BoxSrc& src, float4* o0, float4* o1, int B, int h, int w, int k, int op, int rows_per_strip,
+               const float4* ax, float4* o2) {
+  constexpr size_t bytes = (size_t)R * (SQ ? 8 : 4) * (COLS + 33) * sizeof(double);
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(box_fused_kernel<SQ, COLS, BAYER, NARROW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  });
+  if (err != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "box filter: cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
+  box_fused_kernel<SQ, COLS, BAYER, NARROW, R><<<g, kBoxThreads, bytes, s>>>(src, o0, o1, B, h, w, k, op, rows_per_strip, ax, o2);
+  return YOND_OK;
+}
+
 int box_pass(const BoxSrc& src, bool bayer, float* out0, float* out1, int B, int h, int w, int k, bool with_sq, int op,
              cudaStream_t s, const float* aux = nullptr, float* out2 = nullptr) {
   static const int env_rows = getenv("YOND_BOX_ROWS") ? atoi(getenv("YOND_BOX_ROWS")) : 0;
@@ -777,13 +827,21 @@ int box_pass(const BoxSrc& src, bool bayer, float* out0, float* out1, int B, int
   const float4* ax = reinterpret_cast<const float4*>(aux);
   float4* o2 = reinterpret_cast<float4*>(out2);
   const int opx = with_sq ? op : OP_MEAN;
-#define YOND_BOX(SQ, COLS, BAYER, NARROW) \
-  box_fused_kernel<SQ, COLS, BAYER, NARROW><<<g, kBoxThreads, 0, s>>>(src, o0, o1, B, h, w, k, opx, rows_per_strip, ax, o2)
+  static const int env_r = getenv("YOND_BOX_R") ? atoi(getenv("YOND_BOX_R")) : 4;  // image rows per barrier round
+#define YOND_BOX_R(SQ, COLS, BAYER, NARROW, R) \
+  rc = launch_box<SQ, COLS, BAYER, NARROW, R>(g, s, src, o0, o1, B, h, w, k, opx, rows_per_strip, ax, o2)
+#define YOND_BOX(SQ, COLS, BAYER, NARROW)                          \
+  do {                                                             \
+    if (env_r >= 4) YOND_BOX_R(SQ, COLS, BAYER, NARROW, 4);        \
+    else if (env_r >= 2) YOND_BOX_R(SQ, COLS, BAYER, NARROW, 2);   \
+    else YOND_BOX_R(SQ, COLS, BAYER, NARROW, 1);                   \
+  } while (0)
 #define YOND_BOX_B(SQ, COLS, NARROW)                        \
   do {                                                      \
     if (bayer) YOND_BOX(SQ, COLS, true, NARROW);            \
     else YOND_BOX(SQ, COLS, false, NARROW);                 \
   } while (0)
+  int rc = YOND_OK;
   if (with_sq) {
     if (multi) YOND_BOX_B(true, 256, true);
     else if (narrow) YOND_BOX_B(true, 160, false);
@@ -795,6 +853,8 @@ int box_pass(const BoxSrc& src, bool bayer, float* out0, float* out1, int B, int
   }
 #undef YOND_BOX_B
 #undef YOND_BOX
+#undef YOND_BOX_R
+  if (rc) return rc;
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }
