@@ -58,6 +58,16 @@ int yond_pack_raw(const uint16_t* raw, float* out, int B, int H, int W, const in
  * YOND_SIDD.py:403,463).  in: (B,H,W) float32, out: (B,W,H) for odd k, (B,H,W) for even k.  Pure data movement. */
 int yond_rot90(const float* in, float* out, int B, int H, int W, int k, void* stream);
 
+/* ---- image-quality metrics of the SIDD driver — YOND_SIDD.py:651-652 (per-block raw PSNR / SSIM),
+ * :679-697 (ssim), :700-721 (calculate_ssim); compare_psnr = skimage.metrics.peak_signal_noise_ratio (third-party) ----
+ * a, b: (nimg, H, Wm) float32 mosaics of nblk blocks side by side (Wm = nblk * block width); every block is measured alone.
+ * psnr[nimg*nblk] = 10 log10(data_range^2 / mean((a-b)^2)) with the float32 difference / square and float64 mean skimage
+ * uses for float32 inputs.  ssim[nimg*nblk] = mean over the valid region of the SSIM map of (a*ssim_scale, b*ssim_scale)
+ * (float32 products like `dn*255`, then float64), 11x11 window = outer(window11, window11) (HOST array: cv2.getGaussianKernel(11,
+ * 1.5)), C1 = (0.01*255)^2, C2 = (0.03*255)^2.  Either output may be null.  Results stay on the device. */
+int yond_block_metrics(const float* a, const float* b, int nimg, int H, int Wm, int nblk, double data_range, float ssim_scale,
+                       const double* window11, double* psnr, double* ssim, void* stream);
+
 /* ---- A3/A4 elementwise, for the function-level surface — utils/isp_algos.py:5-14, :17-33 ---- */
 int yond_vst(const float* x, float* z, size_t n, double sigma, double gain, void* stream);
 int yond_inverse_vst(const float* z, float* x, size_t n, double sigma, double gain, int exact, void* stream);
@@ -193,6 +203,9 @@ typedef struct yond_net yond_net_t;
 #define YOND_ARCH_UNET 0     /* UNetSeeInDark  */
 #define YOND_ARCH_GUIDED 1   /* GuidedResUnet  */
 #define YOND_ARCH_SNR 2      /* SNRnet         */
+#define YOND_ARCH_RES2 3     /* ResUnet2 (archs/Unet.py:197-286): GuidedResUnet's graph and state_dict keys, blocks without the
+                                conditioning (ResBlock.forward never uses gamma / beta, archs/modules.py:258-265), LeakyReLU(0.2)
+                                after conv_in, called as net(x) */
 /* Creates a network; weights are set tensor-by-tensor with the reference's state_dict keys. */
 int yond_net_create(int arch, int in_nc, int out_nc, int nf, int res, int norm, yond_net_t** out);
 void yond_net_destroy(yond_net_t* net);

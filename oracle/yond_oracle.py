@@ -356,6 +356,57 @@ def SimpleNLF(lr_raw, hr_raw=None, k=29, setting=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# 8(f)-3  metrics of the SIDD driver                                    YOND_SIDD.py:643-656, :679-721
+# --------------------------------------------------------------------------------------------------
+def compare_psnr(image_true, image_test, data_range=1):
+    """skimage.metrics.peak_signal_noise_ratio (scikit-image is a dependency of the reference that is not installed here;
+    restated from its published source, simple_metrics.py): float32 inputs stay float32 (`_as_floats`), the mean of the squared
+    difference is taken with dtype=float64."""
+    a, b = np.asarray(image_true), np.asarray(image_test)
+    ft = np.float32 if (a.dtype == np.float32 and b.dtype == np.float32) else np.float64
+    a, b = a.astype(ft, copy=False), b.astype(ft, copy=False)
+    err = np.mean((a - b) ** 2, dtype=np.float64)
+    return 10 * np.log10((data_range ** 2) / err)
+
+
+def ssim(prediction, target):  # YOND_SIDD.py:679-697
+    C1 = (0.01 * 255) ** 2
+    C2 = (0.03 * 255) ** 2
+    img1 = prediction.astype(np.float64)
+    img2 = target.astype(np.float64)
+    kernel = cv2.getGaussianKernel(11, 1.5)
+    window = np.outer(kernel, kernel.transpose())
+    mu1 = cv2.filter2D(img1, -1, window)[5:-5, 5:-5]
+    mu2 = cv2.filter2D(img2, -1, window)[5:-5, 5:-5]
+    mu1_sq, mu2_sq, mu1_mu2 = mu1 ** 2, mu2 ** 2, mu1 * mu2
+    sigma1_sq = cv2.filter2D(img1 ** 2, -1, window)[5:-5, 5:-5] - mu1_sq
+    sigma2_sq = cv2.filter2D(img2 ** 2, -1, window)[5:-5, 5:-5] - mu2_sq
+    sigma12 = cv2.filter2D(img1 * img2, -1, window)[5:-5, 5:-5] - mu1_mu2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    return ssim_map.mean()
+
+
+def calculate_ssim(target, ref):  # YOND_SIDD.py:700-721
+    img1 = np.array(target, dtype=np.float64)
+    img2 = np.array(ref, dtype=np.float64)
+    if img1.ndim == 2:
+        return ssim(img1, img2)
+    if img1.shape[2] == 3:
+        return np.array([ssim(img1[:, :, i], img2[:, :, i]) for i in range(3)]).mean()
+    return ssim(np.squeeze(img1), np.squeeze(img2))
+
+
+def sidd_image_metrics(output, hr_raw, nblk=32):  # YOND_SIDD.py:643-656
+    if output.max() <= 0:
+        return -1, -1
+    dn_ = np.array(np.split(output, nblk, axis=-1))
+    hr_ = np.array(np.split(hr_raw, nblk, axis=-1))
+    psnr = np.mean([compare_psnr(dn, hr, data_range=1) for dn, hr in zip(dn_, hr_)])
+    ss = np.mean([calculate_ssim(dn * 255, hr * 255) for dn, hr in zip(dn_, hr_)])
+    return psnr, ss
+
+
+# --------------------------------------------------------------------------------------------------
 # A13  pad to a multiple of 32                                          utils/utils.py:246-252
 # --------------------------------------------------------------------------------------------------
 def get_p2d(shape, base=16):
@@ -419,7 +470,9 @@ def _guided_block(sd, p, x, t, bf16, kind):
     if f"{p}.short_cut.0.weight" in sd:
         x = _bf(F.conv2d(x, W(f"{p}.short_cut.0"), sd[f"{p}.short_cut.0.bias"]), bf16)
     z = F.conv2d(_bf(F.silu(x), bf16), W(f"{p}.conv1"), sd[f"{p}.conv1.bias"], padding=1)
-    if kind == "guided":
+    if kind == "res2":  # ResBlock.forward (archs/modules.py:258-265): gamma / beta are registered but never used
+        z = F.conv2d(_bf(F.silu(z), bf16), W(f"{p}.conv2"), sd[f"{p}.conv2.bias"], padding=1)
+    elif kind == "guided":
         tk = c1(F.silu(c1(t, f"{p}.gamma.0")), f"{p}.gamma.2")
         tb = c1(F.silu(tk), f"{p}.beta.1")
         z = _bf(F.silu(z * tk + tb), bf16)
@@ -433,17 +486,18 @@ def _guided_block(sd, p, x, t, bf16, kind):
 
 
 def guided_forward(sd, x, t, res=True, norm=True, bf16=False, kind="guided"):
-    """GuidedResUnet.forward (archs/Unet.py:424-470) / SNRnet.forward (:332-378).  t: 0-d or (B,) tensor."""
+    """GuidedResUnet.forward (archs/Unet.py:424-470) / SNRnet.forward (:332-378) / ResUnet2.forward (:242-286, kind 'res2':
+    no t, LeakyReLU(0.2) after conv_in).  t: 0-d or (B,) tensor."""
     import torch
     import torch.nn.functional as F
-    t = torch.as_tensor(t, dtype=x.dtype).reshape(-1, 1, 1, 1)
+    t = torch.as_tensor(0.0 if t is None else t, dtype=x.dtype).reshape(-1, 1, 1, 1)
     if norm:
         x, ub = _norm(x)
         t = t / ub
     else:
         t = t.expand(x.shape[0], 1, 1, 1)
     W = lambda n: _bf(sd[n + ".weight"], bf16)
-    h = _bf(F.leaky_relu(F.conv2d(x, sd["conv_in.weight"], sd["conv_in.bias"], padding=1), 0.01), bf16)
+    h = _bf(F.leaky_relu(F.conv2d(x, sd["conv_in.weight"], sd["conv_in.bias"], padding=1), 0.2 if kind == "res2" else 0.01), bf16)
     skips = []
     for lvl in range(1, 5):
         h = _guided_block(sd, f"conv{lvl}", h, t, bf16, kind)
@@ -471,6 +525,8 @@ def net_forward(arch, sd, x, t=None, bf16=False):
         return guided_forward(sd, x, t, res, norm, bf16, "guided")
     if name == "SNRnet":
         return guided_forward(sd, x, t, res, norm, bf16, "snr")
+    if name == "ResUnet2":
+        return guided_forward(sd, x, None, res, norm, bf16, "res2")
     raise NotImplementedError(name)
 
 
@@ -494,7 +550,7 @@ def init_state_dict(arch, seed=0, weight_scale=None):
                      (f"conv{i}_1", nn.Conv2d(c * 2, c, 3, 1, 1)), (f"conv{i}_2", nn.Conv2d(c, c, 3, 1, 1))]
         mods.append(("conv10_1", nn.Conv2d(nf, cout, 1)))
     else:  # GuidedResUnet archs/Unet.py:393-421, SNRnet :301-329; blocks archs/modules.py:163-218
-        guided = arch["name"] == "GuidedResUnet"
+        guided = arch["name"] in ("GuidedResUnet", "ResUnet2")  # ResBlock registers gamma / beta like the guided block
 
         def block(p, ci, co):
             m = [(f"{p}.conv1", nn.Conv2d(co, co, 3, 1, 1)), (f"{p}.conv2", nn.Conv2d(co, co, 3, 1, 1))]

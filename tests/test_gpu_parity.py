@@ -14,6 +14,7 @@ ARCHS = {
     "unet": {"name": "UNetSeeInDark", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
     "gru": {"name": "GuidedResUnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
     "snr": {"name": "SNRnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
+    "res2": {"name": "ResUnet2", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
 }
 PIPE = {"full_est": True, "est_type": "simple+full", "k": 29, "full_dn": False, "vst_type": "exact", "bias_corr": "pre",
         "iter": "iter", "max_iter": 1}
@@ -225,7 +226,7 @@ def test_rot_bayer_bit_exact(Y, golden):
 
 
 # ------------------------------------------------------------------ A14-A17, A20 networks
-@pytest.mark.parametrize("key", ["unet", "gru", "snr"])
+@pytest.mark.parametrize("key", ["unet", "gru", "snr", "res2"])
 def test_network_golden_and_statedict(Y, golden, key):
     g = golden(f"net_{key}")
     arch = ARCHS[key]
@@ -573,6 +574,36 @@ def test_iterdenoise_no_lut_and_out_of_range_on_device(Y, lut_table):
         np.testing.assert_allclose(np.asarray(res["regs"][0]), np.asarray(ref["regs"][0]), rtol=TOL_EST)
         assert len(res["raw_dns"]) == len(ref["raw_dns"])
         assert float(np.abs(res["raw_dns"][0] - ref["raw_dns"][0]).max()) < TOL_ABS
+
+
+# ------------------------------------------------------------------ metrics on the device
+def test_block_metrics_golden(Y, golden):
+    """Raw PSNR / MATLAB-style SSIM per mosaic block on the device vs the reference's own numbers (YOND_SIDD.py:679-721 run by
+    tests/golden/make_golden_metrics.py).  cv2.filter2D evaluates the 121-tap float64 window through a DFT, the kernel sums it
+    directly: agreement to ~1e-9; PSNR to float64 rounding."""
+    g = golden("metrics")
+    nblk = int(g["nblk"])
+    p, s = Y.block_metrics(g["dn"], g["clean"], nblk)
+    np.testing.assert_allclose(s.cpu().numpy()[0], g["ssim_blocks"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(p.cpu().numpy()[0], g["psnr_blocks"], rtol=1e-10)
+    Wb = int(g["Wb"])
+    assert abs(Y.calculate_ssim(g["noisy"][:, :Wb] * 255, g["clean"][:, :Wb] * 255) - float(g["ssim_noisy"])) < 1e-7
+    assert abs(Y.calculate_ssim(g["rgb"], g["rgb2"]) - float(g["ssim_rgb"])) < 1e-7
+    assert abs(Y.compare_psnr(g["dn"][:, :Wb], g["clean"][:, :Wb], data_range=1) - float(g["psnr_blocks"][0])) < 1e-9
+    pm, sm = Y.sidd_image_metrics(g["dn"], g["clean"], nblk)
+    assert abs(pm - g["psnr_blocks"].mean()) < 1e-9 and abs(sm - g["ssim_blocks"].mean()) < 1e-7
+    assert Y.sidd_image_metrics(np.zeros_like(g["dn"]), g["clean"], nblk) == (-1.0, -1.0)
+
+
+def test_block_metrics_sidd_batch_vs_oracle(Y):
+    """A batch of SIDD-shaped mosaics (32 blocks of 256x256) in one call == the oracle's per-image loop."""
+    rng = np.random.default_rng(8)
+    clean = np.stack([np.concatenate([O.synth_clean(rng, 256, 256) for _ in range(32)], -1) for _ in range(2)])
+    dn = (clean + rng.normal(0, 0.01, clean.shape)).astype(np.float32)
+    p, s = Y.block_metrics(dn, clean, 32)
+    for i in range(2):
+        po, so = O.sidd_image_metrics(dn[i], clean[i], 32)
+        assert abs(float(p[i].mean().cpu()) - po) < 1e-9 and abs(float(s[i].mean().cpu()) - so) < 1e-7
 
 
 # ------------------------------------------------------------------ BASELINE configs[3]: 14-bit, noclip, low-light gain

@@ -14,6 +14,7 @@ ARCHS = {
             "res": True, "norm": True},
     "snr": {"name": "SNRnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1,
             "res": True, "norm": True},
+    "res2": {"name": "ResUnet2", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
 }
 PIPE = {"k": 29, "full_dn": False, "vst_type": "exact", "bias_corr": "pre", "iter": "iter", "max_iter": 1}
 
@@ -102,7 +103,7 @@ def test_get_p2d(golden):
         assert O.get_p2d(tuple(int(v) for v in s), base=32) == tuple(int(v) for v in p)
 
 
-@pytest.mark.parametrize("key", ["unet", "gru", "snr"])
+@pytest.mark.parametrize("key", ["unet", "gru", "snr", "res2"])
 def test_networks(golden, key):
     g = golden(f"net_{key}")
     arch = ARCHS[key]
@@ -110,7 +111,7 @@ def test_networks(golden, key):
     assert [str(k) for k in g["keys"]] == list(sd.keys())
     assert [str(s) for s in g["shapes"]] == [str(tuple(v.shape)) for v in sd.values()]
     assert np.array_equal(np.array([crc(v.numpy()) for v in sd.values()], np.uint32), g["sd_crc"])
-    assert int(g["nparams"]) == {"unet": 7760484, "gru": 11173668, "snr": 11176612}[key]
+    assert int(g["nparams"]) == {"unet": 7760484, "gru": 11173668, "snr": 11176612, "res2": 11173668}[key]
     x = torch.from_numpy(g["x"])
     with torch.no_grad():
         y = O.net_forward(arch, sd, x, torch.tensor(0.043) if "guided" in arch else None)
@@ -218,3 +219,19 @@ def test_iterdenoise_c4_frame(golden, lut_table, ratio, wname):
     np.testing.assert_allclose(np.array([np.asarray(r, np.float64) for r in res["regs"]]), g[f"{tag}_regs"], rtol=1e-6)
     for i, dn in enumerate(res["raw_dns"]):
         assert float(np.abs(dn[::4, ::8] - g[f"{tag}_dn{i}_sub"]).max()) < 3e-6
+
+
+# ---- metrics of the SIDD driver ----
+def test_metrics_golden(golden):
+    """The oracle's ssim / calculate_ssim == the reference's on the same images (generated by make_golden_metrics.py)."""
+    g = golden("metrics")
+    nblk = int(g["nblk"])
+    dn_ = np.array(np.split(g["dn"], nblk, axis=-1))
+    hr_ = np.array(np.split(g["clean"], nblk, axis=-1))
+    got = np.array([O.calculate_ssim(d * 255, h * 255) for d, h in zip(dn_, hr_)])
+    np.testing.assert_allclose(got, g["ssim_blocks"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(O.calculate_ssim(g["rgb"], g["rgb2"]), g["ssim_rgb"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose([O.compare_psnr(d, h, data_range=1) for d, h in zip(dn_, hr_)], g["psnr_blocks"], rtol=1e-12)
+    p, s = O.sidd_image_metrics(g["dn"], g["clean"], nblk)
+    np.testing.assert_allclose([p, s], [g["psnr_blocks"].mean(), g["ssim_blocks"].mean()], rtol=1e-12)
+    assert O.sidd_image_metrics(np.zeros_like(g["dn"]), g["clean"], nblk) == (-1, -1)

@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
-ARCH_IDS = {"UNetSeeInDark": 0, "GuidedResUnet": 1, "SNRnet": 2}
+ARCH_IDS = {"UNetSeeInDark": 0, "GuidedResUnet": 1, "SNRnet": 2, "ResUnet2": 3}
 
 
 def conv1x1(in_nc, out_nc):
@@ -234,6 +234,20 @@ class GuidedResUnet(_GuidedBase):
 class SNRnet(_GuidedBase):
     """archs/Unet.py:288-378."""
     _block = SNR_Block
+
+
+class ResBlock(GuidedResidualBlock):
+    """archs/modules.py:235-265 — registers the same conv1 / conv2 / gamma / beta / short_cut modules as the guided block
+    (is_activate=False: SiLU); its forward never touches gamma / beta."""
+
+
+class ResUnet2(_GuidedBase):
+    """archs/Unet.py:197-286: GuidedResUnet's graph without the noise-level conditioning; LeakyReLU(0.2) after conv_in;
+    forward(x, noise_map=None) ignores the second argument."""
+    _block = ResBlock
+
+    def forward(self, x, noise_map=None):
+        return self._forward_nchw(x)
 
 
 def initialize_weights(net):

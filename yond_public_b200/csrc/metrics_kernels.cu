@@ -1,0 +1,137 @@
+// Image-quality metrics of the SIDD driver on the device: raw PSNR and the MATLAB-style SSIM that
+// YOND_SIDD.py:652-653 evaluates per 256x256 block of the mosaic in a CPU worker thread.
+//   reference: YOND_SIDD.py:679-697 (ssim: 11x11 Gaussian window sigma 1.5 from cv2.getGaussianKernel, float64
+//              cv2.filter2D, valid region, C1 = (0.01*255)^2, C2 = (0.03*255)^2), :700-721 (calculate_ssim),
+//              :651-652 (32 blocks split along W, data_range 1 / images scaled by 255);
+//              skimage.metrics.peak_signal_noise_ratio (third-party, not vendored): float32 difference and square for
+//              float32 inputs, float64 mean, 10 log10(range^2 / mse).
+// A mosaic (H, nblk*Wb) holds nblk blocks side by side; every block is measured on its own.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWin = 11, kR = 5;
+constexpr int kTile = 16;               // output pixels per block edge
+constexpr int kIn = kTile + 2 * kR;     // 26 x 26 input tile
+
+struct SsimWin {
+  double w[kWin];
+};
+
+// One thread per valid output pixel; the 26x26 input tiles of both images sit in shared memory as float64
+// (= double(fl32(x * 255)) like `dn*255` -> np.float64).  The 121-tap window is applied as given (outer(kernel, kernel)), five
+// float64 accumulators per pixel.
+__global__ void __launch_bounds__(kTile * kTile) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int Wb,
+                                                             int nblk, float scale, SsimWin win, double* __restrict__ sums) {
+  __shared__ double ta[kIn][kIn + 1], tb[kIn][kIn + 1];
+  __shared__ double red[kTile * kTile / 32];
+  const int blk = blockIdx.z % nblk, img = blockIdx.z / nblk;
+  const size_t Wm = (size_t)nblk * Wb;
+  const float* pa = a + (size_t)img * H * Wm + (size_t)blk * Wb;
+  const float* pb = b + (size_t)img * H * Wm + (size_t)blk * Wb;
+  const int oy0 = blockIdx.y * kTile, ox0 = blockIdx.x * kTile;  // valid-region coordinates
+  const int vh = H - 2 * kR, vw = Wb - 2 * kR;
+  for (int i = threadIdx.x; i < kIn * kIn; i += blockDim.x) {
+    const int ty = i / kIn, tx = i - ty * kIn;
+    const int y = oy0 + ty, x = ox0 + tx;  // input coordinates = valid coordinates + window offset (0..10)
+    double va = 0.0, vb = 0.0;
+    if (y < H && x < Wb) {
+      va = (double)__fmul_rn(pa[(size_t)y * Wm + x], scale);
+      vb = (double)__fmul_rn(pb[(size_t)y * Wm + x], scale);
+    }
+    ta[ty][tx] = va;
+    tb[ty][tx] = vb;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / kTile, lx = threadIdx.x % kTile;
+  double v = 0.0;
+  if (oy0 + ly < vh && ox0 + lx < vw) {
+    double m1 = 0, m2 = 0, s11 = 0, s22 = 0, s12 = 0;
+#pragma unroll 1
+    for (int i = 0; i < kWin; ++i) {
+#pragma unroll
+      for (int j = 0; j < kWin; ++j) {
+        const double w = win.w[i] * win.w[j];
+        const double x1 = ta[ly + i][lx + j], x2 = tb[ly + i][lx + j];
+        m1 += w * x1;
+        m2 += w * x2;
+        s11 += w * (x1 * x1);
+        s22 += w * (x2 * x2);
+        s12 += w * (x1 * x2);
+      }
+    }
+    const double C1 = (0.01 * 255) * (0.01 * 255), C2 = (0.03 * 255) * (0.03 * 255);
+    const double m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+    v = ((2 * m12 + C1) * (2 * (s12 - m12) + C2)) / ((m11 + m22 + C1) * ((s11 - m11) + (s22 - m22) + C2));
+  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < kTile * kTile / 32; ++i) s += red[i];
+    atomicAdd(&sums[blockIdx.z], s);
+  }
+}
+
+// Sum of float32 squared float32 differences per mosaic block, accumulated in float64.
+__global__ void __launch_bounds__(256) sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int Wb, int nblk,
+                                                     double* __restrict__ sums) {
+  const int blk = blockIdx.z % nblk, img = blockIdx.z / nblk;
+  const size_t Wm = (size_t)nblk * Wb;
+  const float* pa = a + (size_t)img * H * Wm + (size_t)blk * Wb;
+  const float* pb = b + (size_t)img * H * Wm + (size_t)blk * Wb;
+  double acc = 0.0;
+  for (int y = blockIdx.y; y < H; y += gridDim.y)
+    for (int x = threadIdx.x; x < Wb; x += blockDim.x) {
+      const float d = __fsub_rn(pa[(size_t)y * Wm + x], pb[(size_t)y * Wm + x]);
+      acc += (double)__fmul_rn(d, d);
+    }
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(&sums[blockIdx.z], s);
+  }
+}
+
+__global__ void metrics_finish_kernel(double* psnr, double* ssim, int n, double npix, double nvalid, double range2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (psnr) psnr[i] = 10.0 * log10(range2 / (psnr[i] / npix));
+  if (ssim) ssim[i] = ssim[i] / nvalid;
+}
+
+}  // namespace
+
+extern "C" int yond_block_metrics(const float* a, const float* b, int nimg, int H, int Wm, int nblk, double data_range, float ssim_scale,
+                                  const double* window11, double* psnr, double* ssim, void* stream) {
+  YOND_REQUIRE(a && b && nimg > 0 && H > 0 && Wm > 0 && nblk > 0 && Wm % nblk == 0, "yond_block_metrics: bad shape");
+  YOND_REQUIRE(psnr || ssim, "yond_block_metrics: no output requested");
+  YOND_REQUIRE((size_t)nimg * nblk <= 65535, "yond_block_metrics: at most 65535 blocks per call");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Wb = Wm / nblk, n = nimg * nblk;
+  if (psnr) {
+    YOND_CUDA_CHECK(cudaMemsetAsync(psnr, 0, sizeof(double) * n, s));
+    dim3 g(1, H < 64 ? H : 64, n);
+    sqdiff_kernel<<<g, 256, 0, s>>>(a, b, H, Wb, nblk, psnr);
+    YOND_LAUNCH_CHECK();
+  }
+  if (ssim) {
+    YOND_REQUIRE(window11 != nullptr, "yond_block_metrics: SSIM needs the 11-tap window (host array)");
+    YOND_REQUIRE(H > 2 * kR && Wb > 2 * kR, "yond_block_metrics: blocks smaller than the SSIM window");
+    SsimWin win;
+    for (int i = 0; i < kWin; ++i) win.w[i] = window11[i];
+    YOND_CUDA_CHECK(cudaMemsetAsync(ssim, 0, sizeof(double) * n, s));
+    dim3 g(ceil_div(Wb - 2 * kR, kTile), ceil_div(H - 2 * kR, kTile), n);
+    ssim_kernel<<<g, kTile * kTile, 0, s>>>(a, b, H, Wb, nblk, ssim_scale, win, ssim);
+    YOND_LAUNCH_CHECK();
+  }
+  metrics_finish_kernel<<<ceil_div(n, 128), 128, 0, s>>>(psnr, ssim, n, (double)H * Wb, (double)(H - 2 * kR) * (Wb - 2 * kR),
+                                                        data_range * data_range);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}

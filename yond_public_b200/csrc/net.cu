@@ -109,7 +109,7 @@ void describe(yond_net* n) {
     }
     add_conv_keys(n, "conv10_1", cout, nf, 1);
   } else {  // GuidedResUnet archs/Unet.py:393-421 / SNRnet :301-329; blocks archs/modules.py:163-218
-    const bool guided = n->arch == YOND_ARCH_GUIDED;
+    const bool guided = n->arch == YOND_ARCH_GUIDED || n->arch == YOND_ARCH_RES2;  // ResBlock registers the same gamma / beta modules
     auto block = [&](const std::string& p, int ci, int co) {
       add_conv_keys(n, p + ".conv1", co, co, 3);
       add_conv_keys(n, p + ".conv2", co, co, 3);
@@ -368,7 +368,8 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
   const float* ubn = n->norm ? ub : nullptr;
   const bool unet = n->arch == YOND_ARCH_UNET;
   const bool guided = n->arch == YOND_ARCH_GUIDED;
-  if (!dry && !unet && t == nullptr) return yond_set_error(YOND_ERR_INVALID, "guided network needs the per-sample t vector");
+  const bool res2 = n->arch == YOND_ARCH_RES2;  // GuidedResUnet's graph without conditioning
+  if (!dry && !unet && !res2 && t == nullptr) return yond_set_error(YOND_ERR_INVALID, "guided network needs the per-sample t vector");
   const double head_tail_flops = 2.0 * B * H * W * (36.0 * nf + 4.0 * nf);
   auto px = [&](int lv) { return (size_t)(H >> lv) * (W >> lv); };
   // Sub-batch of the full-resolution levels.  Measured on B200 (bench.py, 1280 blocks): splitting costs more in
@@ -398,7 +399,7 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
   };
   float* va[10] = {nullptr};
   float* vb[10] = {nullptr};
-  if (!unet) {
+  if (!unet && !res2) {
     FilmAll all{};
     all.n = 9;
     for (int l = 1; l <= 9; ++l) {
@@ -442,7 +443,7 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
     const std::string p = "conv" + std::to_string(l);
     const float* a = va[l] ? va[l] + (size_t)b0 * C : nullptr;
     const float* bb = vb[l] ? vb[l] + (size_t)b0 * C : nullptr;
-    if (guided) {  // z = SiLU(conv1(SiLU(x)) * tk + tb); out = conv2(z) + x
+    if (guided || res2) {  // z = SiLU(conv1(SiLU(x)) * tk + tb); out = conv2(z) + x   (ResUnet2: tk = 1, tb = 0)
       R.conv(p + ".conv1", nb, h, w, xs, nullptr, a, bb, ACT_SILU, 0.f, nullptr, zb, nullptr);
       R.conv(p + ".conv2", nb, h, w, zb, nullptr, nullptr, nullptr, ACT_NONE, 0.f, x, out, nullptr);
     } else {  // SNR: z = SiLU(conv1(SiLU(x)) * a1); out = conv2(z) * a2 + x
@@ -516,7 +517,7 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
       const int nb = B - b0 < SBn ? B - b0 : SBn;
       bf16* s0 = skip0 + (size_t)b0 * px(0) * C0;
       bf16* s1 = skip1 + (size_t)b0 * px(1) * C1;
-      RUN(head_conv_launch(z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->head_w, n->f32["conv_in.bias"], nb, H, W, nf, 0.01f, x0, x0s, s));
+      RUN(head_conv_launch(z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->head_w, n->f32["conv_in.bias"], nb, H, W, nf, res2 ? 0.2f : 0.01f, x0, x0s, s));
       film_join();
       block(1, 0, b0, nb, x0, x0s, z0, s0);
       // stride-2 conv, no activation (modules.py:117-125); the dual store feeds the next block
@@ -576,7 +577,7 @@ extern "C" {
 
 int yond_net_create(int arch, int in_nc, int out_nc, int nf, int res, int norm, yond_net_t** out) {
   YOND_REQUIRE(out != nullptr, "yond_net_create: null output");
-  YOND_REQUIRE(arch >= YOND_ARCH_UNET && arch <= YOND_ARCH_SNR, "yond_net_create: unknown arch %d", arch);
+  YOND_REQUIRE(arch >= YOND_ARCH_UNET && arch <= YOND_ARCH_RES2, "yond_net_create: unknown arch %d", arch);
   YOND_REQUIRE(in_nc == 4 && out_nc == 4, "yond_net_create: only packed-Bayer nets (in_nc = out_nc = 4, nframes = 1) are built");
   YOND_REQUIRE(nf >= 32 && nf % 32 == 0, "yond_net_create: nf must be a multiple of 32 (got %d)", nf);
   yond_net* n = new yond_net();

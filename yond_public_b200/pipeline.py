@@ -24,7 +24,7 @@ def build_net(arch: dict, device="cuda"):
     """globals()[arch['name']](arch) of the reference (YOND_SIDD.py:177)."""
     cls = getattr(archs, arch["name"], None)
     if cls is None:
-        raise NotImplementedError(f"arch '{arch['name']}' is outside the B200 hot path (UNetSeeInDark, GuidedResUnet, SNRnet)")
+        raise NotImplementedError(f"arch '{arch['name']}' is outside the B200 hot path (UNetSeeInDark, GuidedResUnet, SNRnet, ResUnet2)")
     return cls(arch).to(device)
 
 
