@@ -53,6 +53,12 @@ int yond_unpack(const float* rggb, float* bayer, int B, int h, int w, void* stre
 int yond_pack_raw(const uint16_t* raw, float* out, int B, int H, int W, const int* pos4, const float* black4, float white,
                   int clip, int layout, void* stream);
 
+/* Dataset normalisation of the 14-bit drivers — data_process/yond_datasets.py:955-961, :1053-1056:
+ * out = (float32(raw) - black) * ratio / (white - black) on the mosaic itself, float32 arithmetic in that order, unclipped unless
+ * `clip`.  `n` pixels (any shape), 2 B/px read + 4 B/px written.  The result is the `data['lr']` the drivers hand to IterDenoise
+ * with p = {wp: white, bl: black, ratio, scale: (white - black) / ratio}. */
+int yond_ingest_mosaic(const uint16_t* raw, float* out, size_t n, float black, float white, float ratio, int clip, void* stream);
+
 /* CFA canonicalisation — utils/sidd_utils.py:198-213 (rot_bayer = np.rot90 by k quarter turns, counter-clockwise, over the
  * last two axes; the driver rotates every SIDD frame to the RGGB phase before denoising and back afterwards,
  * YOND_SIDD.py:403,463).  in: (B,H,W) float32, out: (B,W,H) for odd k, (B,H,W) for even k.  Pure data movement. */

@@ -76,6 +76,15 @@ def pack_raw_bayer(raw_image, raw_pattern, black_level_per_channel, wp=1023, cli
 # --------------------------------------------------------------------------------------------------
 # A3 / A4  generalized Anscombe VST and its algebraic / exact-unbiased inverse   utils/isp_algos.py:5-33
 # --------------------------------------------------------------------------------------------------
+def normalize_raw(raw, bl, wp, ratio=1, clip=False):
+    """data_process/yond_datasets.py:955-961, :1053-1056: (raw.astype(np.float32) - bl) * ratio / (wp - bl).  bl / wp / ratio are
+    integer scalars in the reference; under the NumPy it was written for (value-based casting) every step stays float32 — cast
+    explicitly so that NumPy 2's stricter scalar promotion does not silently turn the frame into float64."""
+    x = np.asarray(raw).astype(np.float32)
+    out = (x - np.float32(bl)) * np.float32(ratio) / np.float32(np.float32(wp) - np.float32(bl))
+    return np.clip(out, 0.0, 1.0) if clip else out
+
+
 def VST(x, sigma, mu=0, gain=1.0):
     fz = gain * x + (3 / 8) * gain ** 2 + sigma ** 2 - gain * mu
     fz = np.maximum(fz, 0)

@@ -576,6 +576,20 @@ def test_iterdenoise_no_lut_and_out_of_range_on_device(Y, lut_table):
         assert float(np.abs(res["raw_dns"][0] - ref["raw_dns"][0]).max()) < TOL_ABS
 
 
+def test_normalize_raw_bit_exact(Y):
+    """Dataset normalisation of the 14-bit drivers (yond_datasets.py:955-961, :1053-1056) from the uint16 mosaic: bit-exact
+    against the oracle for every ratio / clip / odd size, and a 24 MP frame."""
+    rng = np.random.default_rng(12)
+    for shape, bl, wp, ratio, clip in (((64, 48), 512, 16383, 100, False), ((3, 33, 21), 512, 16383, 1, False),
+                                       ((128, 256), 64, 1023, 1, True), ((4000, 6000), 512, 16383, 200, False)):
+        raw = rng.integers(0, wp + 1, size=shape, dtype=np.uint16)
+        got = Y.normalize_raw(raw, bl, wp, ratio, clip)
+        ref = O.normalize_raw(raw, bl, wp, ratio, clip)
+        assert got.dtype == np.float32 and ref.dtype == np.float32 and np.array_equal(got, ref), (shape, ratio)
+    t = torch.from_numpy(raw.view(np.int16)).cuda()  # device-resident input -> device-resident output
+    assert torch.equal(Y.normalize_raw(t, 512, 16383, 200).cpu(), torch.from_numpy(ref))
+
+
 # ------------------------------------------------------------------ SURVEY 8(f)-3: metrics on the device
 def test_block_metrics_golden(Y, golden):
     """Raw PSNR / MATLAB-style SSIM per mosaic block on the device vs the reference's own numbers (YOND_SIDD.py:679-721 run by

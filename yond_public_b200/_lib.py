@@ -34,6 +34,7 @@ SIGNATURES = {
     "yond_unpack": (_I, [_P, _P, _I, _I, _I, _P]),
     "yond_rot90": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "yond_pack_raw": (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_float, _I, _I, _P]),
+    "yond_ingest_mosaic": (_I, [_P, _P, _SZ, C.c_float, C.c_float, C.c_float, _I, _P]),
     "yond_block_metrics": (_I, [_P, _P, _I, _I, _I, _I, _D, C.c_float, C.POINTER(C.c_double), _P, _P, _P]),
     "yond_vst": (_I, [_P, _P, _SZ, _D, _D, _P]),
     "yond_inverse_vst": (_I, [_P, _P, _SZ, _D, _D, _I, _P]),

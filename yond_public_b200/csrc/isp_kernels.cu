@@ -107,6 +107,41 @@ __global__ void pack_raw_kernel(const uint16_t* __restrict__ raw, float* __restr
   }
 }
 
+// ------------------------------------------------------------------ dataset normalisation of the 14-bit drivers
+// data_process/yond_datasets.py:955-961, :1053-1056: lr = (raw.astype(float32) - bl) * ratio / (wp - bl) on the MOSAIC, float32
+// arithmetic in that order (array op scalar keeps float32 under the NumPy the reference was written for), no clipping unless asked.
+// Reads 2 B/px; eight pixels (one 128-bit load, two 128-bit stores) per thread.
+__global__ void ingest_mosaic_kernel(const uint16_t* __restrict__ raw, float* __restrict__ out, size_t n8, float bl, float ratio, float denom,
+                                     int clip) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(raw) + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = (float)(w[k] & 0xffffu);
+      v[2 * k + 1] = (float)(w[k] >> 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = __fdiv_rn(__fmul_rn(__fsub_rn(v[k], bl), ratio), denom);
+      if (clip) t = fminf(fmaxf(t, 0.f), 1.f);
+      v[k] = t;
+    }
+    float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+__global__ void ingest_mosaic_tail_kernel(const uint16_t* __restrict__ raw, float* __restrict__ out, size_t i0, size_t n, float bl, float ratio,
+                                          float denom, int clip) {
+  const size_t i = i0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = __fdiv_rn(__fmul_rn(__fsub_rn((float)raw[i], bl), ratio), denom);
+  if (clip) t = fminf(fmaxf(t, 0.f), 1.f);
+  out[i] = t;
+}
+
 // ------------------------------------------------------------------ rot_bayer (sidd_utils.py:198-213): np.rot90
 // Quarter turns go through a 32x32 shared-memory tile so that both the global read and the global write are row-contiguous:
 //   k = 1: out[i][j] = in[j][W-1-i]      tile[r][c] = in[j0 + r][W-1-i0-31 + c],   out(i0+a, j0+b) = tile[b][31-a]
@@ -513,6 +548,24 @@ int yond_pack_raw(const uint16_t* raw, float* out, int B, int H, int W, const in
   else
     pack_raw_kernel<1><<<grid_for((size_t)B * (H / 2) * (W / 2)), kBlock, 0, (cudaStream_t)stream>>>(raw, out, B, H, W, q, clip, layout);
   YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+
+int yond_ingest_mosaic(const uint16_t* raw, float* out, size_t n, float black, float white, float ratio, int clip, void* stream) {
+  YOND_REQUIRE(raw && out && n > 0, "yond_ingest_mosaic: null argument");
+  YOND_REQUIRE((uintptr_t)raw % 16 == 0 && (uintptr_t)out % 16 == 0, "yond_ingest_mosaic: 16-byte aligned buffers required");
+  YOND_REQUIRE(white > black, "yond_ingest_mosaic: white level must exceed the black level");
+  const float denom = white - black;  // the reference subtracts the integer levels: exact in float32 for sensor ranges
+  YondProfScope prof("ingest_mosaic", (cudaStream_t)stream, 6.0 * (double)n);
+  const size_t n8 = n / 8;
+  if (n8) {
+    ingest_mosaic_kernel<<<grid_for(n8), kBlock, 0, (cudaStream_t)stream>>>(raw, out, n8, black, ratio, denom, clip);
+    YOND_LAUNCH_CHECK();
+  }
+  if (n % 8) {
+    ingest_mosaic_tail_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(raw, out, n8 * 8, n, black, ratio, denom, clip);
+    YOND_LAUNCH_CHECK();
+  }
   return YOND_OK;
 }
 

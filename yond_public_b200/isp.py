@@ -155,6 +155,25 @@ def pack_raw_bayer(raw, wp=1023, clip=True, raw_pattern=None, black_level_per_ch
 rggb2bayers = rggb2bayer
 
 
+def normalize_raw(raw, bl, wp, ratio=1, clip=False):
+    """The `data['lr']` of the 14-bit dataset drivers (data_process/yond_datasets.py:955-961, :1053-1056):
+    (raw.astype(float32) - bl) * ratio / (wp - bl) on the uint16 mosaic (any shape; NumPy or a 16-bit CUDA tensor), float32 result
+    on the device for tensors / as NumPy for NumPy input.  The low-light gain `ratio` is applied here, which is why the driver's
+    p['scale'] is (wp - bl) / ratio."""
+    dev = _dev()
+    np_in = not torch.is_tensor(raw)
+    if np_in:
+        a = np.ascontiguousarray(np.asarray(raw))
+        assert a.dtype == np.uint16, "the sensor mosaic must be uint16"
+        x = torch.from_numpy(a.view(np.int16)).to(dev)
+    else:
+        assert raw.dtype in (torch.uint16, torch.int16), "the sensor mosaic must be a 16-bit integer tensor"
+        x = raw.to(dev).contiguous()
+    out = torch.empty(x.shape, device=dev, dtype=torch.float32)
+    check(_lib.load().yond_ingest_mosaic(ptr(x), ptr(out), x.numel(), float(bl), float(wp), float(ratio), int(bool(clip)), stream_ptr()))
+    return _back(out, np_in)
+
+
 # ------------------------------------------------------------------ A3 / A4  utils/isp_algos.py:5-33
 def VST(x, sigma, mu=0, gain=1.0):
     if np.isscalar(x) or (isinstance(x, np.ndarray) and x.ndim == 0):
