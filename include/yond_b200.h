@@ -235,7 +235,8 @@ int yond_net_forward_nchw(yond_net_t* net, const float* x, const float* t, float
                           void* workspace, size_t workspace_bytes, void* stream);
 /* FLOPs of the tensor-core conv stack for one forward of this shape (2*MAC, algorithmic, no halo / padding). */
 double yond_net_flops(yond_net_t* net, int B, int H, int W);
-/* 0: tcgen05 implicit-GEMM kernels (product path).  1: CUDA-core direct convolution (debug cross-check only). */
+/* 0: tcgen05 implicit-GEMM kernels (product path).  1: CUDA-core direct convolution (debug cross-check only).
+ * 2: the tcgen05 kernels with the layer fusions off (up-sampling + shortcut, output conv in the last epilogue): A/B checks. */
 int yond_net_set_conv_impl(yond_net_t* net, int impl);
 /* Device time (ms) accumulated by the conv-stack kernels since the last reset, measured with CUDA events on
  * `stream` when profiling is enabled (bench.py's live roofline). */

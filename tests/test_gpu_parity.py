@@ -248,6 +248,11 @@ def test_network_golden_and_statedict(Y, golden, key):
     net2.conv_impl = 1  # CUDA-core cross-check of the same layers
     y1 = net2(x, torch.tensor(0.043, device="cuda")) if "guided" in arch else net2(x)
     assert float((y1 - y).abs().max()) < 1e-4
+    net2.conv_impl = 2  # tensor-core kernels, layer fusions off: the fused output conv is bit-identical to the two-kernel form
+    y2 = net2(x, torch.tensor(0.043, device="cuda")) if "guided" in arch else net2(x)
+    if key == "unet":  # (the guided nets also un-fuse the up-sampling + shortcut layers, whose weights are folded in float64)
+        assert torch.equal(y2, y)
+    assert float((y2 - y).abs().max()) < 1e-4
 
 
 def test_network_requires_cuda(Y):

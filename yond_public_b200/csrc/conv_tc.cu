@@ -100,6 +100,14 @@ struct TcParams {
   const bf16* res;
   bf16* out0;
   bf16* out1;
+  // fused last layer (ConvLayer::tail_*): table [32][4] + [4] floats at smem_tail_off
+  const float* tail_w;
+  const float* tail_b;
+  const float* tail_z;
+  const float* tail_ub;
+  float* tail_y;
+  int tail_res;
+  uint32_t smem_tail_off;
 };
 
 struct TcMaps {
@@ -715,6 +723,121 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   }
 }
 
+// Epilogue of the network's LAST tensor-core layer with the 1x1 output conv fused in (ConvLayer::tail_*): N = 32, so a pixel's
+// channels are two 16-column chunks; warp `part` of a lane quarter takes sub-tile t = part and BOTH chunks, folds
+// out[c] = act(acc * A[c] + Bc[c]) + res[c] straight into the four output sums and writes one float4 per pixel.
+template <bool kScale, bool kRes>
+__device__ __forceinline__ void epilogue_tail(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, uint32_t ptab,
+                                              uint32_t tailtab, int warp, int lane, int total_tiles) {
+  const int q = warp & 3, part = (warp - 2) >> 2;
+  const int row = q * 32 + lane;
+  const int w_i = row & (p.TW - 1), g_i = row / p.TW;
+  const int dh = g_i / p.NB, db = g_i & (p.NB - 1);
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+  const bool lrelu = p.act == ACT_LRELU, silu = p.act == ACT_SILU;
+  const float slope = p.slope;
+  const float bias_l = __ldg(p.bias + lane);  // Cout == 32: lane c holds channel c's parameters
+  sts_f32(ptab + 4 * lane, 1.f);
+  sts_f32(ptab + 128 + 4 * lane, bias_l);
+  __syncwarp();
+  const float4 tb = lds_f4(tailtab + 32 * 16);
+  int as = 0, pacc = 0, b_prev = -1;
+  for (int u = blockIdx.x; u < total_tiles; u += gridDim.x) {
+    const TileCoord tc = decode_tile(p, u);
+    const int t = part;  // this warp's sub-tile (idle when the tile has fewer)
+    const int w = tc.w0 + w_i, h0 = tc.h0 + dh + (p.t_along_h ? t * p.TH : 0);
+    const int bb = tc.b0 + (p.t_along_h ? db : db * p.T + t);
+    const bool ok = t < p.T && w < p.W && h0 < p.H && bb < p.B;
+    const uint32_t pix = ((uint32_t)bb * p.H + h0) * (uint32_t)p.W + w;
+    U8 rr[2];
+    float4 zi = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ub = 1.f;
+    if (ok) {
+      if (kRes) {
+        rr[0] = ldg256(p.res + (size_t)pix * 32);
+        rr[1] = ldg256(p.res + (size_t)pix * 32 + 16);
+      }
+      if (p.tail_res) zi = __ldg(reinterpret_cast<const float4*>(p.tail_z) + pix);
+      if (p.tail_ub) ub = __ldg(p.tail_ub + bb);
+    }
+    if (kScale) {  // per-image A / Bc (NB == 1 is not required here: the table is per warp and reloaded when the image changes)
+      const int b = bb < p.B ? bb : p.B - 1;
+      const int b0 = __shfl_sync(0xffffffffu, b, 0);
+      if (b0 != b_prev) {  // tiles of a CTA share their image for long runs (tile order: n, w, h, b)
+        b_prev = b0;
+        const float sc = __ldg(p.scale + (size_t)b0 * 32 + lane);
+        const float sh = p.shift ? __ldg(p.shift + (size_t)b0 * 32 + lane) : 0.f;
+        sts_f32(ptab + 4 * lane, sc);
+        sts_f32(ptab + 128 + 4 * lane, fmaf(bias_l, sc, sh));
+        __syncwarp();
+      }
+    }
+    mbar_wait(acc_full + 8 * as, pacc);
+    tc_fence_after();
+    if (t < p.T) {
+      float o0 = tb.x, o1 = tb.y, o2 = tb.z, o3 = tb.w;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        uint32_t v[16];
+        tmem_ld16(tmem_row + (uint32_t)((as * p.T + t) * 32 + 16 * k), v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 bc = lds_f4(ptab + 128 + 64 * k + 16 * g);
+          if (kScale) {
+            const float4 a = lds_f4(ptab + 64 * k + 16 * g);
+            f[g * 4 + 0] = fmaf(__uint_as_float(v[g * 4 + 0]), a.x, bc.x); f[g * 4 + 1] = fmaf(__uint_as_float(v[g * 4 + 1]), a.y, bc.y);
+            f[g * 4 + 2] = fmaf(__uint_as_float(v[g * 4 + 2]), a.z, bc.z); f[g * 4 + 3] = fmaf(__uint_as_float(v[g * 4 + 3]), a.w, bc.w);
+          } else {
+            f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + bc.x; f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + bc.y;
+            f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + bc.z; f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + bc.w;
+          }
+        }
+        if (silu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fast_silu(f[j]);
+        } else if (lrelu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * slope);
+        }
+        if (kRes) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 a = unpack_bf16x2(rr[k].v[j]);
+            f[2 * j] += a.x;
+            f[2 * j + 1] += a.y;
+          }
+        }
+        // the unfused layer stores bf16 and the output conv reads it back: keep that rounding, so that the fused result is
+        // bit-identical to the two-kernel form (same float32 accumulation order below)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 a = unpack_bf16x2(pack_bf16x2(f[2 * j], f[2 * j + 1]));
+          f[2 * j] = a.x;
+          f[2 * j + 1] = a.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 wj = lds_f4(tailtab + (uint32_t)(16 * k + j) * 16);
+          o0 = fmaf(f[j], wj.x, o0); o1 = fmaf(f[j], wj.y, o1); o2 = fmaf(f[j], wj.z, o2); o3 = fmaf(f[j], wj.w, o3);
+        }
+      }
+      if (ok) {
+        if (p.tail_res) {
+          const float inv = 1.0f / ub;
+          o0 += zi.x * inv; o1 += zi.y * inv; o2 += zi.z * inv; o3 += zi.w * inv;
+        }
+        reinterpret_cast<float4*>(p.tail_y)[pix] = make_float4(o0 * ub, o1 * ub, o2 * ub, o3 * ub);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+    if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
+  }
+}
+
 template <bool kPair>  // kPair: CTA-pair build (cluster of 2, cta_group::2 instructions); launched with a cluster dimension
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
@@ -746,6 +869,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
+  }
+  if (p.tail_w) {  // [32][4] weights + [4] bias of the fused output conv
+    for (int i = threadIdx.x; i < 132; i += blockDim.x)
+      sts_f32(smem_base + p.smem_tail_off + 4 * i, i < 128 ? __ldg(p.tail_w + i) : __ldg(p.tail_b + i - 128));
   }
   if (warp == 1) {
     if (kPair) {
@@ -1006,7 +1133,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const uint32_t ptab = smem_base + p.smem_epi_off + (uint32_t)(warp - 2) * 256u;
 #define YOND_EPI(S, R, A, V) epilogue_loop<S, R, A, V, kPair>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles)
     const bool few = p.T * (p.NT / 16) <= 8;  // at most two visits per warp and tile: hold two residual rows, not four
-    if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true, 2); else YOND_EPI(true, true, false, 2); }
+    if (!kPair && p.tail_w) {
+      const uint32_t tailtab = smem_base + p.smem_tail_off;
+      if (p.scale && p.res) epilogue_tail<true, true>(p, tmem_base, acc_full, acc_empty, ptab, tailtab, warp, lane, total_tiles);
+      else if (p.scale) epilogue_tail<true, false>(p, tmem_base, acc_full, acc_empty, ptab, tailtab, warp, lane, total_tiles);
+      else if (p.res) epilogue_tail<false, true>(p, tmem_base, acc_full, acc_empty, ptab, tailtab, warp, lane, total_tiles);
+      else epilogue_tail<false, false>(p, tmem_base, acc_full, acc_empty, ptab, tailtab, warp, lane, total_tiles);
+    }
+    else if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true, 2); else YOND_EPI(true, true, false, 2); }
     else if (p.scale) { if (silu) YOND_EPI(true, false, true, 4); else YOND_EPI(true, false, false, 4); }
     else if (p.res) {
       if (few) { if (silu) YOND_EPI(false, true, true, 2); else YOND_EPI(false, true, false, 2); }
@@ -1124,7 +1258,7 @@ int conv_tc_launch(const ConvLayer& Lin, cudaStream_t stream) {
   // (layers with a residual input are bound by their 3 x 64 B per pixel of HBM traffic, not by the MMAs: measured 930 us plain
   // vs 990-1030 us paired for 24.8 M pixels, so they keep the N = 32 form)
   const bool paired = env_paired && L.wpaired && L.mode == CONV_3X3_S1 && L.Cin0 == 32 && L.Cin1 == 0 && L.Cout == 32 && L.Win % 2 == 0 &&
-                      (L.res == nullptr || env_paired > 1);
+                      (L.res == nullptr || env_paired > 1) && L.tail_w == nullptr;
   if (paired) {  // (B,H,W,32) is (B,H,W/2,64): same memory, pixel pairs as 64-channel pixels
     L.Win /= 2;
     L.Cin0 = 64;
@@ -1176,7 +1310,7 @@ int conv_tc_launch(const ConvLayer& Lin, cudaStream_t stream) {
   p.NB = rows / p.TH;
   const int ncb = p.ncb0 + p.ncb1;
   const int nwt = ((L.mode == CONV_3X3_S1 || L.mode == CONV_3X3_S2) ? 9 : 1) * ncb;
-  const size_t smem_budget = 227 * 1024 - 2048 - kEpiWarps * 256;  // dynamic smem minus alignment slack, barriers, parameter rows
+  const size_t smem_budget = 227 * 1024 - 2048 - kEpiWarps * 256 - 1024;  // ... and the table of a fused output conv  // dynamic smem minus alignment slack, barriers, parameter rows
   p.b_stage_bytes = (uint32_t)p.NT * row_bytes;
   YOND_REQUIRE(p.b_stage_bytes % 1024 == 0, "conv_tc: weight stage not 1024-aligned");
   size_t wres_bytes = (size_t)nwt * p.b_stage_bytes;
@@ -1262,7 +1396,8 @@ int conv_tc_launch(const ConvLayer& Lin, cudaStream_t stream) {
   p.smem_b_off = (uint32_t)p.SA * p.a_stage_bytes;
   p.smem_bar_off = (uint32_t)align_up(p.smem_b_off + b_region, 1024);
   p.smem_epi_off = p.smem_bar_off + 512;
-  const size_t smem_bytes = p.smem_epi_off + kEpiWarps * 256 + 1024;  // barriers, parameter rows, alignment slack
+  p.smem_tail_off = p.smem_epi_off + kEpiWarps * 256;
+  const size_t smem_bytes = p.smem_tail_off + 1024 + 1024;  // barriers, parameter rows, output-conv table, alignment slack
   p.acc_stages = 2 * p.T * p.NT <= 512 ? 2 : 1;
   static const int env_split = env_int("YOND_CONV_EPI_SPLIT", 1);
   // Measured inside a GuidedResUnet forward on 8 x 12 MP frames (ncu, profiles/r02_conv_layers_pairing.txt): the pixel-pair
@@ -1295,6 +1430,18 @@ int conv_tc_launch(const ConvLayer& Lin, cudaStream_t stream) {
   p.res = L.res;
   p.out0 = L.out0;
   p.out1 = L.out1;
+  if (L.tail_w) {
+    YOND_REQUIRE(L.mode == CONV_3X3_S1 && L.Cout == 32 && !paired && p.tiles_n == 1 && p.NT == 32 && p.T <= 4 && !p.cta2 && L.tail_b &&
+                     L.tail_y && (L.tail_z || !L.tail_res),
+                 "conv_tc: the fused output conv needs a 3x3 layer with 32 output channels");
+    p.tail_w = L.tail_w;
+    p.tail_b = L.tail_b;
+    p.tail_z = L.tail_z;
+    p.tail_ub = L.tail_ub;
+    p.tail_y = L.tail_y;
+    p.tail_res = L.tail_res;
+    p.epi_split = 0;
+  }
 
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));

@@ -34,6 +34,16 @@ struct ConvLayer {
   const bf16* res;          // [B,Hout,Wout,Cout] or null, added after the activation
   bf16* out0;               // [B,Hout,Wout,Cout]
   bf16* out1;               // optional second output = SiLU(out0 value)
+  // Fused last layer of the network (Cout == 32 only): instead of storing out0, the epilogue applies the 1x1 conv nf -> 4 of
+  // archs/Unet.py:96-103 / :462-469 to the finished pixel, adds the network input and multiplies by the per-sample maximum
+  // (data_inv_normalize): y = (sum_c out[c] * tail_w[c][:] + tail_b + (tail_res ? tail_z / ub : 0)) * ub, float32 NHWC4.
+  // The 64 B/px activation tensor is neither written nor re-read.  tail_w == nullptr: off.
+  const float* tail_w;      // [Cout][4]
+  const float* tail_b;      // [4]
+  const float* tail_z;      // [B,H,W,4] network input (not normalised)
+  const float* tail_ub;     // [B] or null
+  float* tail_y;            // [B,H,W,4]
+  int tail_res;
 };
 
 // Channel block (K slice per pipeline stage) used for a layer: 64 when every source allows it, else 32.

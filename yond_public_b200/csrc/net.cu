@@ -306,6 +306,15 @@ double layer_flops(const LayerW& L, int B, int Hin, int Win) {
   }
 }
 
+struct TailArgs {  // fused output conv of the last tensor-core layer (ConvLayer::tail_*)
+  const float* w;
+  const float* b;
+  const float* z;
+  const float* ub;
+  float* y;
+  int res;
+};
+
 struct Runner {
   yond_net* n;
   cudaStream_t s;
@@ -314,7 +323,7 @@ struct Runner {
   bool dry = false;  // only count FLOPs / workspace
   // One tensor-core conv layer on `B` images (pointers already offset to the first image).
   void conv(const std::string& name, int B, int Hin, int Win, const bf16* src0, const bf16* src1, const float* scale,
-            const float* shift, int act, float slope, const bf16* res, bf16* out0, bf16* out1) {
+            const float* shift, int act, float slope, const bf16* res, bf16* out0, bf16* out1, const TailArgs* tail = nullptr) {
     const LayerW& L = n->conv.at(name);
     const double f = layer_flops(L, B, Hin, Win);
     flops += f;
@@ -339,9 +348,12 @@ struct Runner {
     c.res = res;
     c.out0 = out0;
     c.out1 = out1;
+    if (tail) {
+      c.tail_w = tail->w; c.tail_b = tail->b; c.tail_z = tail->z; c.tail_ub = tail->ub; c.tail_y = tail->y; c.tail_res = tail->res;
+    }
     const bool prof = n->profile && n->ev_used + 2 <= n->events.size();
     if (prof) cudaEventRecord(n->events[n->ev_used], s);
-    rc = n->conv_impl ? conv_ref_launch(c, s) : conv_tc_launch(c, s);
+    rc = n->conv_impl == 1 ? conv_ref_launch(c, s) : conv_tc_launch(c, s);
     if (prof) {
       cudaEventRecord(n->events[n->ev_used + 1], s);
       n->ev_used += 2;
@@ -438,19 +450,22 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
     }
   }
   // One residual block on `nb` images starting at image b0 (FiLM rows are per image): x raw, xs = SiLU(x).
-  auto block = [&](int l, int lv, int b0, int nb, const bf16* x, const bf16* xs, bf16* zb, bf16* out) {
+  auto block = [&](int l, int lv, int b0, int nb, const bf16* x, const bf16* xs, bf16* zb, bf16* out, const TailArgs* tail = nullptr) {
     const int C = n->ch(lv), h = H >> lv, w = W >> lv;
     const std::string p = "conv" + std::to_string(l);
     const float* a = va[l] ? va[l] + (size_t)b0 * C : nullptr;
     const float* bb = vb[l] ? vb[l] + (size_t)b0 * C : nullptr;
     if (guided || res2) {  // z = SiLU(conv1(SiLU(x)) * tk + tb); out = conv2(z) + x   (ResUnet2: tk = 1, tb = 0)
       R.conv(p + ".conv1", nb, h, w, xs, nullptr, a, bb, ACT_SILU, 0.f, nullptr, zb, nullptr);
-      R.conv(p + ".conv2", nb, h, w, zb, nullptr, nullptr, nullptr, ACT_NONE, 0.f, x, out, nullptr);
+      R.conv(p + ".conv2", nb, h, w, zb, nullptr, nullptr, nullptr, ACT_NONE, 0.f, x, out, nullptr, tail);
     } else {  // SNR: z = SiLU(conv1(SiLU(x)) * a1); out = conv2(z) * a2 + x
       R.conv(p + ".conv1", nb, h, w, xs, nullptr, a, nullptr, ACT_SILU, 0.f, nullptr, zb, nullptr);
-      R.conv(p + ".conv2", nb, h, w, zb, nullptr, bb, nullptr, ACT_NONE, 0.f, x, out, nullptr);
+      R.conv(p + ".conv2", nb, h, w, zb, nullptr, bb, nullptr, ACT_NONE, 0.f, x, out, nullptr, tail);
     }
   };
+  // The 1x1 output conv (+ input residual, x ub) rides in the epilogue of the last 3x3 layer: its 64 B/px input is never stored.
+  static const int env_tail = getenv("YOND_FUSE_TAIL") ? atoi(getenv("YOND_FUSE_TAIL")) : 1;
+  const bool fuse_tail = env_tail && !n->conv_impl && nf == 32 && H >= 16;
   const int C0 = n->ch(0), C1 = n->ch(1), C2 = n->ch(2), C3 = n->ch(3), C4 = n->ch(4);
   const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2, H3 = H >> 3, W3 = W >> 3, H4 = H >> 4, W4 = W >> 4;
   // skips of the full-resolution levels (whole batch) and the level-2 hand-over tensors
@@ -504,9 +519,15 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
       R.conv("conv8_2", nb, H1, W1, t8, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c8, nullptr);
       R.conv("upv9", nb, H1, W1, c8, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u9, nullptr);
       R.conv("conv9_1", nb, H, W, u9, skip0 + (size_t)b0 * px(0) * C0, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, t9, nullptr);
-      R.conv("conv9_2", nb, H, W, t9, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c9, nullptr);
-      RUN(tail_conv_launch(c9, n->tail_w, n->f32["conv10_1.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->res, nb,
-                           H, W, nf, y + (size_t)b0 * px(0) * 4, s));
+      if (fuse_tail) {
+        const TailArgs ta{n->tail_w, dry ? nullptr : n->f32["conv10_1.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr,
+                          y + (size_t)b0 * px(0) * 4, n->res};
+        R.conv("conv9_2", nb, H, W, t9, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c9, nullptr, &ta);
+      } else {
+        R.conv("conv9_2", nb, H, W, t9, nullptr, nullptr, nullptr, ACT_LRELU, 0.2f, nullptr, c9, nullptr);
+        RUN(tail_conv_launch(c9, n->tail_w, n->f32["conv10_1.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->res, nb,
+                             H, W, nf, y + (size_t)b0 * px(0) * 4, s));
+      }
     }
   } else {
     bf16* x2 = buf(B, 2, C2);   // pool2 output (raw) and its SiLU: inputs of the level-2 block
@@ -559,9 +580,15 @@ int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, f
         R.conv("upv9", nb, H1, W1, c8, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, u9, nullptr);
         R.conv("conv9.short_cut.0", nb, H, W, u9, skip0 + (size_t)b0 * px(0) * C0, nullptr, nullptr, ACT_NONE, 0.f, nullptr, x0, x0s);
       }
-      block(9, 0, b0, nb, x0, x0s, z0, c9);
-      RUN(tail_conv_launch(c9, n->tail_w, n->f32["conv10.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->res, nb, H, W,
-                           nf, y + (size_t)b0 * px(0) * 4, s));
+      if (fuse_tail) {
+        const TailArgs ta{n->tail_w, dry ? nullptr : n->f32["conv10.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr,
+                          y + (size_t)b0 * px(0) * 4, n->res};
+        block(9, 0, b0, nb, x0, x0s, z0, c9, &ta);
+      } else {
+        block(9, 0, b0, nb, x0, x0s, z0, c9);
+        RUN(tail_conv_launch(c9, n->tail_w, n->f32["conv10.bias"], z + (size_t)b0 * px(0) * 4, ubn ? ubn + b0 : nullptr, n->res, nb, H, W,
+                             nf, y + (size_t)b0 * px(0) * 4, s));
+      }
     }
   }
   film_join();
@@ -654,7 +681,7 @@ double yond_net_flops(yond_net_t* n, int B, int H, int W) {
 }
 
 int yond_net_set_conv_impl(yond_net_t* n, int impl) {
-  n->conv_impl = impl ? 1 : 0;
+  n->conv_impl = impl == 2 ? 2 : (impl ? 1 : 0);  // 2: tensor-core kernels with the layer fusions off (A/B checks)
   return YOND_OK;
 }
 
