@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--net-only", type=int, default=0, help="profile only the network forward on this many 128x128 packed blocks")
 ap.add_argument("--arch", default="gru")
 ap.add_argument("--step", type=int, default=0, help="profile one batched pipeline step over this many images")
+ap.add_argument("--frames", type=int, default=0, help="profile one batched pipeline step over this many 12 MP frames (bench.py's headline workload)")
 ap.add_argument("--time", type=int, default=0, help="with --net-only: time this many forwards with CUDA events instead of profiling")
 ap.add_argument("--frame", default=None, help="HxW packed frame for --net-only, e.g. 1536x2016")
 args = ap.parse_args()
@@ -44,6 +45,18 @@ if args.net_only:
         sys.exit(0)
     torch.cuda.cudart().cudaProfilerStart()
     drv.net.forward_nhwc(z, ub, t if "guided" in arch else None)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+elif args.frames:
+    sd = synth.bench_state_dict(arch, seed=0)
+    drv = Y.YOND_SIDD(arch, bench.PIPE_FRAME, state_dict=sd)
+    fr = bench.synth_frames(args.frames, seed=2024)
+    dev_in = torch.from_numpy(fr.reshape(args.frames, 1, bench.FRAME_H, bench.FRAME_W)).cuda()
+    for i in range(2):
+        drv.iter_denoise_batch(dev_in, dict(bench.P0))
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    drv.iter_denoise_batch(dev_in, dict(bench.P0))
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
 elif args.step:

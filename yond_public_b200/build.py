@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libyond_b200.so")
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(dig)
