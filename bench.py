@@ -44,7 +44,7 @@ WORKLOAD = ("configs[4]/[2]: synthetic 12 MP Bayer frames (4032x3024, 10-bit), 8
             "reference's random init (no checkpoint offline; passes the reference's round-2 guard so both rounds run)")
 WORKLOAD_C2 = ("configs[1]: 1280 synthetic 256x256 Bayer blocks (40 images x 32), GuidedResUnet, SIDD_simple+full_pre_grumix "
                "pipeline (per-image estimate on the mosaic, 32 block-wise VST denoises, SIDD_256 collab estimate, second round)")
-E2E_GROUP_FRAMES = int(os.environ.get("YOND_E2E_GROUP_FRAMES", "4"))
+E2E_GROUP_FRAMES = int(os.environ.get("YOND_E2E_GROUP_FRAMES", "8"))
 E2E_GROUP_IMAGES = int(os.environ.get("YOND_E2E_GROUP", "8"))
 
 
