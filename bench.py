@@ -460,6 +460,15 @@ def run_b200(args):
             "secondary": secondary,
             "cpu_baseline": cpu_base,
         }
+        if world == 1:  # BASELINE configs[4], second half: isolated HBM-kernel sweep (device-resident, ~5 s; tools/hbm_sweep.py)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import hbm_sweep
+                line["kernel_sweep"] = {"what": "pack / unpack / uint16 ingest / estimator (maps + fit) / fused VST front / fused inverse back, isolated, "
+                                                "1 ... 256 MP of Bayer pixels; frac = algorithmic bytes / time / hbm peak",
+                                        "rows": hbm_sweep.sweep(peak_gbs=peak_hbm)}
+            except Exception as e:  # the sweep is an extra: never lose the bench line over it
+                line["kernel_sweep"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
