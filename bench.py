@@ -318,6 +318,25 @@ def run_b200(args):
     value = world * mp_step * args.steps / (ms / 1e3)
     e2e = world * mp_step * args.steps / (ms_e2e / 1e3)
 
+    # the same end-to-end step from uint16 sensor mosaics: the frames quantised to the 10-bit sensor range, H2D of
+    # 2 B/px, dataset normalisation applied on load by the estimator and the VST front end
+    raw16 = np.clip(np.rint(frames_np * 959.0 + 64.0), 0, 1023).astype(np.uint16)
+    host_in16 = torch.from_numpy(raw16.view(np.int16).reshape(N_FRAMES, 1, FRAME_H, FRAME_W)).pin_memory()
+
+    def step_frames_e2e16():
+        last["seq"] = last.get("seq", 0) + 1
+        jobs.append(drv.iter_denoise_host(host_in16, host_outs[last["seq"] % 2], dict(P0), group=E2E_GROUP_FRAMES, wait=False, raw=(64, 1023, 1)))
+        collect(1)
+
+    def e2e16_steps():
+        for _ in range(args.steps):
+            step_frames_e2e16()
+        collect(0)
+    step_frames_e2e16()
+    collect(0)
+    ms_e2e16 = timed(e2e16_steps, 1)
+    e2e16 = world * mp_step * args.steps / (ms_e2e16 / 1e3)
+
     # drop-in call: per-frame IterDenoise(np arrays) -> np arrays through the reference's signature (pageable NumPy in / out)
     def dropin(drv_, arrays, p):
         torch.cuda.synchronize()
@@ -456,6 +475,10 @@ def run_b200(args):
             "roofline_hbm": {"peak_gbs": peak_hbm, "peak_source": peak_src + " hbm_gbs", "bound": "hbm",
                              "measured_in": "the timed region (CUDA events around every stage on the launching stream); bytes = algorithmic bytes per Bayer pixel (SURVEY 8d) x pixels",
                              "kernels": hbm_table(hbm_prof, peak_hbm)},
+            "e2e_raw16": {"value": e2e16, "unit": "MP/s", "ms_per_step": ms_e2e16 / steps, "h2d_bytes_per_step": int(host_in16.numel() * 2),
+                          "d2h_bytes_per_step": int(host_out.numel() * 4),
+                          "api": "the e2e call on uint16 sensor mosaics: iter_denoise_host(..., raw=(black, white, ratio)); the estimator and the "
+                                 "VST front end normalise on load, the float32 input frame never exists"},
             "frame_sharded": frame_sharded,
             "secondary": secondary,
             "cpu_baseline": cpu_base,

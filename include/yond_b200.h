@@ -53,6 +53,12 @@ int yond_unpack(const float* rggb, float* bayer, int B, int h, int w, void* stre
 int yond_pack_raw(const uint16_t* raw, float* out, int B, int H, int W, const int* pos4, const float* black4, float white,
                   int clip, int layout, void* stream);
 
+/* How a uint16 sensor mosaic becomes the float32 frame the path works on (the *_raw16 entry points apply it on load). */
+typedef struct yond_raw_norm {
+  float black, white, ratio; /* out = (float32(raw) - black) * ratio / (white - black), float32 arithmetic in that order */
+  int clip;                  /* clip to [0,1] afterwards */
+} yond_raw_norm;
+
 /* Dataset normalisation of the 14-bit drivers — data_process/yond_datasets.py:955-961, :1053-1056:
  * out = (float32(raw) - black) * ratio / (white - black) on the mosaic itself, float32 arithmetic in that order, unclipped unless
  * `clip`.  `n` pixels (any shape), 2 B/px read + 4 B/px written.  The result is the `data['lr']` the drivers hand to IterDenoise
@@ -110,6 +116,11 @@ typedef struct {
 int yond_vst_fwd(const float* bayer, float* z, float* ub, int B, int H, int W, int pad_l, int pad_r, int pad_t,
                  int pad_b, const yond_vst_params* params_dev, const float* rows, const float* xnodes,
                  int row_stride, void* stream);
+/* The same front end reading the uint16 sensor mosaic (B,H,W) and normalising it on load (2 B/px reads; the
+ * float32 frame of data_process/yond_datasets.py:955-961 / :1053-1056 never exists in memory). */
+int yond_vst_fwd_raw16(const uint16_t* raw, const yond_raw_norm* nrm, float* z, float* ub, int B, int H, int W, int pad_l, int pad_r,
+                       int pad_t, int pad_b, const yond_vst_params* params_dev, const float* rows, const float* xnodes, int row_stride,
+                       void* stream);
 /* ---- A18 back half (YOND_SIDD.py:286,289-298, caller's clip :389/:406): y (B,hp,wp,4) f32 -> clamp(0,1) -> crop ->
  * de-normalise -> inverse VST -> unpack -> /scale -> [clip 0..1] -> Bayer (B,H,W) f32. */
 int yond_vst_inv(const float* y, float* bayer, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
@@ -171,6 +182,11 @@ int yond_masked_sums(const float* lap, const float* mean, const float* var, size
  *   th, index, percent, redo flag, ths[24], npeaks[24].  `work`: yond_nlf_fit_work_bytes(nseg), 256-byte aligned. */
 int yond_nlf_maps_bayer(const float* x, int x_mosaic, const float* y, int y_mosaic, float* var, float* mean, float* lap,
                         int nimg, int nblk, int H, int W, int split_blocks, int k, int mode, float* seg_max, void* work,
+                        void* stream);
+/* The same maps with the FIRST input given as the uint16 sensor mosaic, normalised on load (the second input of the collab mode is
+ * the float32 output of round 1). */
+int yond_nlf_maps_raw16(const uint16_t* x, const yond_raw_norm* nrm, int x_mosaic, const float* y, int y_mosaic, float* var, float* mean,
+                        float* lap, int nimg, int nblk, int H, int W, int split_blocks, int k, int mode, float* seg_max, void* work,
                         void* stream);
 size_t yond_nlf_fit_work_bytes(int nseg);
 int yond_nlf_fit(const float* var, const float* mean, const float* lap, size_t seg_len, int nseg, const double* quants_host,

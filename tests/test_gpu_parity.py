@@ -595,6 +595,36 @@ def test_normalize_raw_bit_exact(Y):
     assert torch.equal(Y.normalize_raw(t, 512, 16383, 200).cpu(), torch.from_numpy(ref))
 
 
+def test_pipeline_on_uint16_mosaic_bit_identical(Y):
+    """the estimator and the VST front end read the uint16 sensor mosaic and normalise on load; the whole
+    two-round pipeline then equals the pipeline fed with the float32 frame normalize_raw() produces (same bits per loaded value) — for 14-bit
+    whole frames with a low-light gain (full_dn) and for SIDD-shaped 10-bit block stacks (incl. the SIDD_256 collab estimate)."""
+    rng = np.random.default_rng(3)
+    sd = O.smoother_state_dict(ARCHS["gru"])
+    cases = [
+        (dict(PIPE_C4), (2, 1, 192, 256), 512, 16383, 100, {"wp": 16383, "bl": 512, "ratio": 100, "scale": (16383 - 512) / 100}),
+        (dict(PIPE), (1, 32, 64, 64), 64, 1023, 1, {"wp": 1023, "bl": 64, "ratio": 1, "scale": 959.0}),
+    ]
+    for pipe, shape, bl, wp, ratio, p in cases:
+        clean = np.stack([O.synth_clean_smooth(rng, shape[2], shape[3] * shape[1]) for _ in range(shape[0])])
+        dn = (clean * (wp - bl) / ratio)
+        raw = np.clip(rng.poisson(np.maximum(dn, 0) / 2.0) * 2.0 + rng.normal(0, 3.0, dn.shape) + bl, 0, wp).astype(np.uint16)
+        raw = raw.reshape(shape[0], shape[2], shape[1], shape[3]).transpose(0, 2, 1, 3).copy()  # (nimg, nblk, H, W)
+        drv = Y.YOND_SIDD(ARCHS["gru"], pipe, state_dict=sd)
+        drv.engine.max_value = 4.0
+        p = dict(p, gain=1, sigma=0)
+        t16 = torch.from_numpy(raw.view(np.int16)).cuda()
+        a = drv.iter_denoise_batch(t16, dict(p), raw=(bl, wp, ratio))
+        xf = Y.normalize_raw(t16, bl, wp, ratio)
+        b = drv.iter_denoise_batch(xf, dict(p))
+        # the maps are bit-identical; the regression sums are combined with float64 atomics (order varies run to run), so the
+        # numbers agree to float64 rounding and the outputs to float32 rounding of the parameters derived from them
+        for i in range(2):
+            np.testing.assert_allclose(np.asarray(a["regs"][i]), np.asarray(b["regs"][i]), rtol=1e-10, equal_nan=True)
+            assert float((a["raw_dns"][i] - b["raw_dns"][i]).abs().max()) < 1e-6, i
+        assert a["rounds"].tolist() == b["rounds"].tolist()
+
+
 # ------------------------------------------------------------------ SURVEY 8(f)-3: metrics on the device
 def test_block_metrics_golden(Y, golden):
     """Raw PSNR / MATLAB-style SSIM per mosaic block on the device vs the reference's own numbers (YOND_SIDD.py:679-721 run by

@@ -21,6 +21,11 @@ class VstParams(C.Structure):
                 ("upper", C.c_float), ("lut_row", C.c_int32), ("table_n", C.c_int32), ("exact_inverse", C.c_int32)]
 
 
+class RawNorm(C.Structure):
+    """yond_raw_norm (include/yond_b200.h): (float32(raw) - black) * ratio / (white - black), optional clip to [0,1]."""
+    _fields_ = [("black", C.c_float), ("white", C.c_float), ("ratio", C.c_float), ("clip", C.c_int)]
+
+
 _P, _I, _SZ, _D, _U64 = C.c_void_p, C.c_int, C.c_size_t, C.c_double, C.c_uint64
 
 # name -> (restype, argtypes); every symbol include/yond_b200.h declares
@@ -42,6 +47,7 @@ SIGNATURES = {
     "yond_lut_apply": (_I, [_P, _P, _SZ, _P, _P, _I, _D, _D, _P]),
     "yond_table_apply": (_I, [_P, _P, _SZ, _P, _P, _I, _P]),
     "yond_vst_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "yond_vst_fwd_raw16": (_I, [_P, C.POINTER(RawNorm), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "yond_vst_inv": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "yond_pack_pad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "yond_crop_unpack": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -53,6 +59,7 @@ SIGNATURES = {
     "yond_score3_bins": (_I, [_P, _P, _SZ, _I, _P, _I, _P, _P, _P]),
     "yond_masked_sums": (_I, [_P, _P, _P, _SZ, _I, _P, _P, _P]),
     "yond_nlf_maps_bayer": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "yond_nlf_maps_raw16": (_I, [_P, C.POINTER(RawNorm), _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "yond_nlf_fit_work_bytes": (_SZ, [_I]),
     "yond_nlf_fit": (_I, [_P, _P, _P, _SZ, _I, C.POINTER(_D), _I, _P, _P, _P, _P]),
     "yond_chain_work_bytes": (_SZ, [_I]),

@@ -65,6 +65,31 @@ __host__ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
+// Sensor mosaic read in place of a float32 Bayer frame: the dataset normalisation of
+// data_process/yond_datasets.py:955-961 / :1053-1056, (float32(raw) - black) * ratio / (white - black) in float32 in that order,
+// is applied on load, so the normalised frame never exists in memory (2 B/px instead of 4 per read).  base == nullptr: float source.
+struct RawNorm {
+  const uint16_t* base;
+  float bl, ratio, denom;
+  int clip;
+};
+__device__ __forceinline__ float raw_norm(uint32_t v, const RawNorm& q) {
+  float t = __fdiv_rn(__fmul_rn(__fsub_rn((float)v, q.bl), q.ratio), q.denom);
+  if (q.clip) t = fminf(fmaxf(t, 0.f), 1.f);
+  return t;
+}
+static inline RawNorm make_raw_norm(const uint16_t* base, const yond_raw_norm* n) {
+  RawNorm q{};
+  if (base && n) {
+    q.base = base;
+    q.bl = n->black;
+    q.ratio = n->ratio;
+    q.denom = n->white - n->black;
+    q.clip = n->clip;
+  }
+  return q;
+}
+
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

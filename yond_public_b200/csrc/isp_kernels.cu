@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict
                                                          float* __restrict__ ub, int H, int W, int pl, int pt, int hp, int wp,
                                                          const yond_vst_params* __restrict__ params,
                                                          const float* __restrict__ rows, const float* __restrict__ xnodes,
-                                                         int row_stride) {
+                                                         int row_stride, RawNorm raw) {
   extern __shared__ float4 tab[];
   __shared__ TabInfo ti;
   const int b = blockIdx.y;
@@ -382,10 +382,18 @@ __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict
   auto refl = [](int t, int n) { t = t < 0 ? -t : t; return t >= n ? 2 * (n - 1) - t : t; };
 #pragma unroll 1
   for (int it = 0; it < kFwdPix && idx < npix; ++it) {
-    const float* r0 = frame + (size_t)(2 * refl(i - pt, h)) * W + 2 * refl(j - pl, w);
-    const float2 a = ldg_stream_f2(reinterpret_cast<const float2*>(r0));
-    const float2 d = ldg_stream_f2(reinterpret_cast<const float2*>(r0 + W));
-    float v[4] = {a.x, a.y, d.x, d.y};
+    const size_t poff = (size_t)(2 * refl(i - pt, h)) * W + 2 * refl(j - pl, w);
+    float v[4];
+    if (raw.base) {  // uint16 sensor mosaic, normalised on load
+      const uint16_t* r16 = raw.base + (size_t)b * H * W + poff;
+      const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(r16)), d = __ldg(reinterpret_cast<const uint32_t*>(r16 + W));
+      v[0] = raw_norm(a & 0xffffu, raw); v[1] = raw_norm(a >> 16, raw); v[2] = raw_norm(d & 0xffffu, raw); v[3] = raw_norm(d >> 16, raw);
+    } else {
+      const float* r0 = frame + poff;
+      const float2 a = ldg_stream_f2(reinterpret_cast<const float2*>(r0));
+      const float2 d = ldg_stream_f2(reinterpret_cast<const float2*>(r0 + W));
+      v[0] = a.x; v[1] = a.y; v[2] = d.x; v[3] = d.y;
+    }
     if (kVst) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -630,7 +638,8 @@ int yond_table_apply(const float* x, float* bias, size_t n, const float* vals, c
 }
 
 static int launch_fwd(bool vst, const float* bayer, float* z, float* ub, int B, int H, int W, int pl, int pr, int pt, int pb,
-                      const yond_vst_params* params, const float* rows, const float* xnodes, int row_stride, void* stream) {
+                      const yond_vst_params* params, const float* rows, const float* xnodes, int row_stride, void* stream,
+                      RawNorm raw = RawNorm{}) {
   YOND_REQUIRE(B > 0 && H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0, "vst_fwd: H,W must be even");
   const int h = H / 2, w = W / 2;
   YOND_REQUIRE(pl >= 0 && pr >= 0 && pt >= 0 && pb >= 0 && pl < w && pr < w && pt < h && pb < h,
@@ -650,9 +659,9 @@ static int launch_fwd(bool vst, const float* bayer, float* z, float* ub, int B, 
     std::call_once(once, [] { attr_err = cudaFuncSetAttribute(vst_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (attr_err != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(vst_fwd_kernel) failed: %s", cudaGetErrorString(attr_err));
     YondProfScope prof("vst_fwd", s, 8.0 * (double)B * H * W);  // 4 R (Bayer f32) + 4 W (z f32) per Bayer pixel
-    vst_fwd_kernel<true><<<grid, kBlock, smem, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, params, rows, xnodes, row_stride);
+    vst_fwd_kernel<true><<<grid, kBlock, smem, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, params, rows, xnodes, row_stride, raw);
   } else {
-    vst_fwd_kernel<false><<<grid, kBlock, 0, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, nullptr, nullptr, nullptr, 0);
+    vst_fwd_kernel<false><<<grid, kBlock, 0, s>>>(bayer, z, ub, H, W, pl, pt, hp, wp, nullptr, nullptr, nullptr, 0, raw);
   }
   YOND_LAUNCH_CHECK();
   return YOND_OK;
@@ -662,6 +671,14 @@ int yond_vst_fwd(const float* bayer, float* z, float* ub, int B, int H, int W, i
                  const yond_vst_params* params_dev, const float* rows, const float* xnodes, int row_stride, void* stream) {
   YOND_REQUIRE(params_dev != nullptr, "yond_vst_fwd: params required");
   return launch_fwd(true, bayer, z, ub, B, H, W, pad_l, pad_r, pad_t, pad_b, params_dev, rows, xnodes, row_stride, stream);
+}
+int yond_vst_fwd_raw16(const uint16_t* raw, const yond_raw_norm* nrm, float* z, float* ub, int B, int H, int W, int pad_l, int pad_r,
+                       int pad_t, int pad_b, const yond_vst_params* params_dev, const float* rows, const float* xnodes, int row_stride,
+                       void* stream) {
+  YOND_REQUIRE(params_dev != nullptr && raw != nullptr && nrm != nullptr, "yond_vst_fwd_raw16: null argument");
+  YOND_REQUIRE(nrm->white > nrm->black && (uintptr_t)raw % 4 == 0 && W % 2 == 0, "yond_vst_fwd_raw16: bad normalisation / alignment");
+  return launch_fwd(true, nullptr, z, ub, B, H, W, pad_l, pad_r, pad_t, pad_b, params_dev, rows, xnodes, row_stride, stream,
+                    make_raw_norm(raw, nrm));
 }
 int yond_pack_pad(const float* bayer, float* z, float* ub, int B, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
                   void* stream) {

@@ -44,6 +44,7 @@ struct BoxSrc {
   float* seg_max;        // optional: per-image maximum of max(x, 0) (atomicMax on the float bits), image = b / imgs_per_seg
   int imgs_per_seg;
   int mosaic_blocks;     // > 0: box-filter image b is block b % n of mosaic b / n (mosaic layout, blocks as separate images)
+  RawNorm raw;           // raw.base != nullptr (Bayer mode only): the source is the uint16 sensor mosaic, normalised on load
 };
 // BORDER_REFLECT_101 for an index at most one image away from the valid range (the filter radius is smaller than the image)
 __device__ __forceinline__ int reflect_once(int i, int n) {
@@ -88,15 +89,17 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
   }
   const int i0 = blockIdx.y * rows_per_strip;
   const int i1 = min(h, i0 + rows_per_strip);
-  const float* colbase;
+  size_t coloff;  // element offset of this thread's column in row 0 of its image
   if (kBayer) {
     const int blk = col_src / src.blk_w;
-    colbase = src.base + (size_t)b * src.img_stride + (size_t)blk * src.blk_stride + 2 * (col_src - blk * src.blk_w);
+    coloff = (size_t)b * src.img_stride + (size_t)blk * src.blk_stride + 2 * (col_src - blk * src.blk_w);
     if (src.mosaic_blocks > 0)
-      colbase += (size_t)(b / src.mosaic_blocks) * (2 * h) * src.row_len + (size_t)(b % src.mosaic_blocks) * src.blk_stride;
+      coloff += (size_t)(b / src.mosaic_blocks) * (2 * h) * src.row_len + (size_t)(b % src.mosaic_blocks) * src.blk_stride;
   } else {
-    colbase = src.base + (size_t)b * src.img_stride + 4 * (size_t)col_src;
+    coloff = (size_t)b * src.img_stride + 4 * (size_t)col_src;
   }
+  const float* colbase = src.base + coloff;
+  const uint16_t* colbase16 = kBayer && src.raw.base ? src.raw.base + coloff : nullptr;
   const uint32_t row_pitch = kBayer ? 2u * (uint32_t)src.row_len : (uint32_t)src.row_len;  // an image stays below 2^32 floats
   float vmax = 0.f;
   double s[NQ];
@@ -110,9 +113,14 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
     }
   };
   auto load = [&](int i) {
-    const float* p = colbase + (uint32_t)reflect_once(i, h) * row_pitch;
+    const uint32_t roff = (uint32_t)reflect_once(i, h) * row_pitch;
+    const float* p = colbase + roff;
     float4 v;
-    if (kBayer) {
+    if (kBayer && colbase16) {  // uint16 mosaic: two 32-bit loads per packed pixel, normalised on load
+      const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(colbase16 + roff));
+      const uint32_t d = __ldg(reinterpret_cast<const uint32_t*>(colbase16 + roff + src.row_len));
+      v = make_float4(raw_norm(a & 0xffffu, src.raw), raw_norm(a >> 16, src.raw), raw_norm(d & 0xffffu, src.raw), raw_norm(d >> 16, src.raw));
+    } else if (kBayer) {
       const float2 a = __ldg(reinterpret_cast<const float2*>(p)), d = __ldg(reinterpret_cast<const float2*>(p + src.row_len));
       v = make_float4(a.x, a.y, d.x, d.y);
     } else {
@@ -915,13 +923,15 @@ int yond_nlf_maps(const float* x, const float* y, float* var, float* mean, float
   return nlf_maps_impl(xs, &ys, false, var, mean, lap, B, h, w, k, mode, work, (cudaStream_t)stream);
 }
 
-int yond_nlf_maps_bayer(const float* x, int x_mosaic, const float* y, int y_mosaic, float* var, float* mean, float* lap, int nimg,
-                        int nblk, int H, int W, int split_blocks, int k, int mode, float* seg_max, void* work, void* stream) {
-  YOND_REQUIRE(x && var && mean && lap && work, "yond_nlf_maps_bayer: null argument");
+static int nlf_maps_bayer_impl(const float* x, const uint16_t* x16, const yond_raw_norm* nrm, int x_mosaic, const float* y, int y_mosaic,
+                               float* var, float* mean, float* lap, int nimg, int nblk, int H, int W, int split_blocks, int k, int mode,
+                               float* seg_max, void* work, void* stream) {
+  YOND_REQUIRE((x || x16) && var && mean && lap && work, "yond_nlf_maps_bayer: null argument");
+  YOND_REQUIRE(!x16 || (nrm && nrm->white > nrm->black && (uintptr_t)x16 % 4 == 0), "yond_nlf_maps_raw16: normalisation / 4-byte aligned mosaic required");
   YOND_REQUIRE(nimg > 0 && nblk > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "yond_nlf_maps_bayer: H,W must be even");
   YOND_REQUIRE(k % 2 == 1 && k >= 3 && k <= kMaxK, "yond_nlf_maps_bayer: odd k <= %d required (got %d)", kMaxK, k);
   YOND_REQUIRE(mode == 0 || (mode == 1 && y != nullptr), "yond_nlf_maps_bayer: collab mode needs the second input");
-  YOND_REQUIRE((uintptr_t)x % 8 == 0 && (!y || (uintptr_t)y % 8 == 0), "yond_nlf_maps_bayer: 8-byte aligned frames required");
+  YOND_REQUIRE((!x || (uintptr_t)x % 8 == 0) && (!y || (uintptr_t)y % 8 == 0), "yond_nlf_maps_bayer: 8-byte aligned frames required");
   cudaStream_t s = (cudaStream_t)stream;
   // split_blocks = 1: every block is its own image for the box filters (SIDD_256, YOND_SIDD.py:65,91-93);
   // split_blocks = 0: the nblk blocks of an image form one mosaic (:315), h x (nblk*w) packed pixels.
@@ -951,10 +961,24 @@ int yond_nlf_maps_bayer(const float* x, int x_mosaic, const float* y, int y_mosa
     return d;
   };
   BoxSrc xs = describe(x, x_mosaic);
+  xs.raw = make_raw_norm(x16, nrm);
   xs.seg_max = seg_max;
   if (seg_max) YOND_CUDA_CHECK(cudaMemsetAsync(seg_max, 0, sizeof(float) * nimg, s));
   BoxSrc ys = describe(y, y_mosaic);
   return nlf_maps_impl(xs, &ys, true, var, mean, lap, B, h, w, k, mode, work, s);
+}
+int yond_nlf_maps_bayer(const float* x, int x_mosaic, const float* y, int y_mosaic, float* var, float* mean, float* lap, int nimg,
+                        int nblk, int H, int W, int split_blocks, int k, int mode, float* seg_max, void* work, void* stream) {
+  YOND_REQUIRE(x != nullptr, "yond_nlf_maps_bayer: null argument");
+  return nlf_maps_bayer_impl(x, nullptr, nullptr, x_mosaic, y, y_mosaic, var, mean, lap, nimg, nblk, H, W, split_blocks, k, mode, seg_max, work,
+                             stream);
+}
+int yond_nlf_maps_raw16(const uint16_t* x, const yond_raw_norm* nrm, int x_mosaic, const float* y, int y_mosaic, float* var, float* mean,
+                        float* lap, int nimg, int nblk, int H, int W, int split_blocks, int k, int mode, float* seg_max, void* work,
+                        void* stream) {
+  YOND_REQUIRE(x != nullptr && nrm != nullptr, "yond_nlf_maps_raw16: null argument");
+  return nlf_maps_bayer_impl(nullptr, x, nrm, x_mosaic, y, y_mosaic, var, mean, lap, nimg, nblk, H, W, split_blocks, k, mode, seg_max, work,
+                             stream);
 }
 
 size_t yond_select_work_bytes(int nseg) { return (size_t)(nseg < 1 ? 1 : nseg) * sizeof(SelectWork) + 256; }

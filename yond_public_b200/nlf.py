@@ -130,13 +130,14 @@ class NlfEstimator:
     DETAIL = 4 + 2 * 24
 
     def estimate_dev(self, x, y=None, k=29, split_blocks=False, x_mosaic=False, y_mosaic=False, nblk=None, seg_max=None,
-                     details=False, step=5):
+                     details=False, step=5, raw=None):
         """SelfNLF (y None) / CollabNLF straight from Bayer frames, everything on the device.
 
         x: blocks layout (nimg, nblk, H, W) or, with x_mosaic, mosaic layout (nimg, H, nblk*W) (`nblk` then required; plain
         frames are nblk = 1 in either layout).  split_blocks: every block is its own image for the box filters (SIDD_256).
         seg_max (optional, (nimg,) f32 CUDA): receives max(x, 0) per image.  Returns regs (nimg, 2) float64 on the
-        device [, detail (nimg, DETAIL)]; nothing is read back."""
+        device [, detail (nimg, DETAIL)]; nothing is read back.  x may be the uint16 sensor mosaic (a 16-bit integer tensor) with
+        raw = _lib.RawNorm(black, white, ratio, clip): it is normalised on load."""
         lib = self.lib
         if x_mosaic:
             nimg, H, Wm = x.shape
@@ -144,7 +145,8 @@ class NlfEstimator:
             W = Wm // nb
         else:
             nimg, nb, H, W = x.shape
-        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        is_raw = x.dtype in (torch.int16, torch.uint16)
+        assert x.is_cuda and x.is_contiguous() and (x.dtype == torch.float32 or (is_raw and raw is not None))
         dev = x.device
         h, wb = H // 2, W // 2
         B, w = (nimg * nb, wb) if split_blocks else (nimg, nb * wb)
@@ -155,8 +157,12 @@ class NlfEstimator:
         mode = 0 if y is None else 1
         if y is not None:
             assert y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and y.numel() == x.numel()
-        check(lib.yond_nlf_maps_bayer(ptr(x), int(bool(x_mosaic)), ptr(y), int(bool(y_mosaic)), ptr(var), ptr(mean), ptr(lap), nimg, nb,
-                                      H, W, int(bool(split_blocks)), int(k), mode, ptr(seg_max), ptr(work), stream_ptr()))
+        if is_raw:
+            check(lib.yond_nlf_maps_raw16(ptr(x), C.byref(raw), int(bool(x_mosaic)), ptr(y), int(bool(y_mosaic)), ptr(var), ptr(mean), ptr(lap),
+                                          nimg, nb, H, W, int(bool(split_blocks)), int(k), mode, ptr(seg_max), ptr(work), stream_ptr()))
+        else:
+            check(lib.yond_nlf_maps_bayer(ptr(x), int(bool(x_mosaic)), ptr(y), int(bool(y_mosaic)), ptr(var), ptr(mean), ptr(lap), nimg, nb,
+                                          H, W, int(bool(split_blocks)), int(k), mode, ptr(seg_max), ptr(work), stream_ptr()))
         quants = np.ascontiguousarray(np.linspace(step, 100, 100 // step, endpoint=True), np.float64)
         regs = torch.empty((nimg, 2), device=dev, dtype=torch.float64)
         detail = torch.empty((nimg, self.DETAIL), device=dev, dtype=torch.float64) if details else None

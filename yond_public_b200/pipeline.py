@@ -173,7 +173,7 @@ class YondEngine:
                                        ptr(rows), ptr(xnodes), stride, ptr(out["regs4"]), ptr(out["ok"]), ptr(work), stream_ptr()))
         return out
 
-    def vst_denoise_dev(self, frames, chain, out, frames_per_row=1, fps=1, select=False, fallback=None, clip01=True):
+    def vst_denoise_dev(self, frames, chain, out, frames_per_row=1, fps=1, select=False, fallback=None, clip01=True, raw=None):
         """VST_Denoiser for frames (B,H,W) with device-filled parameters; writes `out` (plain (B,H,W) or the mosaic layout
         (B/n, H, n*W) for frames_per_row = n).  select: frames of images with chain['ok'] == 0 copy `fallback` instead."""
         B, H, W = frames.shape
@@ -192,8 +192,12 @@ class YondEngine:
         for b0 in range(0, B, cb):
             n = min(cb, B - b0)
             pch = params[b0 * psz:]
-            check(self.lib.yond_vst_fwd(ptr(frames[b0:b0 + n]), ptr(z[:n]), ptr(ub[:n]), n, H, W, pl, pr, pt, pb, ptr(pch),
-                                        ptr(chain["rows"]), ptr(chain["xnodes"]), chain["stride"], st))
+            if raw is not None:  # uint16 sensor mosaic, normalised on load
+                check(self.lib.yond_vst_fwd_raw16(ptr(frames[b0:b0 + n]), C.byref(raw), ptr(z[:n]), ptr(ub[:n]), n, H, W, pl, pr, pt, pb, ptr(pch),
+                                                  ptr(chain["rows"]), ptr(chain["xnodes"]), chain["stride"], st))
+            else:
+                check(self.lib.yond_vst_fwd(ptr(frames[b0:b0 + n]), ptr(z[:n]), ptr(ub[:n]), n, H, W, pl, pr, pt, pb, ptr(pch),
+                                            ptr(chain["rows"]), ptr(chain["xnodes"]), chain["stride"], st))
             (self.forward or self.net.forward_nhwc)(z[:n], ub[:n], t[b0:b0 + n] if self.guided else None, out=y[:n])
             check(self.lib.yond_vst_inv_place(ptr(y[:n]), ptr(out), n, H, W, pl, pr, pt, pb, ptr(pch), int(clip01), frames_per_row, b0,
                                               ptr(chain["ok"]) if select else None, fps, ptr(fallback) if select else None, st))
@@ -413,7 +417,7 @@ class YOND_SIDD:
         return results
 
     # -- the blind two-round pipeline, device-resident and free of host synchronisation -----------------------------
-    def iter_denoise_dev(self, x, p, lr_full=None, timings=None):
+    def iter_denoise_dev(self, x, p, lr_full=None, timings=None, raw=None):
         """IterDenoise (YOND_SIDD.py:301-483, `simple` estimator) for a batch of images: x (nimg, nblk, H, W) CUDA f32 —
         SIDD images of nblk blocks, or full frames with nblk = 1.  Every stage runs once for the whole batch; the noise
         estimate, the reference's guards, the VST constants, the bias rows and the round-2 selection all stay on the device,
@@ -421,8 +425,15 @@ class YOND_SIDD:
 
         Returns device tensors: dn1 / final (nimg, H, nblk*W) (the reference's mosaic layout), regs1 / regs2 (nimg, 4) float64
         = (beta1, beta2 after the guards, gain, sigma) per round (regs2 None without round 2), ok (nimg,) int32 = the round-2
-        result was kept (beta1 >= 0, :445-447)."""
+        result was kept (beta1 >= 0, :445-447).
+
+        raw = (black, white, ratio[, clip]): x is the uint16 SENSOR mosaic (16-bit integer tensor) and the dataset normalisation
+        (raw - black) * ratio / (white - black) of the 14-bit drivers (data_process/yond_datasets.py:955-961, :1053-1056) is applied
+        on load by the estimator and the VST front end — the float32 frame never exists."""
         pipe = self.pipe
+        if raw is not None:
+            assert x.dtype in (torch.int16, torch.uint16) and lr_full is None
+            raw = _lib.RawNorm(float(raw[0]), float(raw[1]), float(raw[2]), int(bool(raw[3])) if len(raw) > 3 else 0)
         assert pipe["full_est"] and "simple" in pipe["est_type"]
         nimg, nblk, H, W = x.shape
         dev = x.device
@@ -450,7 +461,7 @@ class YOND_SIDD:
         seg_max = torch.empty(nimg, device=dev, dtype=torch.float32) if need_max else None
         # ---- round 1: self-calibration on the mosaic (:315, :338-341) or on the full-resolution frame when given
         if lr_full is None:
-            regs = est.estimate_dev(x, None, k, split_blocks=False, seg_max=seg_max)
+            regs = est.estimate_dev(x, None, k, split_blocks=False, seg_max=seg_max, raw=raw)
         else:
             assert nimg == 1
             regs = est.estimate_dev(lr_full.reshape(1, 1, *lr_full.shape[-2:]), None, k)
@@ -462,7 +473,7 @@ class YOND_SIDD:
         ch1 = eng.chain_params(regs, seg_max, nimg, nblk, scale_est, scale, scale if full_dn else scale_est, 1, bias_corr, vst_type)
         frames = x.reshape(nimg * nblk, H, W)
         dn1 = torch.empty((nimg, H, nblk * W), device=dev, dtype=torch.float32)
-        eng.vst_denoise_dev(frames, ch1, dn1, frames_per_row=nblk, fps=nblk)
+        eng.vst_denoise_dev(frames, ch1, dn1, frames_per_row=nblk, fps=nblk, raw=raw)
         mark("denoise_round1")
         res = {"dn1": dn1, "final": dn1, "regs1": ch1["regs4"], "regs2": None, "ok": None, "lr": x, "nblk": nblk}
         if pipe.get("iter") == "iter" and pipe["max_iter"] >= 1:
@@ -474,13 +485,13 @@ class YOND_SIDD:
             sidd = bool(pipe.get("sidd_256", mos_blocks == 32))
             if sidd and nblk == 1:  # a frame (or a full_dn mosaic): the 32 strips are split out of the mosaic layout
                 assert W % 64 == 0, "SIDD_256 splits the packed frame into 32 strips along W (YOND_SIDD.py:91-93)"
-                regs2 = est.estimate_dev(x.reshape(nimg, H, W), dn1, k, split_blocks=True, x_mosaic=True, y_mosaic=True, nblk=32)
+                regs2 = est.estimate_dev(x.reshape(nimg, H, W), dn1, k, split_blocks=True, x_mosaic=True, y_mosaic=True, nblk=32, raw=raw)
             else:
-                regs2 = est.estimate_dev(x, dn1, k, split_blocks=sidd, y_mosaic=True)  # :431 (mode 'collab')
+                regs2 = est.estimate_dev(x, dn1, k, split_blocks=sidd, y_mosaic=True, raw=raw)  # :431 (mode 'collab')
             mark("estimate_collab")
             ch2 = eng.chain_params(regs2, seg_max, nimg, nblk, scale_est, scale, scale_est, 2, bias_corr, vst_type, prev=ch1)
             final = torch.empty_like(dn1)
-            eng.vst_denoise_dev(frames, ch2, final, frames_per_row=nblk, fps=nblk, select=True, fallback=dn1)
+            eng.vst_denoise_dev(frames, ch2, final, frames_per_row=nblk, fps=nblk, select=True, fallback=dn1, raw=raw)
             mark("denoise_round2")
             res.update(final=final, regs2=ch2["regs4"], ok=ch2["ok"])
         return res
@@ -518,17 +529,17 @@ class YOND_SIDD:
             rounds[ok] = 2
         return regs, rounds, gains
 
-    def iter_denoise_batch(self, blocks, p, log=None, timings=None):
+    def iter_denoise_batch(self, blocks, p, log=None, timings=None, raw=None):
         """IterDenoise for a BATCH of SIDD-shaped images (or full frames, nblk = 1) at once: blocks (nimg, nblk, H, W) CUDA
         f32.  Same per-image algorithm and guards as the reference (YOND_SIDD.py:301-483); every device stage runs once for
         all images and the host reads back ONE small array at the end.
         Returns {'raw_dns': [round-1 (nimg,H,nblk*W), final (nimg,H,nblk*W)], 'regs': [(nimg,2) per round; NaN rows in round
         2 where the beta1 < 0 guard kept the round-1 result], 'rounds': (nimg,) number of denoise rounds each image completed}."""
-        res = self.iter_denoise_dev(blocks, p, timings=timings)
+        res = self.iter_denoise_dev(blocks, p, timings=timings, raw=raw)
         regs, rounds, _ = self.read_summary(res)
         return {"raw_dns": [res["dn1"], res["final"]], "regs": regs, "rounds": rounds, "lr_raw": None, "dev": res}
 
-    def iter_denoise_host(self, host_in, host_out, p, group=8, lanes=1, wait=True):
+    def iter_denoise_host(self, host_in, host_out, p, group=8, lanes=1, wait=True, raw=None):
         """End-to-end batched IterDenoise on HOST buffers: host_in (nimg,nblk,H,W) f32 pinned -> host_out (nimg,H,nblk*W) f32
         pinned (final round of every image; full frames are nblk = 1).  Images are processed in groups of `group`.
 
@@ -537,7 +548,9 @@ class YOND_SIDD:
         waits for the device (iter_denoise_dev), the host only enqueues; the per-image numbers are read back once, at the
         end.  wait=False returns a job whose .result() does that read-back: a caller streaming batch after batch submits
         the next batch first, so its first upload runs under the tail of this one (bench.py's e2e keeps two in flight).
-        `lanes` is accepted for compatibility and ignored (round 1 needed host threads to hide the estimator's read-backs)."""
+        `lanes` is accepted for compatibility and ignored (round 1 needed host threads to hide the estimator's read-backs).
+        raw = (black, white, ratio[, clip]): host_in holds uint16 sensor mosaics (int16 / uint16 tensor, half the H2D bytes), see
+        iter_denoise_dev."""
         assert host_in.is_pinned() and host_out.is_pinned(), "pinned host buffers required for asynchronous copies"
         nimg = host_in.shape[0]
         dev = self.device
@@ -545,12 +558,12 @@ class YOND_SIDD:
         sizes = [min(group, nimg - a) for a in range(0, nimg, group)] if isinstance(group, int) else [int(g) for g in group]
         assert sum(sizes) == nimg and min(sizes) > 0, "group sizes must add up to the number of images"
         gmax = max(sizes)
-        key = (tuple(host_in.shape[1:]), gmax)
+        key = (tuple(host_in.shape[1:]), gmax, host_in.dtype)
         io = getattr(self, "_io", None)
         if io is None or io["key"] != key:
             torch.cuda.synchronize(dev)
             io = self._io = dict(key=key, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), seq=0,
-                                 ring=[dict(buf=torch.empty((gmax,) + tuple(host_in.shape[1:]), device=dev), free=None) for _ in range(3)])
+                                 ring=[dict(buf=torch.empty((gmax,) + tuple(host_in.shape[1:]), device=dev, dtype=host_in.dtype), free=None) for _ in range(3)])
         s_in, s_out, ring = io["s_in"], io["s_out"], io["ring"]
         starts = np.concatenate([[0], np.cumsum(sizes)])
         groups = [(int(starts[i]), int(starts[i + 1])) for i in range(len(sizes))]
@@ -575,7 +588,7 @@ class YOND_SIDD:
                 stage_in(g + 1)
             slot = ring[(seq0 + g) % 3]
             cur.wait_event(in_ready[g])
-            res = self.iter_denoise_dev(slot["buf"][:b - a], dict(p))
+            res = self.iter_denoise_dev(slot["buf"][:b - a], dict(p), raw=raw)
             done = torch.cuda.Event()
             done.record(cur)
             slot["free"] = done
