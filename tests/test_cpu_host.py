@@ -82,6 +82,14 @@ def test_no_cpu_fallback(Y):
             Y.pack_raw_bayer(np.zeros((4, 4), np.uint16), raw_pattern=[[0, 1], [3, 2]], black_level_per_channel=[0, 0, 0, 0])
         with pytest.raises(Y._lib.YondError):
             Y.rot_bayer(np.zeros((4, 4), np.float32), [[2, 3], [1, 2]])
+        with pytest.raises(Y._lib.YondError):
+            Y.normalize_raw(np.zeros((4, 8), np.uint16), 512, 16383, 100)
+        with pytest.raises(Y._lib.YondError):
+            Y.calculate_ssim(np.zeros((16, 16), np.float32), np.zeros((16, 16), np.float32))
+        with pytest.raises(Y._lib.YondError):
+            Y.compare_psnr(np.zeros((16, 16), np.float32), np.ones((16, 16), np.float32))
+        with pytest.raises(Y._lib.YondError):
+            Y.ResUnet2(dict(ARCH_UNET, name="ResUnet2"))(torch.zeros(1, 4, 32, 32))
 
 
 def test_synth_module_matches_reference_recipes(Y):
