@@ -37,6 +37,25 @@ def _pinned_stage(nbytes):
     return buf
 
 
+_COPY_POOL = None
+
+
+def _host_copy(dst: np.ndarray, src: np.ndarray):
+    """dst[...] = src for large host arrays with a few threads (NumPy releases the GIL in copyto): the per-call NumPy surface of
+    the reference moves ~150 MB of host memory per 12 MP frame, and one core copies at only ~6-8 GB/s."""
+    n = dst.size * dst.itemsize
+    if n < (8 << 20) or not (dst.flags.c_contiguous and src.flags.c_contiguous):
+        np.copyto(dst, src)
+        return
+    global _COPY_POOL
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="yond-copy")
+    d, s_ = dst.reshape(-1), src.reshape(-1)
+    step = -(-d.size // 4)
+    list(_COPY_POOL.map(lambda i: np.copyto(d[i:i + step], s_[i:i + step]), range(0, d.size, step)))
+
+
 def to_dev(a, dtype=torch.float32):
     """numpy / tensor -> contiguous CUDA tensor; returns (tensor, was_numpy)."""
     dev = _dev()  # raises without CUDA: there is no CPU path
@@ -45,7 +64,7 @@ def to_dev(a, dtype=torch.float32):
         n = src.numel() * src.element_size()
         stage = _pinned_stage(n)[:n].view(src.dtype).view(src.shape)
         torch.cuda.current_stream(dev).synchronize()  # the previous upload out of this buffer has left it
-        stage.copy_(src)
+        _host_copy(stage.numpy(), src.numpy())
         return stage.to(dev, non_blocking=True), True
     if not torch.is_tensor(a):
         a = torch.as_tensor(np.asarray(a, dtype=np.float32))
@@ -68,7 +87,12 @@ def to_host(tensors):
         v.copy_(t, non_blocking=True)
         views.append(v)
     torch.cuda.current_stream(tensors[0].device).synchronize()
-    return [v.numpy().copy() for v in views]
+    outs = []
+    for v in views:
+        o = np.empty(tuple(v.shape), dtype=v.numpy().dtype)
+        _host_copy(o, v.numpy())
+        outs.append(o)
+    return outs
 
 
 def _back(t, was_numpy):
