@@ -37,6 +37,16 @@ def _pinned_stage(nbytes):
     return buf
 
 
+def pinned_view(name, like):
+    """A view shaped / typed like the tensor `like` into a grow-only pinned buffer of this thread named `name`."""
+    n = like.numel() * like.element_size()
+    buf = getattr(_STAGE, name, None)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(int(n), 1 << 20), dtype=torch.uint8).pin_memory()
+        setattr(_STAGE, name, buf)
+    return buf[:n].view(like.dtype).view(like.shape)
+
+
 _COPY_POOL = None
 
 
@@ -75,6 +85,8 @@ def to_dev(a, dtype=torch.float32):
 def to_host(tensors):
     """CUDA tensors -> fresh NumPy arrays through ONE pinned staging region and one synchronisation (a plain .cpu() stages
     every tensor through the driver's bounce buffers at a fraction of the PCIe rate)."""
+    if not tensors:
+        return []
     tensors = [t.contiguous() for t in tensors]
     sizes = [t.numel() * t.element_size() for t in tensors]
     offs = np.concatenate([[0], np.cumsum([(n + 255) // 256 * 256 for n in sizes])]).astype(np.int64)

@@ -405,9 +405,37 @@ class YOND_SIDD:
         full = None
         if data.get("lr_full") is not None:  # the reference loads data['lr_path_full'] from disk (:339-340)
             full, _ = isp.to_dev(data["lr_full"])
-        res = self.iter_denoise_device(blocks, p, lr_full=full)
+        early = {}
+
+        def grab_round1(dn1):  # D2H of the round-1 result on a side stream as soon as it is complete
+            ev = torch.cuda.Event()
+            ev.record()
+            side = getattr(self, "_down_stream", None)
+            if side is None:
+                side = self._down_stream = torch.cuda.Stream(self.device)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                v = isp.pinned_view("round1", dn1[0])
+                v.copy_(dn1[0], non_blocking=True)
+                early["done"] = torch.cuda.Event()
+                early["done"].record(side)
+            dn1.record_stream(side)
+            early["view"] = v
+
+        def host_round1():  # runs while the GPU works on round 2: pinned -> fresh NumPy array
+            early["done"].synchronize()
+            out = np.empty(tuple(early["view"].shape), np.float32)
+            isp._host_copy(out, early["view"].numpy())
+            early["np"] = out
+
+        np_pipe = np_in and self.pipe["full_est"] and "simple" in self.pipe["est_type"]
+        res = self.iter_denoise_device(blocks, p, lr_full=full, after_round1=grab_round1 if np_pipe else None,
+                                       before_summary=host_round1 if np_pipe else None)
         if np_in:  # NumPy in -> NumPy out like the reference; the mosaic of the input never leaves the host
-            dns = isp.to_host(res["raw_dns"])
+            if "np" in early:
+                dns = [early["np"]] + isp.to_host(res["raw_dns"][1:])
+            else:
+                dns = isp.to_host(res["raw_dns"])
             lr_raw = np.concatenate(list(lr), axis=-1) if lr.ndim == 3 else lr
         else:
             dns, lr_raw = list(res["raw_dns"]), res["lr_raw"]()
@@ -417,7 +445,7 @@ class YOND_SIDD:
         return results
 
     # -- the blind two-round pipeline, device-resident and free of host synchronisation -----------------------------
-    def iter_denoise_dev(self, x, p, lr_full=None, timings=None, raw=None):
+    def iter_denoise_dev(self, x, p, lr_full=None, timings=None, raw=None, after_round1=None):
         """IterDenoise (YOND_SIDD.py:301-483, `simple` estimator) for a batch of images: x (nimg, nblk, H, W) CUDA f32 —
         SIDD images of nblk blocks, or full frames with nblk = 1.  Every stage runs once for the whole batch; the noise
         estimate, the reference's guards, the VST constants, the bias rows and the round-2 selection all stay on the device,
@@ -475,6 +503,8 @@ class YOND_SIDD:
         dn1 = torch.empty((nimg, H, nblk * W), device=dev, dtype=torch.float32)
         eng.vst_denoise_dev(frames, ch1, dn1, frames_per_row=nblk, fps=nblk, raw=raw)
         mark("denoise_round1")
+        if after_round1 is not None:  # round 1 is enqueued: a caller may start downloading it under round 2
+            after_round1(dn1)
         res = {"dn1": dn1, "final": dn1, "regs1": ch1["regs4"], "regs2": None, "ok": None, "lr": x, "nblk": nblk}
         if pipe.get("iter") == "iter" and pipe["max_iter"] >= 1:
             assert pipe["max_iter"] == 1, "the shipped configurations use max_iter = 1"
@@ -606,7 +636,7 @@ class YOND_SIDD:
         job = HostJob(self, results, out_done)
         return job.result() if wait else job
 
-    def iter_denoise_device(self, blocks, p, lr_full=None):
+    def iter_denoise_device(self, blocks, p, lr_full=None, after_round1=None, before_summary=None):
         """Device-resident IterDenoise.  `blocks`: (nblk,H,W) CUDA f32 (SIDD layout) or (H,W) frame.
         Returns CUDA tensors in the reference's mosaic layout: (H, nblk*W)."""
         pipe = self.pipe
@@ -622,7 +652,9 @@ class YOND_SIDD:
             return {"raw_dns": [dn], "regs": (0, 0), "lr_raw": mosaic}
         if "simple" not in pipe["est_type"]:
             raise NotImplementedError(f"est_type '{pipe['est_type']}' needs external estimate files / networks (YOND_SIDD.py:316-353)")
-        res = self.iter_denoise_dev(blk[None].contiguous(), p, lr_full=lr_full)
+        res = self.iter_denoise_dev(blk[None].contiguous(), p, lr_full=lr_full, after_round1=after_round1)
+        if before_summary is not None:  # everything is enqueued; host work placed here overlaps round 2
+            before_summary()
         regs, rounds, gs = self.read_summary(res)
         reg = regs[0][0]
         self._log(f"Self Est: K={gs[0][0, 0]:.4f}, b={gs[0][0, 1]:.4f} (beta1={reg[0]:.3e}, beta2={reg[1]:.3e})")
