@@ -66,8 +66,13 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
                                                                 float4* __restrict__ out2) {
   constexpr int NQ = kSq ? 8 : 4;
   constexpr int CH = kCols / 32;           // columns per scan chunk (8 or 5)
-  constexpr int PITCH = kCols + 32 + 1;    // padded: column c sits at c + c / CH, so chunk reads are bank-conflict free
-  extern __shared__ double S[];  // [kRows][NQ][PITCH]
+  // Staging rows.  kCols = 256: 16-byte slots (column pairs) XOR-swizzled, slot s -> s ^ ((s >> 3) & 3): 64-bit accesses of 16
+  // consecutive aligned columns (the column threads' stores, the writers' upper window end) and the scan's 128-bit accesses of
+  // four slots per lane are both bank-conflict free without padding (the padded layout cost every column-indexed access a second
+  // wavefront: 4.3 shared-memory wavefronts per pixel, one third of them conflicts).  kCols = 160: padded, column c at c + c / CH.
+  constexpr bool kSwz = kCols == 256;
+  constexpr int PITCH = kSwz ? kCols : kCols + 32 + 1;
+  extern __shared__ __align__(16) double S[];  // [kRows][NQ][PITCH]
   const int r = k / 2;
   const int outc = kCols - 2 * r;
   const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
@@ -86,6 +91,13 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
     col_src = reflect101(col_out, w);               // BORDER_REFLECT_101
     colthread = c < kCols;
     writer = (c >= r) && (c < r + outc) && (col_out < w);
+  }
+  // Wide layout: the thread that WRITES output column oc is thread oc + r, so that its upper window end P[oc + r] sits at its own
+  // (aligned) position; only the lower end P[oc - r - 1] is an unaligned access.
+  int col_w = col_out;
+  if (!kNarrow) {
+    col_w = blockIdx.x * outc + (c - 2 * r);
+    writer = (c >= 2 * r) && (col_w < w);
   }
   const int i0 = blockIdx.y * rows_per_strip;
   const int i1 = min(h, i0 + rows_per_strip);
@@ -146,7 +158,9 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
   // stdfilt (isp_algos.py:236-241): float32 square of the blurred image, float32 difference, sqrt; explicit
   // round-to-nearest mul/sub: an FMA contraction would skip the float32 rounding of mean^2 the reference has
   auto sd = [](float e2, float e1) { return sqrtf(fmaxf(__fsub_rn(e2, __fmul_rn(e1, e1)), 0.f)); };
-  auto pidx = [](int col) { return col + col / CH; };  // position of block column `col` in the padded prefix row
+  auto pidx = [](int col) {  // position of block column `col` in a staging row
+    return kSwz ? ((((col >> 1) ^ ((col >> 4) & 3)) << 1) | (col & 1)) : col + col / CH;
+  };
   const int my_idx = pidx(c);
   // window = P[hi] - P[lo] (+ P[e1] - P[e0] for the reflected part of a border column in the narrow layout); index -1 = "0"
   int hi_idx, lo_idx, e1_idx = -1, e0_idx = -1;
@@ -162,8 +176,8 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
       e0_idx = pidx(img0 + 2 * (w - 1) - (col_out + r) - 1);
     }
   } else {
-    hi_idx = pidx(c + r);
-    lo_idx = c - r - 1 >= 0 ? pidx(c - r - 1) : -1;
+    hi_idx = pidx(c);
+    lo_idx = c - 2 * r - 1 >= 0 ? pidx(c - 2 * r - 1) : -1;
   }
   auto Srow = [&](int j, int q) { return S + (size_t)(j * NQ + q) * PITCH; };
   for (int i = i0; i < i1; i += kRows) {
@@ -193,10 +207,35 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
     for (int t0 = warp; t0 < nr * NQ; t0 += 2 * (kBoxThreads / 32)) {
       const int t1 = t0 + kBoxThreads / 32;
       const bool two = t1 < nr * NQ;
-      double* rowa = S + (size_t)t0 * PITCH + lane * (CH + 1);  // chunk `lane` starts at column lane*CH, i.e. index lane*CH + lane
-      double* rowb = S + (size_t)(two ? t1 : t0) * PITCH + lane * (CH + 1);
       double la[CH], lb[CH];
       double ra = 0.0, rb = 0.0;
+      if (kSwz) {  // lane = chunk of 8 columns = 4 swizzled slots, 128-bit accesses
+        double2* rowa = reinterpret_cast<double2*>(S + (size_t)t0 * PITCH);
+        double2* rowb = reinterpret_cast<double2*>(S + (size_t)(two ? t1 : t0) * PITCH);
+        const int x = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) {
+          const double2 va = rowa[(4 * lane + j) ^ x], vb = rowb[(4 * lane + j) ^ x];
+          ra += va.x; la[2 * j] = ra; ra += va.y; la[2 * j + 1] = ra;
+          rb += vb.x; lb[2 * j] = rb; rb += vb.y; lb[2 * j + 1] = rb;
+        }
+        double ia = ra, ib = rb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+          if (lane >= o) { ia += ta; ib += tb; }
+        }
+        const double ea = ia - ra, eb = ib - rb;
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) rowa[(4 * lane + j) ^ x] = make_double2(la[2 * j] + ea, la[2 * j + 1] + ea);
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) rowb[(4 * lane + j) ^ x] = make_double2(lb[2 * j] + eb, lb[2 * j + 1] + eb);
+        }
+        continue;
+      }
+      double* rowa = S + (size_t)t0 * PITCH + lane * (CH + 1);  // chunk `lane` starts at column lane*CH, i.e. index lane*CH + lane
+      double* rowb = S + (size_t)(two ? t1 : t0) * PITCH + lane * (CH + 1);
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         ra += rowa[j];
@@ -230,7 +269,7 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
           a[q] = Sq[hi_idx] - (lo_idx >= 0 ? Sq[lo_idx] : 0.0);
           if (kNarrow && e1_idx >= 0) a[q] += Sq[e1_idx] - Sq[e0_idx];
         }
-        const size_t o = ((size_t)b * h + (i + j)) * w + col_out;
+        const size_t o = ((size_t)b * h + (i + j)) * w + col_w;
         const float4 m = make_float4((float)(a[0] * inv), (float)(a[1] * inv), (float)(a[2] * inv), (float)(a[3] * inv));
         if (!kSq || op == OP_MEAN) {
           out0[o] = m;
@@ -805,7 +844,7 @@ BoxSrc packed_src(const float* x, int h, int w) {
 template <bool SQ, int COLS, bool BAYER, bool NARROW, int R>
 int launch_box(dim3 g, cudaStream_t s, const BoxSrc& src, float4* o0, float4* o1, int B, int h, int w, int k, int op, int rows_per_strip,
                const float4* ax, float4* o2) {
-  constexpr size_t bytes = (size_t)R * (SQ ? 8 : 4) * (COLS + 33) * sizeof(double);
+  constexpr size_t bytes = (size_t)R * (SQ ? 8 : 4) * (COLS == 256 ? COLS : COLS + 33) * sizeof(double);  // = [kRows][NQ][PITCH]
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
