@@ -228,6 +228,9 @@ typedef struct yond_net yond_net_t;
 #define YOND_ARCH_RES2 3     /* ResUnet2 (archs/Unet.py:197-286): GuidedResUnet's graph and state_dict keys, blocks without the
                                 conditioning (ResBlock.forward never uses gamma / beta, archs/modules.py:258-265), LeakyReLU(0.2)
                                 after conv_in, called as net(x) */
+#define YOND_ARCH_SELFRES 4  /* SelfResUNet (archs/comp.py:745-802): constant-width residual U-Net (nf down, 2 nf up), max-pool down,
+                                nearest-neighbour up, network input concatenated at the last up level; called as net(x); H, W
+                                multiples of 32 */
 /* Creates a network; weights are set tensor-by-tensor with the reference's state_dict keys. */
 int yond_net_create(int arch, int in_nc, int out_nc, int nf, int res, int norm, yond_net_t** out);
 void yond_net_destroy(yond_net_t* net);

@@ -525,6 +525,56 @@ def guided_forward(sd, x, t, res=True, norm=True, bf16=False, kind="guided"):
     return out
 
 
+def selfres_forward(sd, x, res=False, norm=False, bf16=False, slope=0.1, depth=5):
+    """SelfResUNet.forward (archs/comp.py:778-802) with Res (:830-850), RUP (:804-828), LR (:709-722): constant width (nf down, 2 nf
+    up), max-pool down, nearest-neighbour up, the network INPUT concatenated at the last up level."""
+    import torch
+    import torch.nn.functional as F
+    if norm:
+        x, ub = _norm(x)
+    inp = x
+    W = lambda n: _bf(sd[n + ".weight"], bf16)
+
+    def lr(p, v, k):
+        return _bf(F.leaky_relu(F.conv2d(v, W(p + ".block.0"), sd[p + ".block.0.bias"], padding=k // 2), slope), bf16)
+
+    def res_block(p, v, k=3, first=False):
+        if p + ".short_cut.0.weight" in sd:  # the head's 1x1 runs on the float32 input with float32 weights (like the first conv of the others)
+            w = sd[p + ".short_cut.0.weight"] if first else W(p + ".short_cut.0")
+            v = _bf(F.conv2d(v, w, sd[p + ".short_cut.0.bias"]), bf16)
+        z = lr(p + ".conv_2", lr(p + ".conv_1", v, k), k)
+        return _bf(z + v, bf16)
+
+    blocks = [x]
+    h = res_block("head", x, first=True)
+    for i in range(depth):
+        h = F.max_pool2d(h, 2)
+        if i != depth - 1:
+            blocks.append(h)
+        h = res_block(f"down_path.{i}", h)
+    for i in range(depth):
+        up = h.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)  # RUP.up (:815-820)
+        pool = blocks[-i - 1]
+        p = f"up_path.{i}"
+        if i == depth - 1 and p + ".short_cut.0.weight" in sd:
+            # cat[up, input]: the input part of the 1x1 stays in float32 (4 channels), the 2nf part runs on the tensor cores
+            w = sd[p + ".short_cut.0.weight"]
+            c = up.shape[1]
+            v = F.conv2d(up, _bf(w[:, :c], bf16), sd[p + ".short_cut.0.bias"]) + F.conv2d(pool, w[:, c:])
+            v = _bf(v, bf16)
+            z = lr(p + ".conv_2", lr(p + ".conv_1", v, 3), 3)
+            h = _bf(z + v, bf16)
+        else:
+            h = res_block(p, _bf(torch.cat([up, pool], 1), bf16))
+    h = res_block("last", h, k=1)
+    out = F.conv2d(h, sd["out.weight"], sd["out.bias"])
+    if res:
+        out = out + inp
+    if norm:
+        out = out * ub
+    return out
+
+
 def net_forward(arch, sd, x, t=None, bf16=False):
     name = arch["name"]
     res, norm = arch.get("res", True), arch.get("norm", False)
@@ -536,6 +586,8 @@ def net_forward(arch, sd, x, t=None, bf16=False):
         return guided_forward(sd, x, t, res, norm, bf16, "snr")
     if name == "ResUnet2":
         return guided_forward(sd, x, None, res, norm, bf16, "res2")
+    if name == "SelfResUNet":
+        return selfres_forward(sd, x, res, norm, bf16, arch.get("slope", 0.1), arch.get("depth", 5))
     raise NotImplementedError(name)
 
 
@@ -558,6 +610,22 @@ def init_state_dict(arch, seed=0, weight_scale=None):
             mods += [(f"upv{i}", nn.ConvTranspose2d(c * 2, c, 2, stride=2)),
                      (f"conv{i}_1", nn.Conv2d(c * 2, c, 3, 1, 1)), (f"conv{i}_2", nn.Conv2d(c, c, 3, 1, 1))]
         mods.append(("conv10_1", nn.Conv2d(nf, cout, 1)))
+    elif arch["name"] == "SelfResUNet":  # archs/comp.py:745-776; Res :830-838, RUP :804-813, LR :709-717
+        depth = arch.get("depth", 5)
+
+        def res(p, ci, co, k=3):
+            m = [(f"{p}.conv_1.block.0", nn.Conv2d(co, co, k, padding=k // 2)), (f"{p}.conv_2.block.0", nn.Conv2d(co, co, k, padding=k // 2))]
+            if ci != co:
+                m.append((f"{p}.short_cut.0", nn.Conv2d(ci, co, 1)))
+            return m
+        mods += res("head", cin, nf)
+        for i in range(depth):
+            mods += res(f"down_path.{i}", nf, nf)
+        for i in range(depth):
+            ci = (nf * 2 if i == 0 else nf * 3) if i != depth - 1 else nf * 2 + cin
+            mods += res(f"up_path.{i}", ci, nf * 2)
+        mods += res("last", 2 * nf, 2 * nf, k=1)
+        mods.append(("out", nn.Conv2d(2 * nf, cout, 1)))
     else:  # GuidedResUnet archs/Unet.py:393-421, SNRnet :301-329; blocks archs/modules.py:163-218
         guided = arch["name"] in ("GuidedResUnet", "ResUnet2")  # ResBlock registers gamma / beta like the guided block
 

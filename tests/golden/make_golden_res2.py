@@ -18,6 +18,7 @@ from oracle import yond_oracle as O  # noqa: E402
 from oracle.ref_harness import load_reference, make_driver  # noqa: E402
 
 ARCH = {"name": "ResUnet2", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
+ARCH_SELF = {"name": "SelfResUNet", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}  # archs/comp.py:745-802
 PIPE = {"full_est": True, "est_type": "simple+full", "k": 29, "full_dn": False, "vst_type": "exact", "bias_corr": "pre",
         "iter": "iter", "max_iter": 1}
 
@@ -28,6 +29,11 @@ def crc(a):
 
 def main():
     ref = load_reference()
+    for arch, fname in ((ARCH, "net_res2"), (ARCH_SELF, "net_selfres")):
+        one(ref, arch, fname)
+
+
+def one(ref, ARCH, fname):
     drv = make_driver(ref, ARCH, PIPE, seed=5)
     sd_ref = drv.net.state_dict()
     sd = O.init_state_dict(ARCH, seed=5)
@@ -39,10 +45,10 @@ def main():
     xin[1] *= 0.6
     with torch.no_grad():
         y = drv.net(xin)
-    np.savez_compressed(os.path.join(HERE, "net_res2.npz"), x=xin.numpy(), y=y.numpy(), nparams=sum(v.numel() for v in sd.values()),
+    np.savez_compressed(os.path.join(HERE, fname + ".npz"), x=xin.numpy(), y=y.numpy(), nparams=sum(v.numel() for v in sd.values()),
                         keys=np.array(list(sd.keys())), shapes=np.array([str(tuple(v.shape)) for v in sd.values()]),
                         sd_crc=np.array([crc(v.numpy()) for v in sd.values()], np.uint32))
-    print("wrote net_res2", float(y.abs().max()))
+    print("wrote", fname, float(y.abs().max()))
 
 
 if __name__ == "__main__":

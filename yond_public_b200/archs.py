@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
-ARCH_IDS = {"UNetSeeInDark": 0, "GuidedResUnet": 1, "SNRnet": 2, "ResUnet2": 3}
+ARCH_IDS = {"UNetSeeInDark": 0, "GuidedResUnet": 1, "SNRnet": 2, "ResUnet2": 3, "SelfResUNet": 4}
 
 
 def conv1x1(in_nc, out_nc):
@@ -247,6 +247,44 @@ class ResUnet2(_GuidedBase):
     _block = ResBlock
 
     def forward(self, x, noise_map=None):
+        return self._forward_nchw(x)
+
+
+class LR(nn.Module):  # parameters only — archs/comp.py:709-722
+    def __init__(self, in_size, out_size, ksize=3, slope=0.1):
+        super().__init__()
+        self.block = nn.Sequential(nn.Conv2d(in_size, out_size, kernel_size=ksize, padding=ksize // 2, bias=True),
+                                   nn.LeakyReLU(slope, inplace=False))
+
+
+class Res(nn.Module):  # parameters only — archs/comp.py:830-850 (RUP, :804-828, registers the same modules)
+    def __init__(self, in_size, out_size, slope=0.1, ksize=3):
+        super().__init__()
+        self.conv_1 = LR(out_size, out_size, ksize=ksize, slope=slope)
+        self.conv_2 = LR(out_size, out_size, ksize=ksize, slope=slope)
+        self.short_cut = nn.Sequential(conv1x1(in_size, out_size)) if in_size != out_size else nn.Sequential(OrderedDict([]))
+
+
+class SelfResUNet(_B200Net):
+    """archs/comp.py:745-802: constant-width residual U-Net — Res(4, nf) head, five max-pool + Res(nf, nf) levels,
+    five nearest-neighbour up levels RUP(., 2 nf) that concatenate the pooled features (the network input at the last one),
+    Res(2 nf, 2 nf, ksize=1), 1x1 output.  depth = 5, slope = 0.1 (the class defaults); H and W multiples of 32."""
+
+    def __init__(self, args):
+        args = dict(args)
+        args.setdefault("res", False)
+        super().__init__(args)
+        nf = args["nf"] if "nf" in args else 32
+        assert args.get("depth", 5) == 5 and args.get("slope", 0.1) == 0.1, "the B200 plugin builds the class defaults (depth 5, slope 0.1)"
+        in_nc, out_nc, depth = args["in_nc"], args["out_nc"], 5
+        self.depth = depth
+        self.head = Res(in_nc, nf)
+        self.down_path = nn.ModuleList([Res(nf, nf) for _ in range(depth)])
+        self.up_path = nn.ModuleList([Res((nf * 2 if i == 0 else nf * 3) if i != depth - 1 else nf * 2 + in_nc, nf * 2) for i in range(depth)])
+        self.last = Res(2 * nf, 2 * nf, ksize=1)
+        self.out = conv1x1(2 * nf, out_nc)
+
+    def forward(self, x):
         return self._forward_nchw(x)
 
 

@@ -16,6 +16,7 @@ struct LayerW {
   int mode = 0, Cin0 = 0, Cin1 = 0, Cout = 0;
   std::string wkey, bkey;
   std::string wkey2, bkey2;  // CONV_UPSC: the 1x1 shortcut conv folded behind the transposed conv (wkey / bkey)
+  int wcin = 0;  // input channels of the SOURCE weight tensor when the layer uses only its first Cin0 + Cin1 (0: all)
   bf16* w = nullptr;
   bf16* wpaired = nullptr;  // 32 -> 32 channel 3x3 layers: pixel-pair pack (conv_tc_pack_paired)
   float* bias = nullptr;
@@ -86,7 +87,26 @@ void add_layer(yond_net* n, const std::string& name, int mode, int cin0, int cin
 // state_dict keys in the reference's registration order + the tensor-core layer table
 void describe(yond_net* n) {
   const int nf = n->nf, cin = n->in_nc, cout = n->out_nc;
-  if (n->arch == YOND_ARCH_UNET) {  // archs/Unet.py:17-52
+  if (n->arch == YOND_ARCH_SELFRES) {  // archs/comp.py:745-776; Res :830-838, RUP :804-813, LR :709-717 (depth 5)
+    auto res = [&](const std::string& p, int ci, int co, int k, bool tc_shortcut) {
+      add_conv_keys(n, p + ".conv_1.block.0", co, co, k);
+      add_conv_keys(n, p + ".conv_2.block.0", co, co, k);
+      add_layer(n, p + ".conv_1.block.0", k == 3 ? CONV_3X3_S1 : CONV_1X1, co, 0, co);
+      add_layer(n, p + ".conv_2.block.0", k == 3 ? CONV_3X3_S1 : CONV_1X1, co, 0, co);
+      if (ci != co) {
+        add_conv_keys(n, p + ".short_cut.0", co, ci, 1);
+        if (tc_shortcut) {  // 1x1 on cat[up (2 nf), skip (nf)], or on the 2 nf feature part of cat[up, input]
+          add_layer(n, p + ".short_cut.0", CONV_1X1, 2 * nf, ci == 3 * nf ? nf : 0, co);
+          n->conv[p + ".short_cut.0"].wcin = ci;
+        }
+      }
+    };
+    res("head", cin, nf, 3, false);  // its 4 -> nf shortcut runs on the float32 input (head kernel, centre tap only)
+    for (int i = 0; i < 5; ++i) res("down_path." + std::to_string(i), nf, nf, 3, false);
+    for (int i = 0; i < 5; ++i) res("up_path." + std::to_string(i), i == 0 ? 2 * nf : (i == 4 ? 2 * nf + cin : 3 * nf), 2 * nf, 3, true);
+    res("last", 2 * nf, 2 * nf, 1, false);
+    add_conv_keys(n, "out", cout, 2 * nf, 1);
+  } else if (n->arch == YOND_ARCH_UNET) {  // archs/Unet.py:17-52
     int prev = cin;
     for (int l = 1; l <= 5; ++l) {
       const int c = n->ch(l - 1);
@@ -188,7 +208,7 @@ std::vector<bf16> pack_weights(const LayerW& L, const std::vector<float>& w) {
             const int q = nn / L.Cout, co = nn % L.Cout;
             v = w[(((size_t)ci * L.Cout + co) * 2 + (q >> 1)) * 2 + (q & 1)];
           } else {  // (Cout, Cin, k, k); tap = r*k + s
-            v = w[((size_t)nn * Cin + ci) * taps + tap];
+            v = w[((size_t)nn * (L.wcin ? L.wcin : Cin) + ci) * taps + tap];
           }
           out[(((size_t)cbg * taps + tap) * N + nn) * CB + j] = __float2bfloat16_rn(v);
         }
@@ -273,7 +293,30 @@ int finalize(yond_net* n) {
     }
     L.bias = n->f32[L.bkey];
   }
-  {  // head: (nf,4,3,3) -> [tap][ci][co];  tail: (4,nf,1,1) -> [ci][4]
+  if (n->arch == YOND_ARCH_SELFRES) {  // head shortcut (nf,4,1,1) as the centre tap of a 3x3; out (4,2nf,1,1) -> [ci][4]; input part of the last shortcut
+    const std::vector<float>& hw = n->host["head.short_cut.0.weight"];
+    std::vector<float> h((size_t)36 * n->nf, 0.f);
+    for (int co = 0; co < n->nf; ++co)
+      for (int ci = 0; ci < 4; ++ci) h[((size_t)4 * 4 + ci) * n->nf + co] = hw[(size_t)co * 4 + ci];
+    YOND_CUDA_CHECK(cudaMalloc(&n->head_w, h.size() * sizeof(float)));
+    YOND_CUDA_CHECK(cudaMemcpy(n->head_w, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const int c2 = 2 * n->nf;
+    const std::vector<float>& tw = n->host["out.weight"];
+    std::vector<float> t((size_t)c2 * 4);
+    for (int co = 0; co < 4; ++co)
+      for (int ci = 0; ci < c2; ++ci) t[(size_t)ci * 4 + co] = tw[(size_t)co * c2 + ci];
+    YOND_CUDA_CHECK(cudaMalloc(&n->tail_w, t.size() * sizeof(float)));
+    YOND_CUDA_CHECK(cudaMemcpy(n->tail_w, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const std::vector<float>& sw = n->host["up_path.4.short_cut.0.weight"];  // (2nf, 2nf + 4): the last 4 input channels = network input
+    std::vector<float> win((size_t)c2 * 4);
+    for (int co = 0; co < c2; ++co)
+      for (int ci = 0; ci < 4; ++ci) win[(size_t)co * 4 + ci] = sw[(size_t)co * (c2 + 4) + c2 + ci];
+    const std::string ik = "up_path.4.short_cut.0.weight(input part)";
+    n->host[ik] = win;
+    int rc = upload_f32(n, ik);
+    n->host.erase(ik);
+    if (rc) return rc;
+  } else {  // head: (nf,4,3,3) -> [tap][ci][co];  tail: (4,nf,1,1) -> [ci][4]
     const std::string hk = n->arch == YOND_ARCH_UNET ? "conv1_1.weight" : "conv_in.weight";
     const std::string tk = n->arch == YOND_ARCH_UNET ? "conv10_1.weight" : "conv10.weight";
     const std::vector<float>& hw = n->host[hk];
@@ -362,6 +405,75 @@ struct Runner {
   }
 };
 
+// SelfResUNet.forward (archs/comp.py:778-802): every layer is a tensor-core conv (3x3 / 1x1 + LeakyReLU(0.1) [+ residual]); the two
+// 4-channel 1x1 pieces (head shortcut on the input, input part of the last up-level shortcut) stay in float32.
+int forward_selfres(yond_net* n, const float* z, const float* ub, float* y, int B, int H, int W, void* ws, size_t* ws_bytes, double* flops,
+                    cudaStream_t s) {
+  const bool dry = ws == nullptr;
+  YOND_REQUIRE(H % 32 == 0 && W % 32 == 0, "SelfResUNet: H, W must be multiples of 32 (five 2x2 poolings); got %d x %d", H, W);
+  Bump bump(ws);
+  Runner R;
+  R.n = n;
+  R.s = s;
+  R.dry = dry;
+  const int nf = n->nf, c2 = 2 * nf;
+  const float slope = 0.1f;
+  const float* ubn = n->norm ? ub : nullptr;
+  auto px = [&](int lv) { return (size_t)(H >> lv) * (W >> lv); };
+  auto buf = [&](int lv, int C) { return bump.take<bf16>((size_t)B * px(lv) * C); };
+#define RUN(expr)                                       \
+  do {                                                  \
+    if (!dry && R.rc == YOND_OK) R.rc = (expr);         \
+  } while (0)
+  auto res_block = [&](const std::string& p, int lv, int C, const bf16* x, bf16* t, bf16* out) {  // out = LR(LR(x)) + x
+    R.conv(p + ".conv_1.block.0", B, H >> lv, W >> lv, x, nullptr, nullptr, nullptr, ACT_LRELU, slope, nullptr, t, nullptr);
+    R.conv(p + ".conv_2.block.0", B, H >> lv, W >> lv, t, nullptr, nullptr, nullptr, ACT_LRELU, slope, x, out, nullptr);
+  };
+  bf16* x0 = buf(0, nf);
+  bf16* t0 = buf(0, nf);
+  bf16* h = buf(0, nf);
+  RUN(head_conv_launch(z, ubn, n->head_w, dry ? nullptr : n->f32["head.short_cut.0.bias"], B, H, W, nf, 1.0f, x0, nullptr, s));
+  res_block("head", 0, nf, x0, t0, h);
+  bf16* pool[5];
+  for (int i = 0; i < 5; ++i) {
+    pool[i] = buf(i + 1, nf);
+    bf16* t = buf(i + 1, nf);
+    bf16* hn = buf(i + 1, nf);
+    RUN(maxpool2_launch(h, pool[i], B, H >> i, W >> i, nf, s));
+    res_block("down_path." + std::to_string(i), i + 1, nf, pool[i], t, hn);
+    h = hn;
+  }
+  for (int i = 0; i < 5; ++i) {
+    const int lv = 4 - i, hl = H >> (lv + 1), wl = W >> (lv + 1);  // h lives at level lv + 1
+    const std::string p = "up_path." + std::to_string(i);
+    bf16* c = buf(lv, c2);
+    if (i == 0) {  // cat[up(h) (nf), pool_3 (nf)]: identity shortcut
+      RUN(upcat_launch(h, pool[3], c, B, hl, wl, nf, nf, s));
+    } else {
+      bf16* upx = buf(lv, c2);
+      RUN(upcat_launch(h, nullptr, upx, B, hl, wl, c2, 0, s));
+      if (i < 4) {  // 1x1 on cat[up (2 nf), pool (nf)]
+        R.conv(p + ".short_cut.0", B, H >> lv, W >> lv, upx, pool[3 - i], nullptr, nullptr, ACT_NONE, 0.f, nullptr, c, nullptr);
+      } else {      // 1x1 on cat[up (2 nf), network input (4)]: feature part on the tensor cores, input part in float32
+        R.conv(p + ".short_cut.0", B, H, W, upx, nullptr, nullptr, nullptr, ACT_NONE, 0.f, nullptr, c, nullptr);
+        RUN(add_in4_launch(c, n->f32["up_path.4.short_cut.0.weight(input part)"], z, ubn, B, H, W, c2, s));
+      }
+    }
+    bf16* t = buf(lv, c2);
+    bf16* yb = buf(lv, c2);
+    res_block(p, lv, c2, c, t, yb);
+    h = yb;
+  }
+  bf16* tl = buf(0, c2);
+  bf16* l = buf(0, c2);
+  res_block("last", 0, c2, h, tl, l);
+  RUN(tail_conv_launch(l, n->tail_w, dry ? nullptr : n->f32["out.bias"], z, ubn, n->res, B, H, W, c2, y, s));
+#undef RUN
+  if (ws_bytes) *ws_bytes = align_up(bump.off, 1024);
+  if (flops) *flops = R.flops + 2.0 * B * H * W * (4.0 * nf + 4.0 * c2 + 4.0 * c2);
+  return R.rc;
+}
+
 // One forward pass; with ws == nullptr only measures workspace bytes and FLOPs.
 //
 // Schedule: the two full-resolution levels (0 and 1) hold ~85 % of the activation bytes; they CAN run in sub-batches
@@ -370,6 +482,7 @@ struct Runner {
 // whole batch.  See the measurement note at SBn below: the split is off by default.
 int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, float* y, int B, int H, int W, void* ws,
                  size_t* ws_bytes, double* flops, cudaStream_t s) {
+  if (n->arch == YOND_ARCH_SELFRES) return forward_selfres(n, z, ub, y, B, H, W, ws, ws_bytes, flops, s);
   const bool dry = ws == nullptr;
   Bump bump(ws);
   Runner R;
@@ -604,7 +717,7 @@ extern "C" {
 
 int yond_net_create(int arch, int in_nc, int out_nc, int nf, int res, int norm, yond_net_t** out) {
   YOND_REQUIRE(out != nullptr, "yond_net_create: null output");
-  YOND_REQUIRE(arch >= YOND_ARCH_UNET && arch <= YOND_ARCH_RES2, "yond_net_create: unknown arch %d", arch);
+  YOND_REQUIRE(arch >= YOND_ARCH_UNET && arch <= YOND_ARCH_SELFRES, "yond_net_create: unknown arch %d", arch);
   YOND_REQUIRE(in_nc == 4 && out_nc == 4, "yond_net_create: only packed-Bayer nets (in_nc = out_nc = 4, nframes = 1) are built");
   YOND_REQUIRE(nf >= 32 && nf % 32 == 0, "yond_net_create: nf must be a multiple of 32 (got %d)", nf);
   yond_net* n = new yond_net();

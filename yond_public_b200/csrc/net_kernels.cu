@@ -373,6 +373,54 @@ __global__ void __launch_bounds__(512) film_kernel(const __grid_constant__ FilmA
   }
 }
 
+// ---- nearest-neighbour x2 up-sampling + channel concat (one thread = 8 channels of one output pixel) ---------------
+__global__ void upcat_kernel(const bf16* __restrict__ lo, const bf16* __restrict__ skip, bf16* __restrict__ out, int B, int Hlo, int Wlo,
+                             int C0, int C1) {
+  const int C8 = (C0 + C1) / 8, c08 = C0 / 8, H = 2 * Hlo, W = 2 * Wlo;
+  const size_t total = (size_t)B * H * W * C8;
+  const uint4* lo4 = reinterpret_cast<const uint4*>(lo);
+  const uint4* sk4 = reinterpret_cast<const uint4*>(skip);
+  uint4* out4 = reinterpret_cast<uint4*>(out);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8);
+    size_t p = idx / C8;
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const int b = (int)(p / ((size_t)W * H));
+    out4[idx] = c < c08 ? __ldg(lo4 + (((size_t)b * Hlo + (y >> 1)) * Wlo + (x >> 1)) * c08 + c)
+                        : __ldg(sk4 + p * (C1 / 8) + (c - c08));
+  }
+}
+// ---- act += W_in . (z / ub) for the four network-input channels of a 1x1 conv on cat[features, input] -------------------
+__global__ void add_in4_kernel(bf16* __restrict__ act, const float* __restrict__ w_in, const float* __restrict__ z,
+                               const float* __restrict__ ub, size_t npix, size_t pix_per_img, int C) {
+  extern __shared__ float sw4[];  // [C][4]
+  for (int i = threadIdx.x; i < C * 4; i += blockDim.x) sw4[i] = w_in[i];
+  __syncthreads();
+  const int C8 = C / 8;
+  const size_t total = npix * C8;
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  uint4* a4 = reinterpret_cast<uint4*>(act);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = idx / C8;
+    const int c0 = (int)(idx % C8) * 8;
+    const float inv = ub ? 1.0f / __ldg(ub + pix / pix_per_img) : 1.0f;
+    const float4 zi = __ldg(z4 + pix);
+    const float x0 = zi.x * inv, x1 = zi.y * inv, x2 = zi.z * inv, x3 = zi.w * inv;
+    uint4 u = a4[idx];
+    uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[q]));
+      const float* w0 = sw4 + (c0 + 2 * q) * 4;
+      f.x += w0[0] * x0 + w0[1] * x1 + w0[2] * x2 + w0[3] * x3;
+      f.y += w0[4] * x0 + w0[5] * x1 + w0[6] * x2 + w0[7] * x3;
+      uu[q] = pack2(f.x, f.y);
+    }
+    a4[idx] = make_uint4(uu[0], uu[1], uu[2], uu[3]);
+  }
+}
+
 // ---- layout converts for the nn.Module-level surface (NCHW f32 <-> NHWC4 f32) + per-sample max ---------------
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
@@ -441,6 +489,18 @@ int tail_conv_launch(const bf16* act, const float* w, const float* bias, const f
 int maxpool2_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s) {
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
   maxpool2_kernel<<<cap_grid((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W, C);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+int upcat_launch(const bf16* lo, const bf16* skip, bf16* out, int B, int Hlo, int Wlo, int C0, int C1, cudaStream_t s) {
+  const size_t total = (size_t)B * (2 * Hlo) * (2 * Wlo) * ((C0 + C1) / 8);
+  upcat_kernel<<<cap_grid((total + 255) / 256), 256, 0, s>>>(lo, skip, out, B, Hlo, Wlo, C0, C1);
+  YOND_LAUNCH_CHECK();
+  return YOND_OK;
+}
+int add_in4_launch(bf16* act, const float* w_in, const float* z, const float* ub, int B, int H, int W, int C, cudaStream_t s) {
+  const size_t npix = (size_t)B * H * W;
+  add_in4_kernel<<<cap_grid((npix * (C / 8) + 255) / 256), 256, (size_t)C * 4 * sizeof(float), s>>>(act, w_in, z, ub, npix, (size_t)H * W, C);
   YOND_LAUNCH_CHECK();
   return YOND_OK;
 }

@@ -14,6 +14,11 @@ int head_conv_launch(const float* z, const float* ub, const float* w, const floa
 int tail_conv_launch(const bf16* act, const float* w, const float* bias, const float* z, const float* ub, int res, int B,
                      int H, int W, int nf, float* y, cudaStream_t s);
 int maxpool2_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s);
+// SelfResUNet / GuidedSelfUnet up path (archs/comp.py:815-826): out (B, 2 Hlo, 2 Wlo, C0 + C1) = cat[nearest-neighbour x2 of lo (C0
+// channels), skip (C1 channels at the high resolution; may be null with C1 = 0)], NHWC bf16, C0 and C1 multiples of 8.
+int upcat_launch(const bf16* lo, const bf16* skip, bf16* out, int B, int Hlo, int Wlo, int C0, int C1, cudaStream_t s);
+// act (B,H,W,C) bf16 += w_in[C][4] . (z / ub): the 4 input channels of a 1x1 conv on cat[features, network input], in float32.
+int add_in4_launch(bf16* act, const float* w_in, const float* z, const float* ub, int B, int H, int W, int C, cudaStream_t s);
 struct FilmAll {  // every conditioned block of a network, evaluated by one launch
   FilmWeights fw[9];
   int C[9];
