@@ -231,6 +231,9 @@ typedef struct yond_net yond_net_t;
 #define YOND_ARCH_SELFRES 4  /* SelfResUNet (archs/comp.py:745-802): constant-width residual U-Net (nf down, 2 nf up), max-pool down,
                                 nearest-neighbour up, network input concatenated at the last up level; called as net(x); H, W
                                 multiples of 32 */
+#define YOND_ARCH_GSELF 5    /* GuidedSelfUnet (archs/comp.py:852-910): the same graph with noise-level conditioning — the second conv
+                                of every block and the single conv of every down level are GLRs (conv, z*tk + tb, LeakyReLU);
+                                called as net(x, t); res must be 0 (the reference's res branch cannot run) */
 /* Creates a network; weights are set tensor-by-tensor with the reference's state_dict keys. */
 int yond_net_create(int arch, int in_nc, int out_nc, int nf, int res, int norm, yond_net_t** out);
 void yond_net_destroy(yond_net_t* net);

@@ -525,24 +525,42 @@ def guided_forward(sd, x, t, res=True, norm=True, bf16=False, kind="guided"):
     return out
 
 
-def selfres_forward(sd, x, res=False, norm=False, bf16=False, slope=0.1, depth=5):
+def selfres_forward(sd, x, res=False, norm=False, bf16=False, slope=0.1, depth=5, t=None):
     """SelfResUNet.forward (archs/comp.py:778-802) with Res (:830-850), RUP (:804-828), LR (:709-722): constant width (nf down, 2 nf
-    up), max-pool down, nearest-neighbour up, the network INPUT concatenated at the last up level."""
+    up), max-pool down, nearest-neighbour up, the network INPUT concatenated at the last up level.
+    With t: GuidedSelfUnet.forward (:885-910) — the second conv of every block is a GLR (:912-934: conv, z*tk + tb, LeakyReLU), the
+    down levels are single GLRs without a residual, t is divided by ub (GRes :936-954, GUP :956-983).  Its `res` branch adds a
+    2nf-channel tensor to the 4-channel output and cannot run in the reference: res must be False."""
     import torch
     import torch.nn.functional as F
+    guided = t is not None
+    if guided:
+        assert not res, "GuidedSelfUnet's res branch is broken in the reference (out + x with 4 vs 2nf channels)"
+        t = torch.as_tensor(t, dtype=x.dtype).reshape(-1, 1, 1, 1)
     if norm:
         x, ub = _norm(x)
+        if guided:
+            t = t / ub
+    elif guided:
+        t = t.expand(x.shape[0], 1, 1, 1)
     inp = x
     W = lambda n: _bf(sd[n + ".weight"], bf16)
+    c1 = lambda v, n: F.conv2d(v, sd[n + ".weight"], sd[n + ".bias"])
 
     def lr(p, v, k):
         return _bf(F.leaky_relu(F.conv2d(v, W(p + ".block.0"), sd[p + ".block.0.bias"], padding=k // 2), slope), bf16)
+
+    def glr(p, v, k):  # GLR.forward
+        z = F.conv2d(v, W(p + ".block"), sd[p + ".block.bias"], padding=k // 2)
+        tk = c1(F.silu(c1(t, p + ".gamma.0")), p + ".gamma.2")
+        tb = c1(F.silu(tk), p + ".beta.1")
+        return _bf(F.leaky_relu(z * tk + tb, slope), bf16)
 
     def res_block(p, v, k=3, first=False):
         if p + ".short_cut.0.weight" in sd:  # the head's 1x1 runs on the float32 input with float32 weights (like the first conv of the others)
             w = sd[p + ".short_cut.0.weight"] if first else W(p + ".short_cut.0")
             v = _bf(F.conv2d(v, w, sd[p + ".short_cut.0.bias"]), bf16)
-        z = lr(p + ".conv_2", lr(p + ".conv_1", v, k), k)
+        z = glr(p + ".conv_2", lr(p + ".conv_1", v, k), k) if guided else lr(p + ".conv_2", lr(p + ".conv_1", v, k), k)
         return _bf(z + v, bf16)
 
     blocks = [x]
@@ -551,7 +569,7 @@ def selfres_forward(sd, x, res=False, norm=False, bf16=False, slope=0.1, depth=5
         h = F.max_pool2d(h, 2)
         if i != depth - 1:
             blocks.append(h)
-        h = res_block(f"down_path.{i}", h)
+        h = glr(f"down_path.{i}", h, 3) if guided else res_block(f"down_path.{i}", h)
     for i in range(depth):
         up = h.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)  # RUP.up (:815-820)
         pool = blocks[-i - 1]
@@ -562,7 +580,7 @@ def selfres_forward(sd, x, res=False, norm=False, bf16=False, slope=0.1, depth=5
             c = up.shape[1]
             v = F.conv2d(up, _bf(w[:, :c], bf16), sd[p + ".short_cut.0.bias"]) + F.conv2d(pool, w[:, c:])
             v = _bf(v, bf16)
-            z = lr(p + ".conv_2", lr(p + ".conv_1", v, 3), 3)
+            z = glr(p + ".conv_2", lr(p + ".conv_1", v, 3), 3) if guided else lr(p + ".conv_2", lr(p + ".conv_1", v, 3), 3)
             h = _bf(z + v, bf16)
         else:
             h = res_block(p, _bf(torch.cat([up, pool], 1), bf16))
@@ -588,6 +606,8 @@ def net_forward(arch, sd, x, t=None, bf16=False):
         return guided_forward(sd, x, None, res, norm, bf16, "res2")
     if name == "SelfResUNet":
         return selfres_forward(sd, x, res, norm, bf16, arch.get("slope", 0.1), arch.get("depth", 5))
+    if name == "GuidedSelfUnet":
+        return selfres_forward(sd, x, res, norm, bf16, arch.get("slope", 0.1), arch.get("depth", 5), t=t)
     raise NotImplementedError(name)
 
 
@@ -610,17 +630,23 @@ def init_state_dict(arch, seed=0, weight_scale=None):
             mods += [(f"upv{i}", nn.ConvTranspose2d(c * 2, c, 2, stride=2)),
                      (f"conv{i}_1", nn.Conv2d(c * 2, c, 3, 1, 1)), (f"conv{i}_2", nn.Conv2d(c, c, 3, 1, 1))]
         mods.append(("conv10_1", nn.Conv2d(nf, cout, 1)))
-    elif arch["name"] == "SelfResUNet":  # archs/comp.py:745-776; Res :830-838, RUP :804-813, LR :709-717
-        depth = arch.get("depth", 5)
+    elif arch["name"] in ("SelfResUNet", "GuidedSelfUnet"):  # archs/comp.py:745-776 / :852-883; Res :830-838, RUP :804-813, LR :709-717,
+        depth = arch.get("depth", 5)                            # GLR :912-926, GRes :936-946, GUP :956-966
+        gsu = arch["name"] == "GuidedSelfUnet"
+
+        def glr(p, co, k=3):
+            return [(f"{p}.block", nn.Conv2d(co, co, k, padding=k // 2)), (f"{p}.gamma.0", nn.Conv2d(1, co, 1)),
+                    (f"{p}.gamma.2", nn.Conv2d(co, co, 1)), (f"{p}.beta.1", nn.Conv2d(co, co, 1))]
 
         def res(p, ci, co, k=3):
-            m = [(f"{p}.conv_1.block.0", nn.Conv2d(co, co, k, padding=k // 2)), (f"{p}.conv_2.block.0", nn.Conv2d(co, co, k, padding=k // 2))]
+            m = [(f"{p}.conv_1.block.0", nn.Conv2d(co, co, k, padding=k // 2))]
+            m += glr(f"{p}.conv_2", co, k) if gsu else [(f"{p}.conv_2.block.0", nn.Conv2d(co, co, k, padding=k // 2))]
             if ci != co:
                 m.append((f"{p}.short_cut.0", nn.Conv2d(ci, co, 1)))
             return m
         mods += res("head", cin, nf)
         for i in range(depth):
-            mods += res(f"down_path.{i}", nf, nf)
+            mods += glr(f"down_path.{i}", nf) if gsu else res(f"down_path.{i}", nf, nf)
         for i in range(depth):
             ci = (nf * 2 if i == 0 else nf * 3) if i != depth - 1 else nf * 2 + cin
             mods += res(f"up_path.{i}", ci, nf * 2)

@@ -18,6 +18,7 @@ from oracle import yond_oracle as O  # noqa: E402
 from oracle.ref_harness import load_reference, make_driver  # noqa: E402
 
 ARCH = {"name": "ResUnet2", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}
+ARCH_GSELF = {"name": "GuidedSelfUnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False, "norm": True}  # :852-910
 ARCH_SELF = {"name": "SelfResUNet", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True}  # archs/comp.py:745-802
 PIPE = {"full_est": True, "est_type": "simple+full", "k": 29, "full_dn": False, "vst_type": "exact", "bias_corr": "pre",
         "iter": "iter", "max_iter": 1}
@@ -29,7 +30,7 @@ def crc(a):
 
 def main():
     ref = load_reference()
-    for arch, fname in ((ARCH, "net_res2"), (ARCH_SELF, "net_selfres")):
+    for arch, fname in ((ARCH, "net_res2"), (ARCH_SELF, "net_selfres"), (ARCH_GSELF, "net_gself")):
         one(ref, arch, fname)
 
 
@@ -44,7 +45,7 @@ def one(ref, ARCH, fname):
     xin = torch.from_numpy(rng.uniform(0, 1, (2, 4, 64, 32)).astype(np.float32))
     xin[1] *= 0.6
     with torch.no_grad():
-        y = drv.net(xin)
+        y = drv.net(xin, torch.tensor(0.043, dtype=torch.float32)) if "guided" in ARCH else drv.net(xin)
     np.savez_compressed(os.path.join(HERE, fname + ".npz"), x=xin.numpy(), y=y.numpy(), nparams=sum(v.numel() for v in sd.values()),
                         keys=np.array(list(sd.keys())), shapes=np.array([str(tuple(v.shape)) for v in sd.values()]),
                         sd_crc=np.array([crc(v.numpy()) for v in sd.values()], np.uint32))

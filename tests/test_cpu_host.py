@@ -90,6 +90,10 @@ def test_no_cpu_fallback(Y):
             Y.compare_psnr(np.zeros((16, 16), np.float32), np.ones((16, 16), np.float32))
         with pytest.raises(Y._lib.YondError):
             Y.ResUnet2(dict(ARCH_UNET, name="ResUnet2"))(torch.zeros(1, 4, 32, 32))
+        with pytest.raises(Y._lib.YondError):
+            Y.SelfResUNet(dict(ARCH_UNET, name="SelfResUNet"))(torch.zeros(1, 4, 32, 32))
+        with pytest.raises(Y._lib.YondError):
+            Y.GuidedSelfUnet(dict(ARCH_UNET, name="GuidedSelfUnet", res=False))(torch.zeros(1, 4, 32, 32), torch.tensor(0.04))
 
 
 def test_synth_module_matches_reference_recipes(Y):

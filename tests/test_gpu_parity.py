@@ -16,6 +16,7 @@ ARCHS = {
     "snr": {"name": "SNRnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
     "res2": {"name": "ResUnet2", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
     "selfres": {"name": "SelfResUNet", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
+    "gself": {"name": "GuidedSelfUnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False, "norm": True},
 }
 PIPE = {"full_est": True, "est_type": "simple+full", "k": 29, "full_dn": False, "vst_type": "exact", "bias_corr": "pre",
         "iter": "iter", "max_iter": 1}
@@ -227,7 +228,7 @@ def test_rot_bayer_bit_exact(Y, golden):
 
 
 # ------------------------------------------------------------------ A14-A17, A20 networks
-@pytest.mark.parametrize("key", ["unet", "gru", "snr", "res2", "selfres"])
+@pytest.mark.parametrize("key", ["unet", "gru", "snr", "res2", "selfres", "gself"])
 def test_network_golden_and_statedict(Y, golden, key):
     g = golden(f"net_{key}")
     arch = ARCHS[key]
@@ -256,17 +257,19 @@ def test_network_golden_and_statedict(Y, golden, key):
     assert float((y2 - y).abs().max()) < 1e-4
 
 
-def test_selfres_plugin_in_the_pipeline(Y):
-    """SelfResUNet (archs/comp.py:745-802) as the denoiser of VST_Denoiser (non-guided call, fallback bias table),
-    odd frame size (reflect pad to x32), against the oracle's fp32 path."""
+@pytest.mark.parametrize("key", ["selfres", "gself"])
+def test_comp_plugins_in_the_pipeline(Y, lut_table, key):
+    """SelfResUNet / GuidedSelfUnet (archs/comp.py:745-983) as the denoiser of VST_Denoiser (non-guided call with the
+    fallback bias table / guided call with the BiasLUT), odd frame size (reflect pad to x32), against the oracle's fp32 path."""
     rng = np.random.default_rng(21)
-    arch = ARCHS["selfres"]
+    arch = ARCHS[key]
     noisy = O.synth_noisy(rng, O.synth_clean(rng, 136, 200), 5.0, 7.0, clip=False)
     p = {"wp": 1023, "bl": 64, "ratio": 1, "scale": 959.0, "gain": np.float64(5.3), "sigma": np.float64(6.6)}
     sd = O.init_state_dict(arch, seed=5)
-    drv = Y.YOND_SIDD(arch, PIPE, state_dict=sd, biaslut=None)
+    guided = "guided" in arch
+    drv = Y.YOND_SIDD(arch, PIPE, state_dict=sd, biaslut="default" if guided else None)
     out = drv.VST_Denoiser(noisy, None, "pre", None, denoiser="net", p=dict(p))
-    ref = O.VST_Denoiser(arch, sd, noisy, dict(p), "pre", None)
+    ref = O.VST_Denoiser(arch, sd, noisy, dict(p), "pre", O.BiasLUT(lut_table) if guided else None)
     assert out.shape == noisy.shape and float(np.abs(out - ref).max()) < TOL_ABS
     assert float(np.abs(out - ref).max()) < 2e-4  # actual margin on random-init weights
 

@@ -16,6 +16,7 @@ ARCHS = {
             "res": True, "norm": True},
     "res2": {"name": "ResUnet2", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
     "selfres": {"name": "SelfResUNet", "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": True, "norm": True},
+    "gself": {"name": "GuidedSelfUnet", "guided": True, "in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False, "norm": True},
 }
 PIPE = {"k": 29, "full_dn": False, "vst_type": "exact", "bias_corr": "pre", "iter": "iter", "max_iter": 1}
 
@@ -104,7 +105,7 @@ def test_get_p2d(golden):
         assert O.get_p2d(tuple(int(v) for v in s), base=32) == tuple(int(v) for v in p)
 
 
-@pytest.mark.parametrize("key", ["unet", "gru", "snr", "res2", "selfres"])
+@pytest.mark.parametrize("key", ["unet", "gru", "snr", "res2", "selfres", "gself"])
 def test_networks(golden, key):
     g = golden(f"net_{key}")
     arch = ARCHS[key]
@@ -112,7 +113,7 @@ def test_networks(golden, key):
     assert [str(k) for k in g["keys"]] == list(sd.keys())
     assert [str(s) for s in g["shapes"]] == [str(tuple(v.shape)) for v in sd.values()]
     assert np.array_equal(np.array([crc(v.numpy()) for v in sd.values()], np.uint32), g["sd_crc"])
-    assert int(g["nparams"]) == {"unet": 7760484, "gru": 11173668, "snr": 11176612, "res2": 11173668, "selfres": 512036}[key]
+    assert int(g["nparams"]) == {"unet": 7760484, "gru": 11173668, "snr": 11176612, "res2": 11173668, "selfres": 512036, "gself": 529540}[key]
     x = torch.from_numpy(g["x"])
     with torch.no_grad():
         y = O.net_forward(arch, sd, x, torch.tensor(0.043) if "guided" in arch else None)

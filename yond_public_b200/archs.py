@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
-ARCH_IDS = {"UNetSeeInDark": 0, "GuidedResUnet": 1, "SNRnet": 2, "ResUnet2": 3, "SelfResUNet": 4}
+ARCH_IDS = {"UNetSeeInDark": 0, "GuidedResUnet": 1, "SNRnet": 2, "ResUnet2": 3, "SelfResUNet": 4, "GuidedSelfUnet": 5}
 
 
 def conv1x1(in_nc, out_nc):
@@ -263,6 +263,47 @@ class Res(nn.Module):  # parameters only — archs/comp.py:830-850 (RUP, :804-82
         self.conv_1 = LR(out_size, out_size, ksize=ksize, slope=slope)
         self.conv_2 = LR(out_size, out_size, ksize=ksize, slope=slope)
         self.short_cut = nn.Sequential(conv1x1(in_size, out_size)) if in_size != out_size else nn.Sequential(OrderedDict([]))
+
+
+class GLR(nn.Module):  # parameters only — archs/comp.py:912-934 (conv, z*tk + tb, LeakyReLU)
+    def __init__(self, in_size, out_size, ksize=3, slope=0.1):
+        super().__init__()
+        self.block = nn.Conv2d(in_size, out_size, kernel_size=ksize, padding=ksize // 2, bias=True)
+        self.act = nn.LeakyReLU(slope, inplace=False)
+        self.gamma = nn.Sequential(conv1x1(1, out_size), nn.SiLU(), conv1x1(out_size, out_size))
+        self.beta = nn.Sequential(nn.SiLU(), conv1x1(out_size, out_size))
+
+
+class GRes(nn.Module):  # parameters only — archs/comp.py:936-954 (GUP, :956-983, registers the same modules)
+    def __init__(self, in_size, out_size, slope=0.1, ksize=3):
+        super().__init__()
+        self.conv_1 = LR(out_size, out_size, ksize=ksize)
+        self.conv_2 = GLR(out_size, out_size, ksize=ksize)
+        self.short_cut = nn.Sequential(conv1x1(in_size, out_size)) if in_size != out_size else nn.Sequential(OrderedDict([]))
+
+
+class GuidedSelfUnet(_B200Net):
+    """archs/comp.py:852-910: SelfResUNet's graph with noise-level conditioning (GRes head / last, single GLR down
+    levels, GUP up levels); called as net(x, t).  `res` must be False: the reference's res branch adds the 2nf-channel features to the
+    4-channel output and cannot run."""
+
+    def __init__(self, args):
+        args = dict(args)
+        args.setdefault("res", False)
+        assert not args["res"], "GuidedSelfUnet: res=True cannot run in the reference (archs/comp.py:904-905)"
+        super().__init__(args)
+        nf = args["nf"] if "nf" in args else 32
+        assert args.get("depth", 5) == 5 and args.get("slope", 0.1) == 0.1, "the B200 plugin builds the class defaults (depth 5, slope 0.1)"
+        in_nc, out_nc, depth = args["in_nc"], args["out_nc"], 5
+        self.depth = depth
+        self.head = GRes(in_nc, nf)
+        self.down_path = nn.ModuleList([GLR(nf, nf, 3) for _ in range(depth)])
+        self.up_path = nn.ModuleList([GRes((nf * 2 if i == 0 else nf * 3) if i != depth - 1 else nf * 2 + in_nc, nf * 2) for i in range(depth)])
+        self.last = GRes(2 * nf, 2 * nf, ksize=1)
+        self.out = conv1x1(2 * nf, out_nc)
+
+    def forward(self, x, t):
+        return self._forward_nchw(x, t)
 
 
 class SelfResUNet(_B200Net):

@@ -87,12 +87,26 @@ void add_layer(yond_net* n, const std::string& name, int mode, int cin0, int cin
 // state_dict keys in the reference's registration order + the tensor-core layer table
 void describe(yond_net* n) {
   const int nf = n->nf, cin = n->in_nc, cout = n->out_nc;
-  if (n->arch == YOND_ARCH_SELFRES) {  // archs/comp.py:745-776; Res :830-838, RUP :804-813, LR :709-717 (depth 5)
+  if (n->arch == YOND_ARCH_SELFRES || n->arch == YOND_ARCH_GSELF) {
+    // SelfResUNet archs/comp.py:745-776 (Res :830-838, RUP :804-813, LR :709-717) / GuidedSelfUnet :852-883 (GLR :912-926, GRes :936-946,
+    // GUP :956-966); depth 5
+    const bool gsu = n->arch == YOND_ARCH_GSELF;
+    auto glr = [&](const std::string& p, int co, int k) {  // conv + the conditioning MLPs, in GLR's registration order
+      add_conv_keys(n, p + ".block", co, co, k);
+      add_conv_keys(n, p + ".gamma.0", co, 1, 1);
+      add_conv_keys(n, p + ".gamma.2", co, co, 1);
+      add_conv_keys(n, p + ".beta.1", co, co, 1);
+      add_layer(n, p + ".block", k == 3 ? CONV_3X3_S1 : CONV_1X1, co, 0, co);
+    };
     auto res = [&](const std::string& p, int ci, int co, int k, bool tc_shortcut) {
       add_conv_keys(n, p + ".conv_1.block.0", co, co, k);
-      add_conv_keys(n, p + ".conv_2.block.0", co, co, k);
       add_layer(n, p + ".conv_1.block.0", k == 3 ? CONV_3X3_S1 : CONV_1X1, co, 0, co);
-      add_layer(n, p + ".conv_2.block.0", k == 3 ? CONV_3X3_S1 : CONV_1X1, co, 0, co);
+      if (gsu) {
+        glr(p + ".conv_2", co, k);
+      } else {
+        add_conv_keys(n, p + ".conv_2.block.0", co, co, k);
+        add_layer(n, p + ".conv_2.block.0", k == 3 ? CONV_3X3_S1 : CONV_1X1, co, 0, co);
+      }
       if (ci != co) {
         add_conv_keys(n, p + ".short_cut.0", co, ci, 1);
         if (tc_shortcut) {  // 1x1 on cat[up (2 nf), skip (nf)], or on the 2 nf feature part of cat[up, input]
@@ -102,7 +116,10 @@ void describe(yond_net* n) {
       }
     };
     res("head", cin, nf, 3, false);  // its 4 -> nf shortcut runs on the float32 input (head kernel, centre tap only)
-    for (int i = 0; i < 5; ++i) res("down_path." + std::to_string(i), nf, nf, 3, false);
+    for (int i = 0; i < 5; ++i) {
+      if (gsu) glr("down_path." + std::to_string(i), nf, 3);
+      else res("down_path." + std::to_string(i), nf, nf, 3, false);
+    }
     for (int i = 0; i < 5; ++i) res("up_path." + std::to_string(i), i == 0 ? 2 * nf : (i == 4 ? 2 * nf + cin : 3 * nf), 2 * nf, 3, true);
     res("last", 2 * nf, 2 * nf, 1, false);
     add_conv_keys(n, "out", cout, 2 * nf, 1);
@@ -293,7 +310,7 @@ int finalize(yond_net* n) {
     }
     L.bias = n->f32[L.bkey];
   }
-  if (n->arch == YOND_ARCH_SELFRES) {  // head shortcut (nf,4,1,1) as the centre tap of a 3x3; out (4,2nf,1,1) -> [ci][4]; input part of the last shortcut
+  if (n->arch == YOND_ARCH_SELFRES || n->arch == YOND_ARCH_GSELF) {  // head shortcut (nf,4,1,1) as the centre tap of a 3x3; out (4,2nf,1,1) -> [ci][4]; input part of the last shortcut
     const std::vector<float>& hw = n->host["head.short_cut.0.weight"];
     std::vector<float> h((size_t)36 * n->nf, 0.f);
     for (int co = 0; co < n->nf; ++co)
@@ -407,10 +424,13 @@ struct Runner {
 
 // SelfResUNet.forward (archs/comp.py:778-802): every layer is a tensor-core conv (3x3 / 1x1 + LeakyReLU(0.1) [+ residual]); the two
 // 4-channel 1x1 pieces (head shortcut on the input, input part of the last up-level shortcut) stay in float32.
-int forward_selfres(yond_net* n, const float* z, const float* ub, float* y, int B, int H, int W, void* ws, size_t* ws_bytes, double* flops,
-                    cudaStream_t s) {
+int forward_selfres(yond_net* n, const float* z, const float* ub, const float* tvec, float* y, int B, int H, int W, void* ws, size_t* ws_bytes,
+                    double* flops, cudaStream_t s) {
   const bool dry = ws == nullptr;
+  const bool gsu = n->arch == YOND_ARCH_GSELF;
   YOND_REQUIRE(H % 32 == 0 && W % 32 == 0, "SelfResUNet: H, W must be multiples of 32 (five 2x2 poolings); got %d x %d", H, W);
+  if (!dry && gsu && tvec == nullptr) return yond_set_error(YOND_ERR_INVALID, "guided network needs the per-sample t vector");
+  YOND_REQUIRE(!(gsu && n->res), "GuidedSelfUnet: res must be 0 (archs/comp.py:904-905 adds a 2nf-channel tensor to the output)");
   Bump bump(ws);
   Runner R;
   R.n = n;
@@ -425,9 +445,42 @@ int forward_selfres(yond_net* n, const float* z, const float* ub, float* y, int 
   do {                                                  \
     if (!dry && R.rc == YOND_OK) R.rc = (expr);         \
   } while (0)
-  auto res_block = [&](const std::string& p, int lv, int C, const bf16* x, bf16* t, bf16* out) {  // out = LR(LR(x)) + x
+  // conditioning vectors of the 12 GLRs (GuidedSelfUnet): head.conv_2, down_path.0-4, up_path.0-4.conv_2, last.conv_2
+  float* va[12] = {nullptr};
+  float* vb[12] = {nullptr};
+  if (gsu) {
+    FilmAll all{};
+    all.n = 12;
+    for (int k = 0; k < 12; ++k) {
+      const int C = (k >= 1 && k <= 5) || k == 0 ? nf : c2;
+      const std::string p = k == 0 ? "head.conv_2" : (k <= 5 ? "down_path." + std::to_string(k - 1) : (k <= 10 ? "up_path." + std::to_string(k - 6) + ".conv_2" : "last.conv_2"));
+      va[k] = bump.take<float>((size_t)B * C);
+      vb[k] = bump.take<float>((size_t)B * C);
+      if (!dry) {
+        FilmWeights& fw = all.fw[k];
+        fw.w0 = n->f32[p + ".gamma.0.weight"]; fw.b0 = n->f32[p + ".gamma.0.bias"];
+        fw.w2 = n->f32[p + ".gamma.2.weight"]; fw.b2 = n->f32[p + ".gamma.2.bias"];
+        fw.w3 = n->f32[p + ".beta.1.weight"];  fw.b3 = n->f32[p + ".beta.1.bias"];
+        all.C[k] = C;
+        all.out_a[k] = va[k];
+        all.out_b[k] = vb[k];
+      }
+    }
+    RUN(film_launch(all, tvec, ubn, B, 1, s));
+  }
+  auto film_of = [&](const std::string& p) {
+    if (p == "head") return 0;
+    if (p == "last") return 11;
+    return 6 + (p.back() - '0');  // up_path.i
+  };
+  auto res_block = [&](const std::string& p, int lv, int C, const bf16* x, bf16* t, bf16* out) {  // out = LR|GLR(LR(x)) + x
     R.conv(p + ".conv_1.block.0", B, H >> lv, W >> lv, x, nullptr, nullptr, nullptr, ACT_LRELU, slope, nullptr, t, nullptr);
-    R.conv(p + ".conv_2.block.0", B, H >> lv, W >> lv, t, nullptr, nullptr, nullptr, ACT_LRELU, slope, x, out, nullptr);
+    if (gsu) {
+      const int k = film_of(p);
+      R.conv(p + ".conv_2.block", B, H >> lv, W >> lv, t, nullptr, va[k], vb[k], ACT_LRELU, slope, x, out, nullptr);
+    } else {
+      R.conv(p + ".conv_2.block.0", B, H >> lv, W >> lv, t, nullptr, nullptr, nullptr, ACT_LRELU, slope, x, out, nullptr);
+    }
   };
   bf16* x0 = buf(0, nf);
   bf16* t0 = buf(0, nf);
@@ -440,7 +493,11 @@ int forward_selfres(yond_net* n, const float* z, const float* ub, float* y, int 
     bf16* t = buf(i + 1, nf);
     bf16* hn = buf(i + 1, nf);
     RUN(maxpool2_launch(h, pool[i], B, H >> i, W >> i, nf, s));
-    res_block("down_path." + std::to_string(i), i + 1, nf, pool[i], t, hn);
+    if (gsu)  // one GLR, no residual
+      R.conv("down_path." + std::to_string(i) + ".block", B, H >> (i + 1), W >> (i + 1), pool[i], nullptr, va[1 + i], vb[1 + i], ACT_LRELU, slope,
+             nullptr, hn, nullptr);
+    else
+      res_block("down_path." + std::to_string(i), i + 1, nf, pool[i], t, hn);
     h = hn;
   }
   for (int i = 0; i < 5; ++i) {
@@ -482,7 +539,7 @@ int forward_selfres(yond_net* n, const float* z, const float* ub, float* y, int 
 // whole batch.  See the measurement note at SBn below: the split is off by default.
 int forward_impl(yond_net* n, const float* z, const float* ub, const float* t, float* y, int B, int H, int W, void* ws,
                  size_t* ws_bytes, double* flops, cudaStream_t s) {
-  if (n->arch == YOND_ARCH_SELFRES) return forward_selfres(n, z, ub, y, B, H, W, ws, ws_bytes, flops, s);
+  if (n->arch == YOND_ARCH_SELFRES || n->arch == YOND_ARCH_GSELF) return forward_selfres(n, z, ub, t, y, B, H, W, ws, ws_bytes, flops, s);
   const bool dry = ws == nullptr;
   Bump bump(ws);
   Runner R;
@@ -717,7 +774,7 @@ extern "C" {
 
 int yond_net_create(int arch, int in_nc, int out_nc, int nf, int res, int norm, yond_net_t** out) {
   YOND_REQUIRE(out != nullptr, "yond_net_create: null output");
-  YOND_REQUIRE(arch >= YOND_ARCH_UNET && arch <= YOND_ARCH_SELFRES, "yond_net_create: unknown arch %d", arch);
+  YOND_REQUIRE(arch >= YOND_ARCH_UNET && arch <= YOND_ARCH_GSELF, "yond_net_create: unknown arch %d", arch);
   YOND_REQUIRE(in_nc == 4 && out_nc == 4, "yond_net_create: only packed-Bayer nets (in_nc = out_nc = 4, nframes = 1) are built");
   YOND_REQUIRE(nf >= 32 && nf % 32 == 0, "yond_net_create: nf must be a multiple of 32 (got %d)", nf);
   yond_net* n = new yond_net();

@@ -20,10 +20,10 @@ int upcat_launch(const bf16* lo, const bf16* skip, bf16* out, int B, int Hlo, in
 // act (B,H,W,C) bf16 += w_in[C][4] . (z / ub): the 4 input channels of a 1x1 conv on cat[features, network input], in float32.
 int add_in4_launch(bf16* act, const float* w_in, const float* z, const float* ub, int B, int H, int W, int C, cudaStream_t s);
 struct FilmAll {  // every conditioned block of a network, evaluated by one launch
-  FilmWeights fw[9];
-  int C[9];
-  float* out_a[9];
-  float* out_b[9];
+  FilmWeights fw[12];
+  int C[12];
+  float* out_a[12];
+  float* out_b[12];
   int n;
 };
 int film_launch(const FilmAll& all, const float* t, const float* ub, int B, int guided, cudaStream_t s);
