@@ -216,6 +216,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: run on (and first-touch the pinned staging buffers from) the CPUs of the GPU's own NUMA node
+    numa_node = parallel.bind_to_gpu_numa_node(local) if os.environ.get("YOND_NUMA_BIND", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks, peak_src = measured_peaks()
@@ -475,6 +477,7 @@ def run_b200(args):
             "roofline_hbm": {"peak_gbs": peak_hbm, "peak_source": peak_src + " hbm_gbs", "bound": "hbm",
                              "measured_in": "the timed region (CUDA events around every stage on the launching stream); bytes = algorithmic bytes per Bayer pixel (SURVEY 8d) x pixels",
                              "kernels": hbm_table(hbm_prof, peak_hbm)},
+            "numa_node": numa_node,
             "e2e_raw16": {"value": e2e16, "unit": "MP/s", "ms_per_step": ms_e2e16 / steps, "h2d_bytes_per_step": int(host_in16.numel() * 2),
                           "d2h_bytes_per_step": int(host_out.numel() * 4),
                           "api": "the e2e call on uint16 sensor mosaics: iter_denoise_host(..., raw=(black, white, ratio)); the estimator and the "
