@@ -345,6 +345,20 @@ def test_iterdenoise_golden_random_init(Y, golden, key):
     assert abs(float(res["raw_dns"][0].astype(np.float64).mean()) - float(g["dn0_mean"])) < 1e-5
 
 
+def test_iterdenoise_snrnet_vs_oracle(Y, lut_table):
+    """IterDenoise with the SNR-Net variant (archs/Unet.py:288-378; SNR_Block gates instead of FiLM) against the oracle's fp32 path."""
+    blocks = _blocks(19, 6.0, 9.0)[:, :128, :128].copy()
+    sd = O.init_state_dict(ARCHS["snr"], seed=5)
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+    drv = Y.YOND_SIDD(ARCHS["snr"], PIPE, state_dict=sd)
+    res = drv.IterDenoise({"lr": blocks, "name": "x"}, {"p": dict(p), "img_id": 0})
+    ref = O.IterDenoise(ARCHS["snr"], sd, blocks, dict(p), PIPE, biaslut=O.BiasLUT(lut_table))
+    assert len(res["raw_dns"]) == len(ref["raw_dns"])
+    np.testing.assert_allclose(np.asarray(res["regs"][0]), np.asarray(ref["regs"][0]), rtol=TOL_EST)
+    for a, b in zip(res["raw_dns"], ref["raw_dns"]):
+        assert float(np.abs(a - b).max()) < TOL_ABS
+
+
 @pytest.mark.parametrize("key", ["gru", "unet"])
 def test_iterdenoise_golden_two_rounds(Y, golden, key):
     g = golden(f"iter2_{key}")

@@ -75,7 +75,7 @@ def run_conv_case(mode, impl, B, H, W, cin0, cin1, cout, act=0, use_res=False, u
         return f"rc={rc} {lib.yond_last_error().decode()}"
     got = out0.float().cpu().permute(0, 3, 1, 2)
     err = (got - ref).abs().max().item()
-    tol = 0.02 * max(1.0, ref.abs().max().item())
+    tol = 2.0 ** -7 * max(1.0, ref.abs().max().item())  # bf16 output rounding is 2^-9 of the value; fp32 accumulation-order noise on top
     msg = f"max_err={err:.4g} (|ref|max={ref.abs().max().item():.3g})"
     if dual:
         e1 = (out1.float().cpu().permute(0, 3, 1, 2) - torch.nn.functional.silu(ref)).abs().max().item()

@@ -29,7 +29,7 @@
 // -DYOND_CONV_TIMING: cycle counters in the producer / issuer loops, printed with YOND_CONV_DBG=8 (six clock reads per tile in the
 // issuer otherwise cost ~5 % of a narrow layer)
 #ifdef YOND_CONV_TIMING
-#define YOND_TICK() YOND_TICK()
+#define YOND_TICK() clock64()
 #else
 #define YOND_TICK() 0LL
 #endif
