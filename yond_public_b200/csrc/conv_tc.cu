@@ -460,7 +460,7 @@ __device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t nt, uint32_t
 }
 
 // K steps [K0, K1) of one tap (pixel-pair formulation: the other steps multiply all-zero weights)
-template <int K0, int K1, int TT>
+template <int K0, int K1, int TT, bool kP = false>  // kP: cta_group::2 MMAs (CTA pair)
 __device__ __forceinline__ void issue_tap_range(uint32_t d_tmem, uint32_t nt, uint32_t a_lo0, uint32_t sub_step, uint32_t b_lo0,
                                                 uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t accum) {
   uint32_t al = a_lo0 + 2u * K0, dt = d_tmem;
@@ -468,29 +468,32 @@ __device__ __forceinline__ void issue_tap_range(uint32_t d_tmem, uint32_t nt, ui
   for (int t = 0; t < TT; ++t) {
     uint32_t bl = b_lo0 + 2u * K0;
 #pragma unroll
-    for (int k = K0; k < K1; ++k) umma_step(dt, al, a_hi, bl, b_hi, idesc, k > K0 ? 1u : accum);
+    for (int k = K0; k < K1; ++k) {
+      if (kP) umma_step_pair(dt, al, a_hi, bl, b_hi, idesc, k > K0 ? 1u : accum);
+      else umma_step(dt, al, a_hi, bl, b_hi, idesc, k > K0 ? 1u : accum);
+    }
     al += sub_step - 2u * (K1 - K0);
     dt += nt;
   }
 }
 // Nine taps of a pixel-pair slab (CB = 64: K steps 0,1 = first pixel of the pair, 2,3 = second): the left neighbour pair
 // contributes only its second pixel, the right neighbour pair only its first.
-template <int TT>
+template <int TT, bool kP = false>
 __device__ __forceinline__ void issue_slab_paired(uint32_t d_tmem, uint32_t nt, uint32_t a_stage_lo, uint32_t tap_r16, uint32_t px16,
                                                   uint32_t sub_step, uint32_t b_lo_first, uint32_t b_step16, uint32_t a_hi,
                                                   uint32_t b_hi, uint32_t idesc, uint32_t first_accum) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const uint32_t a0 = a_stage_lo + (uint32_t)r * tap_r16, b0 = b_lo_first + (uint32_t)(r * 3) * b_step16;
-    issue_tap_range<2, 4, TT>(d_tmem, nt, a0, sub_step, b0, a_hi, b_hi, idesc, r ? 1u : first_accum);
-    issue_tap_range<0, 4, TT>(d_tmem, nt, a0 + px16, sub_step, b0 + b_step16, a_hi, b_hi, idesc, 1u);
-    issue_tap_range<0, 2, TT>(d_tmem, nt, a0 + 2u * px16, sub_step, b0 + 2u * b_step16, a_hi, b_hi, idesc, 1u);
+    issue_tap_range<2, 4, TT, kP>(d_tmem, nt, a0, sub_step, b0, a_hi, b_hi, idesc, r ? 1u : first_accum);
+    issue_tap_range<0, 4, TT, kP>(d_tmem, nt, a0 + px16, sub_step, b0 + b_step16, a_hi, b_hi, idesc, 1u);
+    issue_tap_range<0, 2, TT, kP>(d_tmem, nt, a0 + 2u * px16, sub_step, b0 + 2u * b_step16, a_hi, b_hi, idesc, 1u);
   }
 }
 
 // All nine taps of one halo slab as straight-line code (resident weights): the only run-time inputs are a handful of
 // uniform bases and strides, everything else is an immediate.
-template <int KS, int TT>
+template <int KS, int TT, bool kP = false>
 __device__ __forceinline__ void issue_slab_resident(uint32_t d_tmem, uint32_t nt, uint32_t a_stage_lo, uint32_t tap_r16, uint32_t px16,
                                                     uint32_t sub_step, uint32_t b_lo_first, uint32_t b_step16, uint32_t a_hi,
                                                     uint32_t b_hi, uint32_t idesc, uint32_t first_accum) {
@@ -498,8 +501,8 @@ __device__ __forceinline__ void issue_slab_resident(uint32_t d_tmem, uint32_t nt
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int sx = 0; sx < 3; ++sx)
-      issue_tap<KS, TT>(d_tmem, nt, a_stage_lo + (uint32_t)r * tap_r16 + (uint32_t)sx * px16, sub_step,
-                        b_lo_first + (uint32_t)(r * 3 + sx) * b_step16, a_hi, b_hi, idesc, (r | sx) ? 1u : first_accum);
+      issue_tap_range<0, KS, TT, kP>(d_tmem, nt, a_stage_lo + (uint32_t)r * tap_r16 + (uint32_t)sx * px16, sub_step,
+                                     b_lo_first + (uint32_t)(r * 3 + sx) * b_step16, a_hi, b_hi, idesc, (r | sx) ? 1u : first_accum);
 }
 
 // 256-bit global accesses (sm_100): one lane moves a whole 32-byte sector per instruction, so a pixel-per-lane store of
@@ -903,6 +906,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         mbar_expect_tx(w_full, p.ncb0 * p.b_stage_bytes + p.ncb1 * p.b2_stage_bytes);
         for (int i = 0; i < p.ncb0; ++i) tma_load_2d(smem_b + i * p.b_stage_bytes, &maps.w, w_full, 0, i * p.N);
         for (int i = 0; i < p.ncb1; ++i) tma_load_2d(smem_b + p.b2_off + i * p.b2_stage_bytes, &maps.w2, w_full, 0, i * p.Cout);
+      } else if (p.wres && kPair) {  // CTA pair: this CTA keeps its HALF (NT/2 rows) of every weight tile
+        const int nwt = num_wtiles(p);
+        const uint32_t w_full_sig = mapa_shared(w_full, 0);
+        if (sched.rank == 0) mbar_expect_tx(w_full, 2 * nwt * p.b_stage_bytes);
+        for (int i = 0; i < nwt; ++i)
+          tma_load_2d_pair(smem_b + i * p.b_stage_bytes, &maps.w, w_full_sig, 0, i * p.N + sched.rank * (p.NT / 2));
       } else if (p.wres) {  // all weight tiles of this layer stay in smem for the kernel's lifetime
         const int nwt = num_wtiles(p);
         mbar_expect_tx(w_full, nwt * p.b_stage_bytes);
@@ -987,7 +996,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const uint32_t tap_r16 = p.tap_r_off >> 4, px16 = row_bytes >> 4;
     const uint32_t nt = (uint32_t)p.NT;
     const bool leader = elect_one() != 0;
-    if (p.wres) mbar_wait(uw_full, 0);
+    if (p.wres && (!kPair || pair_leader)) mbar_wait(uw_full, 0);  // pair: both halves are counted on the leader's barrier
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     long long t_acc = 0, t_a = 0, t_issue = 0, t_begin = YOND_TICK();
     // CTA pair: only the leader CTA issues (its MMAs drive both SMs' tensor cores); the peer's warp 1 idles
@@ -1012,19 +1021,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const uint32_t b_step16 = p.b_stage_bytes >> 4;
           const uint32_t acc0 = ai ? 1u : 0u;
           if (p.paired && !(p.dbg & 256)) {  // dbg 256: keep the all-zero K steps (cross-check of the skip)
-            if (p.T == 1) issue_slab_paired<1>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
-            else if (p.T == 2) issue_slab_paired<2>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
-            else issue_slab_paired<4>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            if (p.T == 1) issue_slab_paired<1, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else if (p.T == 2) issue_slab_paired<2, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else issue_slab_paired<4, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
           } else if (ksteps == 4) {
-            if (p.T == 1) issue_slab_resident<4, 1>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
-            else if (p.T == 2) issue_slab_resident<4, 2>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
-            else issue_slab_resident<4, 4>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            if (p.T == 1) issue_slab_resident<4, 1, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else if (p.T == 2) issue_slab_resident<4, 2, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else issue_slab_resident<4, 4, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
           } else {
-            if (p.T == 1) issue_slab_resident<2, 1>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
-            else if (p.T == 2) issue_slab_resident<2, 2>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
-            else issue_slab_resident<2, 4>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            if (p.T == 1) issue_slab_resident<2, 1, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else if (p.T == 2) issue_slab_resident<2, 2, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
+            else issue_slab_resident<2, 4, kPair>(d_tmem, nt, a_stage_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, acc0);
           }
-          umma_commit(ua_empty + 8 * sa);
+          if (kPair) umma_commit_pair(ua_empty + 8 * sa);  // frees the stage in both CTAs
+          else umma_commit(ua_empty + 8 * sa);
         } else if (leader && p.wres && p.mode != CONV_3X3_S1 && !(p.dbg & 32)) {
           // resident weights, one tap per stage (stride-2 / 1x1 / transposed / fused up-sampling): one straight-line burst
           uint32_t b_lo0 = (((u_smem_b + (uint32_t)s.widx0 * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
@@ -1327,6 +1337,13 @@ int conv_tc_launch(const ConvLayer& Lin, cudaStream_t stream) {
   // shared-memory reads of the B operand, which is what bounds those layers with single-CTA MMAs.
   static const int env_cta2 = env_int("YOND_CONV_CTA2", 128);  // smallest N tile that runs as a CTA pair (0: never)
   p.cta2 = (conv3 && p.slab && !p.wres && p.CB == 64 && p.NT >= env_cta2 && env_cta2 > 0 && yond_num_sms() >= 2) ? 1 : 0;
+  // ... and for the resident-weight 64-channel 3x3 layers (incl. the pixel-pair layers): an N = 64 MMA reads 4 KB of A and 2 KB of B
+  // per 48 cycles — exactly the 128 B/clk of shared memory — and runs at 57-60 cycles under TMA-write contention; the pair halves B.
+  static const int env_cta2res = env_int("YOND_CONV_CTA2_RES", 0);
+  if (env_cta2res && conv3 && p.slab && p.wres && p.CB == 64 && p.NT == 64 && L.tail_w == nullptr && yond_num_sms() >= 2) {
+    p.cta2 = 1;
+    wres_bytes /= 2;
+  }
   if (p.cta2) p.b_stage_bytes /= 2;  // each CTA of the pair holds NT/2 rows of every weight tile
   // T sub-tiles share each weight tile (and one halo slab): stacked along H when the map is tall enough, else along
   // the batch (sub-tile t = images t, t+T, ... of the tile, so that the 8-row groups keep a uniform stride).  T is
