@@ -176,6 +176,9 @@ int yond_masked_sums(const float* lap, const float* mean, const float* var, size
  *   split_blocks = 1: every block is its own image (SIDD_256, :65,:91-93).  Maps come out packed, (B,h,w,4) with
  *   B = nimg*nblk / w = W/2 (split) or B = nimg / w = nblk*W/2.  `seg_max` (optional, nimg floats): max(x, 0) per image
  *   of the first input — the bound of the fallback bias table (:393, isp_algos.py:101).  `work`: yond_nlf_work_bytes(B,h,w,4).
+ *   mode 0: self maps (y unused); 1: collab maps; 2: collab maps where `var` holds, on entry, the var map of the SELF estimate of
+ *   the same frames in the same geometry — SelfNLF's var is stdfilt(lr, k)**2 and CollabNLF starts from the very same float32
+ *   expression (:66-68, :94-97), so the pass over x is skipped and `var` is updated in place (x is not read).
  * yond_nlf_fit: percentiles -> score3 threshold -> masked sums (with the empty-mask fallbacks of :77-84) -> line fit,
  *   per segment, all on the device: regs_dev (nseg,2) float64 = (beta1, beta2).  `quants_host`: the nq <= 24 ascending
  *   percentiles of get_threshold (np.linspace(step,100,100//step)).  detail_dev (optional, (nseg, 52) float64):

@@ -628,6 +628,22 @@ def test_normalize_raw_bit_exact(Y):
     assert torch.equal(Y.normalize_raw(t, 512, 16383, 200).cpu(), torch.from_numpy(ref))
 
 
+def test_collab_estimate_reuses_self_var_map(Y):
+    """Plain frames: CollabNLF's lr statistics are the self estimate's var map (the same float32 expression, YOND_SIDD.py:66-68 /
+    :94-97), so round 2 skips the box pass over the input; the numbers and images equal the two-pass form."""
+    rng = np.random.default_rng(13)
+    x = torch.from_numpy(np.stack([O.synth_noisy(rng, O.synth_clean_smooth(rng, 192, 320), 4.0, 6.0) for _ in range(3)])[:, None]).cuda()
+    drv = Y.YOND_SIDD(ARCHS["gru"], dict(PIPE_C4), state_dict=O.smoother_state_dict(ARCHS["gru"]))
+    p = {"wp": 1023, "bl": 64, "ratio": 1, "gain": 1, "sigma": 0, "scale": 959.0}
+    a = drv.iter_denoise_batch(x, dict(p))
+    drv.reuse_self_var = False
+    b = drv.iter_denoise_batch(x, dict(p))
+    assert a["rounds"].tolist() == b["rounds"].tolist() == [2, 2, 2]
+    for i in range(2):
+        np.testing.assert_allclose(np.asarray(a["regs"][i]), np.asarray(b["regs"][i]), rtol=1e-10)
+        assert float((a["raw_dns"][i] - b["raw_dns"][i]).abs().max()) < 1e-6
+
+
 def test_pipeline_on_uint16_mosaic_bit_identical(Y):
     """the estimator and the VST front end read the uint16 sensor mosaic and normalise on load; the whole
     two-round pipeline then equals the pipeline fed with the float32 frame normalize_raw() produces (same bits per loaded value) — for 14-bit

@@ -29,7 +29,7 @@ __device__ __forceinline__ float4 sq4(const float4& v) {
 // OP_MEAN_VAR: out0 = mean, out1 = std^2 (SelfNLF's var).  OP_COLLAB: out0 = mean, out1 = std (lap), out2 = aux^2 - std^2
 // with aux = the std map of the other frame (CollabNLF's var).  Squares / difference in float32 with explicit rounding,
 // like the reference's elementwise float32 expressions.
-enum { OP_MEAN = 0, OP_MEAN_STD = 1, OP_STD = 2, OP_MEAN_VAR = 3, OP_COLLAB = 4 };
+enum { OP_MEAN = 0, OP_MEAN_STD = 1, OP_STD = 2, OP_MEAN_VAR = 3, OP_COLLAB = 4, OP_COLLAB_SQ = 5 };  // _SQ: out2 holds aux^2 on entry
 constexpr int kBoxThreads = 256;
 // Where the k x k window reads its pixels from.  kBayer = false: packed frames (B,h,w,4) float32.  kBayer = true: the Bayer
 // mosaic itself (two 64-bit loads per packed pixel, rows 2i and 2i+1) — the estimator then needs no pack pass at all — with
@@ -286,6 +286,11 @@ __global__ void __launch_bounds__(kBoxThreads) box_fused_kernel(BoxSrc src, floa
             out0[o] = m;
             out1[o] = st;
             const float4 ax = __ldg(aux + o), a2 = sq4(ax), s2 = sq4(st);
+            out2[o] = make_float4(__fsub_rn(a2.x, s2.x), __fsub_rn(a2.y, s2.y), __fsub_rn(a2.z, s2.z), __fsub_rn(a2.w, s2.w));
+          } else if (op == OP_COLLAB_SQ) {  // out2 already holds std_k(other frame)^2 (the self estimate's var map): in place
+            out0[o] = m;
+            out1[o] = st;
+            const float4 a2 = out2[o], s2 = sq4(st);
             out2[o] = make_float4(__fsub_rn(a2.x, s2.x), __fsub_rn(a2.y, s2.y), __fsub_rn(a2.z, s2.z), __fsub_rn(a2.w, s2.w));
           } else {
             out0[o] = st;
@@ -914,7 +919,9 @@ int nlf_maps_impl(const BoxSrc& x, const BoxSrc* y, bool bayer, float* var, floa
   float* tmpB = tmpA + n;
   int rc;
   // algorithmic bytes per Bayer pixel: self 4 R + 12 W (lap, mean, var), collab 8 R + 12 W
-  YondProfScope prof(mode == 0 ? "nlf_maps_self (3 box_fused passes)" : "nlf_maps_collab (2 box_fused passes)", s, (mode == 0 ? 16.0 : 20.0) * (double)n);
+  YondProfScope prof(mode == 0 ? "nlf_maps_self (3 box_fused passes)"
+                               : (mode == 1 ? "nlf_maps_collab (2 box_fused passes)" : "nlf_maps_collab (1 box_fused pass, lr statistics reused)"),
+                     s, (mode == 0 ? 16.0 : 20.0) * (double)n);
   BoxSrc x_nomax = x;
   x_nomax.seg_max = nullptr;
   if (mode == 0) {
@@ -924,6 +931,10 @@ int nlf_maps_impl(const BoxSrc& x, const BoxSrc* y, bool bayer, float* var, floa
     const int k2 = k / 3 * 2 + 1;
     if ((rc = box_pass(x_nomax, bayer, tmpB, nullptr, B, h, w, k2, false, OP_MEAN, s))) return rc;
     if ((rc = box_pass(packed_src(tmpB, h, w), false, lap, nullptr, B, h, w, k, true, OP_STD, s))) return rc;
+  } else if (mode == 2) {
+    // `var` holds std_k(lr)^2 from the self estimate of the same frames (SelfNLF's var map IS stdfilt(lr, k)**2, YOND_SIDD.py:66-68 /
+    // :94-97: the same float32 expression): only the statistics of the denoised frame are new
+    if ((rc = box_pass(*y, bayer, mean, lap, B, h, w, k, true, OP_COLLAB_SQ, s, nullptr, var))) return rc;
   } else {
     // std_k(lr) -> tmpA ; mean = blur_k(hr), lap = std_k(hr) ; var = std_lr^2 - std_hr^2
     if ((rc = box_pass(x, bayer, tmpA, nullptr, B, h, w, k, true, OP_STD, s))) return rc;
@@ -969,7 +980,7 @@ static int nlf_maps_bayer_impl(const float* x, const uint16_t* x16, const yond_r
   YOND_REQUIRE(!x16 || (nrm && nrm->white > nrm->black && (uintptr_t)x16 % 4 == 0), "yond_nlf_maps_raw16: normalisation / 4-byte aligned mosaic required");
   YOND_REQUIRE(nimg > 0 && nblk > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "yond_nlf_maps_bayer: H,W must be even");
   YOND_REQUIRE(k % 2 == 1 && k >= 3 && k <= kMaxK, "yond_nlf_maps_bayer: odd k <= %d required (got %d)", kMaxK, k);
-  YOND_REQUIRE(mode == 0 || (mode == 1 && y != nullptr), "yond_nlf_maps_bayer: collab mode needs the second input");
+  YOND_REQUIRE(mode == 0 || ((mode == 1 || mode == 2) && y != nullptr), "yond_nlf_maps_bayer: collab mode needs the second input");
   YOND_REQUIRE((!x || (uintptr_t)x % 8 == 0) && (!y || (uintptr_t)y % 8 == 0), "yond_nlf_maps_bayer: 8-byte aligned frames required");
   cudaStream_t s = (cudaStream_t)stream;
   // split_blocks = 1: every block is its own image for the box filters (SIDD_256, YOND_SIDD.py:65,91-93);

@@ -130,14 +130,16 @@ class NlfEstimator:
     DETAIL = 4 + 2 * 24
 
     def estimate_dev(self, x, y=None, k=29, split_blocks=False, x_mosaic=False, y_mosaic=False, nblk=None, seg_max=None,
-                     details=False, step=5, raw=None):
+                     details=False, step=5, raw=None, reuse_self_var=False):
         """SelfNLF (y None) / CollabNLF straight from Bayer frames, everything on the device.
 
         x: blocks layout (nimg, nblk, H, W) or, with x_mosaic, mosaic layout (nimg, H, nblk*W) (`nblk` then required; plain
         frames are nblk = 1 in either layout).  split_blocks: every block is its own image for the box filters (SIDD_256).
         seg_max (optional, (nimg,) f32 CUDA): receives max(x, 0) per image.  Returns regs (nimg, 2) float64 on the
         device [, detail (nimg, DETAIL)]; nothing is read back.  x may be the uint16 sensor mosaic (a 16-bit integer tensor) with
-        raw = _lib.RawNorm(black, white, ratio, clip): it is normalised on load."""
+        raw = _lib.RawNorm(black, white, ratio, clip): it is normalised on load.
+        reuse_self_var (collab only): the previous call on this estimator was the SELF estimate of the same x in the same geometry,
+        so its var map (= stdfilt(x, k)**2, exactly what CollabNLF computes first) is still in place and the pass over x is skipped."""
         lib = self.lib
         if x_mosaic:
             nimg, H, Wm = x.shape
@@ -154,7 +156,8 @@ class NlfEstimator:
         maps = self._buf("maps3", 3 * n_el * 4, dev).view(torch.float32)
         var, mean, lap = maps[:n_el], maps[n_el:2 * n_el], maps[2 * n_el:3 * n_el]
         work = self._buf("maps", lib.yond_nlf_work_bytes(B, h, w, 4), dev)
-        mode = 0 if y is None else 1
+        mode = 0 if y is None else (2 if reuse_self_var and getattr(self, "_self_key", None) == (x.data_ptr(), B, h, w, int(k)) else 1)
+        self._self_key = (x.data_ptr(), B, h, w, int(k)) if y is None else None
         if y is not None:
             assert y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and y.numel() == x.numel()
         if is_raw:

@@ -445,6 +445,8 @@ class YOND_SIDD:
         return results
 
     # -- the blind two-round pipeline, device-resident and free of host synchronisation -----------------------------
+    reuse_self_var = True  # collab estimate of plain frames starts from the self estimate's var map (one box pass less)
+
     def iter_denoise_dev(self, x, p, lr_full=None, timings=None, raw=None, after_round1=None):
         """IterDenoise (YOND_SIDD.py:301-483, `simple` estimator) for a batch of images: x (nimg, nblk, H, W) CUDA f32 —
         SIDD images of nblk blocks, or full frames with nblk = 1.  Every stage runs once for the whole batch; the noise
@@ -517,7 +519,9 @@ class YOND_SIDD:
                 assert W % 64 == 0, "SIDD_256 splits the packed frame into 32 strips along W (YOND_SIDD.py:91-93)"
                 regs2 = est.estimate_dev(x.reshape(nimg, H, W), dn1, k, split_blocks=True, x_mosaic=True, y_mosaic=True, nblk=32, raw=raw)
             else:
-                regs2 = est.estimate_dev(x, dn1, k, split_blocks=sidd, y_mosaic=True, raw=raw)  # :431 (mode 'collab')
+                # (not SIDD_256: the same box-filter geometry as the self estimate above, whose var map is reused)
+                regs2 = est.estimate_dev(x, dn1, k, split_blocks=sidd, y_mosaic=True, raw=raw,  # :431 (mode 'collab')
+                                         reuse_self_var=(not sidd and lr_full is None and self.reuse_self_var))
             mark("estimate_collab")
             ch2 = eng.chain_params(regs2, seg_max, nimg, nblk, scale_est, scale, scale_est, 2, bias_corr, vst_type, prev=ch1)
             final = torch.empty_like(dn1)
