@@ -628,6 +628,19 @@ def test_normalize_raw_bit_exact(Y):
     assert torch.equal(Y.normalize_raw(t, 512, 16383, 200).cpu(), torch.from_numpy(ref))
 
 
+def test_estimator_with_saturated_region_vs_oracle(Y):
+    """A frame whose upper 40 % is saturated (constant 1.0, lap == 0 over the whole area): the queried percentiles fall into one
+    radix bucket with millions of equal keys (the dense form of the third radix pass); numbers vs the oracle."""
+    rng = np.random.default_rng(29)
+    noisy = O.synth_noisy(rng, O.synth_clean_smooth(rng, 512, 768), 4.0, 6.0)
+    noisy[:204] = 1.0
+    est = Y.nlf._estimator()
+    x = torch.from_numpy(noisy).cuda().reshape(1, 1, 512, 768)
+    regs = est.estimate_dev(x, None, 29).cpu().numpy()[0]
+    ref = O.SelfNLF(O.bayer2rggb(noisy), 29)
+    np.testing.assert_allclose(regs, np.asarray(ref, np.float64), rtol=TOL_EST)
+
+
 def test_collab_estimate_reuses_self_var_map(Y):
     """Plain frames: CollabNLF's lr statistics are the self estimate's var map (the same float32 expression, YOND_SIDD.py:66-68 /
     :94-97), so round 2 skips the box pass over the input; the numbers and images equal the two-pass form."""

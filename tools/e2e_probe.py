@@ -57,3 +57,23 @@ for grp in (2, 4, 8):
     print(f"host path streamed, groups of {grp}: {t:.2f} ms/step")
 t = timed(lambda: drv.iter_denoise_host(host_in, host_outs[0], dict(bench.P0), group=4, wait=True), 4)
 print(f"host path, one batch at a time (wait=True), groups of 4: {t:.2f} ms/step")
+# host time to SUBMIT one streamed step (everything is asynchronous: this is pure host work)
+jobs = []
+torch.cuda.synchronize()
+ts = []
+for i in range(6):
+    t0 = time.perf_counter()
+    jobs.append(drv.iter_denoise_host(host_in, host_outs[i % 2], dict(bench.P0), group=8, wait=False))
+    ts.append((time.perf_counter() - t0) * 1e3)
+    while len(jobs) > 1:
+        jobs.pop(0).result()
+while jobs:
+    jobs.pop(0).result()
+print("host submit ms per step:", [round(t, 1) for t in ts])
+import cProfile, pstats
+pr = cProfile.Profile()
+pr.enable()
+j = drv.iter_denoise_host(host_in, host_outs[0], dict(bench.P0), group=8, wait=False)
+pr.disable()
+j.result()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(14)

@@ -12,9 +12,12 @@ import yond_public_b200 as Y  # noqa: E402
 from yond_public_b200 import nlf  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+flat = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0  # fraction of the frame height that is saturated (constant 1.0): lap == 0 there
 H, W = 3024, 4032
 g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.rand((n, 1, H, W), device="cuda", generator=g) * 0.5
+if flat > 0:
+    x[:, :, :int(H * flat)] = 1.0
 y = (x.reshape(n, H, W) * 0.9 + 0.01).contiguous()
 est = nlf._estimator()
 
@@ -35,4 +38,4 @@ def timeit(fn, reps=5):
 px = n * H * W
 t_self = timeit(lambda: est.estimate_dev(x, None, 29))
 t_collab = timeit(lambda: est.estimate_dev(x, y, 29, y_mosaic=True))
-print(f"frames {n}: self estimate {t_self:.3f} ms ({px * 16 / t_self / 1e6:.0f} GB/s of 16 B/px maps only), collab {t_collab:.3f} ms")
+print(f"frames {n} (flat {flat}): self estimate {t_self:.3f} ms ({px * 16 / t_self / 1e6:.0f} GB/s of 16 B/px maps only), collab {t_collab:.3f} ms")

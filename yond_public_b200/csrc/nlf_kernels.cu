@@ -334,6 +334,7 @@ struct SelectWork {
   int q_slot1[kMaxRanks], q_slot2[kMaxRanks];
   uint32_t q_prefix[kMaxRanks];
   int nslot1, nslot2, nq_live;
+  unsigned int hist2_hits;                  // elements the third pass will count (sum of the queried 22-bit buckets), set by select1
   int level;  // 1 after select0 (q_prefix = 11 bits), 2 after select1 (22 bits)
 };
 
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(kHist1Threads) hist1_kernel(const float* __res
 __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nranks) {
   wk += blockIdx.x;
   __shared__ int s_bin[kMaxRanks], s_s1[kMaxRanks], s_s2[kMaxRanks];
-  __shared__ unsigned int s_rank[kMaxRanks];
+  __shared__ unsigned int s_rank[kMaxRanks], s_cnt[kMaxRanks];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((int)threadIdx.x < nranks) {
     s_s1[threadIdx.x] = wk->q_slot1[threadIdx.x];
@@ -558,6 +559,7 @@ __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nrank
           }
           const int bin = lane * 64 + j;
           s_bin[q] = bin;
+          s_cnt[q] = mine[j];
           wk->q_prefix[q] = (wk->q_prefix[q] << 11) | (uint32_t)bin;
           wk->rank_in[q] = r - run;
         }
@@ -569,13 +571,16 @@ __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nrank
   __syncthreads();
   if (threadIdx.x == 0) {  // queries sharing (bucket, bin) share a third-level histogram
     int ns = 0;
+    unsigned long long hits = 0;
     for (int q = 0; q < nranks; ++q) {
       int found = -1;
       for (int p = 0; p < q && found < 0; ++p)
         if (s_s1[p] == s_s1[q] && s_bin[p] == s_bin[q]) found = s_s2[p];
       s_s2[q] = found >= 0 ? found : ns++;
       wk->q_slot2[q] = s_s2[q];
+      if (found < 0) hits += s_cnt[q];
     }
+    wk->hist2_hits = hits > 0xffffffffull ? 0xffffffffu : (unsigned int)hits;
     wk->nslot2 = ns;
     wk->level = 2;
   }
@@ -583,7 +588,18 @@ __global__ void __launch_bounds__(1024) select1_kernel(SelectWork* wk, int nrank
 // Third radix level.  Only elements whose upper 22 bits equal one of the <= 64 queried prefixes count (~0.2 % of the
 // data): the membership test runs against shared memory (prefix -> slot table + one 2048-bit map per first-level slot),
 // a hit looks its slot up in the query list and takes a global atomic.
+// Hits are rare on natural data, but a frame with a saturated / black region has `lap` == 0 over a large area and then millions of
+// elements fall into ONE (slot, bin): the hit path therefore aggregates per warp (match.any: one atomic per distinct counter and warp)
+// into a per-block copy of the first kHist2Slots slots in shared memory, flushed once — instead of one global atomic per element on a
+// single address (measured: see DESIGN.md).
+// Both forms are launched; select1 has counted how many elements the pass will hit (`hist2_hits`) and each form returns at once when
+// the other one is due: sparse hits (natural data: ~0.2 %) take the lean form with 6 blocks per SM, dense hits the privatised one.
+constexpr int kHist2Slots = 16;
+__device__ __forceinline__ bool hist2_dense(const SelectWork* wk, size_t n) { return (size_t)wk->hist2_hits > n / 16; }
+template <bool privatise>
 __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d, size_t n, SelectWork* wk) {
+  extern __shared__ unsigned int hs2[];  // [kHist2Slots][1024] when privatise
+  if (hist2_dense(wk + blockIdx.y, n) != privatise) return;
   __shared__ signed char s1tab[2048];
   __shared__ unsigned int bm[kMaxRanks * 64];
   __shared__ uint32_t qpre[kMaxRanks];
@@ -592,7 +608,9 @@ __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d,
   d += (size_t)blockIdx.y * n;
   wk += blockIdx.y;
   const int ns1 = wk->nslot1;
+  const int nsh = privatise ? min(wk->nslot2, kHist2Slots) : 0;
   for (int i = threadIdx.x; i < ns1 * 64; i += blockDim.x) bm[i] = 0u;
+  for (int i = threadIdx.x; i < nsh * 1024; i += blockDim.x) hs2[i] = 0u;
   if (threadIdx.x == 0) nq = wk->nq_live;
   load_slot_table(wk, s1tab);
   __syncthreads();
@@ -611,12 +629,29 @@ __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d,
     const uint32_t mid = (k >> 10) & 2047u;
     if (!((bm[s1 * 64 + (mid >> 5)] >> (mid & 31u)) & 1u)) return;
     const uint32_t p22 = k >> 10;
+    int slot = -1;
     for (int q = 0; q < nq; ++q)
       if (qpre[q] == p22) {
-        atomicAdd(&wk->hist2[qs2[q]][k & 1023u], 1u);
+        slot = qs2[q];
         break;
       }
+    if (slot < 0) return;
+    if (!privatise) {
+      atomicAdd(&wk->hist2[slot][k & 1023u], 1u);
+      return;
+    }
+    const uint32_t key = ((uint32_t)slot << 10) | (k & 1023u);
+    const unsigned m = __match_any_sync(__activemask(), key);  // the lanes that are here together with the same counter
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+      if (slot < nsh) atomicAdd(&hs2[key], (unsigned)__popc(m));
+      else atomicAdd(&wk->hist2[slot][k & 1023u], (unsigned)__popc(m));
+    }
   });
+  if (nsh) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nsh * 1024; i += blockDim.x)
+      if (hs2[i]) atomicAdd(&wk->hist2[i >> 10][i & 1023], hs2[i]);
+  }
 }
 __global__ void __launch_bounds__(1024) select2_kernel(SelectWork* wk, int nranks, float* __restrict__ out) {
   wk += blockIdx.x;
@@ -1077,7 +1112,13 @@ int order_stats_impl(const float* data, const float* mean, unsigned int* binmin,
   YOND_LAUNCH_CHECK();
   {
     YondProfScope prof("hist2", s, 4.0 * nel);
-    hist2_kernel<<<g, 256, 0, s>>>(data, seg_len, wk);
+    static std::once_flag h2_once;
+    static cudaError_t h2_err = cudaSuccess;
+    std::call_once(h2_once, [] { h2_err = cudaFuncSetAttribute(hist2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHist2Slots * 1024 * 4); });
+    if (h2_err != cudaSuccess) return yond_set_error(YOND_ERR_CUDA, "cudaFuncSetAttribute(hist2_kernel) failed: %s", cudaGetErrorString(h2_err));
+    hist2_kernel<false><<<g, 256, 0, s>>>(data, seg_len, wk);
+    YOND_LAUNCH_CHECK();
+    hist2_kernel<true><<<g, 256, kHist2Slots * 1024 * sizeof(unsigned int), s>>>(data, seg_len, wk);
   }
   YOND_LAUNCH_CHECK();
   select2_kernel<<<nseg, 1024, 0, s>>>(wk, nranks, out_dev);
