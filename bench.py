@@ -86,11 +86,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.t0 = [], None, gpu_index, 0.0
+
+    def mark(self):  # the timed region starts here; nvidia-smi itself was started earlier so that its start-up cost is not inside
+        self.t0 = time.time()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -99,17 +102,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.time()  # samples after this instant saw an idle GPU: not part of the timed region
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [r for r in self.rows if self.t0 <= r[-1] <= t_end]
+        self.rows = inside if inside else self.rows
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -289,12 +295,13 @@ def run_b200(args):
         jobs.append(drv.iter_denoise_host(host_in, host_outs[last["seq"] % 2], dict(P0), group=E2E_GROUP_FRAMES, wait=False))
         collect(1)
 
-    for _ in range(args.warmup):
-        step_frames()
-    drain()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_frames()
+    drain()
+    sampler.mark()
     net.set_profile(True)  # the timed region itself is profiled: CUDA events around every conv launch / every HBM stage
     net.read_profile(reset=True)
     Y._lib.prof_enable(True)
@@ -491,7 +498,7 @@ def run_b200(args):
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import hbm_sweep
-                line["kernel_sweep"] = {"what": "pack / unpack / uint16 ingest / estimator (maps + fit) / fused VST front / fused inverse back, isolated, "
+                line["kernel_sweep"] = {"what": "pack / unpack / uint16 ingest / estimator (maps + fit) / fused VST front / fused inverse back / sRGB render / block metrics, isolated, "
                                                 "1 ... 256 MP of Bayer pixels; frac = algorithmic bytes / time / hbm peak",
                                         "rows": hbm_sweep.sweep(peak_gbs=peak_hbm)}
             except Exception as e:  # the sweep is an extra: never lose the bench line over it

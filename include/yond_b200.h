@@ -80,6 +80,27 @@ int yond_rot90(const float* in, float* out, int B, int H, int W, int k, void* st
 int yond_block_metrics(const float* a, const float* b, int nimg, int H, int Wm, int nblk, double data_range, float ssim_scale,
                        const double* window11, double* psnr, double* ssim, void* stream);
 
+/* The sRGB pictures' numbers — YOND_SIDD.py:661-665: a, b (nimg, H, Wm, 3) uint8 (BGR or RGB), nblk blocks along W
+ * (np.split(..., axis=-2)).  psnr = 10 log10(255^2 / mean((a-b)^2)) over the block's three channels (scikit-image promotes
+ * integer inputs to float64: exact), ssim = mean of the three per-channel SSIMs, window as above. */
+int yond_block_metrics_rgb8(const uint8_t* a, const uint8_t* b, int nimg, int H, int Wm, int nblk, const double* window11,
+                            double* psnr, double* ssim, void* stream);
+
+/* ---- sRGB render of a mosaic — utils/sidd_utils.py:156-180 (process_sidd_image) with :182-196 (flip_bayer),
+ * :241-247 (demosaic_CV2), :249-252 (apply_gains), :260-266 (apply_ccm, gamma_compression), :270-277 (process), :226-232
+ * (swap_channels) ----
+ * bayer: (B,H,W) float32 in the sensor's CFA phase; flip_lr / flip_ud: the flips that bring that phase to RGGB (flip_bayer; the
+ * picture stays flipped like the reference's).  gains3 = (1/wb_r, 1/wb_g, 1/wb_b), cam2rgb9 = row-normalised inv(cst x rgb2xyz),
+ * both float64 HOST arrays (3x3 host algebra stays with the caller: NumPy on both sides).  One kernel: clip, gains and clip in
+ * float64, truncation to a 14-bit mosaic, OpenCV's edge-aware demosaic (integer), float32 / 16383, CCM and 1/2.2 gamma in float64,
+ * x255, truncation.  bgr: (B,H,W,3) uint8, channel order B, G, R.  H, W even and >= 4. */
+int yond_render_srgb(const float* bayer, uint8_t* bgr, int B, int H, int W, int flip_lr, int flip_ud, const double* gains3,
+                     const double* cam2rgb9, void* stream);
+/* cv2.cvtColor(bayer, cv2.COLOR_BayerBG2RGB_EA) for uint16 mosaics (third party: OpenCV imgproc/demosaicing.cpp, edge-aware
+ * variant), the integer stage of the render on its own: (B,H,W) uint16 -> (B,H,W,3) uint16, site (0,0) of the cell in channel 0.
+ * Bit-exact against opencv-python 4.13.0. */
+int yond_demosaic_ea(const uint16_t* bayer, uint16_t* rgb, int B, int H, int W, void* stream);
+
 /* ---- A3/A4 elementwise, for the function-level surface — utils/isp_algos.py:5-14, :17-33 ---- */
 int yond_vst(const float* x, float* z, size_t n, double sigma, double gain, void* stream);
 int yond_inverse_vst(const float* z, float* x, size_t n, double sigma, double gain, int exact, void* stream);

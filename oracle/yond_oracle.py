@@ -416,6 +416,95 @@ def sidd_image_metrics(output, hr_raw, nblk=32):  # YOND_SIDD.py:643-656
 
 
 # --------------------------------------------------------------------------------------------------
+# 8(f)-3  sRGB render of the SIDD driver                               utils/sidd_utils.py:156-180, :215-277
+# --------------------------------------------------------------------------------------------------
+def demosaic_ea_u16(bayer):
+    """cv2.cvtColor(uint16 (H,W), cv2.COLOR_BayerBG2RGB_EA) — OpenCV's edge-aware demosaic (third-party: opencv-python 4.13.0
+    here, the reference pins no version; imgproc/demosaicing.cpp, Bayer2RGB_EdgeAware).  Restated from its observable behaviour and
+    pinned bit-exactly against cv2 itself in tests/test_oracle_golden.py.  Site (0,0) of the 2x2 cell lands in output channel 0,
+    site (1,1) in channel 2; all arithmetic is integer with round-half-up shifts:
+      green at a colour site = mean of the vertical pair if |left-right| > |down-up| (strict) else of the horizontal pair;
+      the opposite colour at a colour site = mean of the four diagonal neighbours;
+      the two colours at a green site = mean of the horizontal pair / of the vertical pair;
+      the outermost rows and columns repeat their inner neighbours."""
+    b = np.asarray(bayer)
+    H, W = b.shape
+    S = np.pad(b.astype(np.int64), 1, mode="reflect")  # the padding never reaches a surviving pixel (border ring is overwritten)
+
+    def sh(dy, dx):
+        return S[1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+    c, l, r, u, d = sh(0, 0), sh(0, -1), sh(0, 1), sh(-1, 0), sh(1, 0)
+    diag = (sh(-1, -1) + sh(-1, 1) + sh(1, -1) + sh(1, 1) + 2) >> 2
+    hh, vv = (l + r + 1) >> 1, (u + d + 1) >> 1
+    g = np.where(np.abs(l - r) > np.abs(d - u), vv, hh)
+    yy, xx = np.mgrid[0:H, 0:W]
+    ey, ex = yy % 2 == 0, xx % 2 == 0
+    out = np.empty((H, W, 3), np.int64)
+    out[..., 0] = np.where(ey & ex, c, np.where(ey & ~ex, hh, np.where(~ey & ex, vv, diag)))
+    out[..., 1] = np.where(ey == ex, g, c)
+    out[..., 2] = np.where(~ey & ~ex, c, np.where(~ey & ex, hh, np.where(ey & ~ex, vv, diag)))
+    out[:, 0], out[:, -1] = out[:, 1], out[:, -2]
+    out[0], out[-1] = out[1], out[-2]
+    return out.astype(np.uint16)
+
+
+_RGB2XYZ = np.array([[0.4124564, 0.3575761, 0.1804375], [0.2126729, 0.7151522, 0.0721750], [0.0193339, 0.1191920, 0.9503041]])
+
+
+def render_cam2rgb(cst):  # sidd_utils.py:161-170
+    rgb2cam = np.matmul(cst, _RGB2XYZ)
+    cam2rgb = np.linalg.inv(rgb2cam)
+    return cam2rgb / np.sum(cam2rgb, axis=-1, keepdims=True)
+
+
+def flip_bayer(image, bayer_pattern):  # sidd_utils.py:182-196
+    pat = [list(map(int, row)) for row in bayer_pattern]
+    if pat == [[1, 2], [2, 3]]:
+        return image
+    if pat == [[2, 1], [3, 2]]:
+        return np.fliplr(image)
+    if pat == [[2, 3], [1, 2]]:
+        return np.flipud(image)
+    if pat == [[3, 2], [2, 1]]:
+        return np.flipud(np.fliplr(image))
+    raise ValueError("Unknown Bayer pattern.")
+
+
+def process_sidd_image(image, bayer_pattern, wb, cst):
+    """sidd_utils.py:156-180 with process (:270-277), apply_gains (:249-252), demosaic_CV2 (:241-247), apply_ccm (:260-263),
+    gamma_compression (:265-266), swap_channels (:226-232).  Dtype flow kept: float32 image x float64 gains -> float64; the mosaic
+    is truncated to uint16 at 14 bits for the demosaic and comes back as float32 / 16383; CCM and gamma in float64; uint8 by
+    truncation.  Returns (H, W, 3) uint8, BGR, in the flipped orientation (the reference does not flip back)."""
+    image = flip_bayer(np.asarray(image).clip(0, 1), bayer_pattern)
+    H, W = image.shape
+    gains = np.array([1 / wb[0][0], 1 / wb[0][1], 1 / wb[0][1], 1 / wb[0][2]])  # R, G, G, B per 2x2 site (row-major)
+    g = np.empty((H, W), np.float64)
+    for i, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        g[a::2, b::2] = image[a::2, b::2] * gains[i]
+    g = np.clip(g, 0.0, 1.0)
+    q = np.clip(g * 16383, 0, 16383).astype(np.uint16)
+    dem = demosaic_ea_u16(q).astype(np.float32) / 16383
+    ccm = render_cam2rgb(np.asarray(cst, np.float64))
+    rgb = np.sum(dem[:, :, np.newaxis, :] * ccm[np.newaxis, np.newaxis, :, :], axis=-1)
+    rgb = np.maximum(np.clip(rgb, 0.0, 1.0), 1e-8) ** (1.0 / 2.2)
+    return (rgb[:, :, ::-1] * 255.0).astype(np.uint8)
+
+
+def compare_psnr_u8(image_true, image_test, data_range=255):
+    """peak_signal_noise_ratio for two uint8 images (YOND_SIDD.py:663): scikit-image promotes integer inputs to float64."""
+    a, b = np.asarray(image_true).astype(np.float64), np.asarray(image_test).astype(np.float64)
+    return 10 * np.log10((data_range ** 2) / np.mean((a - b) ** 2, dtype=np.float64))
+
+
+def sidd_rgb_metrics(img_dn, img_hr, nblk=32):  # YOND_SIDD.py:660-664
+    dn_ = np.array(np.split(img_dn, nblk, axis=-2))
+    hr_ = np.array(np.split(img_hr, nblk, axis=-2))
+    psnr = np.mean([compare_psnr_u8(d, h, data_range=255) for d, h in zip(dn_, hr_)])
+    ss = np.mean([calculate_ssim(d, h) for d, h in zip(dn_, hr_)])
+    return psnr, ss
+
+
+# --------------------------------------------------------------------------------------------------
 # A13  pad to a multiple of 32                                          utils/utils.py:246-252
 # --------------------------------------------------------------------------------------------------
 def get_p2d(shape, base=16):

@@ -89,6 +89,12 @@ def test_no_cpu_fallback(Y):
         with pytest.raises(Y._lib.YondError):
             Y.compare_psnr(np.zeros((16, 16), np.float32), np.ones((16, 16), np.float32))
         with pytest.raises(Y._lib.YondError):
+            Y.process_sidd_image(np.zeros((8, 8), np.float32), [[1, 2], [2, 3]], np.ones((1, 3)), np.eye(3))
+        with pytest.raises(Y._lib.YondError):
+            Y.demosaic_ea(np.zeros((8, 8), np.uint16))
+        with pytest.raises(Y._lib.YondError):
+            Y.calculate_ssim(np.zeros((16, 16, 3), np.uint8), np.zeros((16, 16, 3), np.uint8))
+        with pytest.raises(Y._lib.YondError):
             Y.ResUnet2(dict(ARCH_UNET, name="ResUnet2"))(torch.zeros(1, 4, 32, 32))
         with pytest.raises(Y._lib.YondError):
             Y.SelfResUNet(dict(ARCH_UNET, name="SelfResUNet"))(torch.zeros(1, 4, 32, 32))

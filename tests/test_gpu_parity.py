@@ -717,6 +717,112 @@ def test_block_metrics_sidd_batch_vs_oracle(Y):
         assert abs(float(p[i].mean().cpu()) - po) < 1e-9 and abs(float(s[i].mean().cpu()) - so) < 1e-7
 
 
+# ------------------------------------------------------------------ sRGB render on the device
+RENDER_PATTERNS = [[[1, 2], [2, 3]], [[2, 1], [3, 2]], [[2, 3], [1, 2]], [[3, 2], [2, 1]]]
+
+
+def _assert_picture_equal(got, want, what):
+    """uint8 pictures: byte-exact.  The only float64 transcendental on the path is the gamma pow; CUDA's and the host libm's may
+    differ in the last ulp, which moves a truncated byte only if 255 x^(1/2.2) lies within ~1e-13 of an integer — one level on at
+    most one pixel in a million is tolerated so that such a tie cannot fail the suite; none has been observed."""
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert diff.max() <= 1 and (diff != 0).sum() <= max(1, diff.size // 1_000_000), f"{what}: {int((diff != 0).sum())} bytes differ"
+
+
+def test_render_golden(Y, golden):
+    """process_sidd_image on the device vs the pictures the unmodified reference rendered (make_golden_render.py): four CFA phases,
+    flat / saturated / out-of-range areas; and the integer demosaic stage alone vs cv2's own output, bit for bit."""
+    g = golden("render")
+    for i, pat in enumerate(RENDER_PATTERNS):
+        got = Y.process_sidd_image(g[f"img{i}"], pat, g[f"wb{i}"], g[f"cst{i}"])
+        assert isinstance(got, np.ndarray) and got.dtype == np.uint8
+        assert np.array_equal(got, g[f"srgb{i}"]), f"pattern {pat}: {int((got != g[f'srgb{i}']).sum())} bytes differ"
+    for j in range(2):
+        assert np.array_equal(Y.demosaic_ea(g[f"bayer{j}"]), g[f"ea{j}"])
+
+
+@pytest.mark.parametrize("H,W", [(4, 4), (6, 10), (34, 130), (256, 8192), (250, 518)])
+def test_demosaic_ea_vs_oracle(Y, H, W):
+    """Integer stage, bit-exact: 14-bit noise, a 2-level image (every gradient comparison ties or flips) and a constant one; widths
+    that are / are not multiples of the tile and of 4; a batch."""
+    rng = np.random.default_rng(H * 7 + W)
+    for hi in (16384, 2):
+        b = rng.integers(0, hi, size=(2, H, W), dtype=np.uint16)
+        got = Y.demosaic_ea(b)
+        for k in range(2):
+            assert np.array_equal(got[k], O.demosaic_ea_u16(b[k])), (H, W, hi, k)
+    b = np.full((H, W), 16383, np.uint16)
+    assert np.array_equal(Y.demosaic_ea(b), O.demosaic_ea_u16(b))
+
+
+@pytest.mark.parametrize("pat", range(4))
+def test_render_sidd_mosaic_vs_oracle(Y, pat):
+    """A SIDD-shaped mosaic (256 x 8192, 32 blocks) through the whole render for each CFA phase, CUDA tensor in -> CUDA tensor out,
+    against the oracle; plus a width that is not a multiple of 4 (byte-store path)."""
+    rng = np.random.default_rng(20 + pat)
+    clean = np.concatenate([O.synth_clean(rng, 256, 256) for _ in range(32)], -1)
+    noisy = O.synth_noisy(rng, clean, 3.0, 4.0, clip=False).astype(np.float32)
+    wb = np.array([[rng.uniform(1.5, 2.5), 1.0, rng.uniform(1.3, 2.2)]])
+    cst = np.array([[0.75, 0.3, -0.05], [-0.35, 1.15, 0.2], [0.03, -0.25, 0.95]]) + rng.normal(0, 0.02, (3, 3))
+    got = Y.process_sidd_image(torch.from_numpy(noisy).cuda(), RENDER_PATTERNS[pat], wb, cst)
+    assert torch.is_tensor(got) and got.is_cuda and got.dtype == torch.uint8 and tuple(got.shape) == (256, 8192, 3)
+    _assert_picture_equal(got.cpu().numpy(), O.process_sidd_image(noisy, RENDER_PATTERNS[pat], wb, cst), f"pattern {pat}")
+    sub = np.ascontiguousarray(noisy[:62, :250])
+    _assert_picture_equal(Y.process_sidd_image(sub, RENDER_PATTERNS[pat], wb, cst),
+                          O.process_sidd_image(sub, RENDER_PATTERNS[pat], wb, cst), f"pattern {pat} 62x250")
+
+
+def test_render_full_frame_properties(Y):
+    """BASELINE frame size (3024 x 4032), properties that need no oracle pass: a constant grey mosaic renders to one colour with the
+    closed-form value; the batched call equals the per-image calls; flipping the input left-right under the mirrored CFA phase gives
+    the same picture (flip_bayer); and a 6 MP crop still equals the oracle."""
+    H, W = 3024, 4032
+    wb = np.array([[2.0, 1.0, 1.6]])
+    cst = np.linalg.inv(O._RGB2XYZ)  # cam == sRGB primaries: cam2rgb = identity after row normalisation
+    flat = torch.full((H, W), 0.25, device="cuda")
+    pic = Y.process_sidd_image(flat, RENDER_PATTERNS[0], wb, cst)
+    want = O.process_sidd_image(np.full((8, 8), 0.25, np.float32), RENDER_PATTERNS[0], wb, cst)[4, 4]
+    assert bool((pic.reshape(-1, 3) == torch.from_numpy(want).cuda()).all())
+    rng = np.random.default_rng(3)
+    frame = O.synth_noisy(rng, O.synth_clean(rng, H, W), 2.0, 3.0).astype(np.float32)
+    t = torch.from_numpy(frame).cuda()
+    both = Y.process_sidd_image(torch.stack([t, flat]), RENDER_PATTERNS[0], wb, cst)
+    one = Y.process_sidd_image(t, RENDER_PATTERNS[0], wb, cst)
+    assert torch.equal(both[0], one) and torch.equal(both[1], pic)
+    mirrored = Y.process_sidd_image(torch.flip(t, dims=[1]).contiguous(), RENDER_PATTERNS[1], wb, cst)
+    assert torch.equal(mirrored, one)
+    crop = frame[:2016, :3024]
+    _assert_picture_equal(Y.process_sidd_image(np.ascontiguousarray(crop), RENDER_PATTERNS[3], wb, cst),
+                          O.process_sidd_image(crop, RENDER_PATTERNS[3], wb, cst), "6 MP crop")
+
+
+def test_rgb_metrics_vs_oracle(Y):
+    """sRGB PSNR / SSIM per block of rendered pictures (YOND_SIDD.py:660-665) vs the oracle's per-block loop, and the whole scoring
+    half of multiprocess_plot through sidd_eval_image."""
+    rng = np.random.default_rng(12)
+    nblk, Hb = 8, 64
+    clean = np.concatenate([O.synth_clean(rng, Hb, Hb) for _ in range(nblk)], -1)
+    noisy = O.synth_noisy(rng, clean, 2.0, 3.0).astype(np.float32)
+    dn = (0.8 * clean + 0.2 * noisy).astype(np.float32)
+    meta = {"bayer_2by2": RENDER_PATTERNS[2], "wb": np.array([[1.9, 1.0, 1.7]]),
+            "cst2": np.array([[0.8, 0.25, -0.05], [-0.3, 1.1, 0.2], [0.02, -0.2, 0.9]])}
+    img_hr = O.process_sidd_image(clean, meta["bayer_2by2"], meta["wb"], meta["cst2"])
+    img_dn = O.process_sidd_image(dn, meta["bayer_2by2"], meta["wb"], meta["cst2"])
+    p, s = Y.block_metrics_rgb8(img_dn, img_hr, nblk)
+    dn_, hr_ = np.array(np.split(img_dn, nblk, axis=-2)), np.array(np.split(img_hr, nblk, axis=-2))
+    np.testing.assert_allclose(p.cpu().numpy()[0], [O.compare_psnr_u8(d, h) for d, h in zip(dn_, hr_)], rtol=1e-13)
+    np.testing.assert_allclose(s.cpu().numpy()[0], [O.calculate_ssim(d, h) for d, h in zip(dn_, hr_)], rtol=0, atol=1e-7)
+    assert abs(Y.compare_psnr(dn_[0], hr_[0], data_range=255) - O.compare_psnr_u8(dn_[0], hr_[0])) < 1e-10
+    assert abs(Y.calculate_ssim(dn_[1], hr_[1]) - O.calculate_ssim(dn_[1], hr_[1])) < 1e-7
+    res = Y.sidd_eval_image([noisy, dn, np.zeros_like(dn)], clean, meta, nblk=nblk)
+    po, so = O.sidd_rgb_metrics(img_dn, img_hr, nblk)
+    pr, sr = O.sidd_image_metrics(dn, clean, nblk)
+    assert abs(res["psnr_rgb"][1] - po) < 1e-9 and abs(res["ssim_rgb"][1] - so) < 1e-7
+    assert abs(res["psnr"][1] - pr) < 1e-9 and abs(res["ssim"][1] - sr) < 1e-7
+    assert res["psnr"][2] == -1.0 and res["img_dn"][2] is None and len(res["psnr_rgb"]) == 2
+    assert np.array_equal(res["img_hr"].cpu().numpy(), img_hr)
+
+
 # ------------------------------------------------------------------ BASELINE configs[3]: 14-bit, noclip, low-light gain
 PIPE_C4 = dict(PIPE, full_dn=True)
 

@@ -237,3 +237,43 @@ def test_metrics_golden(golden):
     p, s = O.sidd_image_metrics(g["dn"], g["clean"], nblk)
     np.testing.assert_allclose([p, s], [g["psnr_blocks"].mean(), g["ssim_blocks"].mean()], rtol=1e-12)
     assert O.sidd_image_metrics(np.zeros_like(g["dn"]), g["clean"], nblk) == (-1, -1)
+
+
+# ---- sRGB render of the SIDD driver ----
+RENDER_PATTERNS = [[[1, 2], [2, 3]], [[2, 1], [3, 2]], [[2, 3], [1, 2]], [[3, 2], [2, 1]]]
+
+
+def test_render_golden(golden):
+    """The oracle's process_sidd_image == the reference's (utils/sidd_utils.py:156-180, with this image's cv2 behind its demosaic),
+    byte for byte, for every CFA phase incl. flat (all-ties), saturated and out-of-range areas (make_golden_render.py)."""
+    g = golden("render")
+    for i, pat in enumerate(RENDER_PATTERNS):
+        assert np.array_equal(g[f"pat{i}"], np.array(pat))
+        got = O.process_sidd_image(g[f"img{i}"], pat, g[f"wb{i}"], g[f"cst{i}"])
+        assert got.dtype == np.uint8 and got.shape == g[f"srgb{i}"].shape
+        assert np.array_equal(got, g[f"srgb{i}"]), f"pattern {pat}"
+    for j in range(2):
+        assert np.array_equal(O.demosaic_ea_u16(g[f"bayer{j}"]), g[f"ea{j}"])
+
+
+def test_demosaic_restatement_matches_cv2():
+    """The edge-aware demosaic restatement against OpenCV itself (the third-party routine behind demosaic_CV2), bit for bit, on
+    seeded mosaics: full 14-bit range, tiny ranges (gradient ties everywhere), constant images, the smallest legal size."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for (h, w, hi) in [(4, 4, 16384), (6, 10, 16384), (64, 96, 16384), (66, 130, 8), (32, 34, 2), (30, 62, 3), (128, 258, 16384)]:
+        b = rng.integers(0, hi, size=(h, w), dtype=np.uint16)
+        assert np.array_equal(O.demosaic_ea_u16(b), cv2.cvtColor(b, cv2.COLOR_BayerBG2RGB_EA)), (h, w, hi)
+    b = np.full((8, 12), 16383, np.uint16)
+    assert np.array_equal(O.demosaic_ea_u16(b), cv2.cvtColor(b, cv2.COLOR_BayerBG2RGB_EA))
+
+
+def test_rgb_metrics_oracle():
+    """compare_psnr on uint8 pictures promotes to float64 (scikit-image's rule for integer inputs); known answer."""
+    a = np.zeros((16, 32, 3), np.uint8)
+    b = np.full((16, 32, 3), 5, np.uint8)
+    np.testing.assert_allclose(O.compare_psnr_u8(a, b), 10 * np.log10(255.0 ** 2 / 25.0), rtol=1e-15)
+    c = np.full((16, 32, 3), 15, np.uint8)
+    p, s = O.sidd_rgb_metrics(np.concatenate([a, b], 1), np.concatenate([b, c], 1), nblk=2)
+    np.testing.assert_allclose(p, 0.5 * (10 * np.log10(255.0 ** 2 / 25.0) + 10 * np.log10(255.0 ** 2 / 100.0)), rtol=1e-15)
+    assert 0 < s < 1

@@ -41,6 +41,9 @@ SIGNATURES = {
     "yond_pack_raw": (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_float, _I, _I, _P]),
     "yond_ingest_mosaic": (_I, [_P, _P, _SZ, C.c_float, C.c_float, C.c_float, _I, _P]),
     "yond_block_metrics": (_I, [_P, _P, _I, _I, _I, _I, _D, C.c_float, C.POINTER(C.c_double), _P, _P, _P]),
+    "yond_block_metrics_rgb8": (_I, [_P, _P, _I, _I, _I, _I, C.POINTER(C.c_double), _P, _P, _P]),
+    "yond_render_srgb": (_I, [_P, _P, _I, _I, _I, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
+    "yond_demosaic_ea": (_I, [_P, _P, _I, _I, _I, _P]),
     "yond_vst": (_I, [_P, _P, _SZ, _D, _D, _P]),
     "yond_inverse_vst": (_I, [_P, _P, _SZ, _D, _D, _I, _P]),
     "yond_lut_row": (_I, [_P, _I, _I, _D, _P, _P]),

@@ -42,9 +42,35 @@ def block_metrics(a, b, nblk=1, data_range=1.0, ssim_scale=255.0, psnr=True, ssi
     return out_p, out_s
 
 
+def _is_u8(a):
+    return (isinstance(a, np.ndarray) and a.dtype == np.uint8) or (torch.is_tensor(a) and a.dtype == torch.uint8)
+
+
+def block_metrics_rgb8(a, b, nblk=1, psnr=True, ssim=True):
+    """a, b: (nimg, H, nblk*Wb, 3) (or (H, nblk*Wb, 3)) uint8 pictures.  Returns device tensors (psnr, ssim), each (nimg, nblk)
+    float64: PSNR at data_range 255 and the channel-mean SSIM of every block, like YOND_SIDD.py:661-665."""
+    ta, _ = to_dev(a, dtype=torch.uint8)
+    tb, _ = to_dev(b, dtype=torch.uint8)
+    if ta.dim() == 3:
+        ta, tb = ta[None], tb[None]
+    ta, tb = ta.contiguous(), tb.contiguous()
+    assert ta.shape == tb.shape and ta.dtype == torch.uint8 and tb.dtype == torch.uint8 and ta.shape[-1] == 3
+    nimg, H, Wm, _ = ta.shape
+    out_p = torch.empty((nimg, nblk), device=ta.device, dtype=torch.float64) if psnr else None
+    out_s = torch.empty((nimg, nblk), device=ta.device, dtype=torch.float64) if ssim else None
+    check(_lib.load().yond_block_metrics_rgb8(ptr(ta), ptr(tb), nimg, H, Wm, int(nblk), _WIN.ctypes.data_as(C.POINTER(C.c_double)),
+                                              ptr(out_p), ptr(out_s), stream_ptr()))
+    return out_p, out_s
+
+
 def compare_psnr(image_true, image_test, data_range=1):
-    """skimage.metrics.peak_signal_noise_ratio for float32 images (YOND_SIDD.py:651)."""
-    p, _ = block_metrics(image_true, image_test, 1, data_range=data_range, ssim=False)
+    """skimage.metrics.peak_signal_noise_ratio: float32 images (YOND_SIDD.py:651) or uint8 (H,W,3) pictures (:663)."""
+    if _is_u8(image_true) and _is_u8(image_test):
+        if data_range != 255:
+            raise ValueError("uint8 pictures are measured at data_range=255")
+        p, _ = block_metrics_rgb8(image_true, image_test, 1, ssim=False)
+    else:
+        p, _ = block_metrics(image_true, image_test, 1, data_range=data_range, ssim=False)
     return float(p.cpu()[0, 0])
 
 
@@ -56,6 +82,11 @@ def ssim(prediction, target):
 
 def calculate_ssim(target, ref):
     """YOND_SIDD.py:700-721: 2-D images, or (H, W, 3) / (H, W, 1) channel means."""
+    if _is_u8(target) and _is_u8(ref) and target.ndim == 3 and target.shape[2] == 3:
+        if tuple(target.shape) != tuple(ref.shape):
+            raise ValueError("Input images must have the same dimensions.")
+        _, s = block_metrics_rgb8(target, ref, 1, psnr=False)
+        return float(s.cpu()[0, 0])
     img1, img2 = np.asarray(target), np.asarray(ref)
     if img1.shape != img2.shape:
         raise ValueError("Input images must have the same dimensions.")
@@ -77,3 +108,40 @@ def sidd_image_metrics(outputs, hr_raw, nblk=32):
         return -1.0, -1.0
     p, s = block_metrics(t, hr_raw, nblk)
     return float(p.mean().cpu()), float(s.mean().cpu())
+
+
+def sidd_rgb_metrics(img_dn, img_hr, nblk=32):
+    """YOND_SIDD.py:660-665: mean over the picture's blocks (split along W) of the sRGB PSNR and SSIM.  (H, nblk*Wb, 3) uint8."""
+    p, s = block_metrics_rgb8(img_dn, img_hr, nblk)
+    return float(p.mean().cpu()), float(s.mean().cpu())
+
+
+def sidd_eval_image(outputs, hr_raw, meta=None, nblk=32, rgb=True):
+    """The scoring half of multiprocess_plot (YOND_SIDD.py:635-668) for one image, all on the device: for every iteration's
+    mosaic in `outputs` ((n_iter, H, nblk*Wb) or a list) the raw PSNR / SSIM against `hr_raw`, and — with `meta` (keys 'bayer_2by2',
+    'wb', 'cst2') and rgb=True, the reference's save_plot branch — the sRGB PSNR / SSIM of the rendered pictures.  An iteration whose
+    output has no positive value scores -1 like the reference and is not rendered.  Returns {'psnr': [...], 'ssim': [...],
+    'psnr_rgb': [...], 'ssim_rgb': [...], 'img_hr': CUDA uint8 picture or None, 'img_dn': [pictures]}."""
+    from .render import process_sidd_image
+    hr, _ = to_dev(hr_raw)
+    res = {"psnr": [], "ssim": [], "psnr_rgb": [], "ssim_rgb": [], "img_hr": None, "img_dn": []}
+    do_rgb = bool(rgb and meta is not None)
+    if do_rgb:
+        res["img_hr"] = process_sidd_image(hr, meta["bayer_2by2"], meta["wb"], meta["cst2"])
+    for out in outputs:
+        t, _ = to_dev(out)
+        if float(t.max()) <= 0:
+            res["psnr"].append(-1.0)
+            res["ssim"].append(-1.0)
+            res["img_dn"].append(None)
+            continue
+        p, s = block_metrics(t, hr, nblk)
+        res["psnr"].append(float(p.mean().cpu()))
+        res["ssim"].append(float(s.mean().cpu()))
+        if do_rgb:
+            img = process_sidd_image(t, meta["bayer_2by2"], meta["wb"], meta["cst2"])
+            pr, sr = block_metrics_rgb8(img, res["img_hr"], nblk)
+            res["psnr_rgb"].append(float(pr.mean().cpu()))
+            res["ssim_rgb"].append(float(sr.mean().cpu()))
+            res["img_dn"].append(img)
+    return res
