@@ -143,7 +143,8 @@ int block_metrics_impl(const char* who, const T* a, const T* b, int nimg, int H,
   const int Wb = Wm / nblk, n = nimg * nblk;
   if (psnr) {
     YOND_CUDA_CHECK(cudaMemsetAsync(psnr, 0, sizeof(double) * n, s));
-    dim3 g(1, H < 64 ? H : 64, n);
+    const int rows_wanted = n >= 1184 ? 1 : 1184 / n;  // ~8 blocks per SM in flight also when one large image is measured
+    dim3 g(1, H < rows_wanted ? H : rows_wanted, n);
     sqdiff_kernel<T><<<g, 256, 0, s>>>(a, b, H, Wb, nblk, nch, psnr);
     YOND_LAUNCH_CHECK();
   }

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
                                                                int B, int H, int W, float slope, bf16* __restrict__ out0,
                                                                bf16* __restrict__ out1) {
   constexpr int nf = 32;
-  __shared__ __align__(16) float4 tile[kHeadPW * kHeadPH];
+  // halo tile, split once per pixel: {hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3)} bf16 pairs (every pixel feeds nine taps)
+  __shared__ __align__(16) uint4 tile[kHeadPW * kHeadPH];
   __shared__ __align__(16) uint32_t stage[8][2][16 * 16];  // per warp: out0 / out1 staging, 16 pixels x 32 bf16
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -140,35 +141,58 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
   }
 
   const int tiles_x = (W + kHeadTW - 1) / kHeadTW, tiles_y = (H + kHeadTH - 1) / kHeadTH;
-  const int ntiles = B * tiles_x * tiles_y;
   const float4* z4 = reinterpret_cast<const float4*>(z);
-  const float2* tile2 = reinterpret_cast<const float2*>(tile);
+  const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
+  // Tile walk without divisions: a block visits tiles blockIdx.x, + gridDim.x, ...; the (image, tile row, tile column) triple
+  // advances by the fixed step (gridDim.x / tiles_x rows, gridDim.x % tiles_x columns) with carries.
+  struct TilePos { int b, ty, tx; };
+  const int step_y = (int)gridDim.x / tiles_x, step_x = (int)gridDim.x % tiles_x;
+  auto advance = [&](TilePos p) {
+    p.tx += step_x;
+    if (p.tx >= tiles_x) { p.tx -= tiles_x; ++p.ty; }
+    p.ty += step_y;
+    while (p.ty >= tiles_y) { p.ty -= tiles_y; ++p.b; }
+    return p;
+  };
+  TilePos cur;
+  {
+    const int per = tiles_x * tiles_y, ti = blockIdx.x;
+    cur.b = ti / per;
+    const int rem = ti - cur.b * per;
+    cur.ty = rem / tiles_x;
+    cur.tx = rem - cur.ty * tiles_x;
+  }
   // software pipeline: the next tile's halo pixels are in flight (registers) while this tile is computed
   float4 pre[kHeadLoads];
-  auto prefetch = [&](int ti) {
-    const int b = ti / (tiles_x * tiles_y), rem = ti % (tiles_x * tiles_y);
-    const int y0 = (rem / tiles_x) * kHeadTH, x0 = (rem % tiles_x) * kHeadTW;
+  auto prefetch = [&](const TilePos& p) {
+    const int y0 = p.ty * kHeadTH, x0 = p.tx * kHeadTW;
 #pragma unroll
     for (int k = 0; k < kHeadLoads; ++k) {
       const int i = threadIdx.x + 256 * k;
       const int yy = y0 + i / kHeadPW - 1, xx = x0 + i % kHeadPW - 1;
       pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < kHeadPW * kHeadPH && yy >= 0 && yy < H && xx >= 0 && xx < W) pre[k] = __ldg(z4 + ((size_t)b * H + yy) * W + xx);
+      if (i < kHeadPW * kHeadPH && yy >= 0 && yy < H && xx >= 0 && xx < W) pre[k] = __ldg(z4 + ((size_t)p.b * H + yy) * W + xx);
     }
   };
-  if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x);
-  for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
-    const int b = ti / (tiles_x * tiles_y), rem = ti % (tiles_x * tiles_y);
-    const int y0 = (rem / tiles_x) * kHeadTH, x0 = (rem % tiles_x) * kHeadTW;
+  if (cur.b < B) prefetch(cur);
+  for (; cur.b < B;) {
+    const TilePos nxt = advance(cur);
+    const int b = cur.b, y0 = cur.ty * kHeadTH, x0 = cur.tx * kHeadTW;
     const float inv = ub ? 1.0f / __ldg(ub + b) : 1.0f;  // the reference divides first, then convolves (modules.py:20)
     __syncthreads();  // previous iteration's readers are done with the tile
 #pragma unroll
     for (int k = 0; k < kHeadLoads; ++k) {
       const int i = threadIdx.x + 256 * k;
-      if (i < kHeadPW * kHeadPH) tile[i] = make_float4(pre[k].x * inv, pre[k].y * inv, pre[k].z * inv, pre[k].w * inv);
+      if (i < kHeadPW * kHeadPH) {
+        uint4 rec;
+        split2(pre[k].x * inv, pre[k].y * inv, rec.x, rec.z);
+        split2(pre[k].z * inv, pre[k].w * inv, rec.y, rec.w);
+        tile[i] = rec;
+      }
     }
     __syncthreads();
-    if (ti + (int)gridDim.x < ntiles) prefetch(ti + gridDim.x);
+    if (nxt.b < B) prefetch(nxt);
+    cur = nxt;
 #pragma unroll 1
     for (int rr = 0; rr < kHeadTH / 8; ++rr) {
       const int row = warp * (kHeadTH / 8) + rr;  // tile row of this m-tile: 16 pixels along x
@@ -176,7 +200,7 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
       float acc[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][2] = bv[nt][0]; acc[nt][1] = acc[nt][3] = bv[nt][1]; }
-      const int cp = t & 1;  // channel pair inside the pixel (float2 index)
+      const int cp = t & 1;  // channel pair inside the pixel
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t ah[4], al[4];
@@ -186,8 +210,9 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
           const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
           for (int rs = 0; rs < 2; ++rs) {
-            const float2 v = tile2[((row + dy) * kHeadPW + g + 8 * rs + dx) * 2 + cp];
-            split2(v.x, v.y, ah[half * 2 + rs], al[half * 2 + rs]);
+            const int word = ((row + dy) * kHeadPW + g + 8 * rs + dx) * 4 + cp;
+            ah[half * 2 + rs] = tile32[word];
+            al[half * 2 + rs] = tile32[word + 2];
           }
         }
 #pragma unroll
@@ -197,16 +222,13 @@ __global__ void __launch_bounds__(256, 2) head_conv_mma_kernel(const float* __re
           mma16816(acc[nt], al, bh[ks][nt][0], bh[ks][nt][1]);
         }
       }
-      {  // tap 8 (dy = dx = 2): all three terms in one k-step
-        uint32_t a[4], h0, l0, h1, l1;
-        const float2 v0 = tile2[((row + 2) * kHeadPW + g + 2) * 2 + cp];
-        const float2 v1 = tile2[((row + 2) * kHeadPW + g + 8 + 2) * 2 + cp];
-        split2(v0.x, v0.y, h0, l0);
-        split2(v1.x, v1.y, h1, l1);
-        a[0] = t < 2 ? h0 : l0;
-        a[1] = t < 2 ? h1 : l1;
-        a[2] = t < 2 ? h0 : 0u;
-        a[3] = t < 2 ? h1 : 0u;
+      {  // tap 8 (dy = dx = 2): all three terms in one k-step (lanes t < 2 carry xh, lanes t >= 2 carry xl)
+        uint32_t a[4];
+        const int word = ((row + 2) * kHeadPW + g + 2) * 4 + cp + (t < 2 ? 0 : 2);
+        a[0] = tile32[word];
+        a[1] = tile32[word + 8 * 4];
+        a[2] = t < 2 ? a[0] : 0u;
+        a[3] = t < 2 ? a[1] : 0u;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) mma16816(acc[nt], a, bs[nt][0], bs[nt][1]);
       }
@@ -303,47 +325,56 @@ __global__ void maxpool2_kernel(const bf16* __restrict__ in, bf16* __restrict__ 
 
 // ---- per-sample conditioning vectors (GuidedResidualBlock gamma/beta, SNR_Block sfm1/sfm2) -------------------
 // out_a = W2 * silu(w0 * t' + b0) + b2 ;  guided: out_b = Wb * silu(out_a) + bb ;  snr: out_b = second MLP(t').
-// t' = t[b] / ub[b] when the network normalises (archs/Unet.py:427-429).  One block handles kFilmS samples so each
-// weight row is read once per kFilmS dot products; a warp owns an output row.
-constexpr int kFilmS = 4;
-__device__ __forceinline__ void film_matvec(const float* __restrict__ Wm, const float* __restrict__ bias, const float* vin /*[S][C]*/,
-                                            int C, int ns, float* vout_smem /*[S][C] or null*/, float* __restrict__ out_g, int b0) {
+// t' = t[b] / ub[b] when the network normalises (archs/Unet.py:427-429).  The work is tiny (0.87 M MACs per sample) and sits on the
+// critical path in front of the first conditioned layer, so it is spread for latency, not throughput: one launch per stage (out_b
+// needs all of out_a), grid = (sample groups, conditioned blocks, row slices); a CTA handles kFilmS samples so each weight row is
+// read once per kFilmS dot products, a warp keeps kFilmRows rows in flight.  Per-row summation order: lane-strided partial sums,
+// then a butterfly — independent of the slicing.
+constexpr int kFilmS = 4, kFilmSlices = 8, kFilmRows = 4;
+__device__ __forceinline__ void film_rows(const float* __restrict__ Wm, const float* __restrict__ bias, const float* vin /*[S][C]*/, int C,
+                                          int ns, int n0, int n1, float* __restrict__ out_g, int b0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int n = warp; n < C; n += nw) {
-    const float* wrow = Wm + (size_t)n * C;
-    float acc[kFilmS];
+  for (int n = n0 + warp * kFilmRows; n < n1; n += nw * kFilmRows) {
+    float acc[kFilmRows][kFilmS];
 #pragma unroll
-    for (int s = 0; s < kFilmS; ++s) acc[s] = 0.f;
+    for (int r = 0; r < kFilmRows; ++r)
+#pragma unroll
+      for (int s = 0; s < kFilmS; ++s) acc[r][s] = 0.f;
     for (int j = lane; j < C; j += 32) {
-      const float wv = __ldg(wrow + j);
+      float wv[kFilmRows];
 #pragma unroll
-      for (int s = 0; s < kFilmS; ++s) acc[s] = fmaf(wv, vin[s * C + j], acc[s]);
-    }
-#pragma unroll
-    for (int s = 0; s < kFilmS; ++s)
-      for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
-    if (lane == 0) {
-      const float bb = bias[n];
+      for (int r = 0; r < kFilmRows; ++r) wv[r] = n + r < n1 ? __ldg(Wm + (size_t)(n + r) * C + j) : 0.f;
 #pragma unroll
       for (int s = 0; s < kFilmS; ++s) {
-        if (s < ns) {
-          const float v = acc[s] + bb;
-          if (vout_smem) vout_smem[s * C + n] = v;
-          out_g[(size_t)(b0 + s) * C + n] = v;
-        }
+        const float x = vin[s * C + j];
+#pragma unroll
+        for (int r = 0; r < kFilmRows; ++r) acc[r][s] = fmaf(wv[r], x, acc[r][s]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kFilmRows; ++r)
+#pragma unroll
+      for (int s = 0; s < kFilmS; ++s)
+        for (int o = 16; o > 0; o >>= 1) acc[r][s] += __shfl_xor_sync(0xffffffffu, acc[r][s], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < kFilmRows; ++r) {
+        if (n + r >= n1) break;
+        const float bb = bias[n + r];
+#pragma unroll
+        for (int s = 0; s < kFilmS; ++s)
+          if (s < ns) out_g[(size_t)(b0 + s) * C + n + r] = acc[r][s] + bb;
       }
     }
   }
 }
-__global__ void __launch_bounds__(512) film_kernel(const __grid_constant__ FilmAll all, const float* __restrict__ t,
-                                                   const float* __restrict__ ub, int B, int guided) {
+__global__ void __launch_bounds__(256) film_kernel(const __grid_constant__ FilmAll all, const float* __restrict__ t,
+                                                   const float* __restrict__ ub, int B, int guided, int stage) {
   const FilmWeights& fw = all.fw[blockIdx.y];  // one conditioned block of the network per blockIdx.y
   const int C = all.C[blockIdx.y];
   float* __restrict__ out_a = all.out_a[blockIdx.y];
   float* __restrict__ out_b = all.out_b[blockIdx.y];
-  extern __shared__ float sv[];  // [S][C] hidden, [S][C] out_a
-  float* hid = sv;
-  float* va = sv + kFilmS * C;
+  extern __shared__ float hid[];  // [S][C] input vector of this stage's matrix
   const int b0 = blockIdx.x * kFilmS;
   const int ns = min(kFilmS, B - b0);
   __shared__ float tt[kFilmS];
@@ -352,25 +383,19 @@ __global__ void __launch_bounds__(512) film_kernel(const __grid_constant__ FilmA
     tt[threadIdx.x] = ub ? __ldg(t + b) / __ldg(ub + b) : __ldg(t + b);
   }
   __syncthreads();
+  const bool from_a = stage == 1 && guided;
+  const float* w_in = stage == 0 ? fw.w0 : fw.w3;
+  const float* b_in = stage == 0 ? fw.b0 : fw.b3;
   for (int i = threadIdx.x; i < kFilmS * C; i += blockDim.x) {
     const int s = i / C, c = i - s * C;
-    hid[i] = silu_f(fmaf(fw.w0[c], tt[s], fw.b0[c]));
+    hid[i] = silu_f(from_a ? out_a[(size_t)min(b0 + s, B - 1) * C + c] : fmaf(w_in[c], tt[s], b_in[c]));
   }
   __syncthreads();
-  film_matvec(fw.w2, fw.b2, hid, C, ns, va, out_a, b0);
-  __syncthreads();
-  if (guided) {
-    for (int i = threadIdx.x; i < kFilmS * C; i += blockDim.x) hid[i] = silu_f(va[i]);
-    __syncthreads();
-    film_matvec(fw.w3, fw.b3, hid, C, ns, nullptr, out_b, b0);
-  } else {
-    for (int i = threadIdx.x; i < kFilmS * C; i += blockDim.x) {
-      const int s = i / C, c = i - s * C;
-      hid[i] = silu_f(fmaf(fw.w3[c], tt[s], fw.b3[c]));
-    }
-    __syncthreads();
-    film_matvec(fw.w4, fw.b4, hid, C, ns, nullptr, out_b, b0);
-  }
+  const int per = (C + kFilmSlices - 1) / kFilmSlices;
+  const int n0 = blockIdx.z * per, n1 = min(C, n0 + per);
+  if (stage == 0) film_rows(fw.w2, fw.b2, hid, C, ns, n0, n1, out_a, b0);
+  else if (guided) film_rows(fw.w3, fw.b3, hid, C, ns, n0, n1, out_b, b0);
+  else film_rows(fw.w4, fw.b4, hid, C, ns, n0, n1, out_b, b0);
 }
 
 // ---- nearest-neighbour x2 up-sampling + channel concat (one thread = 8 channels of one output pixel) ---------------
@@ -507,9 +532,11 @@ int add_in4_launch(bf16* act, const float* w_in, const float* z, const float* ub
 int film_launch(const FilmAll& all, const float* t, const float* ub, int B, int guided, cudaStream_t s) {
   int cmax = 0;
   for (int i = 0; i < all.n; ++i) cmax = all.C[i] > cmax ? all.C[i] : cmax;
-  dim3 grid(ceil_div(B, kFilmS), all.n);
-  film_kernel<<<grid, 512, (size_t)2 * kFilmS * cmax * sizeof(float), s>>>(all, t, ub, B, guided);
-  YOND_LAUNCH_CHECK();
+  dim3 grid(ceil_div(B, kFilmS), all.n, kFilmSlices);
+  for (int stage = 0; stage < 2; ++stage) {
+    film_kernel<<<grid, 256, (size_t)kFilmS * cmax * sizeof(float), s>>>(all, t, ub, B, guided, stage);
+    YOND_LAUNCH_CHECK();
+  }
   return YOND_OK;
 }
 int nchw_to_nhwc4_launch(const float* x, float* z, float* ub, int B, int H, int W, cudaStream_t s) {
