@@ -83,7 +83,7 @@ def synth_frames(n, seed, H=FRAME_H, W=FRAME_W):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.idx, self.t0 = [], None, gpu_index, 0.0
@@ -100,9 +100,20 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    @staticmethod
+    def _when(stamp, fallback):
+        """nvidia-smi's own sample time ('YYYY/MM/DD HH:MM:SS.mmm', local time): its stdout is a pipe and arrives in bursts, so the
+        time a line is READ says little about when it was sampled."""
+        try:
+            import datetime
+            return datetime.datetime.strptime(stamp, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return fallback
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
+            cols = [c.strip() for c in line.split(",")]
+            self.rows.append(cols + [self._when(cols[-1], time.time())])
 
     def stop(self):
         if self.proc is None:
@@ -114,7 +125,9 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        self.t.join(timeout=2)  # the reader drains what nvidia-smi had buffered
         inside = [r for r in self.rows if self.t0 <= r[-1] <= t_end]
+        scope = "timed region" if inside else "warm-up + timed region (no sample fell inside by nvidia-smi's clock)"
         self.rows = inside if inside else self.rows
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
@@ -126,7 +139,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def measured_peaks():
