@@ -998,9 +998,54 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const bool leader = elect_one() != 0;
     if (p.wres && (!kPair || pair_leader)) mbar_wait(uw_full, 0);  // pair: both halves are counted on the leader's barrier
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-    long long t_acc = 0, t_a = 0, t_issue = 0, t_begin = YOND_TICK();
+    long long t_acc = 0, t_a = 0, t_issue = 0, t_dec = 0, t_begin = YOND_TICK();
+    // The commonest shape — 3x3 stride 1, weights resident, ONE halo slab per tile (32 / 64 input channels: the four layers of
+    // each full- and half-resolution block) — gets a loop of its own.  A single warp retires roughly one dependent instruction
+    // every 5 cycles, and tcgen05.mma issue blocks once a few MMAs are queued, so whatever this warp executes between the last
+    // MMA of a tile and the first of the next is time the tensor pipe drains and idles: the generic loop below spends ~1100
+    // cycles per tile there (stage decode, the dispatch on T / K steps / pairing, ring bookkeeping; cycle counters of the
+    // YOND_CONV_TIMING build), 20-25 % of a tile of these layers.  Here everything tile-invariant is hoisted and the dispatch
+    // happens once, outside the loop.
+    const bool fast_slab1 = p.wres && p.slab && p.mode == CONV_3X3_S1 && n_ast == 1 && !kPair && !(p.dbg & (8 | 16 | 32 | 256 | 512)) &&  // dbg 512: generic loop (A/B of this path)
+                            (p.T == 1 || p.T == 2 || p.T == 4);
+    if (fast_slab1) {
+      const uint32_t b_first = (((u_smem_b) & 0x3FFFFu) >> 4) | lo_flags;  // the slab's channel block is 0: widx0 = 0
+      const uint32_t b_step16 = p.b_stage_bytes >> 4;
+      const uint32_t a_bytes = p.a_stage_bytes, acc_cols = (uint32_t)p.T * nt;
+      const int SA = p.SA, nacc = p.acc_stages;
+      auto run = [&](auto issue) {
+        for (int u = sched.first; u < sched.n_units; u += sched.step) {
+          mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
+          mbar_wait(ua_full + 8 * sa, pa);
+          tc_fence_after();
+          if (leader) {
+            issue(u_tmem + (uint32_t)as * acc_cols, (((u_smem_a + (uint32_t)sa * a_bytes) & 0x3FFFFu) >> 4) | lo_flags);
+            umma_commit(ua_empty + 8 * sa);
+            umma_commit(uacc_full + 8 * as);
+          }
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          if (++as == nacc) { as = 0; pacc ^= 1; }
+        }
+      };
+#define YOND_SLAB1(FN) run([&](uint32_t d, uint32_t a_lo) { FN(d, nt, a_lo, tap_r16, px16, sub_step, b_first, b_step16, a_hi, b_hi, idesc, 0u); })
+      if (p.paired) {
+        if (p.T == 1) YOND_SLAB1((issue_slab_paired<1, kPair>));
+        else if (p.T == 2) YOND_SLAB1((issue_slab_paired<2, kPair>));
+        else YOND_SLAB1((issue_slab_paired<4, kPair>));
+      } else if (ksteps == 4) {
+        if (p.T == 1) YOND_SLAB1((issue_slab_resident<4, 1, kPair>));
+        else if (p.T == 2) YOND_SLAB1((issue_slab_resident<4, 2, kPair>));
+        else YOND_SLAB1((issue_slab_resident<4, 4, kPair>));
+      } else {
+        if (p.T == 1) YOND_SLAB1((issue_slab_resident<2, 1, kPair>));
+        else if (p.T == 2) YOND_SLAB1((issue_slab_resident<2, 2, kPair>));
+        else YOND_SLAB1((issue_slab_resident<2, 4, kPair>));
+      }
+#undef YOND_SLAB1
+    }
     // CTA pair: only the leader CTA issues (its MMAs drive both SMs' tensor cores); the peer's warp 1 idles
-    for (int u = (kPair && !pair_leader) ? sched.n_units : sched.first; u < sched.n_units; u += sched.step) {
+    for (int u = (fast_slab1 || (kPair && !pair_leader)) ? sched.n_units : sched.first; u < sched.n_units; u += sched.step) {
       long long tw0 = YOND_TICK();
       mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
       t_acc += YOND_TICK() - tw0;
@@ -1008,8 +1053,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const uint32_t d_tmem = u_tmem + (uint32_t)(as * p.T) * nt;
       const uint32_t d_tmem_tile = d_tmem;
       for (int ai = 0; ai < n_ast; ++ai) {
+        const long long td0 = YOND_TICK();
         const AStage s = decode_astage(p, ai);
         tw0 = YOND_TICK();
+        t_dec += tw0 - td0;
         mbar_wait(ua_full + 8 * sa, pa);
         t_a += YOND_TICK() - tw0;
         tc_fence_after();
@@ -1135,8 +1182,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       if (++as == p.acc_stages) { as = 0; pacc ^= 1; }
     }
     if ((p.dbg & 8) && blockIdx.x == 0 && leader)
-      printf("[conv dbg] issuer: total %lld cyc; issue regions %lld; waiting: accumulator %lld, activations %lld; tiles %d, A stages/tile %d, SA %d SB %d T %d NT %d\n",
-             YOND_TICK() - t_begin, t_issue, t_acc, t_a, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
+      printf("[conv dbg] issuer: total %lld cyc; issue regions %lld; waiting: accumulator %lld, activations %lld; stage decode %lld; tiles %d, A stages/tile %d, SA %d SB %d T %d NT %d\n",
+             YOND_TICK() - t_begin, t_issue, t_acc, t_a, t_dec, (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, n_ast, p.SA, p.SB, p.T, p.NT);
   } else {
     // ===================== epilogue (warps 2..2+kEpiWarps) =====================
     const bool silu = p.act == ACT_SILU;
