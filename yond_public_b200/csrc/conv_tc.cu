@@ -1002,9 +1002,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // The commonest shape — 3x3 stride 1, weights resident, ONE halo slab per tile (32 / 64 input channels: the four layers of
     // each full- and half-resolution block) — gets a loop of its own.  A single warp retires roughly one dependent instruction
     // every 5 cycles, and tcgen05.mma issue blocks once a few MMAs are queued, so whatever this warp executes between the last
-    // MMA of a tile and the first of the next is time the tensor pipe drains and idles: the generic loop below spends ~1100
-    // cycles per tile there (stage decode, the dispatch on T / K steps / pairing, ring bookkeeping; cycle counters of the
-    // YOND_CONV_TIMING build), 20-25 % of a tile of these layers.  Here everything tile-invariant is hoisted and the dispatch
+    // MMA of a tile and the first of the next is time the tensor pipe drains and idles: the generic loop below spends up to
+    // ~1100 cycles per tile there (stage decode, the dispatch on T / K steps / pairing, ring bookkeeping; as seen by the cycle
+    // counters of the YOND_CONV_TIMING build, their own cost included) against 4500-5700 cycles for a tile of these layers.  Here everything tile-invariant is hoisted and the dispatch
     // happens once, outside the loop.
     const bool fast_slab1 = p.wres && p.slab && p.mode == CONV_3X3_S1 && n_ast == 1 && !kPair && !(p.dbg & (8 | 16 | 32 | 256 | 512)) &&  // dbg 512: generic loop (A/B of this path)
                             (p.T == 1 || p.T == 2 || p.T == 4);
