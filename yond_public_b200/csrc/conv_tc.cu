@@ -538,6 +538,14 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 
 template <bool kScale, bool kRes, bool kSilu, int kV, bool kPair>  // kV: visits per group (residual registers held at once)
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, uint32_t ptab,
@@ -1044,8 +1052,64 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
 #undef YOND_SLAB1
     }
+    // The other resident-weight layers (stride-2 3x3, 1x1, ConvT 2x2, the fused up-sampling + shortcut) consume one weight tile per
+    // activation stage, 2-36 stages per tile.  Their stage decode (weight-tile address, and for the skip part of CONV_UPSC a
+    // narrower N and a column offset into the accumulator) does not depend on the tile: it is tabulated once in shared memory
+    // (the unused output-conv table region) and the per-stage work of this warp shrinks to a barrier wait, one 16-byte load and
+    // the MMAs.
+    constexpr int kMaxTabStages = 64;
+    const bool fast_tab = p.wres && p.mode != CONV_3X3_S1 && !kPair && n_ast <= kMaxTabStages && p.tail_w == nullptr &&
+                          !(p.dbg & (8 | 16 | 32 | 512)) && (p.T == 1 || p.T == 2 || p.T == 4);
+    if (fast_tab) {
+      const uint32_t tab = smem_base + p.smem_tail_off;
+      for (int ai = lane; ai < n_ast; ai += 32) {
+        const AStage s = decode_astage(p, ai);
+        uint32_t b_lo0 = (((smem_b + (uint32_t)s.widx0 * p.b_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+        uint32_t id = idesc_full, d_off = 0;
+        if (p.mode == CONV_UPSC && s.sx >= 0) {  // skip part: N = Cout, accumulate into parity s.sx's columns
+          b_lo0 = (((smem_b + p.b2_off + (uint32_t)s.widx0 * p.b2_stage_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+          id = (idesc_full & ~(0x3Fu << 17)) | ((uint32_t)(p.Cout >> 3) << 17);
+          d_off = (uint32_t)(s.sx * p.Cout);
+        }
+        sts_u4(tab + 16u * (uint32_t)ai, b_lo0, id, d_off, 0u);
+      }
+      __syncwarp();
+      const uint32_t a_bytes = p.a_stage_bytes, acc_cols = (uint32_t)p.T * nt;
+      const int SA = p.SA, nacc = p.acc_stages;
+      auto run = [&](auto issue) {
+        for (int u = sched.first; u < sched.n_units; u += sched.step) {
+          mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
+          const uint32_t d_tile = u_tmem + (uint32_t)as * acc_cols;
+          for (int ai = 0; ai < n_ast; ++ai) {
+            mbar_wait(ua_full + 8 * sa, pa);
+            tc_fence_after();
+            if (leader) {
+              const uint4 e = lds_u4(tab + 16u * (uint32_t)ai);
+              issue(d_tile + e.z, (((u_smem_a + (uint32_t)sa * a_bytes) & 0x3FFFFu) >> 4) | lo_flags, e.x, e.y, ai ? 1u : 0u);
+              umma_commit(ua_empty + 8 * sa);
+            }
+            __syncwarp();
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+          }
+          if (leader) umma_commit(uacc_full + 8 * as);
+          __syncwarp();
+          if (++as == nacc) { as = 0; pacc ^= 1; }
+        }
+      };
+#define YOND_TAB(KS, TT) run([&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t id, uint32_t acc) { issue_tap<KS, TT>(d, nt, a_lo, sub_step, b_lo, a_hi, b_hi, id, acc); })
+      if (ksteps == 4) {
+        if (p.T == 1) YOND_TAB(4, 1);
+        else if (p.T == 2) YOND_TAB(4, 2);
+        else YOND_TAB(4, 4);
+      } else {
+        if (p.T == 1) YOND_TAB(2, 1);
+        else if (p.T == 2) YOND_TAB(2, 2);
+        else YOND_TAB(2, 4);
+      }
+#undef YOND_TAB
+    }
     // CTA pair: only the leader CTA issues (its MMAs drive both SMs' tensor cores); the peer's warp 1 idles
-    for (int u = (fast_slab1 || (kPair && !pair_leader)) ? sched.n_units : sched.first; u < sched.n_units; u += sched.step) {
+    for (int u = (fast_slab1 || fast_tab || (kPair && !pair_leader)) ? sched.n_units : sched.first; u < sched.n_units; u += sched.step) {
       long long tw0 = YOND_TICK();
       mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
       t_acc += YOND_TICK() - tw0;
