@@ -1108,8 +1108,63 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
 #undef YOND_TAB
     }
+    // Streamed weights, one halo slab per 64-channel block (the 128- to 512-channel 3x3 layers, normally as CTA pairs): nine taps
+    // per stage, each waiting for its weight tile and handing the ring slot back.  Same hoisting: T is dispatched once, the
+    // stage needs no decode at all (the slab is the whole story for this warp; weight tiles arrive in ring order).
+    const bool fast_stream = !p.wres && p.slab && p.mode == CONV_3X3_S1 && ksteps == 4 && !(p.dbg & (8 | 16 | 32 | 512)) &&
+                             (p.T == 1 || p.T == 2 || p.T == 4);
+    if (fast_stream && (!kPair || pair_leader)) {
+      const uint32_t a_bytes = p.a_stage_bytes, b_bytes = p.b_stage_bytes, acc_cols = (uint32_t)p.T * nt;
+      const int SA = p.SA, SB = p.SB, nacc = p.acc_stages;
+      auto commit = [&](uint32_t bar) {
+        if (kPair) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
+      auto run = [&](auto issue) {
+        for (int u = sched.first; u < sched.n_units; u += sched.step) {
+          mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
+          const uint32_t d_tile = u_tmem + (uint32_t)as * acc_cols;
+          for (int ai = 0; ai < n_ast; ++ai) {
+            mbar_wait(ua_full + 8 * sa, pa);
+            tc_fence_after();
+            if (leader) {
+              const uint32_t a_stage_lo = (((u_smem_a + (uint32_t)sa * a_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+              int lsb = sb, lpb = pb;
+#pragma unroll
+              for (int j = 0; j < 9; ++j) {
+                const uint32_t r = j / 3, sx = j % 3;
+                mbar_wait(ub_full + 8 * lsb, lpb);
+                tc_fence_after();
+                issue(d_tile, a_stage_lo + r * tap_r16 + sx * px16, (((u_smem_b + (uint32_t)lsb * b_bytes) & 0x3FFFFu) >> 4) | lo_flags,
+                      (ai | j) ? 1u : 0u);
+                commit(ub_empty + 8 * lsb);
+                if (++lsb == SB) { lsb = 0; lpb ^= 1; }
+              }
+              commit(ua_empty + 8 * sa);
+            }
+            __syncwarp();
+            sb += 9;  // advance the weight ring by this stage's taps, in converged code
+            while (sb >= SB) { sb -= SB; pb ^= 1; }
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+          }
+          if (leader) commit(uacc_full + 8 * as);
+          __syncwarp();
+          if (++as == nacc) { as = 0; pacc ^= 1; }
+        }
+      };
+#define YOND_STREAM(TT)                                                                                                   \
+  run([&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {                                                      \
+    if (kPair) issue_tap_pair<4, TT>(d, nt, a_lo, sub_step, b_lo, a_hi, b_hi, idesc, acc);                               \
+    else issue_tap<4, TT>(d, nt, a_lo, sub_step, b_lo, a_hi, b_hi, idesc, acc);                                          \
+  })
+      if (p.T == 1) YOND_STREAM(1);
+      else if (p.T == 2) YOND_STREAM(2);
+      else YOND_STREAM(4);
+#undef YOND_STREAM
+    }
     // CTA pair: only the leader CTA issues (its MMAs drive both SMs' tensor cores); the peer's warp 1 idles
-    for (int u = (fast_slab1 || fast_tab || (kPair && !pair_leader)) ? sched.n_units : sched.first; u < sched.n_units; u += sched.step) {
+    for (int u = (fast_slab1 || fast_tab || fast_stream || (kPair && !pair_leader)) ? sched.n_units : sched.first; u < sched.n_units;
+         u += sched.step) {
       long long tw0 = YOND_TICK();
       mbar_wait(uacc_empty + 8 * as, pacc ^ 1);
       t_acc += YOND_TICK() - tw0;
