@@ -65,6 +65,38 @@ __host__ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
+// 32-bit shared-window address of a __shared__ object, opaque to the compiler.  Indexing shared arrays inside hot per-element code
+// otherwise makes nvcc REMATERIALISE the window base (S2R SR_CgaCtaId + shift + add) in front of every access on sm_100 — several
+// extra instructions per element, one of them on the slow S2R path.  Take the address once, then ld.shared with register + immediate.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("" : "+r"(a));
+  return a;
+}
+__device__ __forceinline__ int lds_s8(uint32_t a) {
+  int v;
+  asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4f(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void reds_add(uint32_t a, uint32_t by = 1u) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(by) : "memory");
+}
+
 // Sensor mosaic read in place of a float32 Bayer frame: the dataset normalisation of
 // data_process/yond_datasets.py:955-961 / :1053-1056, (float32(raw) - black) * ratio / (white - black) in float32 in that order,
 // is applied on load, so the normalised frame never exists in memory (2 B/px instead of 4 per read).  base == nullptr: float source.

@@ -300,28 +300,32 @@ struct TabInfo {
   float v1, v2;     // their first node values
   float is0, is1, is2;  // inverse steps of the pieces
 };
-__device__ __forceinline__ float tab_lookup(float xq, const float4* __restrict__ tab, const TabInfo& ti) {
+// tab / ti: 32-bit shared addresses (smem_addr) of the interval records and of the TabInfo; kind and n are held in registers
+__device__ __forceinline__ float tab_lookup(float xq, uint32_t tab, int kind, int n, uint32_t ti) {
   int g;
-  if (ti.kind == 1) {
+  if (kind == 1) {
     g = xq < 0.0625f ? (int)(xq * 2048.f) : 128 + (int)(128.f * (__log2f(xq) + 4.f));
-  } else if (ti.kind == 2) {
-    g = xq < ti.v1 ? (int)(xq * ti.is0) : (xq < ti.v2 ? ti.n1 + (int)((xq - ti.v1) * ti.is1) : ti.n2 + (int)((xq - ti.v2) * ti.is2));
+  } else if (kind == 2) {
+    const float v1 = lds_f32(ti + offsetof(TabInfo, v1)), v2 = lds_f32(ti + offsetof(TabInfo, v2));
+    g = xq < v1 ? (int)(xq * lds_f32(ti + offsetof(TabInfo, is0)))
+                : (xq < v2 ? (int)lds_u32(ti + offsetof(TabInfo, n1)) + (int)((xq - v1) * lds_f32(ti + offsetof(TabInfo, is1)))
+                           : (int)lds_u32(ti + offsetof(TabInfo, n2)) + (int)((xq - v2) * lds_f32(ti + offsetof(TabInfo, is2))));
   } else {
-    int lo = 0, hi = ti.n - 1;  // last interval whose left node is < xq
+    int lo = 0, hi = n - 1;  // last interval whose left node is < xq
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if (tab[mid].x < xq) lo = mid; else hi = mid;
+      if (lds_f32(tab + 16u * (uint32_t)mid) < xq) lo = mid; else hi = mid;
     }
     g = lo;
   }
-  g = max(0, min(g, ti.n - 2));
-  float4 e = tab[g];
-  while (xq > e.w && g < ti.n - 2) e = tab[++g];
-  while (xq < e.x && g > 0) e = tab[--g];
+  g = max(0, min(g, n - 2));
+  float4 e = lds_v4f(tab + 16u * (uint32_t)g);
+  while (xq > e.w && g < n - 2) e = lds_v4f(tab + 16u * (uint32_t)(++g));
+  while (xq < e.x && g > 0) e = lds_v4f(tab + 16u * (uint32_t)(--g));
   return fmaf(fmaxf(xq - e.x, 0.f), e.z, e.y);
 }
 template <bool kVst>
-__global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict__ bayer, float* __restrict__ z,
+__global__ void __launch_bounds__(kBlock, 5) vst_fwd_kernel(const float* __restrict__ bayer, float* __restrict__ z,
                                                          float* __restrict__ ub, int H, int W, int pl, int pt, int hp, int wp,
                                                          const yond_vst_params* __restrict__ params,
                                                          const float* __restrict__ rows, const float* __restrict__ xnodes,
@@ -371,6 +375,9 @@ __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict
     }
   }
   __syncthreads();
+  const uint32_t a_tab = smem_addr(tab), a_ti = smem_addr(&ti);
+  const int t_kind = ti.kind, t_n = ti.n;
+  const float t_last = ti.last, t_ext = ti.ext;
   const float invK = kVst ? 1.0f / c.K : 0.f;
   const float* frame = bayer + (size_t)b * H * W;
   float4* zo = reinterpret_cast<float4*>(z) + (size_t)b * hp * wp;
@@ -402,10 +409,10 @@ __global__ void __launch_bounds__(kBlock) vst_fwd_kernel(const float* __restrict
         if (c.lut_row >= 0) {
           const float xb = fmaxf(x, 0.f);
           if (c.table_n > 0) {
-            bias = tab_lookup(fminf(xb, ti.last), tab, ti);
+            bias = tab_lookup(fminf(xb, t_last), a_tab, t_kind, t_n, a_ti);
           } else {
             const float xe = xb * invK;
-            bias = xe >= ti.ext ? close_form_bias_f(xb, c) : tab_lookup(xe, tab, ti);
+            bias = xe >= t_ext ? close_form_bias_f(xb, c) : tab_lookup(xe, a_tab, t_kind, t_n, a_ti);
           }
         }
         const float zz = vst_f(x, c) - bias;

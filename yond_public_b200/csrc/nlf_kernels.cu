@@ -498,12 +498,13 @@ __global__ void __launch_bounds__(kHist1Threads) hist1_kernel(const float* __res
   for (int i = threadIdx.x; i < nsh * 2048; i += blockDim.x) hs[i] = 0u;
   load_slot_table(wk, s1tab);
   __syncthreads();
-  stream_f4(reinterpret_cast<const float4*>(d), n / 4, [&](float e) {
+  const uint32_t a_tab = smem_addr(s1tab), a_hs = smem_addr(hs);
+  stream_f4(reinterpret_cast<const float4*>(d), n / 4, [=](float e) {
     const uint32_t k = f2key(e);
-    const int s = s1tab[k >> 21];
+    const int s = lds_s8(a_tab + (k >> 21));
     if (s >= 0) {
       const uint32_t mid = (k >> 10) & 2047u;
-      if (s < kHist1Slots) atomicAdd(&hs[s * 2048 + mid], 1u);
+      if (s < kHist1Slots) reds_add(a_hs + 4u * ((uint32_t)s * 2048u + mid));
       else atomicAdd(&wk->hist1[s][mid], 1u);
     }
   });
@@ -622,17 +623,20 @@ __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d,
     atomicOr(&bm[wk->q_slot1[threadIdx.x] * 64 + (mid >> 5)], 1u << (mid & 31u));
   }
   __syncthreads();
-  stream_f4(reinterpret_cast<const float4*>(d), n / 4, [&](float e) {
+  const uint32_t a_tab = smem_addr(s1tab), a_bm = smem_addr(bm), a_qpre = smem_addr(qpre), a_qs2 = smem_addr(qs2);
+  const uint32_t a_hs2 = smem_addr(hs2);
+  const int nq_r = nq;
+  stream_f4(reinterpret_cast<const float4*>(d), n / 4, [=](float e) {
     const uint32_t k = f2key(e);
-    const int s1 = s1tab[k >> 21];
+    const int s1 = lds_s8(a_tab + (k >> 21));
     if (s1 < 0) return;
     const uint32_t mid = (k >> 10) & 2047u;
-    if (!((bm[s1 * 64 + (mid >> 5)] >> (mid & 31u)) & 1u)) return;
+    if (!((lds_u32(a_bm + 4u * ((uint32_t)s1 * 64u + (mid >> 5))) >> (mid & 31u)) & 1u)) return;
     const uint32_t p22 = k >> 10;
     int slot = -1;
-    for (int q = 0; q < nq; ++q)
-      if (qpre[q] == p22) {
-        slot = qs2[q];
+    for (int q = 0; q < nq_r; ++q)
+      if (lds_u32(a_qpre + 4u * q) == p22) {
+        slot = (int)lds_u32(a_qs2 + 4u * q);
         break;
       }
     if (slot < 0) return;
@@ -643,7 +647,7 @@ __global__ void __launch_bounds__(256) hist2_kernel(const float* __restrict__ d,
     const uint32_t key = ((uint32_t)slot << 10) | (k & 1023u);
     const unsigned m = __match_any_sync(__activemask(), key);  // the lanes that are here together with the same counter
     if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
-      if (slot < nsh) atomicAdd(&hs2[key], (unsigned)__popc(m));
+      if (slot < nsh) reds_add(a_hs2 + 4u * key, (unsigned)__popc(m));
       else atomicAdd(&wk->hist2[slot][k & 1023u], (unsigned)__popc(m));
     }
   });
