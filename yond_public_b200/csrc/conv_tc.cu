@@ -547,7 +547,16 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
   return v;
 }
 
-template <bool kScale, bool kRes, bool kSilu, int kV, bool kPair>  // kV: visits per group (residual registers held at once)
+// kRegP (FiLM layers without a residual input whose visits all use ONE 16-channel parameter set — N = 32, or the pixel-pair form, where
+// output columns n and n + 32 are the same channel): the folded scale / shift vectors live in 32 registers and are refreshed when the
+// image changes, instead of eight broadcast LDS.128 per visit (512 B into the register file each, on the shared-memory pipe the MMAs
+// read their operands through; 77 % LSU data-pipe utilisation in the profile of c1.conv1).
+__device__ __forceinline__ bool epilogue_single_set(const TcParams& p) {
+  const int nparts = p.epi_split ? 2 : 4, nchunk = 1 << p.lg_nchunk;
+  const int nsets = nchunk > nparts ? nchunk / nparts : 1;
+  return p.epi_fixed != 0 && nsets <= 2 && (nsets == 1 || (((uint32_t)(nparts << 4) & p.cmask) == 0u));
+}
+template <bool kScale, bool kRes, bool kSilu, int kV, bool kPair, bool kRegP = false>  // kV: visits per group (residual registers held at once)
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t acc_full, uint32_t acc_empty, uint32_t ptab,
                                               int warp, int lane, int total_tiles) {
   const TileSched sched = make_sched<kPair>(p, total_tiles);
@@ -586,6 +595,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   }
   __syncwarp();
   int as = grp, pacc = 0, b_prev = -1;
+  float pa[kRegP && kScale ? 16 : 1], pb[kRegP ? 16 : 1];
+  if (kRegP && !kScale) {  // bias only: constant for the whole kernel
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 bc = lds_f4(ptab + 64 + 16 * g);
+      pb[g * 4 + 0] = bc.x; pb[g * 4 + 1] = bc.y; pb[g * 4 + 2] = bc.z; pb[g * 4 + 3] = bc.w;
+    }
+  }
   for (int u = sched.first + grp * sched.step; u < sched.n_units; u += (split ? 2 : 1) * sched.step) {
     const TileCoord tc = decode_tile(p, sched_tile(p, sched, u));
     const int w = tc.w0 + w_i, h0 = tc.h0 + dh;
@@ -636,6 +653,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
               sts_f32(pslot + 64, fmaf(bias_l, sc, sh));
             }
             __syncwarp();
+            if (kRegP) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 a = lds_f4(ptab + 16 * g), bc = lds_f4(ptab + 64 + 16 * g);
+                pa[g * 4 + 0] = a.x; pa[g * 4 + 1] = a.y; pa[g * 4 + 2] = a.z; pa[g * 4 + 3] = a.w;
+                pb[g * 4 + 0] = bc.x; pb[g * 4 + 1] = bc.y; pb[g * 4 + 2] = bc.z; pb[g * 4 + 3] = bc.w;
+              }
+            }
           }
         }
         mbar_wait(acc_full + 8 * as, pacc);
@@ -651,7 +676,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
           tmem_ld_wait();
           if (!(p.dbg & 2) && ((vmask >> k) & 1u)) {
             float f[16];
-            if (fixed) {
+            if (kRegP) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = kScale ? fmaf(__uint_as_float(v[j]), pa[j], pb[j]) : __uint_as_float(v[j]) + pb[j];
+            } else if (fixed) {
               const uint32_t pt = ptab + 128u * (uint32_t)((k0 + k) & (nsets - 1));
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -1317,7 +1345,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       else epilogue_tail<false, false>(p, tmem_base, acc_full, acc_empty, ptab, tailtab, warp, lane, total_tiles);
     }
     else if (p.scale && p.res) { if (silu) YOND_EPI(true, true, true, 2); else YOND_EPI(true, true, false, 2); }
+    else if (p.scale && epilogue_single_set(p) && !(p.dbg & 1024)) {  // dbg 1024: parameters from shared memory (A/B)
+      if (silu) epilogue_loop<true, false, true, 4, kPair, true>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles);
+      else epilogue_loop<true, false, false, 4, kPair, true>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles);
+    }
     else if (p.scale) { if (silu) YOND_EPI(true, false, true, 4); else YOND_EPI(true, false, false, 4); }
+    else if (p.res && epilogue_single_set(p) && !(p.dbg & 1024)) {
+#define YOND_EPI_R(A, V) epilogue_loop<false, true, A, V, kPair, true>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles)
+      if (few) { if (silu) YOND_EPI_R(true, 2); else YOND_EPI_R(false, 2); }
+      else { if (silu) YOND_EPI_R(true, 4); else YOND_EPI_R(false, 4); }
+#undef YOND_EPI_R
+    }
     else if (p.res) {
       if (few) { if (silu) YOND_EPI(false, true, true, 2); else YOND_EPI(false, true, false, 2); }
       else { if (silu) YOND_EPI(false, true, true, 4); else YOND_EPI(false, true, false, 4); }
