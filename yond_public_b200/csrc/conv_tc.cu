@@ -1360,6 +1360,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       if (few) { if (silu) YOND_EPI(false, true, true, 2); else YOND_EPI(false, true, false, 2); }
       else { if (silu) YOND_EPI(false, true, true, 4); else YOND_EPI(false, true, false, 4); }
     }
+    else if (epilogue_single_set(p) && !(p.dbg & 1024)) {
+      if (silu) epilogue_loop<false, false, true, 4, kPair, true>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles);
+      else epilogue_loop<false, false, false, 4, kPair, true>(p, tmem_base, acc_full, acc_empty, ptab, warp, lane, total_tiles);
+    }
     else { if (silu) YOND_EPI(false, false, true, 4); else YOND_EPI(false, false, false, 4); }
 #undef YOND_EPI
   }
