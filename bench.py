@@ -115,10 +115,12 @@ class ClockSampler:
             cols = [c.strip() for c in line.split(",")]
             self.rows.append(cols + [self._when(cols[-1], time.time())])
 
-    def stop(self):
+    def stop(self, span=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         t_end = time.time()  # samples after this instant saw an idle GPU: not part of the timed region
+        if span is not None:  # host clock around the timed device work itself (under torchrun the first all-reduce of the timing
+            self.t0, t_end = span  # takes several hundred ms during which the GPU idles at its maximum clock)
         time.sleep(0.05)
         self.proc.terminate()
         try:
@@ -256,11 +258,14 @@ def run_b200(args):
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host0 = time.time()
         e0.record()
         for _ in range(steps):
             fn()
         drain()
         e1.record()
+        e1.synchronize()
+        last["timed_span"] = (t_host0, time.time())  # host clock around the device work of this region (clock samples are cut to it)
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -322,7 +327,7 @@ def run_b200(args):
     l0 = Y._lib.launch_count()
     ms = timed(step_frames, args.steps)
     launches = Y._lib.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(last.get("timed_span")) if rank == 0 else None
     prof = net.read_profile(reset=True)
     hbm_prof = Y._lib.prof_read(reset=True)
     net.set_profile(False)
