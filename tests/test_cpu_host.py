@@ -222,3 +222,17 @@ def test_image_parallel_gather_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(res)
+
+
+def test_render_host_algebra(Y):
+    """The 3x3 colour algebra of process_sidd_image stays NumPy on the host (utils/sidd_utils.py:161-170): same matrix as the oracle's,
+    bit for bit; an unknown CFA pattern is rejected before anything touches the device (the reference drops into pdb there)."""
+    from yond_public_b200 import render
+    rng = np.random.default_rng(9)
+    cst = np.array([[0.8, 0.25, -0.05], [-0.3, 1.1, 0.2], [0.02, -0.2, 0.9]]) + rng.normal(0, 0.03, (3, 3))
+    m = render.cam2rgb_matrix(cst)
+    assert m.dtype == np.float64 and np.array_equal(m, O.render_cam2rgb(cst))
+    np.testing.assert_allclose(m.sum(axis=-1), 1.0, rtol=1e-15)
+    assert render._FLIPS[render._pattern_key(np.array([[3, 2], [2, 1]]))] == (1, 1)
+    with pytest.raises(ValueError):
+        Y.process_sidd_image(np.zeros((8, 8), np.float32), [[0, 1], [2, 3]], np.ones((1, 3)), np.eye(3))
