@@ -39,6 +39,11 @@ def main():
         cst = np.array([[0.8, 0.25, -0.05], [-0.3, 1.1, 0.2], [0.02, -0.2, 0.9]]) + rng.normal(0, 0.03, (3, 3))
         out[f"img{i}"], out[f"pat{i}"], out[f"wb{i}"], out[f"cst{i}"] = img, np.array(pat), wb, cst
         out[f"srgb{i}"] = process_sidd_image(img.copy(), pat, wb, cst)
+        if i == 0:  # the sRGB numbers of multiprocess_plot (YOND_SIDD.py:660-665): picture of the noisy mosaic vs picture of the clean one
+            out["srgb_clean0"] = process_sidd_image(clean.astype(np.float32), pat, wb, cst)
+            out["ssim_u8"] = np.float64(ref.Y.calculate_ssim(out["srgb0"], out["srgb_clean0"]))
+            halves = [np.split(out[k], 2, axis=-2) for k in ("srgb0", "srgb_clean0")]
+            out["ssim_u8_blocks"] = np.array([ref.Y.calculate_ssim(a, b) for a, b in zip(*halves)], np.float64)
     # (2) cv2's demosaic alone: full 14-bit range, and a 2-bit range where ties dominate; odd-ish sizes
     for j, (h, w, hi) in enumerate(((34, 50, 16384), (26, 38, 4))):
         b = rng.integers(0, hi, size=(h, w), dtype=np.uint16)

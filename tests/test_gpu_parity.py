@@ -739,6 +739,10 @@ def test_render_golden(Y, golden):
         assert np.array_equal(got, g[f"srgb{i}"]), f"pattern {pat}: {int((got != g[f'srgb{i}']).sum())} bytes differ"
     for j in range(2):
         assert np.array_equal(Y.demosaic_ea(g[f"bayer{j}"]), g[f"ea{j}"])
+    # sRGB SSIM of the rendered pictures: the reference's own calculate_ssim on its uint8 pictures (YOND_SIDD.py:660-665)
+    assert abs(Y.calculate_ssim(g["srgb0"], g["srgb_clean0"]) - float(g["ssim_u8"])) < 1e-7
+    _, sb = Y.block_metrics_rgb8(g["srgb0"], g["srgb_clean0"], 2)
+    np.testing.assert_allclose(sb.cpu().numpy()[0], g["ssim_u8_blocks"], rtol=0, atol=1e-7)
 
 
 @pytest.mark.parametrize("H,W", [(4, 4), (6, 10), (34, 130), (256, 8192), (250, 518)])

@@ -254,6 +254,10 @@ def test_render_golden(golden):
         assert np.array_equal(got, g[f"srgb{i}"]), f"pattern {pat}"
     for j in range(2):
         assert np.array_equal(O.demosaic_ea_u16(g[f"bayer{j}"]), g[f"ea{j}"])
+    # the sRGB numbers of multiprocess_plot on the rendered pictures: the reference's calculate_ssim on uint8 (H,W,3) inputs
+    np.testing.assert_allclose(O.calculate_ssim(g["srgb0"], g["srgb_clean0"]), g["ssim_u8"], rtol=0, atol=1e-12)
+    _, ss = O.sidd_rgb_metrics(g["srgb0"], g["srgb_clean0"], nblk=2)
+    np.testing.assert_allclose(ss, g["ssim_u8_blocks"].mean(), rtol=0, atol=1e-12)
 
 
 def test_demosaic_restatement_matches_cv2():
